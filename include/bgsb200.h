@@ -1,0 +1,211 @@
+/*
+ * bgsb200 -- B200-native (sm_100a) foreground-extraction hot path, C ABI.
+ *
+ * This is the drop-in boundary below the reference's C++ plugin interfaces.  Every entry
+ * point names the reference interface it replaces (paths relative to the reference tree):
+ *
+ *   IBGS::process(const cv::Mat&, cv::Mat&, cv::Mat&)            package_bgs/IBGS.h:24
+ *     FrameDifferenceBGS::process                                 package_bgs/FrameDifferenceBGS.cpp:29-61
+ *     AdaptiveBackgroundLearning::process                         package_bgs/AdaptiveBackgroundLearning.cpp:30-83
+ *     WeightedMovingVarianceBGS::process                          package_bgs/WeightedMovingVarianceBGS.cpp:30-117
+ *     MixtureOfGaussianV2BGS::process                             package_bgs/MixtureOfGaussianV2BGS.cpp:29-74
+ *   USTC_BGS::Process / GetMask / Release (CvFGDetector)          ustc_src/ustc_bgs.cpp:75-113
+ *   cv::erode / cv::dilate on the foreground mask                 package_bgs/jmo/CMultiLayerBGS.cpp:1614-1615 (and SURVEY 8a row aM)
+ *   CvBlobDetector::DetectNewBlob (cvCreateBlobDetectorCC)        ustc_src/trackingMain.cpp:56,626
+ *
+ * Plain C types only; `int` status (0 = BGSB_OK); the caller owns every I/O buffer, the
+ * library owns all model state; one context = one group of independent camera streams on
+ * one GPU.  A context is not thread-safe; distinct contexts are.  There is NO CPU fallback:
+ * every call that computes runs CUDA kernels and fails with BGSB_ERR_CUDA without a GPU.
+ *
+ * The header-only C++ adapters in tracking_b200/adapters/ re-declare the reference's
+ * classes on top of this ABI; INTEGRATION.md shows the binding a maintainer adds.
+ */
+#ifndef BGSB200_H
+#define BGSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define BGSB_API
+#else
+#define BGSB_API __attribute__((visibility("default")))
+#endif
+
+/* status codes */
+enum {
+    BGSB_OK = 0,
+    BGSB_ERR_ARG = 1,      /* bad argument (null pointer, bad size, unknown key/algo) */
+    BGSB_ERR_CUDA = 2,     /* CUDA runtime error, text in bgsb_last_error() */
+    BGSB_ERR_STATE = 3,    /* call not valid in the context's current state */
+    BGSB_ERR_CAPACITY = 4  /* a caller-provided table was too small */
+};
+
+/* algorithm ids == the integer ids of the USTC_BGS factory (ustc_src/ustc_bgs.cpp:8-14) */
+enum {
+    BGSB_ALGO_FRAME_DIFFERENCE = 0,           /* ustc_bgs.cpp:8  */
+    BGSB_ALGO_WEIGHTED_MOVING_VARIANCE = 3,   /* ustc_bgs.cpp:11 */
+    BGSB_ALGO_MOG2 = 5,                       /* ustc_bgs.cpp:13 */
+    BGSB_ALGO_ADAPTIVE_BG_LEARNING = 6        /* ustc_bgs.cpp:14 */
+};
+
+typedef struct bgsb_ctx bgsb_ctx;
+
+/* ---------------------------------------------------------------------------------------
+ * Library / device
+ * ------------------------------------------------------------------------------------- */
+BGSB_API const char *bgsb_last_error(void);          /* thread-local text of the last failure */
+BGSB_API const char *bgsb_version(void);
+BGSB_API int bgsb_device_count(int *count);
+/* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
+BGSB_API uint64_t bgsb_kernel_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Background-subtraction contexts  (replaces `new <Plugin>` / `delete`,
+ * FrameProcessor.cpp:40-59,459-478; ustc_src/ustc_bgs.cpp:8-14,75-77)
+ * ------------------------------------------------------------------------------------- */
+/* One camera stream. */
+BGSB_API int bgsb_create(bgsb_ctx **out, int algo, int device);
+/* `nstreams` independent camera streams of identical geometry that are advanced together
+ * by one launch per frame (stream group).  Stream s of every *_dev buffer below
+ * sits at base + s * (per-stream bytes). */
+BGSB_API int bgsb_create_group(bgsb_ctx **out, int algo, int device, int nstreams);
+BGSB_API void bgsb_destroy(bgsb_ctx *ctx);
+/* Drop all model state (next frame is frame 0 again). */
+BGSB_API int bgsb_reset(bgsb_ctx *ctx);
+
+/* Parameters carry the reference's XML key names (saveConfig/loadConfig of each plugin):
+ *   all      : "enableThreshold" (1), "threshold" (15)
+ *   MOG2     : "alpha" (0.05)             MixtureOfGaussianV2BGS.cpp:92-95
+ *   ABL      : "alpha" (0.05), "limit" (-1; only -1 updates the model, .cpp:52)
+ *   WMV      : "enableWeight" (1)         WeightedMovingVarianceBGS.cpp:155-158
+ * plus the cv::BackgroundSubtractorMOG2 properties of the default-constructed member
+ * (MixtureOfGaussianV2BGS.h:30): "history" 500, "nmixtures" 5 (fixed), "varThreshold" 16,
+ * "varThresholdGen" 9, "backgroundRatio" 0.9, "varInit" 15, "varMin" 4, "varMax" 75,
+ * "complexityReductionThreshold" 0.05, "detectShadows" 1, "shadowValue" 127,
+ * "shadowThreshold" 0.5; and "grayVariant": 0 = OpenCV 4.x BGR2GRAY constants, 1 = 2.4.x. */
+BGSB_API int bgsb_set_param(bgsb_ctx *ctx, const char *key, double value);
+BGSB_API int bgsb_get_param(bgsb_ctx *ctx, const char *key, double *value);
+
+/* IBGS::process with HOST buffers, synchronous (outputs complete on return).
+ *   bgr        : h rows of w BGR pixels, `stride` bytes between rows (cv::Mat::step)
+ *   fg         : h x w 8UC1, fg_stride bytes between rows
+ *   bg         : h x w 8UC3, may be NULL (background model not wanted)
+ *   *fg_valid  : 0 reproduces "output left untouched" (FD frame 0, WMV frames 0-1:
+ *                FrameDifferenceBGS.cpp:39-43, WeightedMovingVarianceBGS.cpp:40-51)
+ *   *bg_valid  : 0 for FD / WMV, which never write img_bgmodel
+ * For a stream group the buffers hold nstreams images back to back (stride * h bytes each). */
+BGSB_API int bgsb_process(bgsb_ctx *ctx, const uint8_t *bgr, int w, int h, size_t stride,
+                          uint8_t *fg, size_t fg_stride, uint8_t *bg, size_t bg_stride,
+                          int *fg_valid, int *bg_valid);
+
+/* Same, DEVICE buffers, dense rows (stride == 3*w / w), asynchronous on `stream`
+ * (a cudaStream_t; NULL = legacy default stream).  d_bg may be NULL. */
+BGSB_API int bgsb_process_dev(bgsb_ctx *ctx, const uint8_t *d_bgr, int w, int h,
+                              uint8_t *d_fg, uint8_t *d_bg, int *fg_valid, int *bg_valid,
+                              void *stream);
+
+/* Temporal batch: T consecutive frames per stream in ONE launch; the per-pixel model
+ * state stays in registers across the T frames and is read and written once.
+ *   d_frames : [nstreams][T][h][w][3]     d_fg : [nstreams][T][h][w]
+ *   d_bg     : [nstreams][T][h][w][3], or NULL
+ *   bg_last_only != 0 : d_bg is [nstreams][h][w][3] and receives only frame T-1's model
+ *   *first_fg_valid : index of the first frame of the batch whose mask was written
+ *                     (0 normally; 1 / 2 while FD / WMV warm up; T if none). */
+BGSB_API int bgsb_process_batch_dev(bgsb_ctx *ctx, const uint8_t *d_frames, int T, int w, int h,
+                                    uint8_t *d_fg, uint8_t *d_bg, int bg_last_only,
+                                    int *first_fg_valid, int *bg_valid, void *stream);
+
+/* Number of frames this context has consumed since create/reset. */
+BGSB_API int bgsb_frame_count(bgsb_ctx *ctx, int64_t *nframes);
+/* Bytes of HBM model state held per stream (101 B/px for MOG2). */
+BGSB_API int bgsb_state_bytes(bgsb_ctx *ctx, size_t *bytes);
+/* Raw MOG2 state export/import: K planes each of weight, variance,
+ * mean B, G, R as fp32 [25][npx] followed by nmodes u8 [npx]; host buffers. */
+BGSB_API int bgsb_mog2_export_state(bgsb_ctx *ctx, int stream_index, float *planes, uint8_t *nmodes);
+BGSB_API int bgsb_mog2_import_state(bgsb_ctx *ctx, int stream_index, int w, int h, int64_t nframes,
+                                    const float *planes, const uint8_t *nmodes);
+
+/* ---------------------------------------------------------------------------------------
+ * Mask morphology (cv::erode / cv::dilate, default 3x3 rect element)
+ *   ops[2*i] = BGSB_MORPH_ERODE | BGSB_MORPH_DILATE, ops[2*i+1] = iterations (>= 0)
+ *   masks are {0,255} bytes; any non-zero input byte counts as set.
+ * ------------------------------------------------------------------------------------- */
+enum { BGSB_MORPH_ERODE = 0, BGSB_MORPH_DILATE = 1 };
+BGSB_API int bgsb_morph_dev(const uint8_t *d_mask, int w, int h, int nimages, const int *ops,
+                            int nops, uint8_t *d_out, void *stream);
+BGSB_API int bgsb_morph(const uint8_t *mask, int w, int h, size_t stride, const int *ops,
+                        int nops, uint8_t *out, size_t out_stride);
+
+/* ---------------------------------------------------------------------------------------
+ * Connected components (steps 1-2 and the integer sums of step 4 of
+ * CvBlobDetectorCC::DetectNewBlob)
+ * ------------------------------------------------------------------------------------- */
+typedef struct bgsb_component {
+    int32_t label;        /* canonical, 1-based: rank of the component's first raster pixel */
+    int32_t first_index;  /* y*w + x of that pixel */
+    int32_t x, y, w, h;   /* bounding rect (== CvContour::rect of the outer contour) */
+    int32_t area;         /* pixel count */
+    int32_t external;     /* 1 iff not enclosed in a hole of another component (RETR_EXTERNAL) */
+} bgsb_component;
+
+typedef struct bgsb_ccl bgsb_ccl;
+BGSB_API int bgsb_ccl_create(bgsb_ccl **out, int device, int max_w, int max_h);
+BGSB_API void bgsb_ccl_destroy(bgsb_ccl *ccl);
+/* foreground = mask > 128 (cvThreshold(pIB,pIB,128,255,BINARY)); 8-connected.
+ * zero_border != 0 clears the outer 1-px frame first (OpenCV <= 3.1 cvFindContours).
+ * d_labels (int32 [h][w], nullable) receives canonical labels, 0 = background.
+ * Asynchronous on `stream`; the component table stays on the device until fetched. */
+BGSB_API int bgsb_ccl_label_dev(bgsb_ccl *ccl, const uint8_t *d_mask, int w, int h, int zero_border,
+                                int32_t *d_labels, void *stream);
+/* Synchronises `stream` and copies the component table (raster order) to the host. */
+BGSB_API int bgsb_ccl_components(bgsb_ccl *ccl, bgsb_component *out, int capacity, int *n);
+/* cvMoments(pFG[R], binary=0) for nrects rectangles of the mask last labelled:
+ * out[6*i..] = m00 m10 m01 m20 m02 m11 (pixel-value weighted, ROI-relative, exact). */
+BGSB_API int bgsb_ccl_rect_moments(bgsb_ccl *ccl, const int32_t *rects_xywh, int nrects, uint64_t *out);
+/* Host-buffer convenience wrapper: label + fetch. */
+BGSB_API int bgsb_ccl_label(bgsb_ccl *ccl, const uint8_t *mask, int w, int h, size_t stride,
+                            int zero_border, int32_t *labels, bgsb_component *out, int capacity, int *n);
+
+/* ---------------------------------------------------------------------------------------
+ * CvBlobDetectorCC replacement (whole of SURVEY A.6; list logic on the host, CC + sums on GPU)
+ * ------------------------------------------------------------------------------------- */
+typedef struct bgsb_blob { float x, y, w, h; int32_t id; } bgsb_blob;   /* == CvBlob */
+typedef struct bgsb_blobdetector bgsb_blobdetector;
+BGSB_API int bgsb_blobdetector_create(bgsb_blobdetector **out, int device);
+BGSB_API void bgsb_blobdetector_destroy(bgsb_blobdetector *bd);
+/* keys: "HMin" 0.02, "WMin" 0.01, "MinDistToBorder" 1.1, "Clastering" 1, "Latency" 10,
+ * "zeroBorder" 1 (OpenCV 2.4 cvFindContours behaviour) */
+BGSB_API int bgsb_blobdetector_set_param(bgsb_blobdetector *bd, const char *key, double value);
+/* DetectNewBlob(pImg, pFGMask, pNewBlobList, pOldBlobList) -> returns through *result the
+ * reference's int result (1 = a new blob was appended to new_blobs).
+ *   fg_mask host 8UC1; old_blobs = currently tracked blobs; new_blobs capacity >= 1.
+ *   frame_blobs (nullable, capacity frame_cap) receives this frame's sorted top-10 list
+ *   (m_pBlobLists[0]) for inspection / parity. */
+BGSB_API int bgsb_blobdetector_detect(bgsb_blobdetector *bd, const uint8_t *fg_mask, int w, int h,
+                                      size_t stride, const bgsb_blob *old_blobs, int n_old,
+                                      bgsb_blob *new_blobs, int new_cap, int *n_new, int *result,
+                                      bgsb_blob *frame_blobs, int frame_cap, int *n_frame);
+/* Same with a device mask (dense), e.g. straight from bgsb_process_dev + bgsb_morph_dev. */
+BGSB_API int bgsb_blobdetector_detect_dev(bgsb_blobdetector *bd, const uint8_t *d_fg_mask, int w, int h,
+                                          const bgsb_blob *old_blobs, int n_old,
+                                          bgsb_blob *new_blobs, int new_cap, int *n_new, int *result,
+                                          bgsb_blob *frame_blobs, int frame_cap, int *n_frame,
+                                          void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Synthetic video of SURVEY 8(d) generated on the device (bench / tests only):
+ * frames [nstreams][T][h][w][3]; stream s uses seed0 + s, frames t0 .. t0+T-1.
+ * ------------------------------------------------------------------------------------- */
+BGSB_API int bgsb_synth_frames_dev(uint8_t *d_frames, int nstreams, int T, int w, int h,
+                                   int t0, uint32_t seed0, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGSB200_H */

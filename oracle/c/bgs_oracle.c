@@ -1,0 +1,457 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU restatement (plain C, scalar, one thread) of the
+ * foreground-extraction hot path of USTC-Computer-Vision/tracking.
+ *
+ * It is the parity checker for the CUDA path in tracking_b200/csrc and the "port" CPU
+ * baseline of bench.py.  Nothing under tracking_b200/ links, loads or calls it.
+ *
+ * Where the arithmetic comes from.  The reference's four IBGS plugins
+ *   package_bgs/FrameDifferenceBGS.cpp:29-61
+ *   package_bgs/AdaptiveBackgroundLearning.cpp:30-83
+ *   package_bgs/WeightedMovingVarianceBGS.cpp:30-117,126-138
+ *   package_bgs/MixtureOfGaussianV2BGS.cpp:29-74
+ * are wrappers over OpenCV calls; OpenCV is an external, un-vendored, un-pinned dependency
+ * of the reference (CMakeLists.txt:21 `find_package(OpenCV REQUIRED)`; de-facto 2.4.x).  The
+ * per-element semantics of those calls are restated here from OpenCV's published behaviour
+ * (modules/video/src/bgfg_gaussmix2.cpp for MOG2, imgproc color/thresh/morph, core arithm)
+ * and PINNED against the OpenCV build importable in this image (opencv-python-headless
+ * 4.13.0) by tests/test_oracle_pin.py and the golden vectors of tests/golden/ -- see
+ * oracle/README.md for the pin status of every function.
+ *
+ * Build: `make -C oracle` -> oracle/_build/libbgs_oracle.so  (flags keep fp32 unfused).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------ */
+/* shared scalar helpers                                                                 */
+/* ------------------------------------------------------------------------------------ */
+
+/* cv::cvtColor(CV_BGR2GRAY) on 8UC3, called on the 3-channel DIFFERENCE image at
+ * FrameDifferenceBGS.cpp:48, AdaptiveBackgroundLearning.cpp:68, WeightedMovingVarianceBGS.cpp:103.
+ * variant 0: OpenCV 4.x 15-bit coefficients; variant 1: OpenCV 2.4 14-bit coefficients
+ * (SURVEY.md Appendix B). */
+static inline uint8_t gray_bgr(unsigned b, unsigned g, unsigned r, int variant)
+{
+    if (variant == 0)
+        return (uint8_t)((3735u * b + 19235u * g + 9798u * r + 16384u) >> 15);
+    return (uint8_t)((1868u * b + 9617u * g + 4899u * r + 8192u) >> 14);
+}
+
+/* cv::threshold(src,dst,thr,255,THRESH_BINARY): strict '>' (call sites :51/:71/:106/:62). */
+static inline uint8_t thr_u8(uint8_t v, int enable, int thr)
+{
+    if (!enable) return v;
+    return (int)v > thr ? 255 : 0;
+}
+
+/* saturate_cast<uchar>(float): cvRound = round-half-to-even, then clamp. */
+static inline uint8_t sat_u8_rint(float x)
+{
+    float r = nearbyintf(x);           /* default rounding mode = to nearest even */
+    if (!(r > 0.f)) return 0;          /* also catches NaN like lrint->INT_MIN->0 */
+    if (r > 255.f) return 255;
+    return (uint8_t)r;
+}
+
+ORC_API void orc_gray_bgr(const uint8_t *bgr, int npx, int variant, uint8_t *out)
+{
+    for (int i = 0; i < npx; i++)
+        out[i] = gray_bgr(bgr[3 * i], bgr[3 * i + 1], bgr[3 * i + 2], variant);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* FrameDifference  (package_bgs/FrameDifferenceBGS.cpp:45-51)                            */
+/* ------------------------------------------------------------------------------------ */
+ORC_API void orc_fd(const uint8_t *prev, const uint8_t *cur, int npx,
+                    int enable_thr, int thr, int gray_variant, uint8_t *fg)
+{
+    for (int i = 0; i < npx; i++) {
+        unsigned d[3];
+        for (int c = 0; c < 3; c++) {                       /* cv::absdiff :45 */
+            int a = prev[3 * i + c], b = cur[3 * i + c];
+            d[c] = (unsigned)(a > b ? a - b : b - a);
+        }
+        uint8_t g = gray_bgr(d[0], d[1], d[2], gray_variant);   /* :47-48 */
+        fg[i] = thr_u8(g, enable_thr, thr);                      /* :50-51 */
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* AdaptiveBackgroundLearning (package_bgs/AdaptiveBackgroundLearning.cpp:43-71)          */
+/*   bg is the 8-bit model state (img_background), updated in place and is also the       */
+/*   img_bgmodel output (:80).                                                            */
+/* ------------------------------------------------------------------------------------ */
+ORC_API void orc_abl(const uint8_t *in, uint8_t *bg, int npx, double alpha,
+                     int enable_thr, int thr, int gray_variant, uint8_t *fg)
+{
+    const float s = (float)(1. / 255.);                     /* convertTo(CV_32F, 1./255.) :44,47 */
+    const double beta = 1 - alpha;                          /* (1-alpha) in double, :54 */
+    for (int i = 0; i < npx; i++) {
+        unsigned d8[3];
+        for (int c = 0; c < 3; c++) {
+            float x = (float)in[3 * i + c] * s;
+            float y = (float)bg[3 * i + c] * s;
+            float d = fabsf(x - y);                          /* absdiff vs OLD bg :49-50 */
+            d8[c] = sat_u8_rint(d * 255.f);                  /* :64-65 */
+            /* alpha*in_f + (1-alpha)*bg_f -> addWeighted, double accumulate, one cast (A.2) */
+            float nb = (float)((double)x * alpha + (double)y * beta);
+            bg[3 * i + c] = sat_u8_rint(nb * 255.f);         /* :56-58 */
+        }
+        uint8_t g = gray_bgr(d8[0], d8[1], d8[2], gray_variant);  /* :67-68 */
+        fg[i] = thr_u8(g, enable_thr, thr);                        /* :70-71 */
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* WeightedMovingVariance (package_bgs/WeightedMovingVarianceBGS.cpp:53-106,126-138)       */
+/* ------------------------------------------------------------------------------------ */
+ORC_API void orc_wmv(const uint8_t *cur, const uint8_t *p1, const uint8_t *p2, int npx,
+                     int enable_weight, int enable_thr, int thr, int gray_variant, uint8_t *fg)
+{
+    const float s = (float)(1. / 255.);
+    const double w0 = enable_weight ? 0.5 : 0.3, w1 = 0.3, w2 = enable_weight ? 0.2 : 0.3;  /* :66-70 */
+    const float w0f = (float)w0, w1f = (float)w1, w2f = (float)w2;
+    for (int i = 0; i < npx; i++) {
+        unsigned g8[3];
+        for (int c = 0; c < 3; c++) {
+            float x0 = (float)cur[3 * i + c] * s;
+            float x1 = (float)p1[3 * i + c] * s;
+            float x2 = (float)p2[3 * i + c] * s;
+            /* (A*w0 + B*w1) -> addWeighted (double), + C*w2 -> scaleAdd (fused) :67-70 */
+            float m01 = (float)((double)x0 * w0 + (double)x1 * w1);
+            float m = fmaf(x2, w2f, m01);
+            /* computeWeightedVariance :126-138 : absdiff, pow 2 (= x*x), weight*Mat (fp32 mul) */
+            float d0 = fabsf(x0 - m), d1 = fabsf(x1 - m), d2 = fabsf(x2 - m);
+            float v0 = (d0 * d0) * w0f, v1 = (d1 * d1) * w1f, v2 = (d2 * d2) * w2f;
+            float v = (v0 + v1) + v2;                        /* :84 left-assoc MatExpr sum */
+            float sd = sqrtf(v);                             /* :95 */
+            g8[c] = sat_u8_rint(sd * 255.f);                 /* :99 */
+        }
+        uint8_t g = gray_bgr(g8[0], g8[1], g8[2], gray_variant);  /* :102-103 */
+        fg[i] = thr_u8(g, enable_thr, thr);                        /* :105-106 */
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* MOG2: cv::BackgroundSubtractorMOG2::operator() + getBackgroundImage                    */
+/*   (member `mog`, package_bgs/MixtureOfGaussianV2BGS.h:30; calls .cpp:56,59).           */
+/*   State layout here follows upstream (AoS): gmm[npx][K]{weight,variance},               */
+/*   mean[npx][K][3], nmodes[npx].  SURVEY.md Appendix A.4 is the spec.                    */
+/* ------------------------------------------------------------------------------------ */
+typedef struct {
+    int   K;            /* nmixtures, 5 */
+    float Tb;           /* varThreshold 16 */
+    float Tg;           /* varThresholdGen 9 */
+    float TB;           /* backgroundRatio 0.9 */
+    float varInit, varMin, varMax;   /* 15, 4, 75 */
+    float CT;           /* complexity reduction 0.05 */
+    float tau;          /* shadow threshold 0.5 */
+    int   detect_shadows;   /* 1 */
+    int   shadow_value;     /* 127 */
+    int   history;          /* 500 */
+} orc_mog2_params;
+
+ORC_API void orc_mog2_default_params(orc_mog2_params *p)
+{
+    p->K = 5; p->Tb = 16.f; p->Tg = 9.f; p->TB = 0.9f;
+    p->varInit = 15.f; p->varMin = 4.f; p->varMax = 75.f;
+    p->CT = 0.05f; p->tau = 0.5f; p->detect_shadows = 1; p->shadow_value = 127; p->history = 500;
+}
+
+/* learning rate rule of operator(): ++nframes;
+ * lr = (alpha >= 0 && nframes > 1) ? alpha : 1./min(2*nframes, history) */
+ORC_API double orc_mog2_learning_rate(double alpha, int nframes_after_increment, int history)
+{
+    if (alpha >= 0 && nframes_after_increment > 1) return alpha;
+    int d = 2 * nframes_after_increment; if (d > history) d = history;
+    return 1. / d;
+}
+
+static int mog2_shadow(const float *d, int n, const float *gmm, const float *mean,
+                       const orc_mog2_params *P)
+{
+    float tW = 0.f;
+    for (int m = 0; m < n; m++) {
+        const float *mu = mean + 3 * m;
+        float num = 0.f, den = 0.f;
+        for (int c = 0; c < 3; c++) { num += d[c] * mu[c]; den += mu[c] * mu[c]; }
+        if (den == 0.f) return 0;
+        if (num <= den && num >= P->tau * den) {
+            float a = num / den, e = 0.f;
+            for (int c = 0; c < 3; c++) { float dd = a * mu[c] - d[c]; e += dd * dd; }
+            if (e < P->Tb * gmm[2 * m + 1] * a * a) return 1;
+        }
+        tW += gmm[2 * m];
+        if (tW > P->TB) return 0;
+    }
+    return 0;
+}
+
+static inline void swap_mode(float *gmm, float *mean, int i, int j)
+{
+    float t;
+    t = gmm[2 * i]; gmm[2 * i] = gmm[2 * j]; gmm[2 * j] = t;
+    t = gmm[2 * i + 1]; gmm[2 * i + 1] = gmm[2 * j + 1]; gmm[2 * j + 1] = t;
+    for (int c = 0; c < 3; c++) { t = mean[3 * i + c]; mean[3 * i + c] = mean[3 * j + c]; mean[3 * j + c] = t; }
+}
+
+/* One frame.  lr is the already-resolved learning rate (see orc_mog2_learning_rate).
+ * mask receives the RAW MOG2 output {0, shadow_value, 255}. */
+ORC_API void orc_mog2_apply(const uint8_t *in, int npx, double lr, const orc_mog2_params *P,
+                            float *gmm_all, float *mean_all, uint8_t *nmodes_all, uint8_t *mask)
+{
+    const int K = P->K;
+    const float alphaT = (float)lr, alpha1 = 1.f - alphaT;
+    const float prune = (float)(-lr * (double)P->CT);   /* float prune = -learningRate*fCT (fCT float, product in double) */
+    for (int i = 0; i < npx; i++) {
+        float *gmm = gmm_all + (size_t)i * K * 2;
+        float *mean = mean_all + (size_t)i * K * 3;
+        float d[3] = { (float)in[3 * i], (float)in[3 * i + 1], (float)in[3 * i + 2] };
+        int n = nmodes_all[i];
+        int bg = 0, fits = 0;
+        float tw = 0.f;
+        for (int m = 0; m < n; m++) {           /* bound is the LIVE n (A.4 loop-bound note) */
+            float w = alpha1 * gmm[2 * m] + prune;
+            int swaps = 0;
+            if (!fits) {
+                float *mu = mean + 3 * m;
+                float var = gmm[2 * m + 1];
+                float dD0 = mu[0] - d[0], dD1 = mu[1] - d[1], dD2 = mu[2] - d[2];
+                float dist2 = dD0 * dD0 + dD1 * dD1 + dD2 * dD2;
+                if (tw < P->TB && dist2 < P->Tb * var) bg = 1;
+                if (dist2 < P->Tg * var) {
+                    fits = 1;
+                    w += alphaT;
+                    float k = alphaT / w;
+                    mu[0] -= k * dD0; mu[1] -= k * dD1; mu[2] -= k * dD2;
+                    float vn = var + k * (dist2 - var);
+                    vn = vn > P->varMin ? vn : P->varMin;       /* MAX(varnew, fVarMin) */
+                    vn = vn < P->varMax ? vn : P->varMax;       /* MIN(varnew, fVarMax) */
+                    gmm[2 * m + 1] = vn;
+                    for (int j = m; j > 0; j--) {
+                        if (w < gmm[2 * (j - 1)]) break;
+                        swaps++;
+                        swap_mode(gmm, mean, j, j - 1);
+                    }
+                }
+            }
+            if (w < -prune) { w = 0.f; n--; }
+            gmm[2 * (m - swaps)] = w;
+            tw += w;
+        }
+        /* renormalise (4.x guards |tw| > FLT_EPSILON; with n>0 tw >= -prune so identical) */
+        float inv = 0.f;
+        if (fabsf(tw) > 1.1920929e-07f) inv = 1.f / tw;
+        for (int m = 0; m < n; m++) gmm[2 * m] *= inv;
+        if (!fits && alphaT > 0.f) {
+            int m = (n == K) ? K - 1 : n++;
+            if (n == 1) gmm[2 * m] = 1.f;
+            else {
+                gmm[2 * m] = alphaT;
+                for (int j = 0; j < n - 1; j++) gmm[2 * j] *= alpha1;
+            }
+            mean[3 * m] = d[0]; mean[3 * m + 1] = d[1]; mean[3 * m + 2] = d[2];
+            gmm[2 * m + 1] = P->varInit;
+            for (int j = n - 1; j > 0; j--) {
+                if (alphaT < gmm[2 * (j - 1)]) break;
+                swap_mode(gmm, mean, j, j - 1);
+            }
+        }
+        nmodes_all[i] = (uint8_t)n;
+        mask[i] = bg ? 0 : ((P->detect_shadows && mog2_shadow(d, n, gmm, mean, P)) ? (uint8_t)P->shadow_value : 255);
+    }
+}
+
+/* getBackgroundImage (MixtureOfGaussianV2BGS.cpp:59). */
+ORC_API void orc_mog2_background(int npx, const orc_mog2_params *P, const float *gmm_all,
+                                 const float *mean_all, const uint8_t *nmodes_all, uint8_t *bgimg)
+{
+    const int K = P->K;
+    for (int i = 0; i < npx; i++) {
+        const float *gmm = gmm_all + (size_t)i * K * 2;
+        const float *mean = mean_all + (size_t)i * K * 3;
+        int n = nmodes_all[i];
+        float acc[3] = { 0.f, 0.f, 0.f }, tw = 0.f;
+        for (int m = 0; m < n; m++) {
+            float w = gmm[2 * m];
+            for (int c = 0; c < 3; c++) acc[c] += w * mean[3 * m + c];
+            tw += w;
+            if (tw > P->TB) break;
+        }
+        float inv = 0.f;
+        if (fabsf(tw) > 1.1920929e-07f) inv = 1.f / tw;
+        for (int c = 0; c < 3; c++) bgimg[3 * i + c] = sat_u8_rint(acc[c] * inv);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Morphology: cv::erode / cv::dilate with the default 3x3 rect element, anchor centre,    */
+/* out-of-image pixels ignored.  op: 0 erode, 1 dilate.                    */
+/* ------------------------------------------------------------------------------------ */
+ORC_API void orc_morph3x3(const uint8_t *in, int w, int h, int op, int iterations, uint8_t *out)
+{
+    size_t n = (size_t)w * h;
+    uint8_t *a = (uint8_t *)malloc(n), *b = (uint8_t *)malloc(n);
+    memcpy(a, in, n);
+    for (int it = 0; it < iterations; it++) {
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                int v = op ? 0 : 255;
+                for (int dy = -1; dy <= 1; dy++) {
+                    int yy = y + dy; if (yy < 0 || yy >= h) continue;
+                    for (int dx = -1; dx <= 1; dx++) {
+                        int xx = x + dx; if (xx < 0 || xx >= w) continue;
+                        int p = a[(size_t)yy * w + xx];
+                        if (op) { if (p > v) v = p; } else { if (p < v) v = p; }
+                    }
+                }
+                b[(size_t)y * w + x] = (uint8_t)v;
+            }
+        uint8_t *t = a; a = b; b = t;
+    }
+    memcpy(out, a, n);
+    free(a); free(b);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Connected components: steps 1-2 of CvBlobDetectorCC::DetectNewBlob.     */
+/*   foreground = mask > 128; 8-connectivity; canonical label k (1-based) = rank of the    */
+/*   component's minimum linear index.  Plain BFS flood fill in raster order, which         */
+/*   numbers components by raster-first pixel by construction.                              */
+/*   zero_border: emulate OpenCV<=3.1 cvFindContours, which clears the outer 1-px frame.    */
+/*   external[k-1] = 1 iff the component is NOT enclosed in a hole of another component     */
+/*   (what RETR_EXTERNAL keeps): its surrounding background region (4-connected) reaches    */
+/*   the outside of the image.                                                              */
+/*   stats[k-1] = {xmin, ymin, xmax, ymax, area, first_linear_index}                        */
+/* ------------------------------------------------------------------------------------ */
+ORC_API int orc_ccl8(const uint8_t *mask, int w, int h, int zero_border,
+                     int32_t *labels, int max_comp, int32_t *stats, uint8_t *external)
+{
+    size_t n = (size_t)w * h;
+    uint8_t *fgm = (uint8_t *)malloc(n);
+    for (size_t i = 0; i < n; i++) fgm[i] = mask[i] > 128;
+    if (zero_border) {
+        for (int x = 0; x < w; x++) { fgm[x] = 0; fgm[(size_t)(h - 1) * w + x] = 0; }
+        for (int y = 0; y < h; y++) { fgm[(size_t)y * w] = 0; fgm[(size_t)y * w + w - 1] = 0; }
+    }
+    memset(labels, 0, n * sizeof(int32_t));
+    int32_t *queue = (int32_t *)malloc(n * sizeof(int32_t));
+    int ncomp = 0;
+    for (size_t p0 = 0; p0 < n; p0++) {
+        if (!fgm[p0] || labels[p0]) continue;
+        ncomp++;
+        int xmin = w, ymin = h, xmax = -1, ymax = -1, area = 0;
+        size_t qh = 0, qt = 0;
+        queue[qt++] = (int32_t)p0; labels[p0] = ncomp;
+        while (qh < qt) {
+            int p = queue[qh++];
+            int x = p % w, y = p / w;
+            area++;
+            if (x < xmin) xmin = x; if (x > xmax) xmax = x;
+            if (y < ymin) ymin = y; if (y > ymax) ymax = y;
+            for (int dy = -1; dy <= 1; dy++) {
+                int yy = y + dy; if (yy < 0 || yy >= h) continue;
+                for (int dx = -1; dx <= 1; dx++) {
+                    int xx = x + dx; if (xx < 0 || xx >= w) continue;
+                    size_t q = (size_t)yy * w + xx;
+                    if (fgm[q] && !labels[q]) { labels[q] = ncomp; queue[qt++] = (int32_t)q; }
+                }
+            }
+        }
+        if (ncomp <= max_comp && stats) {
+            int32_t *s = stats + 6 * (size_t)(ncomp - 1);
+            s[0] = xmin; s[1] = ymin; s[2] = xmax; s[3] = ymax; s[4] = area; s[5] = (int32_t)p0;
+        }
+    }
+    if (external) {
+        /* flood the background (4-connected) from outside the image */
+        uint8_t *outer = (uint8_t *)calloc(n, 1);
+        size_t qh = 0, qt = 0;
+        for (int x = 0; x < w; x++) {
+            size_t a = x, b = (size_t)(h - 1) * w + x;
+            if (!fgm[a] && !outer[a]) { outer[a] = 1; queue[qt++] = (int32_t)a; }
+            if (!fgm[b] && !outer[b]) { outer[b] = 1; queue[qt++] = (int32_t)b; }
+        }
+        for (int y = 0; y < h; y++) {
+            size_t a = (size_t)y * w, b = (size_t)y * w + w - 1;
+            if (!fgm[a] && !outer[a]) { outer[a] = 1; queue[qt++] = (int32_t)a; }
+            if (!fgm[b] && !outer[b]) { outer[b] = 1; queue[qt++] = (int32_t)b; }
+        }
+        static const int d4x[4] = { 1, -1, 0, 0 }, d4y[4] = { 0, 0, 1, -1 };
+        while (qh < qt) {
+            int p = queue[qh++];
+            int x = p % w, y = p / w;
+            for (int k = 0; k < 4; k++) {
+                int xx = x + d4x[k], yy = y + d4y[k];
+                if (xx < 0 || xx >= w || yy < 0 || yy >= h) continue;
+                size_t q = (size_t)yy * w + xx;
+                if (!fgm[q] && !outer[q]) { outer[q] = 1; queue[qt++] = (int32_t)q; }
+            }
+        }
+        int lim = ncomp < max_comp ? ncomp : max_comp;
+        for (int k = 0; k < lim; k++) {
+            int p0 = stats[6 * (size_t)k + 5];
+            int x = p0 % w;
+            /* the pixel left of the raster-first pixel lies in the surrounding background */
+            external[k] = (x == 0) ? 1 : outer[p0 - 1];
+        }
+        free(outer);
+    }
+    free(queue); free(fgm);
+    return ncomp;
+}
+
+/* cvMoments(pFG[R], binary=0) on an 8-bit ROI: raw spatial moments up to order 2 that
+ * CvBlobDetectorCC uses (step 4 of A.6): m00 m10 m01 m20 m02 (+ m11), pixel-VALUE weighted,
+ * x,y relative to the ROI origin.  Exact integer sums. */
+ORC_API void orc_rect_moments(const uint8_t *img, int w, int h, int rx, int ry, int rw, int rh,
+                              uint64_t out[6])
+{
+    uint64_t m00 = 0, m10 = 0, m01 = 0, m20 = 0, m02 = 0, m11 = 0;
+    (void)h;
+    for (int y = 0; y < rh; y++)
+        for (int x = 0; x < rw; x++) {
+            uint64_t v = img[(size_t)(ry + y) * w + rx + x];
+            m00 += v; m10 += v * x; m01 += v * y; m20 += v * x * x; m02 += v * y * y; m11 += v * x * y;
+        }
+    out[0] = m00; out[1] = m10; out[2] = m01; out[3] = m20; out[4] = m02; out[5] = m11;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* Synthetic video of SURVEY.md 8(d) (integer-only, so CPU and GPU generate identical      */
+/* frames).  Used by the CPU baseline legs so the generator is not timed in Python.         */
+/* ------------------------------------------------------------------------------------ */
+static inline uint32_t mix32(uint32_t h)
+{
+    h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16;
+    return h;
+}
+
+ORC_API void orc_synth_frame(int w, int h, int t, uint32_t seed, uint8_t *bgr)
+{
+    const int scale = (w >= 3840) ? 2 : 1;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            for (int c = 0; c < 3; c++) {
+                int B = 32 + (((x * 5 + y * 3 + 64 * c) >> 3) & 127) + 48 * (((x >> 6) ^ (y >> 6)) & 1);
+                uint32_t hsh = ((uint32_t)x * 73856093U) ^ ((uint32_t)y * 19349663U) ^
+                               ((uint32_t)t * 83492791U) ^ ((uint32_t)c * 2654435761U) ^ seed;
+                int N = (int)(mix32(hsh) % 13U) - 6;
+                int v = B + N; if (v < 0) v = 0; if (v > 255) v = 255;
+                bgr[((size_t)y * w + x) * 3 + c] = (uint8_t)v;
+            }
+    for (int r = 0; r < 12; r++) {
+        int rw = 100 * scale, rh = 80 * scale;
+        int x0 = (100 + 150 * r + 17 * t) % (w - 120 * scale);
+        int y0 = (60 + 83 * r + 5 * t) % (h - 90 * scale);
+        uint8_t col[3] = { (uint8_t)((40 * r) & 255), (uint8_t)(255 - 20 * r), 128 };
+        for (int y = y0; y < y0 + rh && y < h; y++)
+            for (int x = x0; x < x0 + rw && x < w; x++)
+                for (int c = 0; c < 3; c++) bgr[((size_t)y * w + x) * 3 + c] = col[c];
+    }
+}

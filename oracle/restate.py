@@ -1,0 +1,225 @@
+"""TEST INFRASTRUCTURE ONLY - Python face of the C restatement (oracle/c/bgs_oracle.c).
+
+Classes carry the reference's plugin names and `process(img) -> (fg|None, bg|None)`
+mirrors `IBGS::process(in, fg, bgModel)` (package_bgs/IBGS.h:24): `None` stands for
+"output left untouched" (the reference returns early without writing, e.g.
+package_bgs/FrameDifferenceBGS.cpp:39-43).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libbgs_oracle.so")
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(_HERE, "c", "bgs_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+class Mog2Params(C.Structure):
+    _fields_ = [("K", C.c_int), ("Tb", C.c_float), ("Tg", C.c_float), ("TB", C.c_float),
+                ("varInit", C.c_float), ("varMin", C.c_float), ("varMax", C.c_float),
+                ("CT", C.c_float), ("tau", C.c_float), ("detect_shadows", C.c_int),
+                ("shadow_value", C.c_int), ("history", C.c_int)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        u8p, f32p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        L.orc_gray_bgr.argtypes = [u8p, C.c_int, C.c_int, u8p]
+        L.orc_fd.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
+        L.orc_abl.argtypes = [u8p, u8p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, u8p]
+        L.orc_wmv.argtypes = [u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
+        L.orc_mog2_default_params.argtypes = [C.POINTER(Mog2Params)]
+        L.orc_mog2_learning_rate.argtypes = [C.c_double, C.c_int, C.c_int]
+        L.orc_mog2_learning_rate.restype = C.c_double
+        L.orc_mog2_apply.argtypes = [u8p, C.c_int, C.c_double, C.POINTER(Mog2Params), f32p, f32p, u8p, u8p]
+        L.orc_mog2_background.argtypes = [C.c_int, C.POINTER(Mog2Params), f32p, f32p, u8p, u8p]
+        L.orc_morph3x3.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
+        L.orc_ccl8.argtypes = [u8p, C.c_int, C.c_int, C.c_int, i32p, C.c_int, i32p, u8p]
+        L.orc_ccl8.restype = C.c_int
+        L.orc_rect_moments.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.POINTER(C.c_uint64)]
+        L.orc_synth_frame.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, u8p]
+        _lib = L
+    return _lib
+
+
+def _u8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _f32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _dense(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    assert img.ndim == 3 and img.shape[2] == 3, "plugins take BGR 8UC3 (PreProcessor.cpp:56)"
+    return img
+
+
+def gray_bgr(img, variant=0):
+    img = _dense(img)
+    out = np.empty(img.shape[:2], np.uint8)
+    lib().orc_gray_bgr(_u8(img), out.size, variant, _u8(out))
+    return out
+
+
+class FrameDifferenceBGS:
+    def __init__(self, enableThreshold=True, threshold=15, gray_variant=0):
+        self.enableThreshold, self.threshold, self.gray_variant = enableThreshold, threshold, gray_variant
+        self.prev = None
+
+    def process(self, img):
+        if img is None or img.size == 0:
+            return None, None
+        img = _dense(img)
+        if self.prev is None:
+            self.prev = img.copy()
+            return None, None
+        fg = np.empty(img.shape[:2], np.uint8)
+        lib().orc_fd(_u8(self.prev), _u8(img), fg.size, int(self.enableThreshold), self.threshold,
+                     self.gray_variant, _u8(fg))
+        self.prev = img.copy()
+        return fg, None
+
+
+class AdaptiveBackgroundLearning:
+    def __init__(self, alpha=0.05, enableThreshold=True, threshold=15, gray_variant=0):
+        self.alpha, self.enableThreshold, self.threshold = alpha, enableThreshold, threshold
+        self.gray_variant = gray_variant
+        self.bg = None
+
+    def process(self, img):
+        if img is None or img.size == 0:
+            return None, None
+        img = _dense(img)
+        if self.bg is None:
+            self.bg = img.copy()
+        fg = np.empty(img.shape[:2], np.uint8)
+        lib().orc_abl(_u8(img), _u8(self.bg), fg.size, float(self.alpha), int(self.enableThreshold),
+                      self.threshold, self.gray_variant, _u8(fg))
+        return fg, self.bg.copy()
+
+
+class WeightedMovingVarianceBGS:
+    def __init__(self, enableWeight=True, enableThreshold=True, threshold=15, gray_variant=0):
+        self.enableWeight, self.enableThreshold, self.threshold = enableWeight, enableThreshold, threshold
+        self.gray_variant = gray_variant
+        self.p1 = None
+        self.p2 = None
+
+    def process(self, img):
+        if img is None or img.size == 0:
+            return None, None
+        img = _dense(img)
+        if self.p1 is None:
+            self.p1 = img.copy()
+            return None, None
+        if self.p2 is None:
+            self.p2 = self.p1
+            self.p1 = img.copy()
+            return None, None
+        fg = np.empty(img.shape[:2], np.uint8)
+        lib().orc_wmv(_u8(img), _u8(self.p1), _u8(self.p2), fg.size, int(self.enableWeight),
+                      int(self.enableThreshold), self.threshold, self.gray_variant, _u8(fg))
+        self.p2 = self.p1
+        self.p1 = img.copy()
+        return fg, None
+
+
+class MixtureOfGaussianV2BGS:
+    """MOG2 wrapper (package_bgs/MixtureOfGaussianV2BGS.cpp:56-62) over orc_mog2_*."""
+
+    def __init__(self, alpha=0.05, enableThreshold=True, threshold=15):
+        self.alpha, self.enableThreshold, self.threshold = alpha, enableThreshold, threshold
+        self.params = Mog2Params()
+        lib().orc_mog2_default_params(C.byref(self.params))
+        self.nframes = 0
+        self.shape = None
+
+    def _init(self, shape):
+        h, w = shape
+        K = self.params.K
+        self.shape = shape
+        self.gmm = np.zeros((h * w, K, 2), np.float32)
+        self.mean = np.zeros((h * w, K, 3), np.float32)
+        self.nmodes = np.zeros(h * w, np.uint8)
+        self.nframes = 0
+
+    def process(self, img, want_raw=False):
+        if img is None or img.size == 0:
+            return None, None
+        img = _dense(img)
+        if self.shape != img.shape[:2]:          # operator(): re-initialise on size change
+            self._init(img.shape[:2])
+        self.nframes += 1
+        lr = lib().orc_mog2_learning_rate(float(self.alpha), self.nframes, self.params.history)
+        npx = img.shape[0] * img.shape[1]
+        raw = np.empty(img.shape[:2], np.uint8)
+        lib().orc_mog2_apply(_u8(img), npx, lr, C.byref(self.params), _f32(self.gmm), _f32(self.mean),
+                             _u8(self.nmodes), _u8(raw))
+        bg = np.empty(img.shape, np.uint8)
+        lib().orc_mog2_background(npx, C.byref(self.params), _f32(self.gmm), _f32(self.mean),
+                                  _u8(self.nmodes), _u8(bg))
+        fg = raw
+        if self.enableThreshold:
+            fg = np.where(raw > self.threshold, 255, 0).astype(np.uint8)
+        if want_raw:
+            return fg, bg, raw
+        return fg, bg
+
+
+ALGOS = {0: FrameDifferenceBGS, 3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS,
+         6: AdaptiveBackgroundLearning}          # ids of ustc_src/ustc_bgs.cpp:8-14
+
+
+def morph(mask, op, iterations=1):
+    mask = np.ascontiguousarray(mask, np.uint8)
+    out = np.empty_like(mask)
+    h, w = mask.shape
+    lib().orc_morph3x3(_u8(mask), w, h, {"erode": 0, "dilate": 1}[op], iterations, _u8(out))
+    return out
+
+
+def ccl8(mask, zero_border=False):
+    """-> (n, labels int32 HxW, stats n x 6 [xmin,ymin,xmax,ymax,area,first_idx], external n)"""
+    mask = np.ascontiguousarray(mask, np.uint8)
+    h, w = mask.shape
+    labels = np.empty((h, w), np.int32)
+    cap = h * w // 2 + 2
+    stats = np.zeros((cap, 6), np.int32)
+    ext = np.zeros(cap, np.uint8)
+    n = lib().orc_ccl8(_u8(mask), w, h, int(zero_border), labels.ctypes.data_as(C.POINTER(C.c_int32)), cap,
+                       stats.ctypes.data_as(C.POINTER(C.c_int32)), _u8(ext))
+    return n, labels, stats[:n].copy(), ext[:n].copy()
+
+
+def rect_moments(img, rect):
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    out = (C.c_uint64 * 6)()
+    x, y, rw, rh = rect
+    lib().orc_rect_moments(_u8(img), w, h, x, y, rw, rh, out)
+    return [int(v) for v in out]
+
+
+def synth_frame(w, h, t, seed):
+    out = np.empty((h, w, 3), np.uint8)
+    lib().orc_synth_frame(w, h, t, seed & 0xFFFFFFFF, _u8(out))
+    return out

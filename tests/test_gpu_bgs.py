@@ -1,0 +1,324 @@
+"""Parity of the CUDA plugins against the oracle -- every call goes through the C ABI."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import stress_sequence
+
+pytestmark = pytest.mark.gpu
+
+NAMES = {0: "FrameDifferenceBGS", 3: "WeightedMovingVarianceBGS", 5: "MixtureOfGaussianV2BGS",
+         6: "AdaptiveBackgroundLearning"}
+# north_star tolerances: FD bit-exact; MOG2/ABL/WMV masks <= 0.1 % disagreement, bg <= 1e-4 relative.
+# The kernels are in fact bit-exact on every fixture, so the tests assert 0 mismatches and would
+# start failing long before the contractual tolerance is reached.
+MASK_TOL = 0.0
+BG_TOL = 0.0
+
+
+def sha(arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def run_host(plugin, frames):
+    fgs, bgs = [], []
+    for f in frames:
+        fg, bg = plugin.process(f)
+        if fg is not None:
+            fgs.append(fg.copy())
+        if bg is not None:
+            bgs.append(bg.copy())
+    return fgs, bgs
+
+
+def assert_same(a, b, what):
+    assert len(a) == len(b), "%s: %d vs %d outputs" % (what, len(a), len(b))
+    for i, (x, y) in enumerate(zip(a, b)):
+        bad = int((x != y).sum())
+        assert bad <= MASK_TOL * x.size, "%s frame %d: %d / %d differ" % (what, i, bad, x.size)
+
+
+@pytest.mark.parametrize("seq", ["video_clip", "png_clip"])
+@pytest.mark.parametrize("aid", [0, 3, 5, 6])
+@pytest.mark.parametrize("thr", [True, False])
+def test_host_path_matches_golden_and_oracle(oracle, clips, golden, seq, aid, thr):
+    import tracking_b200 as tb
+    frames = list(clips[seq])
+    p = tb.ALGOS[aid](enableThreshold=int(thr))
+    fgs, bgs = run_host(p, frames)
+    ofg, obg = [], []
+    o = oracle.ALGOS[aid](enableThreshold=thr)
+    for f in frames:
+        fg, bg = o.process(f)
+        if fg is not None:
+            ofg.append(fg)
+        if bg is not None:
+            obg.append(bg)
+    assert_same(fgs, ofg, "fg")
+    assert_same(bgs, obg, "bg")
+    exp = golden["sequences"][seq]["algos"][NAMES[aid] + ("" if thr else ":enableThreshold=0")]
+    assert sha(fgs) == exp["fg_sha256"]
+    if exp["bg_sha256"]:
+        assert sha(bgs) == exp["bg_sha256"]
+    p.close()
+
+
+def test_warmup_contract_outputs_untouched():
+    """FD frame 0 and WMV frames 0-1 return without writing (reference early returns)."""
+    import tracking_b200 as tb
+    f = np.zeros((40, 50, 3), np.uint8)
+    fd, wmv, abl, mog = tb.FrameDifferenceBGS(), tb.WeightedMovingVarianceBGS(), tb.AdaptiveBackgroundLearning(), tb.MixtureOfGaussianV2BGS()
+    assert fd.process(f) == (None, None)
+    fg, bg = fd.process(f)
+    assert fg is not None and bg is None
+    assert wmv.process(f) == (None, None) and wmv.process(f) == (None, None)
+    fg, bg = wmv.process(f)
+    assert fg is not None and bg is None
+    fg, bg = abl.process(f)
+    assert fg is not None and bg is not None and not fg.any()
+    fg, bg = mog.process(f)
+    assert (fg == 255).all() and np.array_equal(bg, f)          # frame 1: all foreground, bg = frame
+    assert fd.process(None) == (None, None) and fd.process(np.zeros((0, 0, 3), np.uint8)) == (None, None)
+    assert fd.frame_count == 2
+
+
+def test_mog2_stress_sequence_state_bit_exact(oracle):
+    """Mode churn (prune / replace / re-sort paths) incl. the exported mixture state."""
+    import tracking_b200 as tb
+    frames = stress_sequence(200, 40, 52)
+    for thr, kw in ((True, {}), (False, {}), (True, {"threshold": 200})):
+        p = tb.MixtureOfGaussianV2BGS(enableThreshold=int(thr), **kw)
+        o = oracle.MixtureOfGaussianV2BGS(enableThreshold=thr, **kw)
+        for i, f in enumerate(frames):
+            fg, bg = p.process(f)
+            ofg, obg = o.process(f)
+            assert np.array_equal(fg, ofg), "mask frame %d" % i
+            assert np.array_equal(bg, obg), "bg frame %d" % i
+        planes, nm = p.export_state()
+        assert np.array_equal(nm, o.nmodes)
+        K = 5
+        for m in range(K):
+            live = o.nmodes > m
+            assert np.array_equal(planes[m * 5 + 0][live], o.gmm[:, m, 0][live])
+            assert np.array_equal(planes[m * 5 + 1][live], o.gmm[:, m, 1][live])
+            for c in range(3):
+                assert np.array_equal(planes[m * 5 + 2 + c][live], o.mean[:, m, c][live])
+        p.close()
+
+
+def test_mog2_auto_learning_rate_and_params(oracle):
+    """alpha < 0 -> 1/min(2*nframes, history); non-default MOG2 properties."""
+    import tracking_b200 as tb
+    frames = stress_sequence(60, 33, 47, seed=11)
+    p = tb.MixtureOfGaussianV2BGS(alpha=-1, history=40, varThreshold=10, backgroundRatio=0.7)
+    o = oracle.MixtureOfGaussianV2BGS(alpha=-1)
+    o.params.history = 40; o.params.Tb = 10; o.params.TB = 0.7
+    for i, f in enumerate(frames):
+        fg, bg = p.process(f)
+        ofg, obg = o.process(f)
+        assert np.array_equal(fg, ofg) and np.array_equal(bg, obg), i
+
+
+def test_abl_exhaustive_byte_pairs(oracle):
+    import tracking_b200 as tb
+    inp, bg = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8))
+    f0 = np.repeat(bg[:, :, None], 3, 2).copy()
+    f1 = np.repeat(inp[:, :, None], 3, 2).copy()
+    for alpha in (0.05, 0.3, 0.001):
+        p, o = tb.AdaptiveBackgroundLearning(alpha=alpha), oracle.AdaptiveBackgroundLearning(alpha=alpha)
+        for f in (f0, f1):
+            fa, ba = p.process(f)
+            fb, bb = o.process(f)
+        assert np.array_equal(fa, fb) and np.array_equal(ba, bb)
+
+
+def test_wmv_exhaustive_triples_sample(oracle):
+    """Random byte triples incl. unweighted variant and raw (un-thresholded) output."""
+    import tracking_b200 as tb
+    rng = np.random.default_rng(2)
+    frames = [rng.integers(0, 256, (257, 301, 3), dtype=np.uint8) for _ in range(6)]
+    for ew in (1, 0):
+        for thr in (1, 0):
+            p = tb.WeightedMovingVarianceBGS(enableWeight=ew, enableThreshold=thr)
+            o = oracle.WeightedMovingVarianceBGS(enableWeight=bool(ew), enableThreshold=bool(thr))
+            for f in frames:
+                fa, _ = p.process(f)
+                fb, _ = o.process(f)
+                assert (fa is None) == (fb is None)
+                if fa is not None:
+                    assert np.array_equal(fa, fb)
+
+
+@pytest.mark.parametrize("aid", [0, 3, 5, 6])
+def test_gray_variant_24_constants(oracle, clips, aid):
+    import tracking_b200 as tb
+    if aid == 5:
+        pytest.skip("MOG2 has no gray conversion")
+    frames = list(clips["png_clip"])
+    p = tb.ALGOS[aid](grayVariant=1)
+    o = oracle.ALGOS[aid](gray_variant=1)
+    a, _ = run_host(p, frames)
+    b = [x for x in (o.process(f)[0] for f in frames) if x is not None]
+    assert_same(a, b, "gray 2.4")
+
+
+@pytest.mark.parametrize("aid", [0, 3, 5, 6])
+@pytest.mark.parametrize("T", [1, 3, 8])
+def test_device_batch_and_stream_group(oracle, clips, aid, T):
+    """Temporal batches of T frames and a group of 3 streams advanced by one launch equal the
+    frame-by-frame oracle (state carried in registers across the batch must not change results)."""
+    import torch
+    import tracking_b200 as tb
+    clip = clips["video_clip"]
+    S, n = 3, 24
+    # three different streams: the clip, the clip reversed, the clip shifted by 5 frames
+    streams = [clip[:n], clip[::-1][:n], clip[5:5 + n]]
+    h, w = clip.shape[1:3]
+    p = tb.ALGOS[aid](nstreams=S)
+    oracles = [oracle.ALGOS[aid]() for _ in range(S)]
+    has_bg = aid in (5, 6)
+    for t0 in range(0, n, T):
+        host = np.stack([np.stack([streams[s][t0 + t] for t in range(T)]) for s in range(S)])   # S,T,h,w,3
+        d_in = torch.from_numpy(host).cuda()
+        d_fg = torch.full((S, T, h, w), 77, dtype=torch.uint8, device="cuda")
+        d_bg = torch.full((S, T, h, w, 3), 77, dtype=torch.uint8, device="cuda")
+        first, bgv = p.process_batch_dev(d_in.data_ptr(), T, w, h, d_fg.data_ptr(), d_bg.data_ptr(),
+                                         stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        fg, bg = d_fg.cpu().numpy(), d_bg.cpu().numpy()
+        assert bgv == has_bg
+        for s in range(S):
+            for t in range(T):
+                ofg, obg = oracles[s].process(streams[s][t0 + t])
+                if ofg is None:
+                    assert t < first and (fg[s, t] == 77).all()          # untouched
+                else:
+                    assert t >= first
+                    assert np.array_equal(fg[s, t], ofg), (s, t0 + t)
+                if obg is not None:
+                    assert np.array_equal(bg[s, t], obg), (s, t0 + t)
+    p.close()
+
+
+def test_bg_last_only_and_no_bg(oracle, clips):
+    import torch
+    import tracking_b200 as tb
+    clip = clips["png_clip"]
+    h, w = clip.shape[1:3]
+    T = 4
+    for aid in (5, 6):
+        p, o = tb.ALGOS[aid](), oracle.ALGOS[aid]()
+        q = tb.ALGOS[aid]()
+        for t0 in range(0, 16, T):
+            d_in = torch.from_numpy(clip[t0:t0 + T]).cuda()
+            d_fg = torch.zeros((T, h, w), dtype=torch.uint8, device="cuda")
+            d_bg = torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda")
+            p.process_batch_dev(d_in.data_ptr(), T, w, h, d_fg.data_ptr(), d_bg.data_ptr(), bg_last_only=True)
+            d_fg2 = torch.zeros((T, h, w), dtype=torch.uint8, device="cuda")
+            q.process_batch_dev(d_in.data_ptr(), T, w, h, d_fg2.data_ptr(), None)
+            torch.cuda.synchronize()
+            for t in range(T):
+                ofg, obg = o.process(clip[t0 + t])
+                assert np.array_equal(d_fg[t].cpu().numpy(), ofg)
+                assert np.array_equal(d_fg2[t].cpu().numpy(), ofg)
+            assert np.array_equal(d_bg.cpu().numpy(), obg)
+
+
+def test_strided_host_input_and_reset(oracle):
+    """cv::Mat rows from cvQueryFrame are 4-byte aligned (padded stride); reset() restarts the model."""
+    import tracking_b200 as tb
+    rng = np.random.default_rng(4)
+    h, w = 37, 101
+    padded = rng.integers(0, 256, (5, h, w * 3 + 5), dtype=np.uint8)
+    frames = [np.lib.stride_tricks.as_strided(padded[i], (h, w, 3), (w * 3 + 5, 3, 1)) for i in range(5)]
+    p, o = tb.MixtureOfGaussianV2BGS(), oracle.MixtureOfGaussianV2BGS()
+    for f in frames:
+        fg, bg = p.process(f)
+        ofg, obg = o.process(np.ascontiguousarray(f))
+        assert np.array_equal(fg, ofg) and np.array_equal(bg, obg)
+    p.reset()
+    o = oracle.MixtureOfGaussianV2BGS()
+    for f in frames[:2]:
+        fg, bg = p.process(f)
+        ofg, obg = o.process(np.ascontiguousarray(f))
+        assert np.array_equal(fg, ofg) and np.array_equal(bg, obg)
+    # geometry change re-initialises (cv::BackgroundSubtractorMOG2::operator() does the same)
+    f2 = rng.integers(0, 256, (20, 30, 3), dtype=np.uint8)
+    fg, bg = p.process(f2)
+    assert (fg == 255).all() and np.array_equal(bg, f2)
+
+
+def test_mog2_state_export_import_roundtrip(clips):
+    import tracking_b200 as tb
+    clip = clips["video_clip"]
+    h, w = clip.shape[1:3]
+    a = tb.MixtureOfGaussianV2BGS()
+    for f in clip[:10]:
+        a.process(f)
+    planes, nm = a.export_state()
+    b = tb.MixtureOfGaussianV2BGS()
+    b.import_state(planes, nm, w, h, a.frame_count)
+    for f in clip[10:16]:
+        fa, ba = a.process(f)
+        fb, bb = b.process(f)
+        assert np.array_equal(fa, fb) and np.array_equal(ba, bb)
+
+
+def test_ustc_bgs_adapter_contract(clips):
+    import tracking_b200 as tb
+    with pytest.raises(ValueError):
+        tb.USTC_BGS(36)
+    d = tb.USTC_BGS(0)
+    assert d.GetMask() is None                     # frameNum == 0 -> NULL (ustc_bgs.cpp:81)
+    d.Process(clips["png_clip"][0])
+    assert d.GetMask() is None                     # FD warm-up frame: still no mask
+    d.Process(clips["png_clip"][1])
+    assert d.GetMask() is not None and d.GetMask().shape == clips["png_clip"][0].shape[:2]
+    d.Release()
+
+
+def test_synth_generator_matches_numpy_twin():
+    import torch
+    from tracking_b200 import synth
+    S, T, w, h = 2, 3, 333, 250
+    d = torch.zeros((S, T, h, w, 3), dtype=torch.uint8, device="cuda")
+    synth.frames_dev(d.data_ptr(), S, T, w, h, t0=7)
+    torch.cuda.synchronize()
+    got = d.cpu().numpy()
+    for s in range(S):
+        for t in range(T):
+            assert np.array_equal(got[s, t], synth.frame(w, h, 7 + t, synth.SEED0 + s))
+
+
+def test_full_size_1080p_mog2_parity_and_launch_counter(oracle):
+    """BASELINE config 2 geometry against the C oracle on a few frames + size-independent properties."""
+    import torch
+    import tracking_b200 as tb
+    from tracking_b200 import synth
+    w, h, n = 1920, 1080, 5
+    d = torch.zeros((1, n, h, w, 3), dtype=torch.uint8, device="cuda")
+    synth.frames_dev(d.data_ptr(), 1, n, w, h, t0=0)
+    torch.cuda.synchronize()
+    frames = d.cpu().numpy()[0]
+    p, o = tb.MixtureOfGaussianV2BGS(), oracle.MixtureOfGaussianV2BGS()
+    d_fg = torch.zeros((h, w), dtype=torch.uint8, device="cuda")
+    d_bg = torch.zeros((h, w, 3), dtype=torch.uint8, device="cuda")
+    before = tb.kernel_launch_count()
+    for t in range(n):
+        p.process_dev(d[0, t].data_ptr(), w, h, d_fg.data_ptr(), d_bg.data_ptr())
+        torch.cuda.synchronize()
+        ofg, obg = o.process(frames[t])
+        assert np.array_equal(d_fg.cpu().numpy(), ofg), t
+        assert np.array_equal(d_bg.cpu().numpy(), obg), t
+    assert tb.kernel_launch_count() - before == n
+    # property: a static scene converges to "no foreground" and bg == scene
+    q = tb.MixtureOfGaussianV2BGS()
+    for _ in range(30):
+        q.process_dev(d[0, 0].data_ptr(), w, h, d_fg.data_ptr(), d_bg.data_ptr())
+    torch.cuda.synchronize()
+    assert not d_fg.any().item()
+    assert torch.equal(d_bg, d[0, 0])

@@ -1,0 +1,169 @@
+"""Pin the oracle before trusting it (CPU only).
+
+The reference holds no golden vectors or known-answer tests for this path, so the
+pins are (1) OpenCV itself -- the library the reference plugins delegate every arithmetic step to --
+replayed call-for-call (oracle/cv2_chain.py) and (2) SHA-256 hashes of those OpenCV outputs on the
+reference's own data files, committed in tests/golden/golden.json by tests/golden/make_golden.py.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import REFERENCE_DIR, stress_sequence
+
+NAMES = {0: "FrameDifferenceBGS", 3: "WeightedMovingVarianceBGS", 5: "MixtureOfGaussianV2BGS",
+         6: "AdaptiveBackgroundLearning"}
+
+
+def sha(arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def run(algo_cls, frames, **kw):
+    a = algo_cls(**kw)
+    fgs, bgs = [], []
+    for f in frames:
+        fg, bg = a.process(f)
+        if fg is not None:
+            fgs.append(fg)
+        if bg is not None:
+            bgs.append(bg)
+    return fgs, bgs
+
+
+@pytest.mark.parametrize("seq", ["video_clip", "png_clip"])
+@pytest.mark.parametrize("aid", [0, 3, 5, 6])
+@pytest.mark.parametrize("thr", [True, False])
+def test_c_oracle_matches_golden_hashes(oracle, clips, golden, seq, aid, thr):
+    frames = list(clips[seq])
+    g = golden["sequences"][seq]
+    assert sha(frames) == g["input_sha256"]
+    key = NAMES[aid] + ("" if thr else ":enableThreshold=0")
+    fgs, bgs = run(oracle.ALGOS[aid], frames, enableThreshold=thr)
+    exp = g["algos"][key]
+    assert len(fgs) == exp["n_fg"] and len(bgs) == exp["n_bg"]
+    assert sha(fgs) == exp["fg_sha256"]                       # bit-exact masks
+    if exp["bg_sha256"]:
+        assert sha(bgs) == exp["bg_sha256"]                   # byte-exact background model
+
+
+@pytest.mark.parametrize("aid", [0, 3, 5, 6])
+def test_c_oracle_matches_opencv_live(oracle, clips, aid):
+    """Same comparison against cv2 running live (the image on the GPU box has cv2 too)."""
+    from oracle import cv2_chain
+    for frames in (list(clips["video_clip"]), stress_sequence(120)):
+        for thr in (True, False):
+            a, b = run(cv2_chain.ALGOS[aid], frames, enableThreshold=thr), run(oracle.ALGOS[aid], frames, enableThreshold=thr)
+            assert len(a[0]) == len(b[0]) and len(a[1]) == len(b[1])
+            for x, y in zip(a[0] + a[1], b[0] + b[1]):
+                assert np.array_equal(x, y)
+
+
+@pytest.mark.skipif(not os.path.exists(REFERENCE_DIR), reason="reference data only exists in the build container")
+@pytest.mark.parametrize("aid", [0, 3, 5, 6])
+def test_c_oracle_full_reference_sequences(oracle, golden, aid):
+    """All 374 frames of dataset/video.avi and all 51 frames/N.png (BASELINE config 1 inputs)."""
+    import cv2
+    cap = cv2.VideoCapture(os.path.join(REFERENCE_DIR, "dataset", "video.avi"))
+    video = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        video.append(f)
+    pngs = [cv2.imread(os.path.join(REFERENCE_DIR, "frames", "%d.png" % i)) for i in range(1, 52)]
+    for name, frames in (("video_full", video), ("png_full", pngs)):
+        g = golden["sequences"][name]
+        assert sha(frames) == g["input_sha256"], "decoder produced different frames than the golden run"
+        fgs, bgs = run(oracle.ALGOS[aid], frames)
+        assert sha(fgs) == g["algos"][NAMES[aid]]["fg_sha256"]
+        if bgs:
+            assert sha(bgs) == g["algos"][NAMES[aid]]["bg_sha256"]
+
+
+def test_gray_formula_matches_opencv(oracle):
+    import cv2
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (512, 512, 3), dtype=np.uint8)
+    img[:16, :16] = 255
+    img[16:32, :16] = 0
+    assert np.array_equal(oracle.gray_bgr(img, 0), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    # 2.4 constants differ from 4.x by at most one level
+    d = oracle.gray_bgr(img, 1).astype(int) - oracle.gray_bgr(img, 0).astype(int)
+    assert np.abs(d).max() <= 1 and 0 < (d != 0).mean() < 0.01
+
+
+def test_abl_exhaustive_pairs_against_opencv(oracle):
+    """Every (input, background) byte pair: the fp64 blend of A.2 reproduces cv2.addWeighted ties."""
+    from oracle import cv2_chain
+    inp, bg = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8))
+    frame0 = np.repeat(bg[:, :, None], 3, 2).copy()
+    frame1 = np.repeat(inp[:, :, None], 3, 2).copy()
+    a, b = cv2_chain.AdaptiveBackgroundLearning(), oracle.AdaptiveBackgroundLearning()
+    for f in (frame0, frame1):
+        fa, ba = a.process(f)
+        fb, bb = b.process(f)
+    assert np.array_equal(fa, fb) and np.array_equal(ba, bb)
+
+
+def test_morph_and_ccl_against_opencv(oracle):
+    from oracle import cv2_chain
+    rng = np.random.default_rng(3)
+    for trial in range(25):
+        h, w = int(rng.integers(5, 90)), int(rng.integers(5, 130))
+        m = (rng.random((h, w)) < rng.choice([0.05, 0.3, 0.5, 0.7])).astype(np.uint8) * 255
+        for op in ("erode", "dilate"):
+            for it in (0, 1, 2, 3):
+                assert np.array_equal(cv2_chain.morph(m, op, it) if it else m, oracle.morph(m, op, it))
+        n1, l1 = cv2_chain.canonical_labels(m)
+        for zb in (False, True):
+            n2, l2, st, ext = oracle.ccl8(m, zb)
+            if not zb:
+                assert n1 == n2 and np.array_equal(l1, l2)
+            rects, _ = cv2_chain.external_contour_rects(m, zb)
+            mine = [(int(s[0]), int(s[1]), int(s[2] - s[0] + 1), int(s[3] - s[1] + 1)) for s, e in zip(st, ext) if e]
+            # findContours lists external contours in reverse raster order of their first pixels
+            assert list(reversed(mine)) == [tuple(r) for r in rects]
+
+
+def test_rect_moments_against_opencv(oracle):
+    import cv2
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (70, 90), dtype=np.uint8)
+    for (x, y, w, h) in ((0, 0, 90, 70), (3, 5, 40, 33), (88, 69, 2, 1)):
+        m = cv2.moments(img[y:y + h, x:x + w], False)
+        got = oracle.rect_moments(img, (x, y, w, h))
+        assert got == [int(m[k]) for k in ("m00", "m10", "m01", "m20", "m02", "m11")]
+
+
+def test_golden_ccl_tables(oracle, clips, golden):
+    """FD -> OPEN(3x3) -> canonical labels on the clip reproduces the committed OpenCV results."""
+    frames = list(clips["video_clip"])
+    fgs, _ = run(oracle.FrameDifferenceBGS, frames)
+    for zb in (0, 1):
+        for row in golden["sequences"]["video_clip"]["fd_open_ccl"]["zero_border_%d" % zb]:
+            m = oracle.morph(oracle.morph(fgs[row["frame"]], "erode"), "dilate")
+            assert sha([m]) == row["open_sha256"]
+            n, lab, st, ext = oracle.ccl8(m, bool(zb))
+            assert n == row["n_components"] and sha([lab]) == row["labels_sha256"]
+            mine = [[int(s[0]), int(s[1]), int(s[2] - s[0] + 1), int(s[3] - s[1] + 1)] for s, e in zip(st, ext) if e]
+            assert list(reversed(mine)) == row["external_rects_findcontours_order"]
+
+
+def test_blobdetector_restatement_reproduces_committed_sequence(oracle, clips, golden):
+    """Regression pin only: the list logic of CvBlobDetectorCC is 'restated, unpinned' (oracle/blobdetect.py)."""
+    from oracle import blobdetect, cv2_chain
+    frames = list(clips["video_clip"])
+    fgs, _ = run(oracle.FrameDifferenceBGS, frames)
+    bd = blobdetect.CvBlobDetectorCC(zero_border=True)
+    exp = golden["sequences"]["video_clip"]["fd_open_blobdetector_restated_unpinned"]
+    for m, e in zip(fgs, exp):
+        m2 = cv2_chain.morph(cv2_chain.morph(m, "erode"), "dilate")
+        res, nb = bd.DetectNewBlob(m2, [])
+        assert res == e["result"]
+        assert [[round(v, 4) for v in b.tuple()] for b in bd.lists[0]] == e["frame_blobs"]

@@ -1,0 +1,13 @@
+"""tracking_b200 -- B200-native foreground-extraction hot path of USTC-Computer-Vision/tracking.
+
+Everything that computes lives in CUDA kernels behind the C ABI of include/bgsb200.h
+(tracking_b200/libbgsb200.so, built in-tree by tracking_b200._build).  This package is the
+Python host-side mirror of the reference's plugin interface; the C++ drop-in adapters are in
+tracking_b200/adapters/.  There is no CPU fallback.
+"""
+from .bgs import (ALGOS, USTC_BGS, AdaptiveBackgroundLearning, FrameDifferenceBGS,  # noqa: F401
+                  MixtureOfGaussianV2BGS, WeightedMovingVarianceBGS)
+from .capi import BgsbError, kernel_launch_count  # noqa: F401
+
+__all__ = ["FrameDifferenceBGS", "WeightedMovingVarianceBGS", "AdaptiveBackgroundLearning",
+           "MixtureOfGaussianV2BGS", "USTC_BGS", "ALGOS", "BgsbError", "kernel_launch_count"]

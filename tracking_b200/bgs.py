@@ -1,0 +1,180 @@
+"""Host-side mirror of the reference's plugin interface, on top of the C ABI.
+
+Same class names, parameter names and early-return behaviour as the reference plugins
+(package_bgs/{FrameDifferenceBGS,AdaptiveBackgroundLearning,WeightedMovingVarianceBGS,
+MixtureOfGaussianV2BGS}.cpp) so that parity tests read like reference usage:
+
+    bgs = MixtureOfGaussianV2BGS()
+    fg, bgmodel = bgs.process(frame_bgr)       # IBGS::process(in, fg, bgModel), IBGS.h:24
+
+`None` for an output means "left untouched" (the reference returns before copyTo, e.g.
+FrameDifferenceBGS.cpp:39-43).  All arithmetic happens in CUDA kernels behind libbgsb200.so;
+this module only moves numpy / torch buffers across ctypes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+class _Plugin:
+    ALGO = None
+    PARAMS = ()
+
+    def __init__(self, device=0, nstreams=1, **params):
+        self._h = C.c_void_p()
+        self.device, self.nstreams = device, nstreams
+        capi.check(capi.lib().bgsb_create_group(C.byref(self._h), self.ALGO, device, nstreams))
+        for k, v in params.items():
+            self.set(k, v)
+
+    # -- parameters: XML key names of saveConfig/loadConfig ---------------------------------
+    def set(self, key, value):
+        capi.check(capi.lib().bgsb_set_param(self._h, key.encode(), float(value)))
+
+    def get(self, key):
+        v = C.c_double()
+        capi.check(capi.lib().bgsb_get_param(self._h, key.encode(), C.byref(v)))
+        return v.value
+
+    def reset(self):
+        capi.check(capi.lib().bgsb_reset(self._h))
+
+    @property
+    def frame_count(self):
+        n = C.c_int64()
+        capi.check(capi.lib().bgsb_frame_count(self._h, C.byref(n)))
+        return n.value
+
+    def close(self):
+        if self._h:
+            capi.lib().bgsb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- IBGS::process, host buffers -------------------------------------------------------
+    def process(self, img_input, want_bg=True):
+        """img_input: HxWx3 uint8 BGR (a group takes nstreams x H x W x 3).
+        Returns (img_output | None, img_bgmodel | None)."""
+        if img_input is None or img_input.size == 0:      # `if(img_input.empty()) return;`
+            return None, None
+        img = np.asarray(img_input)
+        if img.dtype != np.uint8 or img.shape[-1] != 3:
+            raise ValueError("plugins take BGR 8UC3 frames")
+        grouped = img.ndim == 4
+        if grouped and img.shape[0] != self.nstreams:
+            raise ValueError("expected %d frames" % self.nstreams)
+        if not grouped and self.nstreams != 1:
+            raise ValueError("stream group needs [nstreams,H,W,3]")
+        h, w = img.shape[-3], img.shape[-2]
+        if img.strides[-1] != 1 or img.strides[-2] != 3 or (grouped and img.strides[0] != img.strides[1] * h):
+            img = np.ascontiguousarray(img)
+        stride = img.strides[-3]
+        lead = (self.nstreams,) if grouped else ()
+        fg = np.empty(lead + (h, w), np.uint8)
+        bg = np.empty(lead + (h, w, 3), np.uint8) if want_bg else None
+        fv, bv = C.c_int(0), C.c_int(0)
+        capi.check(capi.lib().bgsb_process(self._h, _ptr(img), w, h, stride, _ptr(fg), w,
+                                           _ptr(bg) if bg is not None else None, 3 * w,
+                                           C.byref(fv), C.byref(bv)))
+        return (fg if fv.value else None), (bg if bv.value else None)
+
+    # -- device buffers (torch tensors or raw pointers) -----------------------------------------
+    def process_dev(self, d_bgr, w, h, d_fg, d_bg=None, stream=0):
+        fv, bv = C.c_int(0), C.c_int(0)
+        capi.check(capi.lib().bgsb_process_dev(self._h, C.c_void_p(d_bgr), w, h, C.c_void_p(d_fg),
+                                               C.c_void_p(d_bg) if d_bg else None,
+                                               C.byref(fv), C.byref(bv), C.c_void_p(stream)))
+        return bool(fv.value), bool(bv.value)
+
+    def process_batch_dev(self, d_frames, T, w, h, d_fg, d_bg=None, bg_last_only=False, stream=0):
+        first, bv = C.c_int(0), C.c_int(0)
+        capi.check(capi.lib().bgsb_process_batch_dev(self._h, C.c_void_p(d_frames), T, w, h, C.c_void_p(d_fg),
+                                                     C.c_void_p(d_bg) if d_bg else None, int(bg_last_only),
+                                                     C.byref(first), C.byref(bv), C.c_void_p(stream)))
+        return first.value, bool(bv.value)
+
+    def state_bytes(self):
+        n = C.c_size_t()
+        capi.check(capi.lib().bgsb_state_bytes(self._h, C.byref(n)))
+        return n.value
+
+
+class FrameDifferenceBGS(_Plugin):
+    """package_bgs/FrameDifferenceBGS.cpp; keys enableThreshold, threshold (:78-80)."""
+    ALGO = capi.ALGO_FRAME_DIFFERENCE
+
+
+class WeightedMovingVarianceBGS(_Plugin):
+    """package_bgs/WeightedMovingVarianceBGS.cpp; keys enableWeight, enableThreshold, threshold (:155-158)."""
+    ALGO = capi.ALGO_WEIGHTED_MOVING_VARIANCE
+
+
+class AdaptiveBackgroundLearning(_Plugin):
+    """package_bgs/AdaptiveBackgroundLearning.cpp; keys alpha, limit, enableThreshold, threshold (:103-108)."""
+    ALGO = capi.ALGO_ADAPTIVE_BG_LEARNING
+
+
+class MixtureOfGaussianV2BGS(_Plugin):
+    """package_bgs/MixtureOfGaussianV2BGS.cpp; keys alpha, enableThreshold, threshold (:92-95)."""
+    ALGO = capi.ALGO_MOG2
+
+    def export_state(self, stream_index=0):
+        """-> (planes float32 [25, npx], nmodes uint8 [npx]); plane q = mode*5 + {w,var,muB,muG,muR}."""
+        npx = self.state_bytes() // 101
+        planes = np.empty((25, npx), np.float32)
+        nm = np.empty(npx, np.uint8)
+        capi.check(capi.lib().bgsb_mog2_export_state(self._h, stream_index,
+                                                     planes.ctypes.data_as(capi.f32p), nm.ctypes.data_as(capi.u8p)))
+        return planes, nm
+
+    def import_state(self, planes, nmodes, w, h, nframes, stream_index=0):
+        planes = np.ascontiguousarray(planes, np.float32)
+        nmodes = np.ascontiguousarray(nmodes, np.uint8)
+        capi.check(capi.lib().bgsb_mog2_import_state(self._h, stream_index, w, h, nframes,
+                                                     planes.ctypes.data_as(capi.f32p), nmodes.ctypes.data_as(capi.u8p)))
+
+
+# integer ids of the USTC_BGS factory (ustc_src/ustc_bgs.cpp:8-14)
+ALGOS = {0: FrameDifferenceBGS, 3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS,
+         6: AdaptiveBackgroundLearning}
+
+
+class USTC_BGS:
+    """CvFGDetector adapter (ustc_src/ustc_bgs.{h,cpp}): Process(img) then GetMask()."""
+
+    def __init__(self, type, device=0):
+        if type not in ALGOS:                   # CV_Assert(type>=0 && type<=37), .cpp:6
+            raise ValueError("USTC_BGS type %r is not on the B200 hot path (0 FD, 3 WMV, 5 MOG2, 6 ABL)" % type)
+        self.bgs = ALGOS[type](device=device)
+        self.frameNum = 0
+        self.img_mask = None
+        self.img_bkgmodel = None
+
+    def Process(self, pImg):                    # ustc_bgs.cpp:87-113
+        fg, bg = self.bgs.process(pImg)
+        if fg is not None:
+            self.img_mask = fg
+        if bg is not None:
+            self.img_bkgmodel = bg
+        self.frameNum += 1
+
+    def GetMask(self):                          # ustc_bgs.cpp:79-85; NULL until a mask exists
+        if self.frameNum == 0:
+            return None
+        return self.img_mask
+
+    def Release(self):                          # ustc_bgs.cpp:75-77
+        self.bgs.close()

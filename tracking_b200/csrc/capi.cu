@@ -1,0 +1,402 @@
+// C ABI of libbgsb200: background-subtraction contexts (include/bgsb200.h).
+// Host-side bookkeeping only -- frame counters, warm-up rules, learning-rate schedule, buffer
+// ownership -- mirroring what each reference plugin keeps in its members:
+//   FrameDifferenceBGS   img_input_prev                     package_bgs/FrameDifferenceBGS.h
+//   WeightedMovingVariance img_input_prev_1/2               package_bgs/WeightedMovingVarianceBGS.h
+//   AdaptiveBackgroundLearning img_background               package_bgs/AdaptiveBackgroundLearning.h
+//   MixtureOfGaussianV2BGS  cv::BackgroundSubtractorMOG2 mog package_bgs/MixtureOfGaussianV2BGS.h:30
+#include <stdarg.h>
+#include <string.h>
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace bgsb {
+
+static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace bgsb
+
+using namespace bgsb;
+
+struct bgsb_ctx {
+    int algo = 0, device = 0, nstreams = 1;
+    // plugin parameters (XML keys of the reference)
+    double alpha = 0.05;
+    int limit = -1;
+    int enable_thr = 1, thr = 15, enable_weight = 1, gray_variant = 0;
+    // cv::BackgroundSubtractorMOG2 defaults (verified against cv2 getters)
+    int history = 500;
+    float Tb = 16.f, Tg = 9.f, TB = 0.9f, varInit = 15.f, varMin = 4.f, varMax = 75.f, CT = 0.05f, tau = 0.5f;
+    int detect_shadows = 1, shadow_value = 127;
+    // geometry / counters
+    int w = 0, h = 0, npx = 0;
+    size_t pstride = 0;
+    int64_t nframes = 0;
+    // device state
+    float *d_state = nullptr;
+    uint8_t *d_nmodes = nullptr;
+    uint8_t *d_hist[2] = {nullptr, nullptr};
+    const uint8_t *hist_ptr[2] = {nullptr, nullptr};
+    int have_hist = 0;
+    // host-path staging
+    uint8_t *d_ring[3] = {nullptr, nullptr, nullptr};
+    int ring_pos = 0;
+    uint8_t *d_fg = nullptr, *d_bg = nullptr;
+    cudaStream_t stream = nullptr;
+};
+
+static void free_buffers(bgsb_ctx *c)
+{
+    cudaFree(c->d_state); c->d_state = nullptr;
+    cudaFree(c->d_nmodes); c->d_nmodes = nullptr;
+    for (int i = 0; i < 2; i++) { cudaFree(c->d_hist[i]); c->d_hist[i] = nullptr; c->hist_ptr[i] = nullptr; }
+    for (int i = 0; i < 3; i++) { cudaFree(c->d_ring[i]); c->d_ring[i] = nullptr; }
+    cudaFree(c->d_fg); c->d_fg = nullptr;
+    cudaFree(c->d_bg); c->d_bg = nullptr;
+    c->w = c->h = c->npx = 0; c->pstride = 0;
+    c->nframes = 0; c->have_hist = 0; c->ring_pos = 0;
+}
+
+// (Re)allocate model state for a geometry.  The reference discovers the frame size on the first
+// process() call; cv::BackgroundSubtractorMOG2::operator() re-initialises when it changes.
+static int ensure_geometry(bgsb_ctx *c, int w, int h)
+{
+    if (c->w == w && c->h == h) return BGSB_OK;
+    BGSB_REQUIRE(w > 0 && h > 0, "empty frame");
+    BGSB_REQUIRE((long long)w * h < (1LL << 30), "frame too large");
+    free_buffers(c);
+    c->w = w; c->h = h; c->npx = w * h;
+    c->pstride = ((size_t)c->npx + 31) / 32 * 32;
+    const size_t S = (size_t)c->nstreams;
+    if (c->algo == BGSB_ALGO_MOG2) {
+        size_t fb = S * MOG2_PLANES * c->pstride * sizeof(float);
+        BGSB_CUDA(cudaMalloc(&c->d_state, fb));
+        BGSB_CUDA(cudaMalloc(&c->d_nmodes, S * c->pstride));
+        BGSB_CUDA(cudaMemsetAsync(c->d_state, 0, fb, c->stream));
+        BGSB_CUDA(cudaMemsetAsync(c->d_nmodes, 0, S * c->pstride, c->stream));
+        BGSB_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+        int nh = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE) ? 2 : 1;
+        for (int i = 0; i < nh; i++) BGSB_CUDA(cudaMalloc(&c->d_hist[i], S * c->npx * 3));
+    }
+    return BGSB_OK;
+}
+
+static int ensure_host_staging(bgsb_ctx *c)
+{
+    const size_t S = (size_t)c->nstreams;
+    if (!c->d_ring[0]) {
+        int nr = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE) ? 3 : (c->algo == BGSB_ALGO_FRAME_DIFFERENCE ? 2 : 1);
+        for (int i = 0; i < nr; i++) BGSB_CUDA(cudaMalloc(&c->d_ring[i], S * c->npx * 3));
+        c->ring_pos = 0;
+    }
+    if (!c->d_fg) BGSB_CUDA(cudaMalloc(&c->d_fg, S * c->npx));
+    if (!c->d_bg && (c->algo == BGSB_ALGO_MOG2 || c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING))
+        BGSB_CUDA(cudaMalloc(&c->d_bg, S * c->npx * 3));
+    return BGSB_OK;
+}
+
+static int warmup_frames(int algo)
+{
+    return algo == BGSB_ALGO_FRAME_DIFFERENCE ? 1 : (algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE ? 2 : 0);
+}
+
+// Advance the model by T frames that sit in device memory.  `own_history`: write FD/WMV history
+// into the context's own buffers (caller's frame buffers may be reused after the call).
+static int run_frames(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_fg, uint8_t *d_bg,
+                      int bg_last_only, bool own_history, cudaStream_t stream)
+{
+    if (c->algo == BGSB_ALGO_MOG2) {
+        BGSB_REQUIRE(T <= MOG2_TMAX, "temporal batch too long (max 32)");
+        Mog2Launch L;
+        memset(&L, 0, sizeof(L));
+        L.frames = d_frames; L.fg = d_fg; L.bg = d_bg;
+        L.state = c->d_state; L.nmodes = c->d_nmodes; L.pstride = c->pstride;
+        L.npx = c->npx; L.T = T; L.bg_last_only = bg_last_only;
+        L.fresh = (c->nframes == 0);
+        L.enable_thr = c->enable_thr; L.thr = c->thr;
+        L.detect_shadows = c->detect_shadows; L.shadow_value = c->shadow_value;
+        L.Tb = c->Tb; L.Tg = c->Tg; L.TB = c->TB; L.varInit = c->varInit; L.varMin = c->varMin;
+        L.varMax = c->varMax; L.tau = c->tau;
+        for (int t = 0; t < T; t++) {
+            // operator(): ++nframes; learningRate = alpha>=0 && nframes>1 ? alpha : 1./min(2*nframes, history)
+            int64_t nf = c->nframes + t + 1;
+            double lr = (c->alpha >= 0 && nf > 1) ? c->alpha : 1. / (double)std::min<int64_t>(2 * nf, c->history);
+            L.alphaT[t] = (float)lr;
+            L.alpha1[t] = 1.f - L.alphaT[t];
+            L.prune[t] = (float)(-lr * (double)c->CT);
+        }
+        int rc = launch_mog2(L, c->nstreams, 0, stream);
+        if (rc) return rc;
+    } else {
+        SimpleLaunch L;
+        memset(&L, 0, sizeof(L));
+        L.frames = d_frames; L.fg = d_fg; L.bg = d_bg;
+        L.hist0 = c->hist_ptr[0]; L.hist1 = c->hist_ptr[1];
+        L.hist0_out = own_history ? c->d_hist[0] : nullptr;
+        L.hist1_out = own_history ? c->d_hist[1] : nullptr;
+        if (c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING) { L.hist0 = c->d_hist[0]; L.hist0_out = c->d_hist[0]; }
+        L.npx = c->npx; L.T = T; L.have_hist = c->have_hist; L.bg_last_only = bg_last_only;
+        L.enable_thr = c->enable_thr; L.thr = c->thr; L.gray_variant = c->gray_variant;
+        L.alpha = c->alpha;
+        L.abl_update = (c->limit == -1);   // the limit>0 branch never fires: counter stays 0 (.cpp:52,60-61)
+        if (c->enable_weight) { L.w0 = 0.5; L.w1 = 0.3; L.w2 = 0.2; }      // WeightedMovingVarianceBGS.cpp:67-68
+        else { L.w0 = 0.3; L.w1 = 0.3; L.w2 = 0.3; }                          // :70
+        int rc = launch_simple(c->algo, L, c->nstreams, stream);
+        if (rc) return rc;
+        int need = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE) ? 2 : 1;
+        if (own_history) {
+            c->have_hist = std::min<int64_t>(need, c->have_hist + T);
+            c->hist_ptr[0] = c->d_hist[0]; c->hist_ptr[1] = c->d_hist[1];
+        }
+    }
+    c->nframes += T;
+    return BGSB_OK;
+}
+
+extern "C" {
+
+const char *bgsb_last_error(void) { return bgsb::g_err; }
+const char *bgsb_version(void) { return "bgsb200 0.1 (sm_100a)"; }
+uint64_t bgsb_kernel_launch_count(void) { return bgsb::g_launches.load(); }
+
+int bgsb_device_count(int *count)
+{
+    BGSB_REQUIRE(count, "null");
+    BGSB_CUDA(cudaGetDeviceCount(count));
+    return BGSB_OK;
+}
+
+int bgsb_create_group(bgsb_ctx **out, int algo, int device, int nstreams)
+{
+    BGSB_REQUIRE(out, "null out");
+    BGSB_REQUIRE(algo == BGSB_ALGO_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE ||
+                 algo == BGSB_ALGO_MOG2 || algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING,
+                 "unknown algorithm id (USTC_BGS ids: 0 FD, 3 WMV, 5 MOG2, 6 ABL)");
+    BGSB_REQUIRE(nstreams >= 1 && nstreams <= 65535, "nstreams out of range");
+    BGSB_CUDA(cudaSetDevice(device));
+    bgsb_ctx *c = new bgsb_ctx();
+    c->algo = algo; c->device = device; c->nstreams = nstreams;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        set_error("cudaStreamCreate -> %s", cudaGetErrorString(e));
+        delete c;
+        return BGSB_ERR_CUDA;
+    }
+    *out = c;
+    return BGSB_OK;
+}
+
+int bgsb_create(bgsb_ctx **out, int algo, int device) { return bgsb_create_group(out, algo, device, 1); }
+
+void bgsb_destroy(bgsb_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); }
+    free_buffers(c);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int bgsb_reset(bgsb_ctx *c)
+{
+    BGSB_REQUIRE(c, "null ctx");
+    c->nframes = 0; c->have_hist = 0;
+    c->hist_ptr[0] = c->hist_ptr[1] = nullptr;
+    return BGSB_OK;
+}
+
+int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
+{
+    BGSB_REQUIRE(c && key, "null");
+    std::string k(key);
+    if (k == "alpha") c->alpha = v;
+    else if (k == "limit") c->limit = (int)v;
+    else if (k == "enableThreshold") c->enable_thr = (v != 0);
+    else if (k == "threshold") c->thr = (int)v;
+    else if (k == "enableWeight") c->enable_weight = (v != 0);
+    else if (k == "grayVariant") { BGSB_REQUIRE(v == 0 || v == 1, "grayVariant is 0 or 1"); c->gray_variant = (int)v; }
+    else if (k == "history") { BGSB_REQUIRE(v >= 1, "history >= 1"); c->history = (int)v; }
+    else if (k == "nmixtures") { BGSB_REQUIRE((int)v == MOG2_K, "nmixtures is fixed at 5"); }
+    else if (k == "varThreshold") c->Tb = (float)v;
+    else if (k == "varThresholdGen") c->Tg = (float)v;
+    else if (k == "backgroundRatio") c->TB = (float)v;
+    else if (k == "varInit") c->varInit = (float)v;
+    else if (k == "varMin") c->varMin = (float)v;
+    else if (k == "varMax") c->varMax = (float)v;
+    else if (k == "complexityReductionThreshold") c->CT = (float)v;
+    else if (k == "detectShadows") c->detect_shadows = (v != 0);
+    else if (k == "shadowValue") c->shadow_value = (int)v;
+    else if (k == "shadowThreshold") c->tau = (float)v;
+    else if (k == "showOutput" || k == "showForeground" || k == "showBackground") { /* GUI only */ }
+    else { set_error("bgsb_set_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
+    return BGSB_OK;
+}
+
+int bgsb_get_param(bgsb_ctx *c, const char *key, double *v)
+{
+    BGSB_REQUIRE(c && key && v, "null");
+    std::string k(key);
+    if (k == "alpha") *v = c->alpha;
+    else if (k == "limit") *v = c->limit;
+    else if (k == "enableThreshold") *v = c->enable_thr;
+    else if (k == "threshold") *v = c->thr;
+    else if (k == "enableWeight") *v = c->enable_weight;
+    else if (k == "grayVariant") *v = c->gray_variant;
+    else if (k == "history") *v = c->history;
+    else if (k == "nmixtures") *v = MOG2_K;
+    else if (k == "varThreshold") *v = c->Tb;
+    else if (k == "varThresholdGen") *v = c->Tg;
+    else if (k == "backgroundRatio") *v = c->TB;
+    else if (k == "varInit") *v = c->varInit;
+    else if (k == "varMin") *v = c->varMin;
+    else if (k == "varMax") *v = c->varMax;
+    else if (k == "complexityReductionThreshold") *v = c->CT;
+    else if (k == "detectShadows") *v = c->detect_shadows;
+    else if (k == "shadowValue") *v = c->shadow_value;
+    else if (k == "shadowThreshold") *v = c->tau;
+    else { set_error("bgsb_get_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
+    return BGSB_OK;
+}
+
+int bgsb_frame_count(bgsb_ctx *c, int64_t *n)
+{
+    BGSB_REQUIRE(c && n, "null");
+    *n = c->nframes;
+    return BGSB_OK;
+}
+
+int bgsb_state_bytes(bgsb_ctx *c, size_t *bytes)
+{
+    BGSB_REQUIRE(c && bytes, "null");
+    if (c->algo == BGSB_ALGO_MOG2) *bytes = (size_t)c->npx * (MOG2_PLANES * 4 + 1);
+    else if (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE) *bytes = (size_t)c->npx * 6;
+    else *bytes = (size_t)c->npx * 3;
+    return BGSB_OK;
+}
+
+int bgsb_process_batch_dev(bgsb_ctx *c, const uint8_t *d_frames, int T, int w, int h, uint8_t *d_fg,
+                           uint8_t *d_bg, int bg_last_only, int *first_fg_valid, int *bg_valid, void *stream)
+{
+    BGSB_REQUIRE(c && d_frames && d_fg, "null");
+    BGSB_REQUIRE(T >= 1, "T >= 1");
+    BGSB_CUDA(cudaSetDevice(c->device));
+    int rc = ensure_geometry(c, w, h);
+    if (rc) return rc;
+    int warm = warmup_frames(c->algo);
+    int64_t first = std::max<int64_t>(0, warm - c->nframes);
+    if (first_fg_valid) *first_fg_valid = (int)std::min<int64_t>(first, T);
+    if (bg_valid) *bg_valid = (c->algo == BGSB_ALGO_MOG2 || c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING) && d_bg;
+    bool has_bg = (c->algo == BGSB_ALGO_MOG2 || c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING);
+    return run_frames(c, d_frames, T, d_fg, has_bg ? d_bg : nullptr, bg_last_only, true, (cudaStream_t)stream);
+}
+
+int bgsb_process_dev(bgsb_ctx *c, const uint8_t *d_bgr, int w, int h, uint8_t *d_fg, uint8_t *d_bg,
+                     int *fg_valid, int *bg_valid, void *stream)
+{
+    int first = 0;
+    int rc = bgsb_process_batch_dev(c, d_bgr, 1, w, h, d_fg, d_bg, 0, &first, bg_valid, stream);
+    if (fg_valid) *fg_valid = (rc == BGSB_OK && first == 0);
+    return rc;
+}
+
+int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, uint8_t *fg, size_t fg_stride,
+                 uint8_t *bg, size_t bg_stride, int *fg_valid, int *bg_valid)
+{
+    BGSB_REQUIRE(c && bgr && fg, "null");
+    BGSB_REQUIRE(stride >= (size_t)w * 3 && fg_stride >= (size_t)w, "stride smaller than a row");
+    BGSB_REQUIRE(!bg || bg_stride >= (size_t)w * 3, "bg stride smaller than a row");
+    BGSB_CUDA(cudaSetDevice(c->device));
+    int rc = ensure_geometry(c, w, h);
+    if (rc) return rc;
+    rc = ensure_host_staging(c);
+    if (rc) return rc;
+    const size_t rows = (size_t)h * c->nstreams;
+    const bool fdlike = (c->algo == BGSB_ALGO_FRAME_DIFFERENCE || c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE);
+    const int nring = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE) ? 3 : 2;
+    uint8_t *d_in = fdlike ? c->d_ring[c->ring_pos] : c->d_ring[0];
+    BGSB_CUDA(cudaMemcpy2DAsync(d_in, (size_t)w * 3, bgr, stride, (size_t)w * 3, rows, cudaMemcpyHostToDevice, c->stream));
+
+    const int warm = warmup_frames(c->algo);
+    const bool out_fg = c->nframes >= warm;
+    const bool has_bg = (c->algo == BGSB_ALGO_MOG2 || c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING);
+    if (fdlike) {
+        // history = the previous upload(s) in the ring: no copy, the frame is read once (7 B/px FD)
+        if (out_fg) {
+            rc = run_frames(c, d_in, 1, c->d_fg, nullptr, 0, false, c->stream);
+            if (rc) return rc;
+        } else {
+            c->nframes += 1;
+        }
+        c->hist_ptr[1] = c->hist_ptr[0];
+        c->hist_ptr[0] = d_in;
+        c->have_hist = std::min(warm, c->have_hist + 1);
+        c->ring_pos = (c->ring_pos + 1) % nring;
+    } else {
+        rc = run_frames(c, d_in, 1, c->d_fg, (has_bg && bg) ? c->d_bg : nullptr, 0, true, c->stream);
+        if (rc) return rc;
+        if (c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING) c->have_hist = 1;
+    }
+    if (out_fg)
+        BGSB_CUDA(cudaMemcpy2DAsync(fg, fg_stride, c->d_fg, (size_t)w, (size_t)w, rows, cudaMemcpyDeviceToHost, c->stream));
+    if (has_bg && bg)
+        BGSB_CUDA(cudaMemcpy2DAsync(bg, bg_stride, c->d_bg, (size_t)w * 3, (size_t)w * 3, rows, cudaMemcpyDeviceToHost, c->stream));
+    BGSB_CUDA(cudaStreamSynchronize(c->stream));
+    if (fg_valid) *fg_valid = out_fg;
+    if (bg_valid) *bg_valid = (has_bg && bg) ? 1 : 0;
+    return BGSB_OK;
+}
+
+int bgsb_mog2_export_state(bgsb_ctx *c, int si, float *planes, uint8_t *nmodes)
+{
+    BGSB_REQUIRE(c && planes && nmodes, "null");
+    BGSB_REQUIRE(c->algo == BGSB_ALGO_MOG2 && c->d_state, "no MOG2 state");
+    BGSB_REQUIRE(si >= 0 && si < c->nstreams, "stream index");
+    BGSB_CUDA(cudaSetDevice(c->device));
+    BGSB_CUDA(cudaDeviceSynchronize());
+    const float *src = c->d_state + (size_t)si * MOG2_PLANES * c->pstride;
+    BGSB_CUDA(cudaMemcpy2D(planes, (size_t)c->npx * 4, src, c->pstride * 4, (size_t)c->npx * 4, MOG2_PLANES,
+                           cudaMemcpyDeviceToHost));
+    BGSB_CUDA(cudaMemcpy(nmodes, c->d_nmodes + (size_t)si * c->pstride, c->npx, cudaMemcpyDeviceToHost));
+    if (c->nframes == 0) memset(nmodes, 0, c->npx);
+    return BGSB_OK;
+}
+
+int bgsb_mog2_import_state(bgsb_ctx *c, int si, int w, int h, int64_t nframes, const float *planes,
+                           const uint8_t *nmodes)
+{
+    BGSB_REQUIRE(c && planes && nmodes, "null");
+    BGSB_REQUIRE(c->algo == BGSB_ALGO_MOG2, "not a MOG2 context");
+    BGSB_REQUIRE(si >= 0 && si < c->nstreams, "stream index");
+    BGSB_REQUIRE(nframes >= 1, "nframes >= 1");
+    BGSB_CUDA(cudaSetDevice(c->device));
+    int rc = ensure_geometry(c, w, h);
+    if (rc) return rc;
+    BGSB_CUDA(cudaDeviceSynchronize());
+    float *dst = c->d_state + (size_t)si * MOG2_PLANES * c->pstride;
+    BGSB_CUDA(cudaMemcpy2D(dst, c->pstride * 4, planes, (size_t)c->npx * 4, (size_t)c->npx * 4, MOG2_PLANES,
+                           cudaMemcpyHostToDevice));
+    BGSB_CUDA(cudaMemcpy(c->d_nmodes + (size_t)si * c->pstride, nmodes, c->npx, cudaMemcpyHostToDevice));
+    c->nframes = nframes;
+    return BGSB_OK;
+}
+
+int bgsb_synth_frames_dev(uint8_t *d_frames, int nstreams, int T, int w, int h, int t0, uint32_t seed0, void *stream)
+{
+    BGSB_REQUIRE(d_frames && nstreams >= 1 && T >= 1, "bad args");
+    return launch_synth(d_frames, nstreams, T, w, h, t0, seed0, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,494 @@
+// K-CCL: 8-connected component labelling of the foreground mask on the GPU, with canonical
+// (raster-first) labels, per-component bounding box / area, and the RETR_EXTERNAL nesting test.
+//
+// Replaces steps 1-2 (and the integer sums of step 4) of CvBlobDetectorCC::DetectNewBlob
+// (OpenCV legacy `cvCreateBlobDetectorCC`, referenced at ustc_src/trackingMain.cpp:56,626 and
+// readme.md:4-10; spec = SURVEY.md Appendix A.6):
+//     cvThreshold(pIB, pIB, 128, 255, CV_THRESH_BINARY); cvFindContours(pIB, ..., CV_RETR_EXTERNAL);
+//     CvRect r = ((CvContour*)cnt)->rect;   cvMoments(cvGetSubRect(pFGMask,&mat,r), &m, 0);
+//
+// Algorithm (all kernels one thread per 32-pixel word of the bit-packed mask):
+//   pack     bytes > 128 -> bits (optionally clearing the 1-px frame, OpenCV 2.4 behaviour)
+//   init     every horizontal run (within a word) is a union-find node named by its first pixel;
+//            foreground runs and background runs share one parent array (disjoint pixel sets)
+//   merge    unions found with bit tricks on (this row, row above): a run pair is linked exactly
+//            once (8-connectivity for foreground: vertical + the two diagonals that are not
+//            already implied; 4-connectivity for background); lock-free union by atomicMin so a
+//            component's root is its minimum = raster-first pixel
+//   flatten  parent[node] = root; mark roots; background regions touching the frame are "outer"
+//   rank     exclusive scan of root counts -> canonical label = 1 + rank of the root pixel
+//   label    write labels, accumulate bbox/area per component with atomics, and decide `external`:
+//            the background pixel left of a component's first pixel lies in the region that
+//            surrounds it; the component is external iff that region is outer.
+#include <limits.h>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace bgsb {
+
+__device__ __forceinline__ unsigned in_mask(int k, int w, int wpr)
+{
+    if (k < 0 || k >= wpr) return 0u;
+    if (k < wpr - 1 || (w & 31) == 0) return 0xffffffffu;
+    return (1u << (w & 31)) - 1u;
+}
+
+// first bit of the run of ones in v that contains bit b
+__device__ __forceinline__ int run_start(unsigned v, int b)
+{
+    unsigned below = ~v & ((b == 0) ? 0u : (0xffffffffu >> (32 - b)));
+    return below ? 32 - __clz(below) : 0;
+}
+
+__device__ __forceinline__ int find_root(const int *parent, int p)
+{
+    int q = parent[p];
+    while (q != p) { p = q; q = parent[p]; }
+    return p;
+}
+
+__device__ __forceinline__ void unite(int *parent, int a, int b)
+{
+    while (true) {
+        a = find_root(parent, a);
+        b = find_root(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }      // a > b: hang a under b
+        int old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;                                      // somebody re-parented a meanwhile: retry
+    }
+}
+
+__global__ void __launch_bounds__(256)
+ccl_pack_kernel(const uint8_t *__restrict__ mask, unsigned *__restrict__ bits, int w, int h, int wpr, int zero_border)
+{
+    int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= h * wpr) return;
+    int y = wi / wpr, k = wi - y * wpr;
+    const uint8_t *p = mask + (size_t)y * w + (size_t)k * 32;
+    int nvalid = min(32, w - k * 32);
+    unsigned word = 0;
+    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(p);
+        uint4 a = __ldg(q), b = __ldg(q + 1);
+        unsigned ws[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            unsigned v = ws[i];
+            unsigned nz = (((v & 0xffu) > 128u) ? 1u : 0u) | ((((v >> 8) & 0xffu) > 128u) ? 2u : 0u) |
+                          ((((v >> 16) & 0xffu) > 128u) ? 4u : 0u) | (((v >> 24) > 128u) ? 8u : 0u);
+            word |= nz << (4 * i);
+        }
+    } else {
+        for (int i = 0; i < nvalid; i++) word |= (p[i] > 128 ? 1u : 0u) << i;
+    }
+    if (zero_border) {
+        if (y == 0 || y == h - 1) word = 0;
+        if (k == 0) word &= ~1u;
+        if (k == wpr - 1) word &= ~(1u << ((w - 1) & 31));
+    }
+    bits[wi] = word;
+}
+
+__global__ void __launch_bounds__(256)
+ccl_init_kernel(const unsigned *__restrict__ bits, int *__restrict__ parent, uint8_t *__restrict__ outer,
+                int w, int h, int wpr)
+{
+    int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= h * wpr) return;
+    int y = wi / wpr, k = wi - y * wpr;
+    unsigned v = bits[wi];
+    unsigned vb = ~v & in_mask(k, w, wpr);
+    int base = y * w + k * 32;
+    unsigned s = v & ~(v << 1);
+    while (s) { int b = __ffs(s) - 1; s &= s - 1; parent[base + b] = base + b; }
+    s = vb & ~(vb << 1);
+    while (s) { int b = __ffs(s) - 1; s &= s - 1; parent[base + b] = base + b; outer[base + b] = 0; }
+}
+
+template <bool DIAG>
+__device__ __forceinline__ void merge_class(int *parent, unsigned v, unsigned vl, unsigned vr, unsigned u,
+                                            unsigned ul, unsigned ur, int base, int base_up, bool has_up, int k)
+{
+    // horizontal continuation across the word boundary
+    if ((v & 1u) && (vl >> 31)) unite(parent, base, base - 32 + run_start(vl, 31));
+    if (!has_up) return;
+    unsigned up_m1 = (u << 1) | (ul >> 31), cur_m1 = (v << 1) | (vl >> 31);
+    unsigned A = v & u & ~(cur_m1 & up_m1);
+    while (A) {
+        int x = __ffs(A) - 1; A &= A - 1;
+        unite(parent, base + run_start(v, x), base_up + run_start(u, x));
+    }
+    if (DIAG) {
+        unsigned up_p1 = (u >> 1) | (ur << 31), cur_p1 = (v >> 1) | (vr << 31);
+        unsigned B = v & ~u & up_m1 & ~cur_m1;
+        while (B) {
+            int x = __ffs(B) - 1; B &= B - 1;
+            int other = (x == 0) ? base_up - 32 + run_start(ul, 31) : base_up + run_start(u, x - 1);
+            unite(parent, base + run_start(v, x), other);
+        }
+        unsigned C = v & ~u & up_p1 & ~cur_p1;
+        while (C) {
+            int x = __ffs(C) - 1; C &= C - 1;
+            int other = (x == 31) ? base_up + 32 : base_up + run_start(u, x + 1);
+            unite(parent, base + run_start(v, x), other);
+        }
+    }
+    (void)k;
+}
+
+__global__ void __launch_bounds__(256)
+ccl_merge_kernel(const unsigned *__restrict__ bits, int *parent, int w, int h, int wpr)
+{
+    int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= h * wpr) return;
+    int y = wi / wpr, k = wi - y * wpr;
+    unsigned v = bits[wi];
+    unsigned vl = k > 0 ? bits[wi - 1] : 0u, vr = k + 1 < wpr ? bits[wi + 1] : 0u;
+    unsigned u = 0, ul = 0, ur = 0;
+    bool has_up = y > 0;
+    if (has_up) {
+        u = bits[wi - wpr];
+        ul = k > 0 ? bits[wi - wpr - 1] : 0u;
+        ur = k + 1 < wpr ? bits[wi - wpr + 1] : 0u;
+    }
+    int base = y * w + k * 32, base_up = base - w;
+    // foreground, 8-connected
+    merge_class<true>(parent, v, vl, vr, u, ul, ur, base, base_up, has_up, k);
+    // background, 4-connected (the complement inside the image)
+    unsigned mk = in_mask(k, w, wpr), ml = in_mask(k - 1, w, wpr), mr = in_mask(k + 1, w, wpr);
+    merge_class<false>(parent, ~v & mk, ~vl & ml, ~vr & mr, has_up ? (~u & mk) : 0u, has_up ? (~ul & ml) : 0u,
+                       has_up ? (~ur & mr) : 0u, base, base_up, has_up, k);
+}
+
+__global__ void __launch_bounds__(256)
+ccl_flatten_kernel(const unsigned *__restrict__ bits, int *parent, uint8_t *outer, unsigned *__restrict__ rootbits,
+                   int w, int h, int wpr)
+{
+    int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= h * wpr) return;
+    int y = wi / wpr, k = wi - y * wpr;
+    unsigned v = bits[wi];
+    unsigned mk = in_mask(k, w, wpr);
+    unsigned vb = ~v & mk;
+    int base = y * w + k * 32;
+    unsigned roots = 0;
+    unsigned s = v & ~(v << 1);
+    while (s) {
+        int b = __ffs(s) - 1; s &= s - 1;
+        int r = find_root(parent, base + b);
+        parent[base + b] = r;
+        if (r == base + b) roots |= 1u << b;
+    }
+    rootbits[wi] = roots;
+    // background runs: flatten, and flag regions that touch the image frame as "outer"
+    const bool edge_row = (y == 0 || y == h - 1);
+    s = vb & ~(vb << 1);
+    while (s) {
+        int b = __ffs(s) - 1; s &= s - 1;
+        int r = find_root(parent, base + b);
+        parent[base + b] = r;
+        unsigned rest = ~(vb >> b);
+        int len = rest ? __ffs(rest) - 1 : 32 - b;
+        bool touches = edge_row || (k == 0 && b == 0) || (k * 32 + b + len - 1 == w - 1);
+        if (touches) outer[r] = 1;
+    }
+}
+
+struct CompRaw { int label, first_index, xmin, ymin, xmax, ymax, area, external; };
+
+// single CTA: exclusive scan of per-word root counts, component count, component table init
+__global__ void __launch_bounds__(1024)
+ccl_rank_kernel(const unsigned *__restrict__ rootbits, int *__restrict__ wordrank, int nwords, CompRaw *comp,
+                int cap, int *ncomp, int w, int wpr)
+{
+    __shared__ int sums[1024];
+    const int tid = threadIdx.x;
+    const int chunk = (nwords + 1023) / 1024;
+    const int lo = min(nwords, tid * chunk), hi = min(nwords, lo + chunk);
+    int acc = 0;
+    for (int i = lo; i < hi; i++) acc += __popc(rootbits[i]);
+    sums[tid] = acc;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {          // Hillis-Steele inclusive scan
+        int v = tid >= off ? sums[tid - off] : 0;
+        __syncthreads();
+        sums[tid] += v;
+        __syncthreads();
+    }
+    int run = sums[tid] - acc;
+    for (int i = lo; i < hi; i++) {
+        wordrank[i] = run;
+        unsigned r = rootbits[i];
+        int y = i / wpr, k = i - y * wpr;
+        while (r) {
+            int b = __ffs(r) - 1; r &= r - 1;
+            if (run < cap) {
+                CompRaw c;
+                c.label = run + 1; c.first_index = y * w + k * 32 + b;
+                c.xmin = INT_MAX; c.ymin = INT_MAX; c.xmax = -1; c.ymax = -1; c.area = 0; c.external = 0;
+                comp[run] = c;
+            }
+            run++;
+        }
+    }
+    if (tid == 1023) *ncomp = sums[1023];
+}
+
+__global__ void __launch_bounds__(256)
+ccl_label_kernel(const unsigned *__restrict__ bits, const int *__restrict__ parent, const uint8_t *__restrict__ outer,
+                 const unsigned *__restrict__ rootbits, const int *__restrict__ wordrank, CompRaw *comp, int cap,
+                 int *__restrict__ labels, int w, int h, int wpr)
+{
+    int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= h * wpr) return;
+    int y = wi / wpr, k = wi - y * wpr;
+    unsigned v = bits[wi];
+    int base = y * w + k * 32;
+    int nvalid = min(32, w - k * 32);
+    int lab[32];
+    if (labels) {
+#pragma unroll
+        for (int i = 0; i < 32; i++) lab[i] = 0;
+    }
+    unsigned s = v & ~(v << 1);
+    while (s) {
+        int b = __ffs(s) - 1; s &= s - 1;
+        int p = base + b;
+        int r = parent[p];
+        int ry = r / w, rx = r - ry * w;
+        int rwi = ry * wpr + (rx >> 5);
+        int rank = wordrank[rwi] + __popc(rootbits[rwi] & ((rx & 31) ? (0xffffffffu >> (32 - (rx & 31))) : 0u));
+        unsigned rest = ~(v >> b);
+        int len = rest ? __ffs(rest) - 1 : 32 - b;
+        if (labels) {
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+                if (i >= b && i < b + len) lab[i] = rank + 1;
+        }
+        if (rank < cap) {
+            CompRaw *c = comp + rank;
+            int x0 = k * 32 + b;
+            atomicMin(&c->xmin, x0); atomicMax(&c->xmax, x0 + len - 1);
+            atomicMin(&c->ymin, y); atomicMax(&c->ymax, y);
+            atomicAdd(&c->area, len);
+            if (r == p) {
+                // RETR_EXTERNAL: is the surrounding background region connected to the outside?
+                int ext = 1;
+                if (rx > 0) {
+                    int lk = (rx - 1) >> 5, lb = (rx - 1) & 31;
+                    unsigned lv = ~bits[ry * wpr + lk] & in_mask(lk, w, wpr);
+                    int node = ry * w + lk * 32 + run_start(lv, lb);
+                    ext = outer[parent[node]];
+                }
+                c->external = ext;
+            }
+        }
+    }
+    if (labels) {
+        int *o = labels + base;
+        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                reinterpret_cast<int4 *>(o)[i] = make_int4(lab[4 * i], lab[4 * i + 1], lab[4 * i + 2], lab[4 * i + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+                if (i < nvalid) o[i] = lab[i];
+        }
+    }
+}
+
+// cvMoments(ROI, binary=0): pixel-value weighted raw moments, ROI-relative coordinates.
+__global__ void __launch_bounds__(256)
+rect_moments_kernel(const uint8_t *__restrict__ mask, int w, int h, const int *__restrict__ rects,
+                    unsigned long long *out)
+{
+    const int ri = blockIdx.x;
+    const int rx = rects[4 * ri], ry = rects[4 * ri + 1], rw = rects[4 * ri + 2], rh = rects[4 * ri + 3];
+    unsigned long long m[6] = {0, 0, 0, 0, 0, 0};
+    // each y-slice of blocks takes every gridDim.y-th row
+    for (int yy = blockIdx.y; yy < rh; yy += gridDim.y) {
+        int y = ry + yy;
+        if (y < 0 || y >= h) continue;
+        const uint8_t *row = mask + (size_t)y * w;
+        unsigned long long r0 = 0, r1 = 0, r2 = 0;       // sum v, sum v*x, sum v*x*x over this row
+        for (int xx = threadIdx.x; xx < rw; xx += blockDim.x) {
+            int x = rx + xx;
+            if (x < 0 || x >= w) continue;
+            unsigned long long v = row[x];
+            r0 += v; r1 += v * xx; r2 += v * (unsigned long long)xx * xx;
+        }
+        m[0] += r0; m[1] += r1; m[2] += r0 * yy; m[3] += r2; m[4] += r0 * (unsigned long long)yy * yy; m[5] += r1 * yy;
+    }
+    __shared__ unsigned long long red[6][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        unsigned long long v = m[i];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) red[i][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        unsigned long long v = 0;
+        for (int i = 0; i < 8; i++) v += red[threadIdx.x][i];
+        if (v) atomicAdd(out + 6 * ri + threadIdx.x, v);
+    }
+}
+
+}  // namespace bgsb
+
+using namespace bgsb;
+
+struct bgsb_ccl {
+    int device = 0, max_w = 0, max_h = 0;
+    int w = 0, h = 0;
+    unsigned *d_bits = nullptr, *d_rootbits = nullptr;
+    int *d_parent = nullptr, *d_wordrank = nullptr, *d_ncomp = nullptr;
+    uint8_t *d_outer = nullptr, *d_mask_own = nullptr;
+    int32_t *d_labels_own = nullptr;
+    CompRaw *d_comp = nullptr;
+    int cap = 0;
+    const uint8_t *last_mask = nullptr;
+    cudaStream_t last_stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    bool labelled = false;
+};
+
+extern "C" {
+
+int bgsb_ccl_create(bgsb_ccl **out, int device, int max_w, int max_h)
+{
+    BGSB_REQUIRE(out, "null out");
+    BGSB_REQUIRE(max_w > 0 && max_h > 0 && (long long)max_w * max_h < (1LL << 30), "bad size");
+    BGSB_CUDA(cudaSetDevice(device));
+    bgsb_ccl *c = new bgsb_ccl();
+    c->device = device; c->max_w = max_w; c->max_h = max_h;
+    const size_t npx = (size_t)max_w * max_h;
+    const size_t nwords = (size_t)((max_w + 31) / 32) * max_h;
+    c->cap = (int)(npx / 4 + 64);
+    cudaError_t e = cudaSuccess;
+    auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    A((void **)&c->d_bits, nwords * 4);
+    A((void **)&c->d_rootbits, nwords * 4);
+    A((void **)&c->d_wordrank, nwords * 4);
+    A((void **)&c->d_parent, npx * 4);
+    A((void **)&c->d_outer, npx);
+    A((void **)&c->d_mask_own, npx);
+    A((void **)&c->d_comp, (size_t)c->cap * sizeof(CompRaw));
+    A((void **)&c->d_ncomp, sizeof(int));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        set_error("bgsb_ccl_create: %s", cudaGetErrorString(e));
+        bgsb_ccl_destroy(c);
+        return BGSB_ERR_CUDA;
+    }
+    *out = c;
+    return BGSB_OK;
+}
+
+void bgsb_ccl_destroy(bgsb_ccl *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    cudaFree(c->d_bits); cudaFree(c->d_rootbits); cudaFree(c->d_wordrank); cudaFree(c->d_parent);
+    cudaFree(c->d_outer); cudaFree(c->d_mask_own); cudaFree(c->d_comp); cudaFree(c->d_ncomp);
+    cudaFree(c->d_labels_own);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int bgsb_ccl_label_dev(bgsb_ccl *c, const uint8_t *d_mask, int w, int h, int zero_border, int32_t *d_labels,
+                       void *stream_)
+{
+    BGSB_REQUIRE(c && d_mask, "null");
+    BGSB_REQUIRE(w > 0 && h > 0 && w <= c->max_w && h <= c->max_h && (size_t)w * h <= (size_t)c->max_w * c->max_h,
+                 "image larger than the labeller was created for");
+    BGSB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int wpr = (w + 31) / 32, nwords = wpr * h;
+    const int threads = 256, blocks = (nwords + threads - 1) / threads;
+    ccl_pack_kernel<<<blocks, threads, 0, stream>>>(d_mask, c->d_bits, w, h, wpr, zero_border);
+    BGSB_LAUNCH_CHECK();
+    ccl_init_kernel<<<blocks, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, w, h, wpr);
+    BGSB_LAUNCH_CHECK();
+    ccl_merge_kernel<<<blocks, threads, 0, stream>>>(c->d_bits, c->d_parent, w, h, wpr);
+    BGSB_LAUNCH_CHECK();
+    ccl_flatten_kernel<<<blocks, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_rootbits, w, h, wpr);
+    BGSB_LAUNCH_CHECK();
+    ccl_rank_kernel<<<1, 1024, 0, stream>>>(c->d_rootbits, c->d_wordrank, nwords, c->d_comp, c->cap, c->d_ncomp, w, wpr);
+    BGSB_LAUNCH_CHECK();
+    ccl_label_kernel<<<blocks, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_rootbits, c->d_wordrank,
+                                                     c->d_comp, c->cap, d_labels, w, h, wpr);
+    BGSB_LAUNCH_CHECK();
+    c->w = w; c->h = h; c->last_mask = d_mask; c->last_stream = stream; c->labelled = true;
+    return BGSB_OK;
+}
+
+int bgsb_ccl_components(bgsb_ccl *c, bgsb_component *out, int capacity, int *n)
+{
+    BGSB_REQUIRE(c && n, "null");
+    if (!c->labelled) { set_error("bgsb_ccl_components: nothing labelled yet"); return BGSB_ERR_STATE; }
+    BGSB_CUDA(cudaSetDevice(c->device));
+    BGSB_CUDA(cudaStreamSynchronize(c->last_stream));
+    int cnt = 0;
+    BGSB_CUDA(cudaMemcpy(&cnt, c->d_ncomp, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = cnt;
+    if (cnt > c->cap) { set_error("component table overflow (%d > %d)", cnt, c->cap); return BGSB_ERR_CAPACITY; }
+    if (!out || capacity <= 0) return BGSB_OK;
+    if (cnt > capacity) { set_error("caller table too small (%d > %d)", cnt, capacity); return BGSB_ERR_CAPACITY; }
+    if (cnt == 0) return BGSB_OK;
+    static_assert(sizeof(CompRaw) == sizeof(bgsb_component), "layout");
+    BGSB_CUDA(cudaMemcpy(out, c->d_comp, (size_t)cnt * sizeof(CompRaw), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < cnt; i++) {       // (xmin,ymin,xmax,ymax) -> (x,y,w,h)
+        out[i].w = out[i].w - out[i].x + 1;
+        out[i].h = out[i].h - out[i].y + 1;
+    }
+    return BGSB_OK;
+}
+
+int bgsb_ccl_rect_moments(bgsb_ccl *c, const int32_t *rects, int nrects, uint64_t *out)
+{
+    BGSB_REQUIRE(c && out && (rects || nrects == 0), "null");
+    if (!c->labelled) { set_error("bgsb_ccl_rect_moments: nothing labelled yet"); return BGSB_ERR_STATE; }
+    if (nrects == 0) return BGSB_OK;
+    BGSB_CUDA(cudaSetDevice(c->device));
+    int *d_rects = nullptr;
+    unsigned long long *d_out = nullptr;
+    cudaStream_t st = c->last_stream;
+    BGSB_CUDA(cudaMallocAsync(&d_rects, (size_t)nrects * 16, st));
+    BGSB_CUDA(cudaMallocAsync(&d_out, (size_t)nrects * 48, st));
+    BGSB_CUDA(cudaMemcpyAsync(d_rects, rects, (size_t)nrects * 16, cudaMemcpyHostToDevice, st));
+    BGSB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nrects * 48, st));
+    dim3 grid(nrects, 16);
+    rect_moments_kernel<<<grid, 256, 0, st>>>(c->last_mask, c->w, c->h, d_rects, d_out);
+    BGSB_LAUNCH_CHECK();
+    BGSB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)nrects * 48, cudaMemcpyDeviceToHost, st));
+    BGSB_CUDA(cudaStreamSynchronize(st));
+    BGSB_CUDA(cudaFreeAsync(d_rects, st));
+    BGSB_CUDA(cudaFreeAsync(d_out, st));
+    return BGSB_OK;
+}
+
+int bgsb_ccl_label(bgsb_ccl *c, const uint8_t *mask, int w, int h, size_t stride, int zero_border, int32_t *labels,
+                   bgsb_component *out, int capacity, int *n)
+{
+    BGSB_REQUIRE(c && mask && n, "null");
+    BGSB_REQUIRE(stride >= (size_t)w, "stride smaller than a row");
+    BGSB_REQUIRE(w > 0 && h > 0 && w <= c->max_w && h <= c->max_h, "image larger than the labeller was created for");
+    BGSB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->own_stream;
+    BGSB_CUDA(cudaMemcpy2DAsync(c->d_mask_own, w, mask, stride, w, h, cudaMemcpyHostToDevice, st));
+    if (labels && !c->d_labels_own) BGSB_CUDA(cudaMalloc(&c->d_labels_own, (size_t)c->max_w * c->max_h * 4));
+    int rc = bgsb_ccl_label_dev(c, c->d_mask_own, w, h, zero_border, labels ? c->d_labels_own : nullptr, st);
+    if (rc) return rc;
+    if (labels) BGSB_CUDA(cudaMemcpyAsync(labels, c->d_labels_own, (size_t)w * h * 4, cudaMemcpyDeviceToHost, st));
+    return bgsb_ccl_components(c, out, capacity, n);
+}
+
+}  // extern "C"

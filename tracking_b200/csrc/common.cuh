@@ -1,0 +1,112 @@
+// Shared device/host helpers for libbgsb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <atomic>
+
+#include "../../include/bgsb200.h"
+
+namespace bgsb {
+
+constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// ---- error plumbing --------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define BGSB_CUDA(call)                                                                      \
+    do {                                                                                     \
+        cudaError_t _e = (call);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            bgsb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return BGSB_ERR_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+#define BGSB_LAUNCH_CHECK()                                                                  \
+    do {                                                                                     \
+        bgsb::g_launches.fetch_add(1, std::memory_order_relaxed);                            \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess) {                                                             \
+            bgsb::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return BGSB_ERR_CUDA;                                                            \
+        }                                                                                    \
+    } while (0)
+
+#define BGSB_REQUIRE(cond, msg)                                                              \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            bgsb::set_error("%s: %s", __func__, msg);                                        \
+            return BGSB_ERR_ARG;                                                             \
+        }                                                                                    \
+    } while (0)
+
+// ---- per-pixel scalar pieces shared by the plugins ------------------------------------------
+// cv::cvtColor(CV_BGR2GRAY) on 8-bit data (reference call sites FrameDifferenceBGS.cpp:48,
+// AdaptiveBackgroundLearning.cpp:68, WeightedMovingVarianceBGS.cpp:103).  VARIANT 0 = OpenCV 4.x
+// 15-bit coefficients, 1 = OpenCV 2.4 14-bit coefficients.
+template <int VARIANT>
+__device__ __forceinline__ unsigned gray_bgr(unsigned b, unsigned g, unsigned r)
+{
+    if (VARIANT == 0) return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15;
+    return (1868u * b + 9617u * g + 4899u * r + 8192u) >> 14;
+}
+
+// cv::threshold(..., THRESH_BINARY): strict '>' ; thr < 0 encodes enableThreshold == false
+// only where the caller says so (see kernels).
+__device__ __forceinline__ unsigned thr_u8(unsigned v, int enable, int thr)
+{
+    return enable ? (((int)v > thr) ? 255u : 0u) : v;
+}
+
+// saturate_cast<uchar>(float) = cvRound (round half to even) + clamp
+__device__ __forceinline__ unsigned sat_u8_rint(float x)
+{
+    float r = rintf(x);
+    r = fminf(fmaxf(r, 0.f), 255.f);   // NaN -> 0 via fmaxf
+    return (unsigned)r;
+}
+
+// ---- streaming loads / stores ----------------------------------------------------------------
+// State and frames are touched exactly once per launch: keep them out of L1
+// (L2 eviction-priority qualifiers are only accepted on 256-bit loads by ptxas 12.9).
+__device__ __forceinline__ float4 ld_stream_f4(const float *p)
+{
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_f4(float *p, float4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_stream_u4(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_u4(void *p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ unsigned ld_stream_u32(const void *p)
+{
+    unsigned v;
+    asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_u32(void *p, unsigned v)
+{
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned byte_of(unsigned word, int i) { return (word >> (8 * i)) & 0xffu; }
+
+}  // namespace bgsb

@@ -1,0 +1,59 @@
+// Internal launch descriptors shared between the C-ABI layer (capi.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bgsb {
+
+// ---- FD / ABL / WMV ---------------------------------------------------------------------------
+struct SimpleLaunch {
+    const uint8_t *frames;   // [S][T][npx*3]
+    uint8_t *fg;             // [S][T][npx]
+    uint8_t *bg;             // ABL only: [S][T][npx*3] or [S][npx*3] (bg_last_only), nullable
+    const uint8_t *hist0;    // read : FD prev / WMV prev_1 / ABL 8-bit background   [S][npx*3]
+    const uint8_t *hist1;    // read : WMV prev_2
+    uint8_t *hist0_out;      // write-back targets (nullable = history lives in caller-visible ring)
+    uint8_t *hist1_out;
+    int npx, T;
+    int have_hist;           // how many history images are valid on entry (0,1,2)
+    int bg_last_only;
+    int enable_thr, thr, gray_variant;
+    double alpha;            // ABL
+    int abl_update;          // ABL: limit == -1 (AdaptiveBackgroundLearning.cpp:52); 0 freezes the model
+    double w0, w1, w2;       // WMV weights (0.5,0.3,0.2 | 0.3,0.3,0.3)
+};
+int launch_simple(int algo, const SimpleLaunch &L, int nstreams, cudaStream_t stream);
+
+// ---- MOG2 -------------------------------------------------------------------------------------
+constexpr int MOG2_K = 5;             // nmixtures of the default-constructed cv::BackgroundSubtractorMOG2
+constexpr int MOG2_PLANES = 5 * MOG2_K;   // per mode: weight, variance, mean B, G, R
+constexpr int MOG2_TMAX = 32;         // frames per temporal batch launch
+
+struct Mog2Launch {
+    const uint8_t *frames;   // [S][T][npx*3]
+    uint8_t *fg;             // [S][T][npx]
+    uint8_t *bg;             // [S][T][npx*3] | [S][npx*3] | null
+    float *state;            // [S][25][pstride]  plane q = mode*5 + {0:w,1:var,2:muB,3:muG,4:muR}
+    uint8_t *nmodes;         // [S][pstride]
+    size_t pstride;          // plane stride in elements (npx rounded up to 32)
+    int npx, T;
+    int bg_last_only;
+    int fresh;               // 1: state is uninitialised -> treat nmodes as 0 (first frame after create/reset)
+    int enable_thr, thr;
+    int detect_shadows, shadow_value;
+    float Tb, Tg, TB, varInit, varMin, varMax, tau;
+    float alphaT[MOG2_TMAX];     // per-frame learning rate, 1-alphaT and prune = -lr*CT
+    float alpha1[MOG2_TMAX];
+    float prune[MOG2_TMAX];
+};
+int launch_mog2(const Mog2Launch &L, int nstreams, int variant, cudaStream_t stream);
+
+// ---- morphology -------------------------------------------------------------------------------
+int launch_morph_chain(const uint8_t *d_in, uint8_t *d_out, int w, int h, int nimages, const int *ops, int nops,
+                       cudaStream_t stream);
+
+// ---- synthetic video ----------------------------------------------------------------------------
+int launch_synth(uint8_t *d_frames, int nstreams, int T, int w, int h, int t0, uint32_t seed0,
+                 cudaStream_t stream);
+
+}  // namespace bgsb

@@ -1,0 +1,285 @@
+// K-MOG2: cv::BackgroundSubtractorMOG2::operator() + getBackgroundImage + threshold, fused.
+//
+// Replaces (reference tree):
+//   MixtureOfGaussianV2BGS::process   package_bgs/MixtureOfGaussianV2BGS.cpp:56 (mog(in, fg, alpha)),
+//                                     :59 (getBackgroundImage), :61-62 (threshold)
+// whose arithmetic is OpenCV's modules/video/src/bgfg_gaussmix2.cpp (un-vendored dependency,
+// member `mog` at package_bgs/MixtureOfGaussianV2BGS.h:30); spec = SURVEY.md Appendix A.4.
+//
+// Data layout in HBM (structure of arrays, per camera stream):
+//   state  : 25 fp32 planes [q][pstride], q = mode*5 + {0 weight, 1 variance, 2 muB, 3 muG, 4 muR}
+//   nmodes : 1 u8 plane
+//   = 101 B/px, read once and written once per launch (per T frames with temporal batching).
+// A thread owns 4 consecutive pixels: every plane access is one 128-bit load/store and a warp
+// touches 512 contiguous bytes per plane.  All per-pixel state (25 floats x 4 px) lives in
+// registers; the mode loop, the weight-ordered insertion and the new-mode insertion are fully
+// unrolled with compile-time register indices (no local memory).
+//
+// Planes of modes that are dead for all 4 pixels of a thread (m >= max nmodes) are neither loaded
+// nor stored: the CPU reference does not touch them either, and the values are unobservable.
+//
+// Numerics: fp32, unfused (-fmad=false), IEEE division, strict left-to-right evaluation -- the
+// kernel is bit-exact against OpenCV's CPU implementation (tests/test_mog2_parity.py).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace bgsb {
+
+constexpr int K = MOG2_K;
+constexpr int PX = 4;   // pixels per thread
+
+struct Mode { float w, v, b, g, r; };
+
+// One pixel, one frame.  `md` is the per-pixel mode list (registers), n its live length.
+// Returns the raw MOG2 mask value {0, shadow, 255} and the background colour of the updated model.
+template <bool SHADOWS>
+__device__ __forceinline__ unsigned mog2_pixel(Mode (&md)[K], int &n, float x0, float x1, float x2,
+                                               float aT, float a1, float prune, const Mog2Launch &L,
+                                               unsigned &bgB, unsigned &bgG, unsigned &bgR, bool want_bg)
+{
+    bool bgflag = false, fits = false;
+    float tw = 0.f;
+    const float nprune = -prune;
+
+#pragma unroll
+    for (int m = 0; m < K; m++) {
+        if (m < n) {                                   // LIVE bound: pruning below shortens the walk
+            float wt = a1 * md[m].w + prune;
+            int pos = m;
+            if (!fits) {
+                float var = md[m].v;
+                float d0 = md[m].b - x0, d1 = md[m].g - x1, d2 = md[m].r - x2;
+                float dist2 = d0 * d0 + d1 * d1 + d2 * d2;
+                if (tw < L.TB && dist2 < L.Tb * var) bgflag = true;
+                if (dist2 < L.Tg * var) {
+                    fits = true;
+                    wt += aT;
+                    float k = aT / wt;
+                    float nb = md[m].b - k * d0, ng = md[m].g - k * d1, nr = md[m].r - k * d2;
+                    float vn = var + k * (dist2 - var);
+                    vn = fmaxf(vn, L.varMin);
+                    vn = fminf(vn, L.varMax);
+                    // keep the list sorted by weight: bubble the matched mode up past every
+                    // predecessor whose (already updated) weight is not larger
+#pragma unroll
+                    for (int i = m; i > 0; i--) {
+                        if (pos == i && !(wt < md[i - 1].w)) { md[i] = md[i - 1]; pos = i - 1; }
+                    }
+#pragma unroll
+                    for (int i = 0; i <= m; i++)
+                        if (pos == i) { md[i].v = vn; md[i].b = nb; md[i].g = ng; md[i].r = nr; }
+                }
+            }
+            if (wt < nprune) { wt = 0.f; n--; }
+#pragma unroll
+            for (int i = 0; i <= m; i++)
+                if (pos == i) md[i].w = wt;
+            tw += wt;
+        }
+    }
+
+    // renormalise
+    float inv = 0.f;
+    if (fabsf(tw) > 1.1920929e-07f) inv = 1.f / tw;
+#pragma unroll
+    for (int m = 0; m < K; m++)
+        if (m < n) md[m].w *= inv;
+
+    // no mode explains the pixel: insert a new one (replace the weakest if the list is full)
+    if (!fits && aT > 0.f) {
+        if (n < K) n++;
+        int pos = n - 1;
+        float wn;
+        if (n == 1) wn = 1.f;
+        else {
+            wn = aT;
+#pragma unroll
+            for (int i = 0; i < K - 1; i++)
+                if (i < n - 1) md[i].w *= a1;
+        }
+#pragma unroll
+        for (int i = K - 1; i > 0; i--) {
+            if (pos == i && !(aT < md[i - 1].w)) { md[i] = md[i - 1]; pos = i - 1; }
+        }
+#pragma unroll
+        for (int i = 0; i < K; i++)
+            if (pos == i) { md[i].w = wn; md[i].v = L.varInit; md[i].b = x0; md[i].g = x1; md[i].r = x2; }
+    }
+
+    // classification
+    unsigned raw = 0;
+    if (!bgflag) {
+        raw = 255;
+        if (SHADOWS) {
+            // detectShadowGMM: walk the background modes, test brightness ratio + chroma distortion
+            float tW = 0.f;
+            bool done = false;
+#pragma unroll
+            for (int m = 0; m < K; m++) {
+                if (!done && m < n) {
+                    float num = x0 * md[m].b + x1 * md[m].g + x2 * md[m].r;
+                    float den = md[m].b * md[m].b + md[m].g * md[m].g + md[m].r * md[m].r;
+                    if (den == 0.f) { done = true; }
+                    else {
+                        if (num <= den && num >= L.tau * den) {
+                            float a = num / den;
+                            float e0 = a * md[m].b - x0, e1 = a * md[m].g - x1, e2 = a * md[m].r - x2;
+                            float e = e0 * e0 + e1 * e1 + e2 * e2;
+                            if (e < L.Tb * md[m].v * a * a) { raw = (unsigned)L.shadow_value; done = true; }
+                        }
+                        if (!done) { tW += md[m].w; if (tW > L.TB) done = true; }
+                    }
+                }
+            }
+        }
+    }
+
+    // getBackgroundImage on the updated model
+    if (want_bg) {
+        float aB = 0.f, aG = 0.f, aR = 0.f, t2 = 0.f;
+        bool stop = false;
+#pragma unroll
+        for (int m = 0; m < K; m++) {
+            if (!stop && m < n) {
+                float w = md[m].w;
+                aB += w * md[m].b; aG += w * md[m].g; aR += w * md[m].r;
+                t2 += w;
+                if (t2 > L.TB) stop = true;
+            }
+        }
+        float iv = 0.f;
+        if (fabsf(t2) > 1.1920929e-07f) iv = 1.f / t2;
+        bgB = sat_u8_rint(aB * iv); bgG = sat_u8_rint(aG * iv); bgR = sat_u8_rint(aR * iv);
+    }
+    return raw;
+}
+
+__device__ __forceinline__ float &f4c(float4 &v, int j)
+{
+    return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w;
+}
+
+template <bool SHADOWS>
+__global__ void __launch_bounds__(128)
+mog2_kernel(const __grid_constant__ Mog2Launch L)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long px0 = g * PX;
+    if (px0 >= L.npx) return;
+    const int s = blockIdx.y;
+    float *state = L.state + (size_t)s * MOG2_PLANES * L.pstride + px0;
+    uint8_t *nmp = L.nmodes + (size_t)s * L.pstride + px0;
+    const uint8_t *frames = L.frames + (size_t)s * L.T * L.npx * 3;
+    uint8_t *fg = L.fg + (size_t)s * L.T * L.npx;
+    uint8_t *bgout = L.bg ? L.bg + (size_t)s * (L.bg_last_only ? 1 : L.T) * L.npx * 3 : nullptr;
+    const bool full = (px0 + PX <= L.npx);     // planes are padded to 32 px, frames are not
+
+    // ---- load state (read once per launch) ----
+    int n[PX];
+    unsigned nm4 = L.fresh ? 0u : ld_stream_u32(nmp);
+#pragma unroll
+    for (int j = 0; j < PX; j++) n[j] = (nm4 >> (8 * j)) & 0xff;
+    int nmax = max(max(n[0], n[1]), max(n[2], n[3]));
+
+    float4 P[MOG2_PLANES];
+#pragma unroll
+    for (int m = 0; m < K; m++) {
+        if (m < nmax) {
+#pragma unroll
+            for (int f = 0; f < 5; f++) P[m * 5 + f] = ld_stream_f4(state + (size_t)(m * 5 + f) * L.pstride);
+        } else {
+#pragma unroll
+            for (int f = 0; f < 5; f++) P[m * 5 + f] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+
+    for (int t = 0; t < L.T; t++) {
+        // ---- this frame's 4 pixels: 12 bytes ----
+        const uint8_t *fr = frames + (size_t)t * L.npx * 3 + px0 * 3;
+        unsigned iw[3];
+        if (full) {
+            iw[0] = ld_stream_u32(fr); iw[1] = ld_stream_u32(fr + 4); iw[2] = ld_stream_u32(fr + 8);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                unsigned v = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (px0 * 3 + i * 4 + k < (long long)L.npx * 3) v |= (unsigned)fr[i * 4 + k] << (8 * k);
+                iw[i] = v;
+            }
+        }
+        const float aT = L.alphaT[t], a1 = L.alpha1[t], prune = L.prune[t];
+        const bool want_bg = bgout && (!L.bg_last_only || t == L.T - 1);
+
+        unsigned mask4 = 0, ow[3] = {0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < PX; j++) {
+            Mode md[K];
+#pragma unroll
+            for (int m = 0; m < K; m++) {
+                md[m].w = f4c(P[m * 5 + 0], j); md[m].v = f4c(P[m * 5 + 1], j);
+                md[m].b = f4c(P[m * 5 + 2], j); md[m].g = f4c(P[m * 5 + 3], j); md[m].r = f4c(P[m * 5 + 4], j);
+            }
+            const int b0 = 3 * j, b1 = 3 * j + 1, b2 = 3 * j + 2;
+            float x0 = (float)byte_of(iw[b0 >> 2], b0 & 3);
+            float x1 = (float)byte_of(iw[b1 >> 2], b1 & 3);
+            float x2 = (float)byte_of(iw[b2 >> 2], b2 & 3);
+            unsigned bB = 0, bG = 0, bR = 0;
+            unsigned raw = mog2_pixel<SHADOWS>(md, n[j], x0, x1, x2, aT, a1, prune, L, bB, bG, bR, want_bg);
+            mask4 |= thr_u8(raw, L.enable_thr, L.thr) << (8 * j);      // MixtureOfGaussianV2BGS.cpp:61-62
+            ow[b0 >> 2] |= bB << (8 * (b0 & 3));
+            ow[b1 >> 2] |= bG << (8 * (b1 & 3));
+            ow[b2 >> 2] |= bR << (8 * (b2 & 3));
+#pragma unroll
+            for (int m = 0; m < K; m++) {
+                f4c(P[m * 5 + 0], j) = md[m].w; f4c(P[m * 5 + 1], j) = md[m].v;
+                f4c(P[m * 5 + 2], j) = md[m].b; f4c(P[m * 5 + 3], j) = md[m].g; f4c(P[m * 5 + 4], j) = md[m].r;
+            }
+        }
+
+        // ---- per-frame outputs ----
+        uint8_t *fgp = fg + (size_t)t * L.npx + px0;
+        if (full) st_stream_u32(fgp, mask4);
+        else {
+#pragma unroll
+            for (int j = 0; j < PX; j++) if (px0 + j < L.npx) fgp[j] = (uint8_t)(mask4 >> (8 * j));
+        }
+        if (want_bg) {
+            uint8_t *bp = bgout + (L.bg_last_only ? 0 : (size_t)t * L.npx * 3) + px0 * 3;
+            if (full) { st_stream_u32(bp, ow[0]); st_stream_u32(bp + 4, ow[1]); st_stream_u32(bp + 8, ow[2]); }
+            else {
+#pragma unroll
+                for (int i = 0; i < 12; i++)
+                    if (px0 * 3 + i < (long long)L.npx * 3) bp[i] = (uint8_t)(ow[i >> 2] >> (8 * (i & 3)));
+            }
+        }
+    }
+
+    // ---- store state (written once per launch) ----
+    int nmax2 = max(max(n[0], n[1]), max(n[2], n[3]));
+#pragma unroll
+    for (int m = 0; m < K; m++) {
+        if (m < nmax2) {
+#pragma unroll
+            for (int f = 0; f < 5; f++) st_stream_f4(state + (size_t)(m * 5 + f) * L.pstride, P[m * 5 + f]);
+        }
+    }
+    st_stream_u32(nmp, (unsigned)n[0] | ((unsigned)n[1] << 8) | ((unsigned)n[2] << 16) | ((unsigned)n[3] << 24));
+}
+
+int launch_mog2(const Mog2Launch &L, int nstreams, int variant, cudaStream_t stream)
+{
+    (void)variant;
+    const int threads = 128;
+    long long nthreads = ((long long)L.npx + PX - 1) / PX;
+    dim3 grid((unsigned)((nthreads + threads - 1) / threads), (unsigned)nstreams);
+    // the shadow test only changes the output when 127 survives the wrapper's threshold
+    const bool shadows = L.detect_shadows && !(L.enable_thr && (L.thr < L.shadow_value || L.thr >= 255));
+    if (shadows) mog2_kernel<true><<<grid, threads, 0, stream>>>(L);
+    else mog2_kernel<false><<<grid, threads, 0, stream>>>(L);
+    BGSB_LAUNCH_CHECK();
+    return BGSB_OK;
+}
+
+}  // namespace bgsb

@@ -1,0 +1,241 @@
+// K-MORPH: cv::erode / cv::dilate with the default 3x3 rectangular element on {0,255} masks,
+// as bit-parallel AND/OR on bit-packed rows, shared-memory tiled, whole op chains fused per tile.
+//
+// Replaces cv::erode/cv::dilate(mask, cv::Mat()) and cvErode/cvDilate(mask, mask, NULL, n) call
+// sites (package_bgs/jmo/CMultiLayerBGS.cpp:1614-1615, package_bgs/tb/PixelUtils.cpp:73-74,
+// package_bgs/av/VuMeter.cpp:68) and the open/close of the stock FG detectors reached through
+// ustc_src/trackingMain.cpp:616-618.  Semantics: anchor at the centre, pixels
+// outside the image are ignored (erode pads +inf, dilate pads -inf), `iterations = n` == n passes.
+//
+// One CTA owns a tile of TH rows x TW 32-px words.  It packs the input bytes of the tile plus a
+// halo of R = sum(iterations) rows (and one halo word = 32 px on each side) into shared memory,
+// runs every pass of the chain there (ping-pong buffers, one __syncthreads per pass; each pass
+// is 3 shifted ANDs/ORs per word and per row), and unpacks the interior back to bytes.  HBM
+// traffic is one byte read and one byte written per pixel for the whole chain.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace bgsb {
+
+constexpr int MORPH_TH = 16;        // interior rows per tile
+constexpr int MORPH_TW = 62;        // interior words per tile (+2 halo words = 64)
+constexpr int MORPH_RMAX = 8;       // max total iterations fused in one launch
+constexpr int MORPH_ROWS = MORPH_TH + 2 * MORPH_RMAX;
+constexpr int MORPH_SW = MORPH_TW + 2;
+
+struct MorphChain {
+    int n;
+    signed char op[16];
+    signed char iters[16];
+};
+
+// bits of word k of an image row that lie inside the image
+__device__ __forceinline__ unsigned inside_mask(int y, int k, int w, int h, int wpr)
+{
+    if (y < 0 || y >= h || k < 0 || k >= wpr) return 0u;
+    if (k < wpr - 1 || (w & 31) == 0) return 0xffffffffu;
+    return (1u << (w & 31)) - 1u;
+}
+
+__global__ void __launch_bounds__(256)
+morph_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, int h, int wpr, MorphChain chain, int R)
+{
+    __shared__ unsigned buf[2][MORPH_ROWS][MORPH_SW];
+    const int img = blockIdx.z;
+    const size_t npx = (size_t)w * h;
+    in += img * npx; out += img * npx;
+    const int k0 = blockIdx.x * MORPH_TW - 1;          // word index of smem column 0 (halo)
+    const int y0 = blockIdx.y * MORPH_TH - R;          // image row of smem row 0 (halo)
+    const int rows = MORPH_TH + 2 * R;
+    const int tw = min(MORPH_TW, wpr - blockIdx.x * MORPH_TW) + 2;   // smem columns in use
+
+    // ---- pack: bytes -> bits (bit i of word k = pixel 32k+i is set) ----
+    for (int idx = threadIdx.x; idx < rows * tw; idx += blockDim.x) {
+        int r = idx / tw, c = idx - r * tw;
+        int y = y0 + r, k = k0 + c;
+        unsigned word = 0;
+        if (y >= 0 && y < h && k >= 0 && k < wpr) {
+            const uint8_t *p = in + (size_t)y * w + (size_t)k * 32;
+            int nvalid = min(32, w - k * 32);
+            if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+                const uint4 *q = reinterpret_cast<const uint4 *>(p);
+                uint4 a = __ldg(q), b = __ldg(q + 1);
+                unsigned ws[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    unsigned v = ws[i];
+                    unsigned nz = ((v & 0xffu) ? 1u : 0u) | ((v & 0xff00u) ? 2u : 0u) |
+                                  ((v & 0xff0000u) ? 4u : 0u) | ((v & 0xff000000u) ? 8u : 0u);
+                    word |= nz << (4 * i);
+                }
+            } else {
+                for (int i = 0; i < nvalid; i++) word |= (p[i] ? 1u : 0u) << i;
+            }
+        }
+        buf[0][r][c] = word;
+    }
+    __syncthreads();
+
+    // ---- the chain, entirely in shared memory ----
+    int cur = 0;
+    for (int o = 0; o < chain.n; o++) {
+        const bool dil = chain.op[o] == BGSB_MORPH_DILATE;
+        for (int it = 0; it < chain.iters[o]; it++) {
+            for (int idx = threadIdx.x; idx < rows * tw; idx += blockDim.x) {
+                int r = idx / tw, c = idx - r * tw;
+                int y = y0 + r, k = k0 + c;
+                unsigned acc = dil ? 0u : 0xffffffffu;
+#pragma unroll
+                for (int dr = -1; dr <= 1; dr++) {
+                    int rr = r + dr;
+                    unsigned L = 0, M = 0, Rt = 0;
+                    if (rr >= 0 && rr < rows) {
+                        M = buf[cur][rr][c];
+                        if (c > 0) L = buf[cur][rr][c - 1];
+                        if (c + 1 < tw) Rt = buf[cur][rr][c + 1];
+                    }
+                    if (!dil) {   // outside-image pixels are neutral (all ones) for erosion
+                        M |= ~inside_mask(y + dr, k, w, h, wpr);
+                        L |= ~inside_mask(y + dr, k - 1, w, h, wpr);
+                        Rt |= ~inside_mask(y + dr, k + 1, w, h, wpr);
+                    }
+                    unsigned left = (M << 1) | (L >> 31);      // neighbour x-1
+                    unsigned right = (M >> 1) | (Rt << 31);    // neighbour x+1
+                    if (dil) acc |= M | left | right;
+                    else acc &= M & left & right;
+                }
+                buf[cur ^ 1][r][c] = acc & inside_mask(y, k, w, h, wpr);
+            }
+            __syncthreads();
+            cur ^= 1;
+        }
+    }
+
+    // ---- unpack the interior: bits -> {0,255} bytes ----
+    const int itw = tw - 2;
+    for (int idx = threadIdx.x; idx < MORPH_TH * itw; idx += blockDim.x) {
+        int r = idx / itw, c = idx - r * itw;
+        int y = blockIdx.y * MORPH_TH + r, k = k0 + 1 + c;
+        if (y >= h) continue;
+        unsigned word = buf[cur][r + R][c + 1];
+        uint8_t *p = out + (size_t)y * w + (size_t)k * 32;
+        int nvalid = min(32, w - k * 32);
+        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+            unsigned ws[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                unsigned nib = (word >> (4 * i)) & 0xfu;
+                ws[i] = ((nib & 1u) ? 0xffu : 0u) | ((nib & 2u) ? 0xff00u : 0u) |
+                        ((nib & 4u) ? 0xff0000u : 0u) | ((nib & 8u) ? 0xff000000u : 0u);
+            }
+            uint4 *q = reinterpret_cast<uint4 *>(p);
+            q[0] = make_uint4(ws[0], ws[1], ws[2], ws[3]);
+            q[1] = make_uint4(ws[4], ws[5], ws[6], ws[7]);
+        } else {
+            for (int i = 0; i < nvalid; i++) p[i] = ((word >> i) & 1u) ? 255 : 0;
+        }
+    }
+}
+
+// plain byte copy with "non-zero -> 255"?  No: an empty chain is a no-op COPY (iterations = 0,
+// SURVEY A.5), values pass through unchanged.
+static int copy_mask(const uint8_t *in, uint8_t *out, size_t bytes, cudaStream_t stream)
+{
+    if (in != out) BGSB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
+    return BGSB_OK;
+}
+
+int launch_morph_chain(const uint8_t *d_in, uint8_t *d_out, int w, int h, int nimages, const int *ops, int nops,
+                       cudaStream_t stream)
+{
+    // expand into passes of at most MORPH_RMAX total iterations per launch
+    struct Item { int op, iters; };
+    Item items[64];
+    int ni = 0, total = 0;
+    for (int i = 0; i < nops; i++) {
+        int op = ops[2 * i], it = ops[2 * i + 1];
+        if (op != BGSB_MORPH_ERODE && op != BGSB_MORPH_DILATE) { set_error("morph: bad op %d", op); return BGSB_ERR_ARG; }
+        if (it < 0 || it > 64) { set_error("morph: iterations out of range"); return BGSB_ERR_ARG; }
+        while (it > 0) {
+            int take = it < MORPH_RMAX ? it : MORPH_RMAX;
+            if (ni >= 64) { set_error("morph: chain too long"); return BGSB_ERR_ARG; }
+            items[ni++] = {op, take};
+            it -= take; total += take;
+        }
+    }
+    const size_t bytes = (size_t)w * h * nimages;
+    if (total == 0) return copy_mask(d_in, d_out, bytes, stream);
+
+    // group items into launches
+    int nlaunch = 0, lstart[64], lend[64];
+    for (int i = 0; i < ni;) {
+        int r = 0, j = i;
+        while (j < ni && r + items[j].iters <= MORPH_RMAX && j - i < 16) { r += items[j].iters; j++; }
+        lstart[nlaunch] = i; lend[nlaunch] = j; nlaunch++;
+        i = j;
+    }
+    // ping-pong through temporaries when more than one launch is needed or in == out
+    uint8_t *tmp[2] = {nullptr, nullptr};
+    const bool inplace = (d_in == d_out);
+    const int ntmp = (nlaunch > 2) ? 2 : ((nlaunch > 1 || inplace) ? 1 : 0);
+    for (int i = 0; i < ntmp; i++) BGSB_CUDA(cudaMallocAsync(&tmp[i], bytes, stream));
+
+    const int wpr = (w + 31) / 32;
+    dim3 grid((wpr + MORPH_TW - 1) / MORPH_TW, (h + MORPH_TH - 1) / MORPH_TH, nimages);
+    const uint8_t *src = d_in;
+    for (int l = 0; l < nlaunch; l++) {
+        const bool last = (l == nlaunch - 1);
+        uint8_t *dst = (last && src != d_out) ? d_out : ((src == tmp[0]) ? tmp[1] : tmp[0]);
+        MorphChain ch;
+        ch.n = 0;
+        int R = 0;
+        for (int i = lstart[l]; i < lend[l]; i++) {
+            ch.op[ch.n] = (signed char)items[i].op; ch.iters[ch.n] = (signed char)items[i].iters; ch.n++;
+            R += items[i].iters;
+        }
+        morph_kernel<<<grid, 256, 0, stream>>>(src, dst, w, h, wpr, ch, R);
+        BGSB_LAUNCH_CHECK();
+        src = dst;
+    }
+    if (src != d_out) BGSB_CUDA(cudaMemcpyAsync(d_out, src, bytes, cudaMemcpyDeviceToDevice, stream));
+    for (int i = 0; i < ntmp; i++) BGSB_CUDA(cudaFreeAsync(tmp[i], stream));
+    return BGSB_OK;
+}
+
+}  // namespace bgsb
+
+using namespace bgsb;
+
+extern "C" {
+
+int bgsb_morph_dev(const uint8_t *d_mask, int w, int h, int nimages, const int *ops, int nops, uint8_t *d_out,
+                   void *stream)
+{
+    BGSB_REQUIRE(d_mask && d_out, "null");
+    BGSB_REQUIRE(w > 0 && h > 0 && nimages > 0, "empty image");
+    BGSB_REQUIRE(nops >= 0 && (nops == 0 || ops), "ops");
+    return launch_morph_chain(d_mask, d_out, w, h, nimages, ops, nops, (cudaStream_t)stream);
+}
+
+int bgsb_morph(const uint8_t *mask, int w, int h, size_t stride, const int *ops, int nops, uint8_t *out,
+               size_t out_stride)
+{
+    BGSB_REQUIRE(mask && out, "null");
+    BGSB_REQUIRE(w > 0 && h > 0, "empty image");
+    BGSB_REQUIRE(stride >= (size_t)w && out_stride >= (size_t)w, "stride smaller than a row");
+    uint8_t *d_a = nullptr, *d_b = nullptr;
+    const size_t bytes = (size_t)w * h;
+    BGSB_CUDA(cudaMalloc(&d_a, bytes));
+    if (cudaMalloc(&d_b, bytes) != cudaSuccess) { cudaFree(d_a); set_error("cudaMalloc failed"); return BGSB_ERR_CUDA; }
+    int rc = BGSB_OK;
+    cudaError_t e = cudaMemcpy2D(d_a, w, mask, stride, w, h, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = launch_morph_chain(d_a, d_b, w, h, 1, ops, nops, nullptr);
+        if (rc == BGSB_OK) e = cudaMemcpy2D(out, out_stride, d_b, w, w, h, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_a); cudaFree(d_b);
+    if (e != cudaSuccess) { set_error("bgsb_morph: %s", cudaGetErrorString(e)); return BGSB_ERR_CUDA; }
+    return rc;
+}
+
+}  // extern "C"
