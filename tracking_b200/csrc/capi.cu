@@ -35,7 +35,7 @@ struct bgsb_ctx {
     double alpha = 0.05;
     int limit = -1;
     int enable_thr = 1, thr = 15, enable_weight = 1, gray_variant = 0;
-    // cv::BackgroundSubtractorMOG2 defaults (verified against cv2 getters)
+    // cv::BackgroundSubtractorMOG2 defaults
     int history = 500;
     float Tb = 16.f, Tg = 9.f, TB = 0.9f, varInit = 15.f, varMin = 4.f, varMax = 75.f, CT = 0.05f, tau = 0.5f;
     int detect_shadows = 1, shadow_value = 127;
