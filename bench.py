@@ -37,7 +37,7 @@ if ROOT not in sys.path:
 
 W, H = 1920, 1080
 NPX = W * H
-FRAMES_PER_STEP = 32
+FRAMES_PER_STEP = 256         # 8.5 s of 30 fps video per step; ~23 ms of GPU time
 NFRAMES_RESIDENT = 128          # distinct synthetic frames kept in HBM (796 MB) and cycled
 MOG2_BYTES_PER_PX = 209         # in 3 + state 101 read + 101 write + mask 1 + bg 3  
 METRIC = "MOG2 Mpixel/s at 1080p"
@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -76,9 +76,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -87,7 +87,12 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
-        for r in self.rows:
+        rows = [r for (ts, r) in self.rows if t_begin is None or (t_begin <= ts <= t_end + 0.15)]
+        window = "timed region"
+        if len(rows) < 2:            # region shorter than the sampling period: widen to the load phase around it
+            rows = [r for (ts, r) in self.rows if t_begin is None or (t_begin - 1.0 <= ts <= t_end + 1.0)]
+            window = "timed region +-1 s (region shorter than 2 samples)"
+        for r in rows:
             try:
                 sm.append(float(r[0])); smax = float(r[1])
             except Exception:
@@ -96,7 +101,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def cpu_reference_run(steps, warmup, frames_per_step):
@@ -163,13 +168,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    F, K, Wm = FRAMES_PER_STEP, args.steps, args.warmup
+    F, K, Wm = args.frames_per_step, args.steps, args.warmup
     stream = torch.cuda.current_stream().cuda_stream
     frames = torch.empty((NFRAMES_RESIDENT, H, W, 3), dtype=torch.uint8, device="cuda")
     synth.frames_dev(frames.data_ptr(), 1, NFRAMES_RESIDENT, W, H, t0=0, seed0=synth.SEED0 + rank, stream=stream)
     d_fg = torch.empty((H, W), dtype=torch.uint8, device="cuda")
     d_bg = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
-    bgs = tb.MixtureOfGaussianV2BGS(device=local)
+    bgs = tb.MixtureOfGaussianV2BGS(device=local, kernelVariant=args.kernel_variant)
     fptr = [frames[i].data_ptr() for i in range(NFRAMES_RESIDENT)]
     fgp, bgp = d_fg.data_ptr(), d_bg.data_ptr()
 
@@ -178,12 +183,13 @@ def run_ours(args):
         for t in range(F):
             bgs.process_dev(fptr[(base + t) % NFRAMES_RESIDENT], W, H, fgp, bgp, stream=stream)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # nvidia-smi needs ~0.3 s before its first sample: start it ahead of the warm-up
     for i in range(Wm):
         step(i)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    t_begin = time.perf_counter()
     launches0 = capi.kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -191,7 +197,8 @@ def run_ours(args):
         step(Wm + i)
     ev1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    t_end = time.perf_counter()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     launches = capi.kernel_launch_count() - launches0
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -215,6 +222,24 @@ def run_ours(args):
             traffic = None
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, tb, capi, frames, F, K, world, local, barrier)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cdt, cores, threads = cpu_reference_run(8, 1, 4)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "32 frames (8 steps x 4) of the same synthetic 1080p stream after 4 warm-up frames; OpenCV "
+                         "call-for-call replay of MixtureOfGaussianV2BGS::process on %d host cores, %.1f s" % (cores, cdt)}
+    return finish(args, rank, world, value, K, Wm, ms_max, F, clocks, e2e, launches, achieved, peak, traffic, peak_src,
+                  alg_bytes, launch_ms, cpu)
+
+
+def run_e2e(args, tb, capi, frames, F, K, world, local, barrier):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
     nh = 16
     h_in = torch.empty((nh, H, W, 3), dtype=torch.uint8).pin_memory()
     h_in.copy_(frames[:nh].cpu())
@@ -247,14 +272,15 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = world * Ke * F * NPX / te.item() / 1e6
     assert int(h_fg.max()) in (0, 255)
+    return {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": F * NPX * 3, "d2h_bytes_per_step": F * NPX * 4,
+            "steps": Ke,
+            "note": "bgsb_process (IBGS::process boundary): pinned host BGR frame in, mask + background image out, "
+                    "synchronous per frame"}
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cdt, cores, threads = cpu_reference_run(8, 1, 4)
-        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "32 frames (8 steps x 4) of the same synthetic 1080p stream after 4 warm-up frames; OpenCV "
-                         "call-for-call replay of MixtureOfGaussianV2BGS::process on %d host cores, %.1f s" % (cores, cdt)}
 
+def finish(args, rank, world, value, K, Wm, ms_max, F, clocks, e2e, launches, achieved, peak, traffic, peak_src,
+           alg_bytes, launch_ms, cpu):
+    import torch.distributed as dist
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -263,8 +289,7 @@ def run_ours(args):
                            "streams_per_gpu": 1, "parallelism": "independent camera streams, %d GPU(s), no collective" % world,
                            "l2": "inputs larger than L2: 209 MB model state + 796 MB of resident frames cycled"},
                 "clocks": clocks,
-                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": F * NPX * 3, "d2h_bytes_per_step": F * NPX * 4,
-                        "note": "bgsb_process (IBGS::process boundary): pinned host BGR frame in, mask + background image out, synchronous per frame"},
+                "e2e": e2e,
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "kernel": "mog2_kernel", "peak_source": peak_src,
@@ -284,6 +309,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
+    ap.add_argument("--frames-per-step", type=int, default=FRAMES_PER_STEP)
+    ap.add_argument("--kernel-variant", type=int, default=0, help="0 production MOG2 kernel, 1 straight restatement (A/B)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3          # timing rule: W >= 3

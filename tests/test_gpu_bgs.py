@@ -86,12 +86,13 @@ def test_warmup_contract_outputs_untouched():
     assert fd.frame_count == 2
 
 
-def test_mog2_stress_sequence_state_bit_exact(oracle):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_mog2_stress_sequence_state_bit_exact(oracle, variant):
     """Mode churn (prune / replace / re-sort paths) incl. the exported mixture state."""
     import tracking_b200 as tb
     frames = stress_sequence(200, 40, 52)
     for thr, kw in ((True, {}), (False, {}), (True, {"threshold": 200})):
-        p = tb.MixtureOfGaussianV2BGS(enableThreshold=int(thr), **kw)
+        p = tb.MixtureOfGaussianV2BGS(enableThreshold=int(thr), kernelVariant=variant, **kw)
         o = oracle.MixtureOfGaussianV2BGS(enableThreshold=thr, **kw)
         for i, f in enumerate(frames):
             fg, bg = p.process(f)
@@ -104,6 +105,38 @@ def test_mog2_stress_sequence_state_bit_exact(oracle):
         for m in range(K):
             live = o.nmodes > m
             assert np.array_equal(planes[m * 5 + 0][live], o.gmm[:, m, 0][live])
+            assert np.array_equal(planes[m * 5 + 1][live], o.gmm[:, m, 1][live])
+            for c in range(3):
+                assert np.array_equal(planes[m * 5 + 2 + c][live], o.mean[:, m, c][live])
+        p.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_mog2_variants_on_reference_clip_temporal_batches(oracle, clips, variant):
+    """Both kernels, T in {1, 5, 32}, raw {0,127,255} output (shadow path) on the reference video clip."""
+    import torch
+    import tracking_b200 as tb
+    clip = clips["video_clip"]
+    h, w = clip.shape[1:3]
+    for T in (1, 5, 32):
+        p = tb.MixtureOfGaussianV2BGS(kernelVariant=variant, enableThreshold=0)
+        o = oracle.MixtureOfGaussianV2BGS(enableThreshold=False)
+        for t0 in range(0, 30, T):
+            tt = min(T, 32 - t0)
+            d_in = torch.from_numpy(clip[t0:t0 + tt]).cuda()
+            d_fg = torch.zeros((tt, h, w), dtype=torch.uint8, device="cuda")
+            d_bg = torch.zeros((tt, h, w, 3), dtype=torch.uint8, device="cuda")
+            p.process_batch_dev(d_in.data_ptr(), tt, w, h, d_fg.data_ptr(), d_bg.data_ptr())
+            torch.cuda.synchronize()
+            for t in range(tt):
+                ofg, obg = o.process(clip[t0 + t])
+                assert np.array_equal(d_fg[t].cpu().numpy(), ofg), (T, t0 + t)
+                assert np.array_equal(d_bg[t].cpu().numpy(), obg), (T, t0 + t)
+        planes, nm = p.export_state()
+        assert np.array_equal(nm, o.nmodes)
+        for m in range(5):
+            live = o.nmodes > m
+            assert np.array_equal(planes[m * 5][live], o.gmm[:, m, 0][live])
             assert np.array_equal(planes[m * 5 + 1][live], o.gmm[:, m, 1][live])
             for c in range(3):
                 assert np.array_equal(planes[m * 5 + 2 + c][live], o.mean[:, m, c][live])

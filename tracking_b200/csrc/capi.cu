@@ -39,6 +39,7 @@ struct bgsb_ctx {
     int history = 500;
     float Tb = 16.f, Tg = 9.f, TB = 0.9f, varInit = 15.f, varMin = 4.f, varMax = 75.f, CT = 0.05f, tau = 0.5f;
     int detect_shadows = 1, shadow_value = 127;
+    int mog2_variant = 0;      // 0 production kernel (mog2_fast.cu), 1 straight restatement kernel (mog2.cu)
     // geometry / counters
     int w = 0, h = 0, npx = 0;
     size_t pstride = 0;
@@ -137,7 +138,7 @@ static int run_frames(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_fg
             L.alpha1[t] = 1.f - L.alphaT[t];
             L.prune[t] = (float)(-lr * (double)c->CT);
         }
-        int rc = launch_mog2(L, c->nstreams, 0, stream);
+        int rc = launch_mog2(L, c->nstreams, c->mog2_variant, stream);
         if (rc) return rc;
     } else {
         SimpleLaunch L;
@@ -240,6 +241,7 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     else if (k == "detectShadows") c->detect_shadows = (v != 0);
     else if (k == "shadowValue") c->shadow_value = (int)v;
     else if (k == "shadowThreshold") c->tau = (float)v;
+    else if (k == "kernelVariant") { BGSB_REQUIRE(v == 0 || v == 1, "kernelVariant is 0 or 1"); c->mog2_variant = (int)v; }
     else if (k == "showOutput" || k == "showForeground" || k == "showBackground") { /* GUI only */ }
     else { set_error("bgsb_set_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
     return BGSB_OK;
@@ -267,6 +269,7 @@ int bgsb_get_param(bgsb_ctx *c, const char *key, double *v)
     else if (k == "detectShadows") *v = c->detect_shadows;
     else if (k == "shadowValue") *v = c->shadow_value;
     else if (k == "shadowThreshold") *v = c->tau;
+    else if (k == "kernelVariant") *v = c->mog2_variant;
     else { set_error("bgsb_get_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
     return BGSB_OK;
 }
