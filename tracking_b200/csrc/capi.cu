@@ -126,6 +126,7 @@ static int run_frames(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_fg
         L.state = c->d_state; L.nmodes = c->d_nmodes; L.pstride = c->pstride;
         L.npx = c->npx; L.T = T; L.bg_last_only = bg_last_only;
         L.fresh = (c->nframes == 0);
+        L.fast_ok = 1;
         L.enable_thr = c->enable_thr; L.thr = c->thr;
         L.detect_shadows = c->detect_shadows; L.shadow_value = c->shadow_value;
         L.Tb = c->Tb; L.Tg = c->Tg; L.TB = c->TB; L.varInit = c->varInit; L.varMin = c->varMin;
@@ -137,6 +138,7 @@ static int run_frames(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_fg
             L.alphaT[t] = (float)lr;
             L.alpha1[t] = 1.f - L.alphaT[t];
             L.prune[t] = (float)(-lr * (double)c->CT);
+            if (!(L.alphaT[t] >= 1e-4f && L.alphaT[t] <= 1.f)) L.fast_ok = 0;
         }
         int rc = launch_mog2(L, c->nstreams, c->mog2_variant, stream);
         if (rc) return rc;

@@ -39,6 +39,7 @@ struct Mog2Launch {
     int npx, T;
     int bg_last_only;
     int fresh;               // 1: state is uninitialised -> treat nmodes as 0 (first frame after create/reset)
+    int fast_ok;             // learning rates are inside the range the fast path's unguarded division is exact for
     int enable_thr, thr;
     int detect_shadows, shadow_value;
     float Tb, Tg, TB, varInit, varMin, varMax, tau;
