@@ -1,0 +1,283 @@
+// Drop-in replacements for four plugins of the reference, same class names, same public shape, same
+// XML keys and files, same stdout banners and imshow windows -- the arithmetic runs on a B200 through
+// the C ABI of include/bgsb200.h (libbgsb200.so).  Header-only; link with -lbgsb200.
+//
+//   FrameDifferenceBGS           replaces package_bgs/FrameDifferenceBGS.{h,cpp}
+//   WeightedMovingVarianceBGS    replaces package_bgs/WeightedMovingVarianceBGS.{h,cpp}
+//   AdaptiveBackgroundLearning   replaces package_bgs/AdaptiveBackgroundLearning.{h,cpp}
+//   MixtureOfGaussianV2BGS       replaces package_bgs/MixtureOfGaussianV2BGS.{h,cpp}
+//
+// FrameProcessor (FrameProcessor.cpp:40-59,163), USTC_BGS (ustc_src/ustc_bgs.cpp:8-14,94), Demo.cpp:179
+// and Demo2.cpp:160 keep compiling and calling `new <Class>` / `bgs->process(in, fg, bg)` unchanged.
+// Error convention of the reference is kept: an empty input returns silently with the outputs untouched;
+// a failing GPU call throws cv::Exception through CV_Assert (Main.cpp:63-72 catches it).
+#pragma once
+#include <iostream>
+#include <string>
+
+#include <opencv2/opencv.hpp>
+
+#include "IBGS.h"
+#include "bgsb200.h"
+
+namespace bgsb_adapter {
+
+class PluginBase : public IBGS
+{
+protected:
+  bgsb_ctx *ctx;
+  bool firstTime;
+  cv::Mat img_foreground, img_background;   // members of the reference classes; own the outputs
+
+  explicit PluginBase(int algo) : ctx(0), firstTime(true)
+  {
+    int rc = bgsb_create(&ctx, algo, 0);
+    if (rc != BGSB_OK) std::cerr << "bgsb200: " << bgsb_last_error() << std::endl;
+    CV_Assert(rc == BGSB_OK);
+  }
+  virtual ~PluginBase() { bgsb_destroy(ctx); }
+
+  void set(const char *key, double v) { CV_Assert(bgsb_set_param(ctx, key, v) == BGSB_OK); }
+
+  // Runs one frame; returns which outputs were produced (reference early returns leave them untouched).
+  void run(const cv::Mat &img_input, bool &fg_valid, bool &bg_valid, bool want_bg)
+  {
+    CV_Assert(img_input.type() == CV_8UC3);     // PreProcessor.cpp:56 hands BGR 8UC3 frames to every plugin
+    img_foreground.create(img_input.rows, img_input.cols, CV_8UC1);
+    if (want_bg) img_background.create(img_input.rows, img_input.cols, CV_8UC3);
+    int fv = 0, bv = 0;
+    int rc = bgsb_process(ctx, img_input.data, img_input.cols, img_input.rows, (size_t)img_input.step,
+                          img_foreground.data, (size_t)img_foreground.step,
+                          want_bg ? img_background.data : 0, want_bg ? (size_t)img_background.step : 0, &fv, &bv);
+    if (rc != BGSB_OK) std::cerr << "bgsb200: " << bgsb_last_error() << std::endl;
+    CV_Assert(rc == BGSB_OK);
+    fg_valid = fv != 0;
+    bg_valid = bv != 0;
+  }
+};
+
+}  // namespace bgsb_adapter
+
+// ---------------------------------------------------------------------------------------------------------------
+class FrameDifferenceBGS : public bgsb_adapter::PluginBase
+{
+private:
+  bool enableThreshold;
+  int threshold;
+  bool showOutput;
+
+public:
+  FrameDifferenceBGS() : PluginBase(BGSB_ALGO_FRAME_DIFFERENCE), enableThreshold(true), threshold(15), showOutput(true)
+  {
+    std::cout << "FrameDifferenceBGS()" << std::endl;
+  }
+  ~FrameDifferenceBGS() { std::cout << "~FrameDifferenceBGS()" << std::endl; }
+
+  void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
+  {
+    (void)img_bgmodel;                       // never written (FrameDifferenceBGS.cpp:29-61)
+    if (img_input.empty()) return;
+    loadConfig();
+    if (firstTime) saveConfig();
+    bool fg, bg;
+    run(img_input, fg, bg, false);
+    if (!fg) return;                         // first frame: only remembered (.cpp:39-43)
+    if (showOutput) cv::imshow("Frame Difference", img_foreground);
+    img_foreground.copyTo(img_output);
+    firstTime = false;
+  }
+
+private:
+  void saveConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/FrameDifferenceBGS.xml", 0, CV_STORAGE_WRITE);
+    cvWriteInt(fs, "enableThreshold", enableThreshold);
+    cvWriteInt(fs, "threshold", threshold);
+    cvWriteInt(fs, "showOutput", showOutput);
+    cvReleaseFileStorage(&fs);
+  }
+  void loadConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/FrameDifferenceBGS.xml", 0, CV_STORAGE_READ);
+    enableThreshold = cvReadIntByName(fs, 0, "enableThreshold", true);
+    threshold = cvReadIntByName(fs, 0, "threshold", 15);
+    showOutput = cvReadIntByName(fs, 0, "showOutput", true);
+    cvReleaseFileStorage(&fs);
+    set("enableThreshold", enableThreshold);
+    set("threshold", threshold);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+class WeightedMovingVarianceBGS : public bgsb_adapter::PluginBase
+{
+private:
+  bool enableWeight;
+  bool enableThreshold;
+  int threshold;
+  bool showOutput;
+
+public:
+  WeightedMovingVarianceBGS() : PluginBase(BGSB_ALGO_WEIGHTED_MOVING_VARIANCE), enableWeight(true),
+    enableThreshold(true), threshold(15), showOutput(true)
+  {
+    std::cout << "WeightedMovingVarianceBGS()" << std::endl;
+  }
+  ~WeightedMovingVarianceBGS() { std::cout << "~WeightedMovingVarianceBGS()" << std::endl; }
+
+  void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
+  {
+    (void)img_bgmodel;                       // never written (WeightedMovingVarianceBGS.cpp:30-117)
+    if (img_input.empty()) return;
+    loadConfig();
+    if (firstTime) saveConfig();
+    bool fg, bg;
+    run(img_input, fg, bg, false);
+    if (!fg) return;                         // first two frames fill the history (.cpp:40-51)
+    if (showOutput) cv::imshow("W Moving Variance", img_foreground);
+    img_foreground.copyTo(img_output);
+    firstTime = false;
+  }
+
+private:
+  void saveConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/WeightedMovingVarianceBGS.xml", 0, CV_STORAGE_WRITE);
+    cvWriteInt(fs, "enableWeight", enableWeight);
+    cvWriteInt(fs, "enableThreshold", enableThreshold);
+    cvWriteInt(fs, "threshold", threshold);
+    cvWriteInt(fs, "showOutput", showOutput);
+    cvReleaseFileStorage(&fs);
+  }
+  void loadConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/WeightedMovingVarianceBGS.xml", 0, CV_STORAGE_READ);
+    enableWeight = cvReadIntByName(fs, 0, "enableWeight", true);
+    enableThreshold = cvReadIntByName(fs, 0, "enableThreshold", true);
+    threshold = cvReadIntByName(fs, 0, "threshold", 15);
+    showOutput = cvReadIntByName(fs, 0, "showOutput", true);
+    cvReleaseFileStorage(&fs);
+    set("enableWeight", enableWeight);
+    set("enableThreshold", enableThreshold);
+    set("threshold", threshold);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+class AdaptiveBackgroundLearning : public bgsb_adapter::PluginBase
+{
+private:
+  double alpha;
+  long limit;
+  bool enableThreshold;
+  int threshold;
+  bool showForeground;
+  bool showBackground;
+
+public:
+  AdaptiveBackgroundLearning() : PluginBase(BGSB_ALGO_ADAPTIVE_BG_LEARNING), alpha(0.05), limit(-1),
+    enableThreshold(true), threshold(15), showForeground(true), showBackground(true)
+  {
+    std::cout << "AdaptiveBackgroundLearning()" << std::endl;
+  }
+  ~AdaptiveBackgroundLearning() { std::cout << "~AdaptiveBackgroundLearning()" << std::endl; }
+
+  void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
+  {
+    if (img_input.empty()) return;
+    loadConfig();
+    if (firstTime) saveConfig();
+    bool fg, bg;
+    run(img_input, fg, bg, true);
+    if (showForeground) cv::imshow("A-Learning FG", img_foreground);
+    if (showBackground) cv::imshow("A-Learning BG", img_background);
+    img_foreground.copyTo(img_output);       // AdaptiveBackgroundLearning.cpp:79-80
+    img_background.copyTo(img_bgmodel);
+    firstTime = false;
+  }
+
+private:
+  void saveConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/AdaptiveBackgroundLearning.xml", 0, CV_STORAGE_WRITE);
+    cvWriteReal(fs, "alpha", alpha);
+    cvWriteInt(fs, "limit", limit);
+    cvWriteInt(fs, "enableThreshold", enableThreshold);
+    cvWriteInt(fs, "threshold", threshold);
+    cvWriteInt(fs, "showForeground", showForeground);
+    cvWriteInt(fs, "showBackground", showBackground);
+    cvReleaseFileStorage(&fs);
+  }
+  void loadConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/AdaptiveBackgroundLearning.xml", 0, CV_STORAGE_READ);
+    alpha = cvReadRealByName(fs, 0, "alpha", 0.05);
+    limit = cvReadIntByName(fs, 0, "limit", -1);
+    enableThreshold = cvReadIntByName(fs, 0, "enableThreshold", true);
+    threshold = cvReadIntByName(fs, 0, "threshold", 15);
+    showForeground = cvReadIntByName(fs, 0, "showForeground", true);
+    showBackground = cvReadIntByName(fs, 0, "showBackground", true);
+    cvReleaseFileStorage(&fs);
+    set("alpha", alpha);
+    set("limit", (double)limit);
+    set("enableThreshold", enableThreshold);
+    set("threshold", threshold);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+class MixtureOfGaussianV2BGS : public bgsb_adapter::PluginBase
+{
+private:
+  double alpha;
+  bool enableThreshold;
+  int threshold;
+  bool showOutput;
+
+public:
+  MixtureOfGaussianV2BGS() : PluginBase(BGSB_ALGO_MOG2), alpha(0.05), enableThreshold(true), threshold(15), showOutput(true)
+  {
+    std::cout << "MixtureOfGaussianV2BGS()" << std::endl;
+  }
+  ~MixtureOfGaussianV2BGS() { std::cout << "~MixtureOfGaussianV2BGS()" << std::endl; }
+
+  void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
+  {
+    if (img_input.empty()) return;
+    loadConfig();
+    if (firstTime) saveConfig();
+    bool fg, bg;
+    run(img_input, fg, bg, true);            // mog(in, fg, alpha) + getBackgroundImage + threshold, one kernel
+    if (showOutput)
+    {
+      cv::imshow("GMM (Zivkovic&Heijden)", img_foreground);
+      cv::imshow("GMM BKG (Zivkovic&Heijden)", img_background);
+    }
+    img_foreground.copyTo(img_output);       // MixtureOfGaussianV2BGS.cpp:70-71
+    img_background.copyTo(img_bgmodel);
+    firstTime = false;
+  }
+
+private:
+  void saveConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/MixtureOfGaussianV2BGS.xml", 0, CV_STORAGE_WRITE);
+    cvWriteReal(fs, "alpha", alpha);
+    cvWriteInt(fs, "enableThreshold", enableThreshold);
+    cvWriteInt(fs, "threshold", threshold);
+    cvWriteInt(fs, "showOutput", showOutput);
+    cvReleaseFileStorage(&fs);
+  }
+  void loadConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/MixtureOfGaussianV2BGS.xml", 0, CV_STORAGE_READ);
+    alpha = cvReadRealByName(fs, 0, "alpha", 0.05);
+    enableThreshold = cvReadIntByName(fs, 0, "enableThreshold", true);
+    threshold = cvReadIntByName(fs, 0, "threshold", 15);
+    showOutput = cvReadIntByName(fs, 0, "showOutput", true);
+    cvReleaseFileStorage(&fs);
+    set("alpha", alpha);
+    set("enableThreshold", enableThreshold);
+    set("threshold", threshold);
+  }
+};

@@ -1,0 +1,27 @@
+// Syntax check of the header-only adapters (tests/test_abi.py): the reference's call patterns must compile.
+#include "ustc_bgs_b200.h"
+
+int compile_check_calls()
+{
+    // FrameProcessor.cpp:40-59,157-167 pattern
+    IBGS *plugins[4] = {new FrameDifferenceBGS, new WeightedMovingVarianceBGS, new MixtureOfGaussianV2BGS,
+                        new AdaptiveBackgroundLearning};
+    cv::Mat img_input, img_bgs, img_bkgmodel;
+    for (int i = 0; i < 4; i++) {
+        plugins[i]->process(img_input, img_bgs, img_bkgmodel);
+        delete plugins[i];
+    }
+    // ustc_src/trackingMain.cpp:33-35,613-615 pattern
+    CvFGDetector *fg = new USTC_BGS(5);
+    IplImage *frame = 0;
+    fg->Process(frame);
+    IplImage *mask = fg->GetMask();
+    // :626 pattern
+    CvBlobDetector *bd = cvCreateBlobDetectorCC_B200();
+    CvBlobSeq newb, oldb;
+    int r = bd->DetectNewBlob(frame, mask, &newb, &oldb);
+    bgsbMorph(mask, BGSB_MORPH_ERODE, 1);
+    bd->Release();
+    fg->Release();
+    return r;
+}

@@ -1,0 +1,108 @@
+// CvFGDetector / CvBlobDetector side of the boundary (OpenCV 2.4 legacy blob-tracking pipeline).
+//
+//   USTC_BGS              same class as ustc_src/ustc_bgs.h:58-76 / ustc_bgs.cpp:3-113, restricted to the
+//                         four B200 plugins (ids 0 FD, 3 WMV, 5 MOG2, 6 ABL of the factory, .cpp:8-14)
+//   BgsbBlobDetectorCC    CvBlobDetector with the behaviour of cvCreateBlobDetectorCC()
+//                         (ustc_src/trackingMain.cpp:56 module table, :626 creation)
+//   cvCreateBlobDetectorCC_B200()  factory with the signature the module table expects (:46-51)
+//
+// ustc_src/trackingMain.cpp needs two edits to use them: `type` (:34) set to 0/3/5/6, and the
+// "BD_CC" row of the detector table (:56) pointing at cvCreateBlobDetectorCC_B200.
+#pragma once
+#include <vector>
+
+#include "opencv2/legacy/blobtrack.hpp"
+
+#include "bgsb_plugins.h"
+
+class USTC_BGS : public CvFGDetector
+{
+public:
+    int frameNum;
+    IplImage *c_mask;
+    IBGS *bgs;
+    cv::Mat img_mask;
+    cv::Mat img_bkgmodel;
+    cv::Mat img_input;
+    IplImage b;
+
+    USTC_BGS(int type) : frameNum(0), c_mask(0), bgs(0)
+    {
+        CV_Assert(type >= 0 && type <= 37);                 // ustc_bgs.cpp:6
+        switch (type) {
+        case 0: bgs = new FrameDifferenceBGS; break;        // ustc_bgs.cpp:8
+        case 3: bgs = new WeightedMovingVarianceBGS; break; // :11
+        case 5: bgs = new MixtureOfGaussianV2BGS; break;    // :13
+        case 6: bgs = new AdaptiveBackgroundLearning; break;// :14
+        default: CV_Assert(!"this plugin id is not on the B200 hot path (0 FD, 3 WMV, 5 MOG2, 6 ABL)");
+        }
+    }
+    ~USTC_BGS() {}
+
+    void Release() { delete bgs; bgs = 0; }                 // ustc_bgs.cpp:75-77
+
+    IplImage *GetMask()                                      // ustc_bgs.cpp:79-85
+    {
+        if (frameNum == 0) return NULL;
+        return c_mask;     // NULL until the plugin produced its first mask (FD/WMV warm-up frames)
+    }
+
+    void Process(IplImage *pImg)                             // ustc_bgs.cpp:87-113
+    {
+        img_input = cv::Mat(pImg);
+        bgs->process(img_input, img_mask, img_bkgmodel);
+        if (!img_mask.empty()) {
+            b = img_mask.operator IplImage();
+            c_mask = &b;
+        }
+        frameNum++;
+    }
+};
+
+class BgsbBlobDetectorCC : public CvBlobDetector
+{
+    bgsb_blobdetector *bd;
+
+public:
+    BgsbBlobDetectorCC() : bd(0)
+    {
+        CV_Assert(bgsb_blobdetector_create(&bd, 0) == BGSB_OK);
+    }
+    ~BgsbBlobDetectorCC() { bgsb_blobdetector_destroy(bd); }
+    void Release() { delete this; }
+
+    // CvBlobDetectorCC::DetectNewBlob: returns 1 and appends to pNewBlobList when a new blob is confirmed
+    int DetectNewBlob(IplImage * /*pImg*/, IplImage *pFGMask, CvBlobSeq *pNewBlobList, CvBlobSeq *pOldBlobList)
+    {
+        CV_Assert(pFGMask && pFGMask->nChannels == 1 && pFGMask->depth == IPL_DEPTH_8U);
+        std::vector<bgsb_blob> old;
+        if (pOldBlobList)
+            for (int i = 0; i < pOldBlobList->GetBlobNum(); i++) {
+                CvBlob *p = pOldBlobList->GetBlob(i);
+                bgsb_blob o = {p->x, p->y, p->w, p->h, p->ID};
+                old.push_back(o);
+            }
+        bgsb_blob nb[1];
+        int n_new = 0, result = 0;
+        int rc = bgsb_blobdetector_detect(bd, (const uint8_t *)pFGMask->imageData, pFGMask->width, pFGMask->height,
+                                          (size_t)pFGMask->widthStep, old.empty() ? 0 : &old[0], (int)old.size(),
+                                          nb, 1, &n_new, &result, 0, 0, 0);
+        CV_Assert(rc == BGSB_OK);
+        if (result && n_new == 1 && pNewBlobList) {
+            CvBlob B = cvBlob(nb[0].x, nb[0].y, nb[0].w, nb[0].h);
+            pNewBlobList->AddBlob(&B);
+        }
+        return result;
+    }
+};
+
+inline CvBlobDetector *cvCreateBlobDetectorCC_B200() { return new BgsbBlobDetectorCC; }
+
+// cvErode / cvDilate(mask, mask, NULL, n) on an 8-bit single-channel IplImage, on the GPU.
+inline void bgsbMorph(IplImage *mask, int op /* BGSB_MORPH_ERODE | BGSB_MORPH_DILATE */, int iterations)
+{
+    int ops[2] = {op, iterations};
+    CV_Assert(mask && mask->nChannels == 1);
+    CV_Assert(bgsb_morph((const uint8_t *)mask->imageData, mask->width, mask->height, (size_t)mask->widthStep, ops, 1,
+                         (uint8_t *)mask->imageData, (size_t)mask->widthStep) == BGSB_OK);
+}

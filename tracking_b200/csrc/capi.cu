@@ -55,6 +55,9 @@ struct bgsb_ctx {
     int ring_pos = 0;
     uint8_t *d_fg = nullptr, *d_bg = nullptr;
     cudaStream_t stream = nullptr;
+    // host-path chunk pipeline: upload / compute / download overlap inside one synchronous call
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_up[8] = {}, ev_k[8] = {};
 };
 
 static void free_buffers(bgsb_ctx *c)
@@ -115,16 +118,18 @@ static int warmup_frames(int algo)
 
 // Advance the model by T frames that sit in device memory.  `own_history`: write FD/WMV history
 // into the context's own buffers (caller's frame buffers may be reused after the call).
-static int run_frames(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_fg, uint8_t *d_bg,
-                      int bg_last_only, bool own_history, cudaStream_t stream)
+// Launch the kernel for pixels [p0, p0+pcount) of the frame(s); p0 must be a multiple of 32.
+// A sub-range is only used for single-stream, single-frame calls (host-path chunk pipelining).
+static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_fg, uint8_t *d_bg,
+                        int bg_last_only, bool own_history, cudaStream_t stream, size_t p0, int pcount)
 {
     if (c->algo == BGSB_ALGO_MOG2) {
         BGSB_REQUIRE(T <= MOG2_TMAX, "temporal batch too long (max 32)");
         Mog2Launch L;
         memset(&L, 0, sizeof(L));
-        L.frames = d_frames; L.fg = d_fg; L.bg = d_bg;
-        L.state = c->d_state; L.nmodes = c->d_nmodes; L.pstride = c->pstride;
-        L.npx = c->npx; L.T = T; L.bg_last_only = bg_last_only;
+        L.frames = d_frames + p0 * 3; L.fg = d_fg + p0; L.bg = d_bg ? d_bg + p0 * 3 : nullptr;
+        L.state = c->d_state + p0; L.nmodes = c->d_nmodes + p0; L.pstride = c->pstride;
+        L.npx = pcount; L.T = T; L.bg_last_only = bg_last_only;
         L.fresh = (c->nframes == 0);
         L.fast_ok = 1;
         L.enable_thr = c->enable_thr; L.thr = c->thr;
@@ -145,12 +150,13 @@ static int run_frames(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_fg
     } else {
         SimpleLaunch L;
         memset(&L, 0, sizeof(L));
-        L.frames = d_frames; L.fg = d_fg; L.bg = d_bg;
-        L.hist0 = c->hist_ptr[0]; L.hist1 = c->hist_ptr[1];
-        L.hist0_out = own_history ? c->d_hist[0] : nullptr;
-        L.hist1_out = own_history ? c->d_hist[1] : nullptr;
-        if (c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING) { L.hist0 = c->d_hist[0]; L.hist0_out = c->d_hist[0]; }
-        L.npx = c->npx; L.T = T; L.have_hist = c->have_hist; L.bg_last_only = bg_last_only;
+        L.frames = d_frames + p0 * 3; L.fg = d_fg + p0; L.bg = d_bg ? d_bg + p0 * 3 : nullptr;
+        L.hist0 = c->hist_ptr[0] ? c->hist_ptr[0] + p0 * 3 : nullptr;
+        L.hist1 = c->hist_ptr[1] ? c->hist_ptr[1] + p0 * 3 : nullptr;
+        L.hist0_out = (own_history && c->d_hist[0]) ? c->d_hist[0] + p0 * 3 : nullptr;
+        L.hist1_out = (own_history && c->d_hist[1]) ? c->d_hist[1] + p0 * 3 : nullptr;
+        if (c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING) { L.hist0 = c->d_hist[0] + p0 * 3; L.hist0_out = c->d_hist[0] + p0 * 3; }
+        L.npx = pcount; L.T = T; L.have_hist = c->have_hist; L.bg_last_only = bg_last_only;
         L.enable_thr = c->enable_thr; L.thr = c->thr; L.gray_variant = c->gray_variant;
         L.alpha = c->alpha;
         L.abl_update = (c->limit == -1);   // the limit>0 branch never fires: counter stays 0 (.cpp:52,60-61)
@@ -158,13 +164,29 @@ static int run_frames(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_fg
         else { L.w0 = 0.3; L.w1 = 0.3; L.w2 = 0.3; }                          // :70
         int rc = launch_simple(c->algo, L, c->nstreams, stream);
         if (rc) return rc;
+    }
+    return BGSB_OK;
+}
+
+// Bookkeeping after T frames went through launch_range.
+static void advance(bgsb_ctx *c, int T, bool own_history)
+{
+    if (c->algo != BGSB_ALGO_MOG2 && own_history) {
         int need = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE) ? 2 : 1;
-        if (own_history) {
-            c->have_hist = std::min<int64_t>(need, c->have_hist + T);
-            c->hist_ptr[0] = c->d_hist[0]; c->hist_ptr[1] = c->d_hist[1];
-        }
+        c->have_hist = (int)std::min<int64_t>(need, (int64_t)c->have_hist + T);
+        c->hist_ptr[0] = c->d_hist[0]; c->hist_ptr[1] = c->d_hist[1];
     }
     c->nframes += T;
+}
+
+// Advance the model by T frames that sit in device memory.  `own_history`: write FD/WMV history
+// into the context's own buffers (caller's frame buffers may be reused after the call).
+static int run_frames(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_fg, uint8_t *d_bg,
+                      int bg_last_only, bool own_history, cudaStream_t stream)
+{
+    int rc = launch_range(c, d_frames, T, d_fg, d_bg, bg_last_only, own_history, stream, 0, c->npx);
+    if (rc) return rc;
+    advance(c, T, own_history);
     return BGSB_OK;
 }
 
@@ -210,6 +232,9 @@ void bgsb_destroy(bgsb_ctx *c)
     if (c->stream) { cudaStreamSynchronize(c->stream); }
     free_buffers(c);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    for (int i = 0; i < 8; i++) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]); }
     delete c;
 }
 
@@ -332,35 +357,71 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
     const bool fdlike = (c->algo == BGSB_ALGO_FRAME_DIFFERENCE || c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE);
     const int nring = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE) ? 3 : 2;
     uint8_t *d_in = fdlike ? c->d_ring[c->ring_pos] : c->d_ring[0];
-    BGSB_CUDA(cudaMemcpy2DAsync(d_in, (size_t)w * 3, bgr, stride, (size_t)w * 3, rows, cudaMemcpyHostToDevice, c->stream));
-
     const int warm = warmup_frames(c->algo);
     const bool out_fg = c->nframes >= warm;
     const bool has_bg = (c->algo == BGSB_ALGO_MOG2 || c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING);
-    if (fdlike) {
-        // history = the previous upload(s) in the ring: no copy, the frame is read once (7 B/px FD)
-        if (out_fg) {
-            rc = run_frames(c, d_in, 1, c->d_fg, nullptr, 0, false, c->stream);
-            if (rc) return rc;
-        } else {
-            c->nframes += 1;
+    const bool want_bg = has_bg && bg;
+    // FD / WMV: history = the previous upload(s) in the ring -- no copy, the frame is read once
+    const bool own_hist = !fdlike;
+
+    // Large single frames are cut into row bands (multiples of 32 rows): the upload of band i+1, the
+    // kernel on band i and the download of band i-1 overlap on three streams (pixels are independent),
+    // so a synchronous IBGS::process costs ~max(H2D, D2H) instead of H2D + kernel + D2H.
+    int nchunks = 1, band = h;
+    if (c->nstreams == 1 && (size_t)w * h * 3 >= (1u << 20) && out_fg) {
+        band = ((h + 3) / 4 + 31) / 32 * 32;
+        nchunks = (h + band - 1) / band;
+        if (nchunks > 8) { nchunks = 1; band = h; }
+    }
+    if (nchunks > 1 && !c->s_h2d) {
+        BGSB_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        BGSB_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 8; i++) {
+            BGSB_CUDA(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
+            BGSB_CUDA(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
         }
+    }
+    if (nchunks == 1) {
+        BGSB_CUDA(cudaMemcpy2DAsync(d_in, (size_t)w * 3, bgr, stride, (size_t)w * 3, rows, cudaMemcpyHostToDevice, c->stream));
+        if (out_fg) {
+            rc = launch_range(c, d_in, 1, c->d_fg, want_bg ? c->d_bg : nullptr, 0, own_hist, c->stream, 0, c->npx);
+            if (rc) return rc;
+            BGSB_CUDA(cudaMemcpy2DAsync(fg, fg_stride, c->d_fg, (size_t)w, (size_t)w, rows, cudaMemcpyDeviceToHost, c->stream));
+            if (want_bg)
+                BGSB_CUDA(cudaMemcpy2DAsync(bg, bg_stride, c->d_bg, (size_t)w * 3, (size_t)w * 3, rows, cudaMemcpyDeviceToHost, c->stream));
+        }
+        BGSB_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+        for (int i = 0; i < nchunks; i++) {
+            const int r0 = i * band, nr = std::min(band, h - r0);
+            const size_t p0 = (size_t)r0 * w;
+            BGSB_CUDA(cudaMemcpy2DAsync(d_in + p0 * 3, (size_t)w * 3, bgr + (size_t)r0 * stride, stride, (size_t)w * 3, nr,
+                                        cudaMemcpyHostToDevice, c->s_h2d));
+            BGSB_CUDA(cudaEventRecord(c->ev_up[i], c->s_h2d));
+            BGSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up[i], 0));
+            rc = launch_range(c, d_in, 1, c->d_fg, want_bg ? c->d_bg : nullptr, 0, own_hist, c->stream, p0, nr * w);
+            if (rc) return rc;
+            BGSB_CUDA(cudaEventRecord(c->ev_k[i], c->stream));
+            BGSB_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_k[i], 0));
+            BGSB_CUDA(cudaMemcpy2DAsync(fg + (size_t)r0 * fg_stride, fg_stride, c->d_fg + p0, (size_t)w, (size_t)w, nr,
+                                        cudaMemcpyDeviceToHost, c->s_d2h));
+            if (want_bg)
+                BGSB_CUDA(cudaMemcpy2DAsync(bg + (size_t)r0 * bg_stride, bg_stride, c->d_bg + p0 * 3, (size_t)w * 3,
+                                            (size_t)w * 3, nr, cudaMemcpyDeviceToHost, c->s_d2h));
+        }
+        BGSB_CUDA(cudaStreamSynchronize(c->s_d2h));
+        BGSB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (out_fg) advance(c, 1, own_hist);
+    else c->nframes += 1;
+    if (fdlike) {
         c->hist_ptr[1] = c->hist_ptr[0];
         c->hist_ptr[0] = d_in;
         c->have_hist = std::min(warm, c->have_hist + 1);
         c->ring_pos = (c->ring_pos + 1) % nring;
-    } else {
-        rc = run_frames(c, d_in, 1, c->d_fg, (has_bg && bg) ? c->d_bg : nullptr, 0, true, c->stream);
-        if (rc) return rc;
-        if (c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING) c->have_hist = 1;
     }
-    if (out_fg)
-        BGSB_CUDA(cudaMemcpy2DAsync(fg, fg_stride, c->d_fg, (size_t)w, (size_t)w, rows, cudaMemcpyDeviceToHost, c->stream));
-    if (has_bg && bg)
-        BGSB_CUDA(cudaMemcpy2DAsync(bg, bg_stride, c->d_bg, (size_t)w * 3, (size_t)w * 3, rows, cudaMemcpyDeviceToHost, c->stream));
-    BGSB_CUDA(cudaStreamSynchronize(c->stream));
     if (fg_valid) *fg_valid = out_fg;
-    if (bg_valid) *bg_valid = (has_bg && bg) ? 1 : 0;
+    if (bg_valid) *bg_valid = want_bg ? 1 : 0;
     return BGSB_OK;
 }
 
