@@ -158,6 +158,9 @@ typedef struct bgsb_component {
 
 typedef struct bgsb_ccl bgsb_ccl;
 BGSB_API int bgsb_ccl_create(bgsb_ccl **out, int device, int max_w, int max_h);
+/* A labeller that can take up to max_images masks of one geometry per call (one launch sequence for
+ * all camera streams of a group instead of one per stream). */
+BGSB_API int bgsb_ccl_create_batch(bgsb_ccl **out, int device, int max_w, int max_h, int max_images);
 BGSB_API void bgsb_ccl_destroy(bgsb_ccl *ccl);
 /* foreground = mask > 128 (cvThreshold(pIB,pIB,128,255,BINARY)); 8-connected.
  * zero_border != 0 clears the outer 1-px frame first (OpenCV <= 3.1 cvFindContours).
@@ -165,8 +168,13 @@ BGSB_API void bgsb_ccl_destroy(bgsb_ccl *ccl);
  * Asynchronous on `stream`; the component table stays on the device until fetched. */
 BGSB_API int bgsb_ccl_label_dev(bgsb_ccl *ccl, const uint8_t *d_mask, int w, int h, int zero_border,
                                 int32_t *d_labels, void *stream);
+/* nimages dense masks back to back ([nimages][h][w]); d_labels nullable, [nimages][h][w]. */
+BGSB_API int bgsb_ccl_label_batch_dev(bgsb_ccl *ccl, const uint8_t *d_masks, int w, int h, int nimages,
+                                      int zero_border, int32_t *d_labels, void *stream);
 /* Synchronises `stream` and copies the component table (raster order) to the host. */
 BGSB_API int bgsb_ccl_components(bgsb_ccl *ccl, bgsb_component *out, int capacity, int *n);
+/* Same for image `image` of the last batch. */
+BGSB_API int bgsb_ccl_components_of(bgsb_ccl *ccl, int image, bgsb_component *out, int capacity, int *n);
 /* cvMoments(pFG[R], binary=0) for nrects rectangles of the mask last labelled:
  * out[6*i..] = m00 m10 m01 m20 m02 m11 (pixel-value weighted, ROI-relative, exact). */
 BGSB_API int bgsb_ccl_rect_moments(bgsb_ccl *ccl, const int32_t *rects_xywh, int nrects, uint64_t *out);

@@ -86,6 +86,28 @@ def test_ccl_labels_stats_external_bit_exact(oracle):
     cc.close()
 
 
+def test_ccl_batch_of_images(oracle):
+    """One launch sequence for a group of masks (one per camera stream) == per-image results."""
+    import torch
+    from tracking_b200 import blobs
+    rng = np.random.default_rng(9)
+    S, h, w = 5, 97, 203
+    ms = np.stack([(rng.random((h, w)) < p).astype(np.uint8) * 255 for p in (0.02, 0.3, 0.5, 0.7, 0.0)])
+    d = torch.from_numpy(ms).cuda()
+    lab = torch.zeros((S, h, w), dtype=torch.int32, device="cuda")
+    cc = blobs.ConnectedComponents(w, h, max_images=S)
+    for zb in (False, True):
+        cc.label_batch_dev(d.data_ptr(), w, h, S, zb, lab.data_ptr())
+        torch.cuda.synchronize()
+        for i in range(S):
+            on, olab, ost, oext = oracle.ccl8(ms[i], zb)
+            comps = cc.components(i)
+            assert len(comps) == on and np.array_equal(lab[i].cpu().numpy(), olab)
+            assert [c["external"] for c in comps] == [int(e) for e in oext]
+            assert [c["area"] for c in comps] == [int(s[4]) for s in ost]
+    cc.close()
+
+
 def test_ccl_golden_tables(oracle, clips, golden):
     """BASELINE config 1 shape: FD -> OPEN -> CC on the reference video clip vs committed OpenCV results."""
     import tracking_b200 as tb

@@ -1,0 +1,208 @@
+#!/usr/bin/env python
+"""Secondary measurements for the BASELINE.json configs that are not the headline bench line
+(config 1 = parity case, 3 = ABL/WMV x16 streams, 4 = full pipeline x64 streams, 5 = 4K temporal batches),
+plus kernel-level figures for FD / morphology / CC and a PCIe probe.  One JSON object per line.
+
+    python tools/bench_configs.py [--quick]
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import tracking_b200 as tb                      # noqa: E402
+from tracking_b200 import blobs, capi, synth    # noqa: E402
+
+PEAK = 6539.5
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timed(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+def out(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def simple_streams(algo_cls, name, bpp, S=16, w=1920, h=1080, NT=6, iters=40):
+    st = torch.cuda.current_stream().cuda_stream
+    frames = torch.empty((NT, S, h, w, 3), dtype=torch.uint8, device="cuda")
+    for t in range(NT):        # layout per time step: [S][1][h][w][3]
+        synth.frames_dev(frames[t].data_ptr(), S, 1, w, h, t0=t, stream=st)
+    fg = torch.empty((S, h, w), dtype=torch.uint8, device="cuda")
+    bg = torch.empty((S, h, w, 3), dtype=torch.uint8, device="cuda")
+    p = algo_cls(nstreams=S)
+    k = [0]
+
+    def step():
+        p.process_dev(frames[k[0] % NT].data_ptr(), w, h, fg.data_ptr(), bg.data_ptr(), stream=st)
+        k[0] += 1
+    dt = timed(step, iters, warm=4)
+    px = S * w * h
+    out(config="3" if name != "FD" else "fd", algo=name, streams=S, resolution=[w, h], ms_per_step=dt * 1e3,
+        mpixel_s=px / dt / 1e6, algorithmic_bytes_per_px=bpp, achieved_gbs=px * bpp / dt / 1e9,
+        frac_of_measured_peak=px * bpp / dt / 1e9 / PEAK)
+    p.close()
+
+
+def mog2_batches(S, w, h, Ts, label, iters=6):
+    st = torch.cuda.current_stream().cuda_stream
+    Tmax = max(Ts)
+    frames = torch.empty((S, Tmax, h, w, 3), dtype=torch.uint8, device="cuda")
+    synth.frames_dev(frames.data_ptr(), S, Tmax, w, h, t0=0, stream=st)
+    for T in Ts:
+        p = tb.MixtureOfGaussianV2BGS(nstreams=S)
+        fr = frames[:, :T].contiguous()
+        fg = torch.empty((S, T, h, w), dtype=torch.uint8, device="cuda")
+        bg = torch.empty((S, T, h, w, 3), dtype=torch.uint8, device="cuda")
+
+        def step():
+            p.process_batch_dev(fr.data_ptr(), T, w, h, fg.data_ptr(), bg.data_ptr(), stream=st)
+        n_warm = max(3, 48 // T)
+        dt = timed(step, iters, warm=n_warm)
+        px = S * T * w * h
+        nm = np.concatenate([p.export_state(s)[1] for s in range(min(S, 2))])
+        live = 9 + 40 * float(nm.mean())
+        out(config=label, algo="MOG2", streams=S, T=T, resolution=[w, h], ms_per_launch=dt * 1e3, mpixel_s=px / dt / 1e6,
+            mean_live_modes=float(nm.mean()), dense_model_bytes_per_px_frame=202.0 / T + 7,
+            dense_equiv_gbs=px * (202.0 / T + 7) / dt / 1e9)
+        p.close()
+        del fg, bg, fr
+
+
+def pipeline(S=64, w=1920, h=1080, NT=3, iters=6):
+    st = torch.cuda.current_stream().cuda_stream
+    frames = torch.empty((NT, S, h, w, 3), dtype=torch.uint8, device="cuda")
+    for t in range(NT):
+        synth.frames_dev(frames[t].data_ptr(), S, 1, w, h, t0=t, stream=st)
+    fg = torch.empty((S, h, w), dtype=torch.uint8, device="cuda")
+    clean = torch.empty((S, h, w), dtype=torch.uint8, device="cuda")
+    p = tb.MixtureOfGaussianV2BGS(nstreams=S)
+    cc = blobs.ConnectedComponents(w, h, max_images=S)
+    k = [0]
+    parts = {"mog2": 0.0, "morph": 0.0, "cc": 0.0}
+
+    def step(measure=False):
+        f = frames[k[0] % NT]
+        k[0] += 1
+        p.process_dev(f.data_ptr(), w, h, fg.data_ptr(), None, stream=st)
+        blobs.morph_dev(fg.data_ptr(), w, h, S, [("erode", 1), ("dilate", 1)], clean.data_ptr(), stream=st)
+        cc.label_batch_dev(clean.data_ptr(), w, h, S, True, None, stream=st)
+    for _ in range(20):         # let the models settle
+        step()
+    dt = timed(step, iters, warm=2)
+    ncomp = len(cc.components(0))
+    px = S * w * h
+    out(config="4", algo="MOG2+OPEN+CC", streams=S, resolution=[w, h], ms_per_step=dt * 1e3, mpixel_s=px / dt / 1e6,
+        components_stream0=ncomp, dense_model_bytes_per_px=218, dense_equiv_gbs=px * 218 / dt / 1e9)
+    # stage split
+    f = frames[0]
+    t_m = timed(lambda: p.process_dev(f.data_ptr(), w, h, fg.data_ptr(), None, stream=st), iters, warm=1)
+    t_o = timed(lambda: blobs.morph_dev(fg.data_ptr(), w, h, S, [("erode", 1), ("dilate", 1)], clean.data_ptr(), stream=st), iters, warm=1)
+    t_c = timed(lambda: cc.label_batch_dev(clean.data_ptr(), w, h, S, True, None, stream=st), iters, warm=1)
+    out(config="4-split", mog2_ms=t_m * 1e3, morph_ms=t_o * 1e3, cc_ms=t_c * 1e3,
+        morph_gbs=px * 2 / t_o / 1e9, cc_gbs_no_label_image=px * 1 / t_c / 1e9)
+    cc.close()
+    p.close()
+
+
+def config1(clip):
+    """FD + OPEN + CC on the reference video clip: parity case, timed per frame through the host API."""
+    fd = tb.FrameDifferenceBGS()
+    bd = blobs.CvBlobDetectorCC()
+    for f in clip[:4]:                      # first calls pay CUDA module loading and allocations
+        fg, _ = fd.process(f)
+        if fg is not None:
+            bd.DetectNewBlob(blobs.morph(fg, [("erode", 1), ("dilate", 1)]), [])
+    t0 = time.perf_counter()
+    n = 0
+    for f in clip[4:]:
+        fg, _ = fd.process(f)
+        if fg is None:
+            continue
+        m = blobs.morph(fg, [("erode", 1), ("dilate", 1)])
+        bd.DetectNewBlob(m, [])
+        n += 1
+    dt = time.perf_counter() - t0
+    out(config="1", algo="FD+OPEN+CvBlobDetectorCC (host API, per frame sync)", frames=n, resolution=list(clip.shape[2:0:-1]),
+        ms_per_frame=dt / n * 1e3)
+
+
+def pcie_probe(w=1920, h=1080):
+    hin = torch.empty((h, w, 3), dtype=torch.uint8).pin_memory()
+    hout = torch.empty((h, w, 4), dtype=torch.uint8).pin_memory()
+    din = torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
+    dout = torch.empty((h, w, 4), dtype=torch.uint8, device="cuda")
+    t_up = timed(lambda: din.copy_(hin, non_blocking=True), 50)
+    t_dn = timed(lambda: hout.copy_(dout, non_blocking=True), 50)
+    s2 = torch.cuda.Stream()
+
+    def both():
+        din.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hout.copy_(dout, non_blocking=True)
+    t_b = timed(both, 50)
+    torch.cuda.synchronize()
+    out(probe="pcie", h2d_gbs=hin.numel() / t_up / 1e9, d2h_gbs=hout.numel() / t_dn / 1e9,
+        frame_up_us=t_up * 1e6, frame_down_us=t_dn * 1e6, both_us=t_b * 1e6,
+        e2e_ceiling_mpixel_s=w * h / max(t_up, t_dn) / 1e6)
+
+
+def ccl_kernel_probe(w=1920, h=1080):
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(0)
+    for name, dens in (("sparse blobs", None), ("salt noise 0.2%", 0.002), ("random 30%", 0.3)):
+        if dens is None:
+            m = np.zeros((h, w), np.uint8)
+            for r in range(12):
+                m[60 + 83 * r % (h - 90):60 + 83 * r % (h - 90) + 80, (100 + 150 * r) % (w - 120):(100 + 150 * r) % (w - 120) + 100] = 255
+        else:
+            m = (rng.random((h, w)) < dens).astype(np.uint8) * 255
+        d = torch.from_numpy(m).cuda()
+        lab = torch.empty((h, w), dtype=torch.int32, device="cuda")
+        cc = blobs.ConnectedComponents(w, h)
+        t1 = timed(lambda: cc.label_dev(d.data_ptr(), w, h, True, lab.data_ptr(), stream=st), 30)
+        t0 = timed(lambda: cc.label_dev(d.data_ptr(), w, h, True, None, stream=st), 30)
+        n = len(cc.components())
+        out(probe="ccl", mask=name, components=n, us_with_labels=t1 * 1e6, us_table_only=t0 * 1e6,
+            gbs_5B_per_px=w * h * 5 / t1 / 1e9)
+        cc.close()
+
+
+def main():
+    quick = "--quick" in sys.argv
+    torch.cuda.set_device(0)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "clips.npz"))
+    config1(z["video_clip"])
+    pcie_probe()
+    simple_streams(tb.FrameDifferenceBGS, "FD", 7 + 3)        # device path also writes the 3 B/px history
+    simple_streams(tb.AdaptiveBackgroundLearning, "ABL", 10)
+    simple_streams(tb.WeightedMovingVarianceBGS, "WMV", 10 + 6)  # device path writes both history images
+    ccl_kernel_probe()
+    pipeline(S=16 if quick else 64)
+    mog2_batches(1, 1920, 1080, [1, 4, 8, 16], "2-T")
+    mog2_batches(4 if quick else 16, 3840, 2160, [1, 4, 8, 16], "5")
+
+
+if __name__ == "__main__":
+    main()

@@ -47,10 +47,10 @@ def dilate(mask, iterations=1):
 
 
 class ConnectedComponents:
-    def __init__(self, max_w, max_h, device=0):
+    def __init__(self, max_w, max_h, device=0, max_images=1):
         self._h = C.c_void_p()
-        self.max_w, self.max_h = max_w, max_h
-        capi.check(capi.lib().bgsb_ccl_create(C.byref(self._h), device, max_w, max_h))
+        self.max_w, self.max_h, self.max_images = max_w, max_h, max_images
+        capi.check(capi.lib().bgsb_ccl_create_batch(C.byref(self._h), device, max_w, max_h, max_images))
 
     def close(self):
         if self._h:
@@ -82,11 +82,16 @@ class ConnectedComponents:
         capi.check(capi.lib().bgsb_ccl_label_dev(self._h, C.c_void_p(d_mask), w, h, int(zero_border),
                                                  C.c_void_p(d_labels) if d_labels else None, C.c_void_p(stream)))
 
-    def components(self):
+    def label_batch_dev(self, d_masks, w, h, nimages, zero_border=False, d_labels=None, stream=0):
+        """nimages dense masks back to back -> one launch sequence for all of them."""
+        capi.check(capi.lib().bgsb_ccl_label_batch_dev(self._h, C.c_void_p(d_masks), w, h, nimages, int(zero_border),
+                                                       C.c_void_p(d_labels) if d_labels else None, C.c_void_p(stream)))
+
+    def components(self, image=0):
         n = C.c_int(0)
-        capi.check(capi.lib().bgsb_ccl_components(self._h, None, 0, C.byref(n)))
+        capi.check(capi.lib().bgsb_ccl_components_of(self._h, image, None, 0, C.byref(n)))
         comps = (capi.Component * max(n.value, 1))()
-        capi.check(capi.lib().bgsb_ccl_components(self._h, comps, max(n.value, 1), C.byref(n)))
+        capi.check(capi.lib().bgsb_ccl_components_of(self._h, image, comps, max(n.value, 1), C.byref(n)))
         return [dict(label=c.label, first_index=c.first_index, x=c.x, y=c.y, w=c.w, h=c.h, area=c.area,
                      external=c.external) for c in comps[:n.value]]
 

@@ -58,7 +58,10 @@ SIGNATURES = {
     "bgsb_morph_dev": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, intp, C.c_int, vp, vp]),
     "bgsb_morph": (C.c_int, [vp, C.c_int, C.c_int, C.c_size_t, intp, C.c_int, vp, C.c_size_t]),
     "bgsb_ccl_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int]),
+    "bgsb_ccl_create_batch": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int]),
     "bgsb_ccl_destroy": (None, [vp]),
+    "bgsb_ccl_label_batch_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "bgsb_ccl_components_of": (C.c_int, [vp, C.c_int, C.POINTER(Component), C.c_int, intp]),
     "bgsb_ccl_label_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "bgsb_ccl_components": (C.c_int, [vp, C.POINTER(Component), C.c_int, intp]),
     "bgsb_ccl_rect_moments": (C.c_int, [vp, i32p, C.c_int, C.POINTER(C.c_uint64)]),

@@ -49,11 +49,25 @@ __device__ __forceinline__ int find_root(const int *parent, int p)
     return p;
 }
 
+// find with path halving: every visited node is re-pointed at its grandparent.  Re-pointing uses
+// atomicMin so that parents only ever decrease (an ancestor always has a smaller index), which keeps
+// the lock-free unions below valid while other threads compress the same paths.
+__device__ __forceinline__ int find_compress(int *parent, int p)
+{
+    int q = parent[p];
+    while (q != p) {
+        int g = parent[q];
+        if (g != q) atomicMin(&parent[p], g);
+        p = q; q = g;
+    }
+    return p;
+}
+
 __device__ __forceinline__ void unite(int *parent, int a, int b)
 {
     while (true) {
-        a = find_root(parent, a);
-        b = find_root(parent, b);
+        a = find_compress(parent, a);
+        b = find_compress(parent, b);
         if (a == b) return;
         if (a < b) { int t = a; a = b; b = t; }      // a > b: hang a under b
         int old = atomicMin(&parent[a], b);
@@ -63,10 +77,12 @@ __device__ __forceinline__ void unite(int *parent, int a, int b)
 }
 
 __global__ void __launch_bounds__(256)
-ccl_pack_kernel(const uint8_t *__restrict__ mask, unsigned *__restrict__ bits, int w, int h, int wpr, int zero_border)
+ccl_pack_kernel(const uint8_t *__restrict__ mask, unsigned *__restrict__ bits, int w, int h, int wpr, int zero_border,
+                size_t img_px, size_t img_words)
 {
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= h * wpr) return;
+    mask += blockIdx.y * img_px; bits += blockIdx.y * img_words;
     int y = wi / wpr, k = wi - y * wpr;
     const uint8_t *p = mask + (size_t)y * w + (size_t)k * 32;
     int nvalid = min(32, w - k * 32);
@@ -95,10 +111,12 @@ ccl_pack_kernel(const uint8_t *__restrict__ mask, unsigned *__restrict__ bits, i
 
 __global__ void __launch_bounds__(256)
 ccl_init_kernel(const unsigned *__restrict__ bits, int *__restrict__ parent, uint8_t *__restrict__ outer,
-                int w, int h, int wpr)
+                int *__restrict__ blockcount, int w, int h, int wpr, size_t img_px, size_t img_words, int nblocks)
 {
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x == 0) blockcount[blockIdx.y * (size_t)(nblocks + 1) + blockIdx.x] = 0;
     if (wi >= h * wpr) return;
+    bits += blockIdx.y * img_words; parent += blockIdx.y * img_px; outer += blockIdx.y * img_px;
     int y = wi / wpr, k = wi - y * wpr;
     unsigned v = bits[wi];
     unsigned vb = ~v & in_mask(k, w, wpr);
@@ -141,10 +159,11 @@ __device__ __forceinline__ void merge_class(int *parent, unsigned v, unsigned vl
 }
 
 __global__ void __launch_bounds__(256)
-ccl_merge_kernel(const unsigned *__restrict__ bits, int *parent, int w, int h, int wpr)
+ccl_merge_kernel(const unsigned *__restrict__ bits, int *parent, int w, int h, int wpr, size_t img_px, size_t img_words)
 {
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= h * wpr) return;
+    bits += blockIdx.y * img_words; parent += blockIdx.y * img_px;
     int y = wi / wpr, k = wi - y * wpr;
     unsigned v = bits[wi];
     unsigned vl = k > 0 ? bits[wi - 1] : 0u, vr = k + 1 < wpr ? bits[wi + 1] : 0u;
@@ -166,10 +185,12 @@ ccl_merge_kernel(const unsigned *__restrict__ bits, int *parent, int w, int h, i
 
 __global__ void __launch_bounds__(256)
 ccl_flatten_kernel(const unsigned *__restrict__ bits, int *parent, uint8_t *outer, unsigned *__restrict__ rootbits,
-                   int w, int h, int wpr)
+                   int *__restrict__ blockcount, int w, int h, int wpr, size_t img_px, size_t img_words, int nblocks)
 {
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= h * wpr) return;
+    bits += blockIdx.y * img_words; parent += blockIdx.y * img_px; outer += blockIdx.y * img_px;
+    rootbits += blockIdx.y * img_words; blockcount += blockIdx.y * (size_t)(nblocks + 1);
     int y = wi / wpr, k = wi - y * wpr;
     unsigned v = bits[wi];
     unsigned mk = in_mask(k, w, wpr);
@@ -184,6 +205,7 @@ ccl_flatten_kernel(const unsigned *__restrict__ bits, int *parent, uint8_t *oute
         if (r == base + b) roots |= 1u << b;
     }
     rootbits[wi] = roots;
+    if (roots) atomicAdd(&blockcount[blockIdx.x], __popc(roots));     // roots per 256-word block, for the rank scan
     // background runs: flatten, and flag regions that touch the image frame as "outer"
     const bool edge_row = (y == 0 || y == h - 1);
     s = vb & ~(vb << 1);
@@ -200,17 +222,17 @@ ccl_flatten_kernel(const unsigned *__restrict__ bits, int *parent, uint8_t *oute
 
 struct CompRaw { int label, first_index, xmin, ymin, xmax, ymax, area, external; };
 
-// single CTA: exclusive scan of per-word root counts, component count, component table init
+// one CTA per image: exclusive scan of the per-block root counts (nblocks <= a few thousand)
 __global__ void __launch_bounds__(1024)
-ccl_rank_kernel(const unsigned *__restrict__ rootbits, int *__restrict__ wordrank, int nwords, CompRaw *comp,
-                int cap, int *ncomp, int w, int wpr)
+ccl_blockscan_kernel(int *blockcount, int nblocks, int *ncomp)
 {
     __shared__ int sums[1024];
+    int *bc = blockcount + blockIdx.x * (size_t)(nblocks + 1);
     const int tid = threadIdx.x;
-    const int chunk = (nwords + 1023) / 1024;
-    const int lo = min(nwords, tid * chunk), hi = min(nwords, lo + chunk);
+    const int chunk = (nblocks + 1023) / 1024;
+    const int lo = min(nblocks, tid * chunk), hi = min(nblocks, lo + chunk);
     int acc = 0;
-    for (int i = lo; i < hi; i++) acc += __popc(rootbits[i]);
+    for (int i = lo; i < hi; i++) acc += bc[i];
     sums[tid] = acc;
     __syncthreads();
     for (int off = 1; off < 1024; off <<= 1) {          // Hillis-Steele inclusive scan
@@ -220,31 +242,59 @@ ccl_rank_kernel(const unsigned *__restrict__ rootbits, int *__restrict__ wordran
         __syncthreads();
     }
     int run = sums[tid] - acc;
-    for (int i = lo; i < hi; i++) {
-        wordrank[i] = run;
-        unsigned r = rootbits[i];
-        int y = i / wpr, k = i - y * wpr;
-        while (r) {
-            int b = __ffs(r) - 1; r &= r - 1;
-            if (run < cap) {
-                CompRaw c;
-                c.label = run + 1; c.first_index = y * w + k * 32 + b;
-                c.xmin = INT_MAX; c.ymin = INT_MAX; c.xmax = -1; c.ymax = -1; c.area = 0; c.external = 0;
-                comp[run] = c;
-            }
-            run++;
-        }
+    for (int i = lo; i < hi; i++) { int c = bc[i]; bc[i] = run; run += c; }
+    if (tid == 1023) { bc[nblocks] = sums[1023]; ncomp[blockIdx.x] = sums[1023]; }
+}
+
+// per 256-word block: exclusive rank of every word's roots, component table rows initialised
+__global__ void __launch_bounds__(256)
+ccl_rank_kernel(const unsigned *__restrict__ rootbits, int *__restrict__ wordrank, const int *__restrict__ blockcount,
+                CompRaw *comp, int cap, int w, int h, int wpr, size_t img_words, int nblocks)
+{
+    __shared__ int wsum[8];
+    rootbits += blockIdx.y * img_words; wordrank += blockIdx.y * img_words;
+    blockcount += blockIdx.y * (size_t)(nblocks + 1); comp += blockIdx.y * (size_t)cap;
+    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nwords = h * wpr;
+    unsigned r = wi < nwords ? rootbits[wi] : 0u;
+    int c = __popc(r);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
     }
-    if (tid == 1023) *ncomp = sums[1023];
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    int base = blockcount[blockIdx.x];
+    for (int i = 0; i < wid; i++) base += wsum[i];
+    int run = base + incl - c;
+    if (wi >= nwords) return;
+    wordrank[wi] = run;
+    const int y = wi / wpr, k = wi - y * wpr;
+    while (r) {
+        int b = __ffs(r) - 1; r &= r - 1;
+        if (run < cap) {
+            CompRaw cr;
+            cr.label = run + 1; cr.first_index = y * w + k * 32 + b;
+            cr.xmin = INT_MAX; cr.ymin = INT_MAX; cr.xmax = -1; cr.ymax = -1; cr.area = 0; cr.external = 0;
+            comp[run] = cr;
+        }
+        run++;
+    }
 }
 
 __global__ void __launch_bounds__(256)
 ccl_label_kernel(const unsigned *__restrict__ bits, const int *__restrict__ parent, const uint8_t *__restrict__ outer,
                  const unsigned *__restrict__ rootbits, const int *__restrict__ wordrank, CompRaw *comp, int cap,
-                 int *__restrict__ labels, int w, int h, int wpr)
+                 int *__restrict__ labels, int w, int h, int wpr, size_t img_px, size_t img_words)
 {
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= h * wpr) return;
+    bits += blockIdx.y * img_words; parent += blockIdx.y * img_px; outer += blockIdx.y * img_px;
+    rootbits += blockIdx.y * img_words; wordrank += blockIdx.y * img_words; comp += blockIdx.y * (size_t)cap;
+    if (labels) labels += blockIdx.y * img_px;
     int y = wi / wpr, k = wi - y * wpr;
     unsigned v = bits[wi];
     int base = y * w + k * 32;
@@ -345,10 +395,12 @@ rect_moments_kernel(const uint8_t *__restrict__ mask, int w, int h, const int *_
 using namespace bgsb;
 
 struct bgsb_ccl {
-    int device = 0, max_w = 0, max_h = 0;
-    int w = 0, h = 0;
+    int device = 0, max_w = 0, max_h = 0, max_images = 1;
+    int w = 0, h = 0, nimages = 0;
+    size_t img_px = 0, img_words = 0;      // per-image strides of the work buffers
+    int max_blocks = 0;
     unsigned *d_bits = nullptr, *d_rootbits = nullptr;
-    int *d_parent = nullptr, *d_wordrank = nullptr, *d_ncomp = nullptr;
+    int *d_parent = nullptr, *d_wordrank = nullptr, *d_ncomp = nullptr, *d_blockcount = nullptr;
     uint8_t *d_outer = nullptr, *d_mask_own = nullptr;
     int32_t *d_labels_own = nullptr;
     CompRaw *d_comp = nullptr;
@@ -361,26 +413,30 @@ struct bgsb_ccl {
 
 extern "C" {
 
-int bgsb_ccl_create(bgsb_ccl **out, int device, int max_w, int max_h)
+int bgsb_ccl_create_batch(bgsb_ccl **out, int device, int max_w, int max_h, int max_images)
 {
     BGSB_REQUIRE(out, "null out");
     BGSB_REQUIRE(max_w > 0 && max_h > 0 && (long long)max_w * max_h < (1LL << 30), "bad size");
+    BGSB_REQUIRE(max_images >= 1 && max_images <= 4096, "max_images out of range");
     BGSB_CUDA(cudaSetDevice(device));
     bgsb_ccl *c = new bgsb_ccl();
-    c->device = device; c->max_w = max_w; c->max_h = max_h;
-    const size_t npx = (size_t)max_w * max_h;
-    const size_t nwords = (size_t)((max_w + 31) / 32) * max_h;
-    c->cap = (int)(npx / 4 + 64);
+    c->device = device; c->max_w = max_w; c->max_h = max_h; c->max_images = max_images;
+    c->img_px = (size_t)max_w * max_h;
+    c->img_words = (size_t)((max_w + 31) / 32) * max_h;
+    c->max_blocks = (int)((c->img_words + 255) / 256);
+    c->cap = (int)(c->img_px / 4 + 64);
+    const size_t N = (size_t)max_images;
     cudaError_t e = cudaSuccess;
     auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
-    A((void **)&c->d_bits, nwords * 4);
-    A((void **)&c->d_rootbits, nwords * 4);
-    A((void **)&c->d_wordrank, nwords * 4);
-    A((void **)&c->d_parent, npx * 4);
-    A((void **)&c->d_outer, npx);
-    A((void **)&c->d_mask_own, npx);
-    A((void **)&c->d_comp, (size_t)c->cap * sizeof(CompRaw));
-    A((void **)&c->d_ncomp, sizeof(int));
+    A((void **)&c->d_bits, N * c->img_words * 4);
+    A((void **)&c->d_rootbits, N * c->img_words * 4);
+    A((void **)&c->d_wordrank, N * c->img_words * 4);
+    A((void **)&c->d_parent, N * c->img_px * 4);
+    A((void **)&c->d_outer, N * c->img_px);
+    A((void **)&c->d_mask_own, c->img_px);
+    A((void **)&c->d_comp, N * (size_t)c->cap * sizeof(CompRaw));
+    A((void **)&c->d_ncomp, N * sizeof(int));
+    A((void **)&c->d_blockcount, N * (size_t)(c->max_blocks + 1) * sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         set_error("bgsb_ccl_create: %s", cudaGetErrorString(e));
@@ -391,6 +447,11 @@ int bgsb_ccl_create(bgsb_ccl **out, int device, int max_w, int max_h)
     return BGSB_OK;
 }
 
+int bgsb_ccl_create(bgsb_ccl **out, int device, int max_w, int max_h)
+{
+    return bgsb_ccl_create_batch(out, device, max_w, max_h, 1);
+}
+
 void bgsb_ccl_destroy(bgsb_ccl *c)
 {
     if (!c) return;
@@ -398,58 +459,77 @@ void bgsb_ccl_destroy(bgsb_ccl *c)
     cudaDeviceSynchronize();
     cudaFree(c->d_bits); cudaFree(c->d_rootbits); cudaFree(c->d_wordrank); cudaFree(c->d_parent);
     cudaFree(c->d_outer); cudaFree(c->d_mask_own); cudaFree(c->d_comp); cudaFree(c->d_ncomp);
-    cudaFree(c->d_labels_own);
+    cudaFree(c->d_blockcount); cudaFree(c->d_labels_own);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
+}
+
+int bgsb_ccl_label_batch_dev(bgsb_ccl *c, const uint8_t *d_masks, int w, int h, int nimages, int zero_border,
+                             int32_t *d_labels, void *stream_)
+{
+    BGSB_REQUIRE(c && d_masks, "null");
+    BGSB_REQUIRE(w > 0 && h > 0 && (size_t)w * h <= c->img_px && (size_t)((w + 31) / 32) * h <= c->img_words,
+                 "image larger than the labeller was created for");
+    BGSB_REQUIRE(nimages >= 1 && nimages <= c->max_images, "more images than the labeller was created for");
+    BGSB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int wpr = (w + 31) / 32, nwords = wpr * h;
+    const int threads = 256, nblocks = (nwords + threads - 1) / threads;
+    const size_t ipx = (size_t)w * h, iw = (size_t)nwords;       // dense per-image strides for this geometry
+    dim3 grid(nblocks, nimages);
+    ccl_pack_kernel<<<grid, threads, 0, stream>>>(d_masks, c->d_bits, w, h, wpr, zero_border, ipx, iw);
+    BGSB_LAUNCH_CHECK();
+    ccl_init_kernel<<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_blockcount, w, h, wpr, ipx, iw, nblocks);
+    BGSB_LAUNCH_CHECK();
+    ccl_merge_kernel<<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, w, h, wpr, ipx, iw);
+    BGSB_LAUNCH_CHECK();
+    ccl_flatten_kernel<<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_rootbits, c->d_blockcount,
+                                                     w, h, wpr, ipx, iw, nblocks);
+    BGSB_LAUNCH_CHECK();
+    ccl_blockscan_kernel<<<nimages, 1024, 0, stream>>>(c->d_blockcount, nblocks, c->d_ncomp);
+    BGSB_LAUNCH_CHECK();
+    ccl_rank_kernel<<<grid, threads, 0, stream>>>(c->d_rootbits, c->d_wordrank, c->d_blockcount, c->d_comp, c->cap, w, h, wpr,
+                                                  iw, nblocks);
+    BGSB_LAUNCH_CHECK();
+    ccl_label_kernel<<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_rootbits, c->d_wordrank,
+                                                   c->d_comp, c->cap, d_labels, w, h, wpr, ipx, iw);
+    BGSB_LAUNCH_CHECK();
+    c->w = w; c->h = h; c->nimages = nimages; c->last_mask = d_masks; c->last_stream = stream; c->labelled = true;
+    return BGSB_OK;
 }
 
 int bgsb_ccl_label_dev(bgsb_ccl *c, const uint8_t *d_mask, int w, int h, int zero_border, int32_t *d_labels,
                        void *stream_)
 {
-    BGSB_REQUIRE(c && d_mask, "null");
-    BGSB_REQUIRE(w > 0 && h > 0 && w <= c->max_w && h <= c->max_h && (size_t)w * h <= (size_t)c->max_w * c->max_h,
-                 "image larger than the labeller was created for");
-    BGSB_CUDA(cudaSetDevice(c->device));
-    cudaStream_t stream = (cudaStream_t)stream_;
-    const int wpr = (w + 31) / 32, nwords = wpr * h;
-    const int threads = 256, blocks = (nwords + threads - 1) / threads;
-    ccl_pack_kernel<<<blocks, threads, 0, stream>>>(d_mask, c->d_bits, w, h, wpr, zero_border);
-    BGSB_LAUNCH_CHECK();
-    ccl_init_kernel<<<blocks, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, w, h, wpr);
-    BGSB_LAUNCH_CHECK();
-    ccl_merge_kernel<<<blocks, threads, 0, stream>>>(c->d_bits, c->d_parent, w, h, wpr);
-    BGSB_LAUNCH_CHECK();
-    ccl_flatten_kernel<<<blocks, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_rootbits, w, h, wpr);
-    BGSB_LAUNCH_CHECK();
-    ccl_rank_kernel<<<1, 1024, 0, stream>>>(c->d_rootbits, c->d_wordrank, nwords, c->d_comp, c->cap, c->d_ncomp, w, wpr);
-    BGSB_LAUNCH_CHECK();
-    ccl_label_kernel<<<blocks, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_rootbits, c->d_wordrank,
-                                                     c->d_comp, c->cap, d_labels, w, h, wpr);
-    BGSB_LAUNCH_CHECK();
-    c->w = w; c->h = h; c->last_mask = d_mask; c->last_stream = stream; c->labelled = true;
-    return BGSB_OK;
+    return bgsb_ccl_label_batch_dev(c, d_mask, w, h, 1, zero_border, d_labels, stream_);
 }
 
-int bgsb_ccl_components(bgsb_ccl *c, bgsb_component *out, int capacity, int *n)
+int bgsb_ccl_components_of(bgsb_ccl *c, int image, bgsb_component *out, int capacity, int *n)
 {
     BGSB_REQUIRE(c && n, "null");
     if (!c->labelled) { set_error("bgsb_ccl_components: nothing labelled yet"); return BGSB_ERR_STATE; }
+    BGSB_REQUIRE(image >= 0 && image < c->nimages, "image index");
     BGSB_CUDA(cudaSetDevice(c->device));
     BGSB_CUDA(cudaStreamSynchronize(c->last_stream));
     int cnt = 0;
-    BGSB_CUDA(cudaMemcpy(&cnt, c->d_ncomp, sizeof(int), cudaMemcpyDeviceToHost));
+    BGSB_CUDA(cudaMemcpy(&cnt, c->d_ncomp + image, sizeof(int), cudaMemcpyDeviceToHost));
     *n = cnt;
     if (cnt > c->cap) { set_error("component table overflow (%d > %d)", cnt, c->cap); return BGSB_ERR_CAPACITY; }
     if (!out || capacity <= 0) return BGSB_OK;
     if (cnt > capacity) { set_error("caller table too small (%d > %d)", cnt, capacity); return BGSB_ERR_CAPACITY; }
     if (cnt == 0) return BGSB_OK;
     static_assert(sizeof(CompRaw) == sizeof(bgsb_component), "layout");
-    BGSB_CUDA(cudaMemcpy(out, c->d_comp, (size_t)cnt * sizeof(CompRaw), cudaMemcpyDeviceToHost));
+    BGSB_CUDA(cudaMemcpy(out, c->d_comp + (size_t)image * c->cap, (size_t)cnt * sizeof(CompRaw), cudaMemcpyDeviceToHost));
     for (int i = 0; i < cnt; i++) {       // (xmin,ymin,xmax,ymax) -> (x,y,w,h)
         out[i].w = out[i].w - out[i].x + 1;
         out[i].h = out[i].h - out[i].y + 1;
     }
     return BGSB_OK;
+}
+
+int bgsb_ccl_components(bgsb_ccl *c, bgsb_component *out, int capacity, int *n)
+{
+    return bgsb_ccl_components_of(c, 0, out, capacity, n);
 }
 
 int bgsb_ccl_rect_moments(bgsb_ccl *c, const int32_t *rects, int nrects, uint64_t *out)
@@ -480,11 +560,11 @@ int bgsb_ccl_label(bgsb_ccl *c, const uint8_t *mask, int w, int h, size_t stride
 {
     BGSB_REQUIRE(c && mask && n, "null");
     BGSB_REQUIRE(stride >= (size_t)w, "stride smaller than a row");
-    BGSB_REQUIRE(w > 0 && h > 0 && w <= c->max_w && h <= c->max_h, "image larger than the labeller was created for");
+    BGSB_REQUIRE(w > 0 && h > 0 && (size_t)w * h <= c->img_px, "image larger than the labeller was created for");
     BGSB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->own_stream;
     BGSB_CUDA(cudaMemcpy2DAsync(c->d_mask_own, w, mask, stride, w, h, cudaMemcpyHostToDevice, st));
-    if (labels && !c->d_labels_own) BGSB_CUDA(cudaMalloc(&c->d_labels_own, (size_t)c->max_w * c->max_h * 4));
+    if (labels && !c->d_labels_own) BGSB_CUDA(cudaMalloc(&c->d_labels_own, c->img_px * 4));
     int rc = bgsb_ccl_label_dev(c, c->d_mask_own, w, h, zero_border, labels ? c->d_labels_own : nullptr, st);
     if (rc) return rc;
     if (labels) BGSB_CUDA(cudaMemcpyAsync(labels, c->d_labels_own, (size_t)w * h * 4, cudaMemcpyDeviceToHost, st));
