@@ -89,8 +89,8 @@ BGSB_API int bgsb_reset(bgsb_ctx *ctx);
  * "varThresholdGen" 9, "backgroundRatio" 0.9, "varInit" 15, "varMin" 4, "varMax" 75,
  * "complexityReductionThreshold" 0.05, "detectShadows" 1, "shadowValue" 127,
  * "shadowThreshold" 0.5; and "grayVariant": 0 = OpenCV 4.x BGR2GRAY constants, 1 = 2.4.x;
- * "kernelVariant" (MOG2): 0 = production kernel (dominant-mode fast path), 1 = straight
- * restatement kernel -- identical results, kept for A/B measurements. */
+ * "kernelVariant" (MOG2): 0 = production kernels, 1 = straight restatement kernel, 2 / 3 = earlier
+ * generations of the fast kernel -- identical results, kept for A/B measurements. */
 BGSB_API int bgsb_set_param(bgsb_ctx *ctx, const char *key, double value);
 BGSB_API int bgsb_get_param(bgsb_ctx *ctx, const char *key, double *value);
 

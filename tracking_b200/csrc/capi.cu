@@ -39,7 +39,7 @@ struct bgsb_ctx {
     int history = 500;
     float Tb = 16.f, Tg = 9.f, TB = 0.9f, varInit = 15.f, varMin = 4.f, varMax = 75.f, CT = 0.05f, tau = 0.5f;
     int detect_shadows = 1, shadow_value = 127;
-    int mog2_variant = 0;      // 0 production kernel (mog2_fast.cu), 1 straight restatement kernel (mog2.cu)
+    int mog2_variant = 0;      // see launch_mog2 (mog2.cu): 0 production, 1 straight restatement, 2/3 earlier generations
     // geometry / counters
     int w = 0, h = 0, npx = 0;
     size_t pstride = 0;
@@ -268,7 +268,7 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     else if (k == "detectShadows") c->detect_shadows = (v != 0);
     else if (k == "shadowValue") c->shadow_value = (int)v;
     else if (k == "shadowThreshold") c->tau = (float)v;
-    else if (k == "kernelVariant") { BGSB_REQUIRE(v == 0 || v == 1, "kernelVariant is 0 or 1"); c->mog2_variant = (int)v; }
+    else if (k == "kernelVariant") { BGSB_REQUIRE(v >= 0 && v <= 3 && v == (int)v, "kernelVariant is 0..3"); c->mog2_variant = (int)v; }
     else if (k == "showOutput" || k == "showForeground" || k == "showBackground") { /* GUI only */ }
     else { set_error("bgsb_set_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
     return BGSB_OK;
