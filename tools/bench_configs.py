@@ -65,29 +65,31 @@ def simple_streams(algo_cls, name, bpp, S=16, w=1920, h=1080, NT=6, iters=40):
     p.close()
 
 
-def mog2_batches(S, w, h, Ts, label, iters=6):
+def mog2_batches(S, w, h, Ts, label, NF=48, iters=2):
+    """Temporal batches on one continuous stream: NF consecutive frames are cycled, every T divides NF, so every
+    setting sees exactly the same video (same share of generic-path pixels)."""
     st = torch.cuda.current_stream().cuda_stream
-    Tmax = max(Ts)
-    frames = torch.empty((S, Tmax, h, w, 3), dtype=torch.uint8, device="cuda")
-    synth.frames_dev(frames.data_ptr(), S, Tmax, w, h, t0=0, stream=st)
+    frames = torch.empty((S, NF, h, w, 3), dtype=torch.uint8, device="cuda")
+    synth.frames_dev(frames.data_ptr(), S, NF, w, h, t0=0, stream=st)
     for T in Ts:
         p = tb.MixtureOfGaussianV2BGS(nstreams=S)
-        fr = frames[:, :T].contiguous()
+        nwin = NF // T
+        wins = [frames[:, i * T:(i + 1) * T].contiguous() for i in range(nwin)]
         fg = torch.empty((S, T, h, w), dtype=torch.uint8, device="cuda")
         bg = torch.empty((S, T, h, w, 3), dtype=torch.uint8, device="cuda")
 
-        def step():
-            p.process_batch_dev(fr.data_ptr(), T, w, h, fg.data_ptr(), bg.data_ptr(), stream=st)
-        n_warm = max(3, 48 // T)
-        dt = timed(step, iters, warm=n_warm)
-        px = S * T * w * h
+        def sweep():
+            for i in range(nwin):
+                p.process_batch_dev(wins[i].data_ptr(), T, w, h, fg.data_ptr(), bg.data_ptr(), stream=st)
+        dt = timed(sweep, iters, warm=2)              # seconds per NF frames
+        px = S * NF * w * h
         nm = np.concatenate([p.export_state(s)[1] for s in range(min(S, 2))])
-        live = 9 + 40 * float(nm.mean())
-        out(config=label, algo="MOG2", streams=S, T=T, resolution=[w, h], ms_per_launch=dt * 1e3, mpixel_s=px / dt / 1e6,
-            mean_live_modes=float(nm.mean()), dense_model_bytes_per_px_frame=202.0 / T + 7,
-            dense_equiv_gbs=px * (202.0 / T + 7) / dt / 1e9)
+        out(config=label, algo="MOG2", streams=S, T=T, resolution=[w, h], us_per_frame_per_stream=dt / NF / S * 1e6,
+            mpixel_s=px / dt / 1e6, mean_live_modes=float(nm.mean()),
+            live_bytes_per_px_frame=(2 + 40 * float(nm.mean())) / T + 7,
+            dense_model_bytes_per_px_frame=202.0 / T + 7)
         p.close()
-        del fg, bg, fr
+        del fg, bg, wins
 
 
 def pipeline(S=64, w=1920, h=1080, NT=3, iters=6):
@@ -200,8 +202,9 @@ def main():
     simple_streams(tb.WeightedMovingVarianceBGS, "WMV", 10 + 6)  # device path writes both history images
     ccl_kernel_probe()
     pipeline(S=16 if quick else 64)
-    mog2_batches(1, 1920, 1080, [1, 4, 8, 16], "2-T")
-    mog2_batches(4 if quick else 16, 3840, 2160, [1, 4, 8, 16], "5")
+    mog2_batches(1, 1920, 1080, [1, 2, 4, 8, 16], "2-T")
+    mog2_batches(16, 1920, 1080, [1, 4, 16], "16x1080p-T")
+    mog2_batches(4 if quick else 16, 3840, 2160, [1, 4, 8, 16], "5", NF=16 if quick else 32)
 
 
 if __name__ == "__main__":

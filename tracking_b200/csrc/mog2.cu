@@ -144,12 +144,13 @@ mog2_kernel(const __grid_constant__ Mog2Launch L)
 
 int launch_mog2_fast(const Mog2Launch &L, int nstreams, cudaStream_t stream);
 int launch_mog2_t1v4(const Mog2Launch &L, int nstreams, int px, cudaStream_t stream);
+int launch_mog2_fused(const Mog2Launch &L, int nstreams, cudaStream_t stream);
 
-// variant: 0 production (T==1: generation-4 kernel, 2 px/thread; T>1: batch kernel), 1 straight restatement,
+// variant: 0 production (T==1: generation-4 kernel, 2 px/thread; T>1: temporal-fusion kernel), 1 straight restatement,
 //          2 generation-3 T==1 kernel (4 px/thread, mog2_fast.cu), 3 generation-4 with 4 px/thread
 int launch_mog2(const Mog2Launch &L, int nstreams, int variant, cudaStream_t stream)
 {
-    if (variant == 0) return L.T == 1 ? launch_mog2_t1v4(L, nstreams, 2, stream) : launch_mog2_fast(L, nstreams, stream);
+    if (variant == 0) return L.T == 1 ? launch_mog2_t1v4(L, nstreams, 2, stream) : launch_mog2_fused(L, nstreams, stream);
     if (variant == 2) return launch_mog2_fast(L, nstreams, stream);
     if (variant == 3) return L.T == 1 ? launch_mog2_t1v4(L, nstreams, 4, stream) : launch_mog2_fast(L, nstreams, stream);
     const int threads = 128;
