@@ -111,6 +111,15 @@ static int ensure_host_staging(bgsb_ctx *c)
     return BGSB_OK;
 }
 
+// Host<->device image copy: a plain 1D copy when the host rows are dense (one DMA descriptor), a pitched
+// copy otherwise (cv::Mat rows from cvQueryFrame are 4-byte aligned and may carry padding).
+static cudaError_t copy_rows(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows,
+                             cudaMemcpyKind kind, cudaStream_t st)
+{
+    if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * rows, kind, st);
+    return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st);
+}
+
 static int warmup_frames(int algo)
 {
     return algo == BGSB_ALGO_FRAME_DIFFERENCE ? 1 : (algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE ? 2 : 0);
@@ -382,20 +391,20 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
         }
     }
     if (nchunks == 1) {
-        BGSB_CUDA(cudaMemcpy2DAsync(d_in, (size_t)w * 3, bgr, stride, (size_t)w * 3, rows, cudaMemcpyHostToDevice, c->stream));
+        BGSB_CUDA(copy_rows(d_in, (size_t)w * 3, bgr, stride, (size_t)w * 3, rows, cudaMemcpyHostToDevice, c->stream));
         if (out_fg) {
             rc = launch_range(c, d_in, 1, c->d_fg, want_bg ? c->d_bg : nullptr, 0, own_hist, c->stream, 0, c->npx);
             if (rc) return rc;
-            BGSB_CUDA(cudaMemcpy2DAsync(fg, fg_stride, c->d_fg, (size_t)w, (size_t)w, rows, cudaMemcpyDeviceToHost, c->stream));
+            BGSB_CUDA(copy_rows(fg, fg_stride, c->d_fg, (size_t)w, (size_t)w, rows, cudaMemcpyDeviceToHost, c->stream));
             if (want_bg)
-                BGSB_CUDA(cudaMemcpy2DAsync(bg, bg_stride, c->d_bg, (size_t)w * 3, (size_t)w * 3, rows, cudaMemcpyDeviceToHost, c->stream));
+                BGSB_CUDA(copy_rows(bg, bg_stride, c->d_bg, (size_t)w * 3, (size_t)w * 3, rows, cudaMemcpyDeviceToHost, c->stream));
         }
         BGSB_CUDA(cudaStreamSynchronize(c->stream));
     } else {
         for (int i = 0; i < nchunks; i++) {
             const int r0 = i * band, nr = std::min(band, h - r0);
             const size_t p0 = (size_t)r0 * w;
-            BGSB_CUDA(cudaMemcpy2DAsync(d_in + p0 * 3, (size_t)w * 3, bgr + (size_t)r0 * stride, stride, (size_t)w * 3, nr,
+            BGSB_CUDA(copy_rows(d_in + p0 * 3, (size_t)w * 3, bgr + (size_t)r0 * stride, stride, (size_t)w * 3, nr,
                                         cudaMemcpyHostToDevice, c->s_h2d));
             BGSB_CUDA(cudaEventRecord(c->ev_up[i], c->s_h2d));
             BGSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up[i], 0));
@@ -403,10 +412,10 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
             if (rc) return rc;
             BGSB_CUDA(cudaEventRecord(c->ev_k[i], c->stream));
             BGSB_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_k[i], 0));
-            BGSB_CUDA(cudaMemcpy2DAsync(fg + (size_t)r0 * fg_stride, fg_stride, c->d_fg + p0, (size_t)w, (size_t)w, nr,
+            BGSB_CUDA(copy_rows(fg + (size_t)r0 * fg_stride, fg_stride, c->d_fg + p0, (size_t)w, (size_t)w, nr,
                                         cudaMemcpyDeviceToHost, c->s_d2h));
             if (want_bg)
-                BGSB_CUDA(cudaMemcpy2DAsync(bg + (size_t)r0 * bg_stride, bg_stride, c->d_bg + p0 * 3, (size_t)w * 3,
+                BGSB_CUDA(copy_rows(bg + (size_t)r0 * bg_stride, bg_stride, c->d_bg + p0 * 3, (size_t)w * 3,
                                             (size_t)w * 3, nr, cudaMemcpyDeviceToHost, c->s_d2h));
         }
         BGSB_CUDA(cudaStreamSynchronize(c->s_d2h));
