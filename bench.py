@@ -37,7 +37,8 @@ if ROOT not in sys.path:
 
 W, H = 1920, 1080
 NPX = W * H
-FRAMES_PER_STEP = 256         # 8.5 s of 30 fps video per step; ~23 ms of GPU time
+FRAMES_PER_STEP = 1024        # 34 s of 30 fps video per step; ~36 ms of GPU time, so that K >= 10 steps span several
+                               # nvidia-smi clock samples
 NFRAMES_RESIDENT = 128          # distinct synthetic frames kept in HBM (796 MB) and cycled
 MOG2_BYTES_PER_PX = 209         # dense model: in 3 + state 101 read + 101 write + mask 1 + bg 3  
 MOG2_FIXED_BYTES_PER_PX = 9     # in 3 + nmodes 1 read + 1 write + mask 1 + bg 3
