@@ -162,6 +162,9 @@ BGSB_API int bgsb_ccl_create(bgsb_ccl **out, int device, int max_w, int max_h);
  * all camera streams of a group instead of one per stream). */
 BGSB_API int bgsb_ccl_create_batch(bgsb_ccl **out, int device, int max_w, int max_h, int max_images);
 BGSB_API void bgsb_ccl_destroy(bgsb_ccl *ccl);
+/* "forceBackgroundPass" (default 0): label the background of every image for the RETR_EXTERNAL test even when
+ * no bounding box lies inside another (A/B and tests; results are identical). */
+BGSB_API int bgsb_ccl_set_param(bgsb_ccl *ccl, const char *key, double value);
 /* foreground = mask > 128 (cvThreshold(pIB,pIB,128,255,BINARY)); 8-connected.
  * zero_border != 0 clears the outer 1-px frame first (OpenCV <= 3.1 cvFindContours).
  * d_labels (int32 [h][w], nullable) receives canonical labels, 0 = background.

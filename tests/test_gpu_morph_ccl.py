@@ -86,6 +86,36 @@ def test_ccl_labels_stats_external_bit_exact(oracle):
     cc.close()
 
 
+def test_ccl_nesting_paths(oracle):
+    """RETR_EXTERNAL nesting: rings with islands (background pass needed) and plain blobs (skipped), both with the
+    pass forced and with the bounding-box pre-check deciding."""
+    from tracking_b200 import blobs
+    h, w = 120, 200
+    yy, xx = np.mgrid[0:h, 0:w]
+    nested = np.zeros((h, w), np.uint8)
+    for cy, cx, r in ((40, 50, 30), (70, 140, 40)):
+        d = (yy - cy) ** 2 + (xx - cx) ** 2
+        nested[(d < r * r) & (d >= (r - 4) ** 2)] = 255       # ring
+        nested[d < 16] = 255                                   # island inside the ring
+        nested[(np.abs(yy - cy) < 8) & (np.abs(xx - cx - 12) < 2)] = 255
+    plain = np.zeros((h, w), np.uint8)
+    plain[10:30, 10:50] = 255; plain[60:100, 90:130] = 255
+    # bbox strictly inside another bbox but NOT in a hole (an L-shaped blob around a small one)
+    tricky = np.zeros((h, w), np.uint8)
+    tricky[10:100, 10:20] = 255; tricky[90:100, 10:150] = 255; tricky[30:40, 60:70] = 255
+    cc = blobs.ConnectedComponents(w, h)
+    for force in (0, 1):
+        cc.set("forceBackgroundPass", force)
+        for m in (nested, plain, tricky):
+            for zb in (False, True):
+                n, lab, comps = cc.label(m, zero_border=zb)
+                on, olab, ost, oext = oracle.ccl8(m, zb)
+                assert n == on and np.array_equal(lab, olab)
+                assert [c["external"] for c in comps] == [int(e) for e in oext], (force, zb)
+    assert sum(1 - int(e) for e in oracle.ccl8(nested)[3]) >= 2          # the fixture really has nested components
+    cc.close()
+
+
 def test_ccl_batch_of_images(oracle):
     """One launch sequence for a group of masks (one per camera stream) == per-image results."""
     import torch

@@ -52,6 +52,9 @@ class ConnectedComponents:
         self.max_w, self.max_h, self.max_images = max_w, max_h, max_images
         capi.check(capi.lib().bgsb_ccl_create_batch(C.byref(self._h), device, max_w, max_h, max_images))
 
+    def set(self, key, value):
+        capi.check(capi.lib().bgsb_ccl_set_param(self._h, key.encode(), float(value)))
+
     def close(self):
         if self._h:
             capi.lib().bgsb_ccl_destroy(self._h)

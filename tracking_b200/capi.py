@@ -60,6 +60,7 @@ SIGNATURES = {
     "bgsb_ccl_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int]),
     "bgsb_ccl_create_batch": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int]),
     "bgsb_ccl_destroy": (None, [vp]),
+    "bgsb_ccl_set_param": (C.c_int, [vp, C.c_char_p, C.c_double]),
     "bgsb_ccl_label_batch_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "bgsb_ccl_components_of": (C.c_int, [vp, C.c_int, C.POINTER(Component), C.c_int, intp]),
     "bgsb_ccl_label_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),

@@ -7,20 +7,26 @@
 //     cvThreshold(pIB, pIB, 128, 255, CV_THRESH_BINARY); cvFindContours(pIB, ..., CV_RETR_EXTERNAL);
 //     CvRect r = ((CvContour*)cnt)->rect;   cvMoments(cvGetSubRect(pFGMask,&mat,r), &m, 0);
 //
-// Algorithm (all kernels one thread per 32-pixel word of the bit-packed mask):
+// Algorithm (all kernels one thread per 32-pixel word of the bit-packed mask; every launch covers a
+// whole batch of images, blockIdx.y = image):
 //   pack     bytes > 128 -> bits (optionally clearing the 1-px frame, OpenCV 2.4 behaviour)
-//   init     every horizontal run (within a word) is a union-find node named by its first pixel;
-//            foreground runs and background runs share one parent array (disjoint pixel sets)
+//   init     every horizontal run (within a word) is a union-find node named by its first pixel
 //   merge    unions found with bit tricks on (this row, row above): a run pair is linked exactly
-//            once (8-connectivity for foreground: vertical + the two diagonals that are not
-//            already implied; 4-connectivity for background); lock-free union by atomicMin so a
-//            component's root is its minimum = raster-first pixel
-//   flatten  parent[node] = root; mark roots; background regions touching the frame are "outer"
-//   rank     exclusive scan of root counts -> canonical label = 1 + rank of the root pixel
-//   label    write labels, accumulate bbox/area per component with atomics, and decide `external`:
-//            the background pixel left of a component's first pixel lies in the region that
-//            surrounds it; the component is external iff that region is outer.
+//            once (8-connectivity: vertical + the two diagonals that are not already implied);
+//            lock-free union by atomicMin with path halving, so a component's root is its
+//            minimum = raster-first pixel
+//   flatten  parent[node] = root; mark roots; count roots per 256-word block
+//   rank     scan of the block counts + in-block scan -> canonical label = 1 + rank of the root
+//   label    write labels, accumulate bbox/area per component with atomics
+//   nest     RETR_EXTERNAL drops components enclosed in a hole of another one.  That requires the
+//            enclosed component's bounding box to lie STRICTLY inside the other's, so one small
+//            kernel checks the boxes; only images where such a pair exists run the background pass:
+//   bg pass  the same init/merge/flatten on the 4-connected background; regions touching the frame
+//            are "outer"; the background pixel left of a component's first pixel lies in the region
+//            surrounding it, and the component is external iff that region is outer.
+//            (Typical masks have no such pair and skip it: the background is >98 % of the pixels.)
 #include <limits.h>
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -109,22 +115,31 @@ ccl_pack_kernel(const uint8_t *__restrict__ mask, unsigned *__restrict__ bits, i
     bits[wi] = word;
 }
 
+// BG = false: foreground runs;  BG = true: background runs (only for images flagged by the nest check)
+template <bool BG>
 __global__ void __launch_bounds__(256)
 ccl_init_kernel(const unsigned *__restrict__ bits, int *__restrict__ parent, uint8_t *__restrict__ outer,
-                int *__restrict__ blockcount, int w, int h, int wpr, size_t img_px, size_t img_words, int nblocks)
+                int *__restrict__ blockcount, const int *__restrict__ need_bg, int w, int h, int wpr, size_t img_px,
+                size_t img_words, int nblocks)
 {
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (threadIdx.x == 0) blockcount[blockIdx.y * (size_t)(nblocks + 1) + blockIdx.x] = 0;
+    if (BG) { if (!need_bg[blockIdx.y]) return; }
+    else if (threadIdx.x == 0) {
+        blockcount[blockIdx.y * (size_t)(nblocks + 1) + blockIdx.x] = 0;
+        if (blockIdx.x == 0) (const_cast<int *>(need_bg))[blockIdx.y] = 0;
+    }
     if (wi >= h * wpr) return;
     bits += blockIdx.y * img_words; parent += blockIdx.y * img_px; outer += blockIdx.y * img_px;
     int y = wi / wpr, k = wi - y * wpr;
     unsigned v = bits[wi];
-    unsigned vb = ~v & in_mask(k, w, wpr);
+    if (BG) v = ~v & in_mask(k, w, wpr);
     int base = y * w + k * 32;
     unsigned s = v & ~(v << 1);
-    while (s) { int b = __ffs(s) - 1; s &= s - 1; parent[base + b] = base + b; }
-    s = vb & ~(vb << 1);
-    while (s) { int b = __ffs(s) - 1; s &= s - 1; parent[base + b] = base + b; outer[base + b] = 0; }
+    while (s) {
+        int b = __ffs(s) - 1; s &= s - 1;
+        parent[base + b] = base + b;
+        if (BG) outer[base + b] = 0;
+    }
 }
 
 template <bool DIAG>
@@ -158,14 +173,18 @@ __device__ __forceinline__ void merge_class(int *parent, unsigned v, unsigned vl
     (void)k;
 }
 
+template <bool BG>
 __global__ void __launch_bounds__(256)
-ccl_merge_kernel(const unsigned *__restrict__ bits, int *parent, int w, int h, int wpr, size_t img_px, size_t img_words)
+ccl_merge_kernel(const unsigned *__restrict__ bits, int *parent, const int *__restrict__ need_bg, int w, int h, int wpr,
+                 size_t img_px, size_t img_words)
 {
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (BG && !need_bg[blockIdx.y]) return;
     if (wi >= h * wpr) return;
     bits += blockIdx.y * img_words; parent += blockIdx.y * img_px;
     int y = wi / wpr, k = wi - y * wpr;
     unsigned v = bits[wi];
+    if (!BG && v == 0) return;                     // no foreground in this word: nothing to link
     unsigned vl = k > 0 ? bits[wi - 1] : 0u, vr = k + 1 < wpr ? bits[wi + 1] : 0u;
     unsigned u = 0, ul = 0, ur = 0;
     bool has_up = y > 0;
@@ -175,48 +194,55 @@ ccl_merge_kernel(const unsigned *__restrict__ bits, int *parent, int w, int h, i
         ur = k + 1 < wpr ? bits[wi - wpr + 1] : 0u;
     }
     int base = y * w + k * 32, base_up = base - w;
-    // foreground, 8-connected
-    merge_class<true>(parent, v, vl, vr, u, ul, ur, base, base_up, has_up, k);
-    // background, 4-connected (the complement inside the image)
-    unsigned mk = in_mask(k, w, wpr), ml = in_mask(k - 1, w, wpr), mr = in_mask(k + 1, w, wpr);
-    merge_class<false>(parent, ~v & mk, ~vl & ml, ~vr & mr, has_up ? (~u & mk) : 0u, has_up ? (~ul & ml) : 0u,
-                       has_up ? (~ur & mr) : 0u, base, base_up, has_up, k);
+    if (!BG) {
+        merge_class<true>(parent, v, vl, vr, u, ul, ur, base, base_up, has_up, k);          // 8-connected
+    } else {
+        // background = complement inside the image, 4-connected
+        unsigned mk = in_mask(k, w, wpr), ml = in_mask(k - 1, w, wpr), mr = in_mask(k + 1, w, wpr);
+        merge_class<false>(parent, ~v & mk, ~vl & ml, ~vr & mr, has_up ? (~u & mk) : 0u, has_up ? (~ul & ml) : 0u,
+                           has_up ? (~ur & mr) : 0u, base, base_up, has_up, k);
+    }
 }
 
+template <bool BG>
 __global__ void __launch_bounds__(256)
 ccl_flatten_kernel(const unsigned *__restrict__ bits, int *parent, uint8_t *outer, unsigned *__restrict__ rootbits,
-                   int *__restrict__ blockcount, int w, int h, int wpr, size_t img_px, size_t img_words, int nblocks)
+                   int *__restrict__ blockcount, const int *__restrict__ need_bg, int w, int h, int wpr, size_t img_px,
+                   size_t img_words, int nblocks)
 {
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (BG && !need_bg[blockIdx.y]) return;
     if (wi >= h * wpr) return;
     bits += blockIdx.y * img_words; parent += blockIdx.y * img_px; outer += blockIdx.y * img_px;
     rootbits += blockIdx.y * img_words; blockcount += blockIdx.y * (size_t)(nblocks + 1);
     int y = wi / wpr, k = wi - y * wpr;
     unsigned v = bits[wi];
-    unsigned mk = in_mask(k, w, wpr);
-    unsigned vb = ~v & mk;
     int base = y * w + k * 32;
-    unsigned roots = 0;
-    unsigned s = v & ~(v << 1);
-    while (s) {
-        int b = __ffs(s) - 1; s &= s - 1;
-        int r = find_root(parent, base + b);
-        parent[base + b] = r;
-        if (r == base + b) roots |= 1u << b;
-    }
-    rootbits[wi] = roots;
-    if (roots) atomicAdd(&blockcount[blockIdx.x], __popc(roots));     // roots per 256-word block, for the rank scan
-    // background runs: flatten, and flag regions that touch the image frame as "outer"
-    const bool edge_row = (y == 0 || y == h - 1);
-    s = vb & ~(vb << 1);
-    while (s) {
-        int b = __ffs(s) - 1; s &= s - 1;
-        int r = find_root(parent, base + b);
-        parent[base + b] = r;
-        unsigned rest = ~(vb >> b);
-        int len = rest ? __ffs(rest) - 1 : 32 - b;
-        bool touches = edge_row || (k == 0 && b == 0) || (k * 32 + b + len - 1 == w - 1);
-        if (touches) outer[r] = 1;
+    if (!BG) {
+        unsigned roots = 0;
+        unsigned s = v & ~(v << 1);
+        while (s) {
+            int b = __ffs(s) - 1; s &= s - 1;
+            int r = find_root(parent, base + b);
+            parent[base + b] = r;
+            if (r == base + b) roots |= 1u << b;
+        }
+        rootbits[wi] = roots;
+        if (roots) atomicAdd(&blockcount[blockIdx.x], __popc(roots));     // roots per 256-word block, for the rank scan
+    } else {
+        // background runs: flatten, and flag regions that touch the image frame as "outer"
+        unsigned vb = ~v & in_mask(k, w, wpr);
+        const bool edge_row = (y == 0 || y == h - 1);
+        unsigned s = vb & ~(vb << 1);
+        while (s) {
+            int b = __ffs(s) - 1; s &= s - 1;
+            int r = find_root(parent, base + b);
+            parent[base + b] = r;
+            unsigned rest = ~(vb >> b);
+            int len = rest ? __ffs(rest) - 1 : 32 - b;
+            bool touches = edge_row || (k == 0 && b == 0) || (k * 32 + b + len - 1 == w - 1);
+            if (touches) outer[r] = 1;
+        }
     }
 }
 
@@ -325,17 +351,7 @@ ccl_label_kernel(const unsigned *__restrict__ bits, const int *__restrict__ pare
             atomicMin(&c->xmin, x0); atomicMax(&c->xmax, x0 + len - 1);
             atomicMin(&c->ymin, y); atomicMax(&c->ymax, y);
             atomicAdd(&c->area, len);
-            if (r == p) {
-                // RETR_EXTERNAL: is the surrounding background region connected to the outside?
-                int ext = 1;
-                if (rx > 0) {
-                    int lk = (rx - 1) >> 5, lb = (rx - 1) & 31;
-                    unsigned lv = ~bits[ry * wpr + lk] & in_mask(lk, w, wpr);
-                    int node = ry * w + lk * 32 + run_start(lv, lb);
-                    ext = outer[parent[node]];
-                }
-                c->external = ext;
-            }
+            if (r == p) c->external = 1;           // provisional; nested components are found by the bg pass
         }
     }
     if (labels) {
@@ -350,6 +366,63 @@ ccl_label_kernel(const unsigned *__restrict__ bits, const int *__restrict__ pare
                 if (i < nvalid) o[i] = lab[i];
         }
     }
+}
+
+// Does any component's bounding box lie strictly inside another's?  (Necessary for a component to sit in a
+// hole of another one.)  grid = (16 tiles of 256 components, images); the j-loop runs over shared-memory tiles.
+// More than 4096 components: not worth checking, run the bg pass.  need_bg[] was zeroed by ccl_init_kernel<false>.
+__global__ void __launch_bounds__(256)
+ccl_nest_kernel(const CompRaw *__restrict__ comp, const int *__restrict__ ncomp, int cap, int *__restrict__ need_bg)
+{
+    __shared__ int4 box[256];
+    const int img = blockIdx.y;
+    const int n = ncomp[img];
+    if (n > 4096 || n > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) need_bg[img] = 1; return; }
+    if ((int)(blockIdx.x * 256) >= n) return;
+    const CompRaw *c = comp + (size_t)img * cap;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+    if (i < n) { x0 = c[i].xmin; y0 = c[i].ymin; x1 = c[i].xmax; y1 = c[i].ymax; }
+    bool inside = false;
+    for (int t0 = 0; t0 < n; t0 += 256) {
+        const int j = t0 + threadIdx.x;
+        box[threadIdx.x] = j < n ? make_int4(c[j].xmin, c[j].ymin, c[j].xmax, c[j].ymax) : make_int4(1 << 30, 1 << 30, -1, -1);
+        __syncthreads();
+        if (i < n) {
+#pragma unroll 8
+            for (int q = 0; q < 256; q++) {
+                const int4 b = box[q];
+                inside |= (b.x < x0) & (b.y < y0) & (b.z > x1) & (b.w > y1);
+            }
+        }
+        __syncthreads();
+    }
+    if (inside) need_bg[img] = 1;
+}
+
+// After the bg pass: a component is external iff the background region left of its first pixel is outer.
+__global__ void __launch_bounds__(256)
+ccl_resolve_external_kernel(const unsigned *__restrict__ bits, const int *__restrict__ parent,
+                            const uint8_t *__restrict__ outer, CompRaw *comp, const int *__restrict__ ncomp, int cap,
+                            const int *__restrict__ need_bg, int w, int wpr, size_t img_px, size_t img_words)
+{
+    const int img = blockIdx.y;
+    if (!need_bg[img]) return;
+    const int n = min(ncomp[img], cap);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bits += img * img_words; parent += img * img_px; outer += img * img_px;
+    CompRaw *c = comp + (size_t)img * cap + i;
+    const int r = c->first_index;
+    const int ry = r / w, rx = r - ry * w;
+    int ext = 1;
+    if (rx > 0) {
+        const int lk = (rx - 1) >> 5, lb = (rx - 1) & 31;
+        const unsigned lv = ~bits[ry * wpr + lk] & in_mask(lk, w, wpr);
+        const int node = ry * w + lk * 32 + run_start(lv, lb);
+        ext = outer[parent[node]];
+    }
+    c->external = ext;
 }
 
 // cvMoments(ROI, binary=0): pixel-value weighted raw moments, ROI-relative coordinates.
@@ -400,7 +473,8 @@ struct bgsb_ccl {
     size_t img_px = 0, img_words = 0;      // per-image strides of the work buffers
     int max_blocks = 0;
     unsigned *d_bits = nullptr, *d_rootbits = nullptr;
-    int *d_parent = nullptr, *d_wordrank = nullptr, *d_ncomp = nullptr, *d_blockcount = nullptr;
+    int *d_parent = nullptr, *d_wordrank = nullptr, *d_ncomp = nullptr, *d_blockcount = nullptr, *d_need_bg = nullptr;
+    int force_bg = 0;                       // 1: always run the background pass (A/B and tests)
     uint8_t *d_outer = nullptr, *d_mask_own = nullptr;
     int32_t *d_labels_own = nullptr;
     CompRaw *d_comp = nullptr;
@@ -437,6 +511,7 @@ int bgsb_ccl_create_batch(bgsb_ccl **out, int device, int max_w, int max_h, int 
     A((void **)&c->d_comp, N * (size_t)c->cap * sizeof(CompRaw));
     A((void **)&c->d_ncomp, N * sizeof(int));
     A((void **)&c->d_blockcount, N * (size_t)(c->max_blocks + 1) * sizeof(int));
+    A((void **)&c->d_need_bg, N * sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         set_error("bgsb_ccl_create: %s", cudaGetErrorString(e));
@@ -459,7 +534,7 @@ void bgsb_ccl_destroy(bgsb_ccl *c)
     cudaDeviceSynchronize();
     cudaFree(c->d_bits); cudaFree(c->d_rootbits); cudaFree(c->d_wordrank); cudaFree(c->d_parent);
     cudaFree(c->d_outer); cudaFree(c->d_mask_own); cudaFree(c->d_comp); cudaFree(c->d_ncomp);
-    cudaFree(c->d_blockcount); cudaFree(c->d_labels_own);
+    cudaFree(c->d_blockcount); cudaFree(c->d_need_bg); cudaFree(c->d_labels_own);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -479,12 +554,13 @@ int bgsb_ccl_label_batch_dev(bgsb_ccl *c, const uint8_t *d_masks, int w, int h, 
     dim3 grid(nblocks, nimages);
     ccl_pack_kernel<<<grid, threads, 0, stream>>>(d_masks, c->d_bits, w, h, wpr, zero_border, ipx, iw);
     BGSB_LAUNCH_CHECK();
-    ccl_init_kernel<<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_blockcount, w, h, wpr, ipx, iw, nblocks);
+    ccl_init_kernel<false><<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_blockcount, c->d_need_bg,
+                                                        w, h, wpr, ipx, iw, nblocks);
     BGSB_LAUNCH_CHECK();
-    ccl_merge_kernel<<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, w, h, wpr, ipx, iw);
+    ccl_merge_kernel<false><<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_need_bg, w, h, wpr, ipx, iw);
     BGSB_LAUNCH_CHECK();
-    ccl_flatten_kernel<<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_rootbits, c->d_blockcount,
-                                                     w, h, wpr, ipx, iw, nblocks);
+    ccl_flatten_kernel<false><<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_rootbits,
+                                                           c->d_blockcount, c->d_need_bg, w, h, wpr, ipx, iw, nblocks);
     BGSB_LAUNCH_CHECK();
     ccl_blockscan_kernel<<<nimages, 1024, 0, stream>>>(c->d_blockcount, nblocks, c->d_ncomp);
     BGSB_LAUNCH_CHECK();
@@ -494,7 +570,40 @@ int bgsb_ccl_label_batch_dev(bgsb_ccl *c, const uint8_t *d_masks, int w, int h, 
     ccl_label_kernel<<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_rootbits, c->d_wordrank,
                                                    c->d_comp, c->cap, d_labels, w, h, wpr, ipx, iw);
     BGSB_LAUNCH_CHECK();
+    // RETR_EXTERNAL: background pass only for images where a bounding box lies strictly inside another
+    if (c->force_bg) {
+        std::vector<int> ones(nimages, 1);
+        BGSB_CUDA(cudaMemcpyAsync(c->d_need_bg, ones.data(), nimages * sizeof(int), cudaMemcpyHostToDevice, stream));
+        BGSB_CUDA(cudaStreamSynchronize(stream));
+    } else {
+        ccl_nest_kernel<<<dim3(16, nimages), 256, 0, stream>>>(c->d_comp, c->d_ncomp, c->cap, c->d_need_bg);
+        BGSB_LAUNCH_CHECK();
+    }
+    ccl_init_kernel<true><<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_blockcount, c->d_need_bg,
+                                                       w, h, wpr, ipx, iw, nblocks);
+    BGSB_LAUNCH_CHECK();
+    ccl_merge_kernel<true><<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_need_bg, w, h, wpr, ipx, iw);
+    BGSB_LAUNCH_CHECK();
+    ccl_flatten_kernel<true><<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_rootbits,
+                                                          c->d_blockcount, c->d_need_bg, w, h, wpr, ipx, iw, nblocks);
+    BGSB_LAUNCH_CHECK();
+    {
+        // at most cap components per image; the kernel exits early past the real count
+        const int maxc = std::min(c->cap, (int)(((size_t)w * h + 3) / 4 + 1));
+        dim3 rgrid((maxc + 255) / 256, nimages);
+        ccl_resolve_external_kernel<<<rgrid, 256, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_comp, c->d_ncomp,
+                                                               c->cap, c->d_need_bg, w, wpr, ipx, iw);
+        BGSB_LAUNCH_CHECK();
+    }
     c->w = w; c->h = h; c->nimages = nimages; c->last_mask = d_masks; c->last_stream = stream; c->labelled = true;
+    return BGSB_OK;
+}
+
+int bgsb_ccl_set_param(bgsb_ccl *c, const char *key, double v)
+{
+    BGSB_REQUIRE(c && key, "null");
+    if (std::string(key) == "forceBackgroundPass") c->force_bg = (v != 0);
+    else { set_error("bgsb_ccl_set_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
     return BGSB_OK;
 }
 
