@@ -7,6 +7,8 @@
  *   IBGS::process(const cv::Mat&, cv::Mat&, cv::Mat&)            package_bgs/IBGS.h:24
  *     FrameDifferenceBGS::process                                 package_bgs/FrameDifferenceBGS.cpp:29-61
  *     AdaptiveBackgroundLearning::process                         package_bgs/AdaptiveBackgroundLearning.cpp:30-83
+ *     StaticFrameDifferenceBGS::process  (sibling, 8f N3)          package_bgs/StaticFrameDifferenceBGS.cpp:29-57
+ *     WeightedMovingMeanBGS::process     (sibling, 8f N3)          package_bgs/WeightedMovingMeanBGS.cpp:30-103
  *     WeightedMovingVarianceBGS::process                          package_bgs/WeightedMovingVarianceBGS.cpp:30-117
  *     MixtureOfGaussianV2BGS::process                             package_bgs/MixtureOfGaussianV2BGS.cpp:29-74
  *   USTC_BGS::Process / GetMask / Release (CvFGDetector)          ustc_src/ustc_bgs.cpp:75-113
@@ -49,6 +51,8 @@ enum {
 /* algorithm ids == the integer ids of the USTC_BGS factory (ustc_src/ustc_bgs.cpp:8-14) */
 enum {
     BGSB_ALGO_FRAME_DIFFERENCE = 0,           /* ustc_bgs.cpp:8  */
+    BGSB_ALGO_STATIC_FRAME_DIFFERENCE = 1,    /* ustc_bgs.cpp:9   sibling plugin */
+    BGSB_ALGO_WEIGHTED_MOVING_MEAN = 2,       /* ustc_bgs.cpp:10  sibling plugin */
     BGSB_ALGO_WEIGHTED_MOVING_VARIANCE = 3,   /* ustc_bgs.cpp:11 */
     BGSB_ALGO_MOG2 = 5,                       /* ustc_bgs.cpp:13 */
     BGSB_ALGO_ADAPTIVE_BG_LEARNING = 6        /* ustc_bgs.cpp:14 */
@@ -83,7 +87,7 @@ BGSB_API int bgsb_reset(bgsb_ctx *ctx);
  *   all      : "enableThreshold" (1), "threshold" (15)
  *   MOG2     : "alpha" (0.05)             MixtureOfGaussianV2BGS.cpp:92-95
  *   ABL      : "alpha" (0.05), "limit" (-1; only -1 updates the model, .cpp:52)
- *   WMV      : "enableWeight" (1)         WeightedMovingVarianceBGS.cpp:155-158
+ *   WMV, WMM : "enableWeight" (1)         WeightedMovingVarianceBGS.cpp:155-158, WeightedMovingMeanBGS.cpp
  * plus the cv::BackgroundSubtractorMOG2 properties of the default-constructed member
  * (MixtureOfGaussianV2BGS.h:30): "history" 500, "nmixtures" 5 (fixed), "varThreshold" 16,
  * "varThresholdGen" 9, "backgroundRatio" 0.9, "varInit" 15, "varMin" 4, "varMax" 75,
@@ -100,7 +104,7 @@ BGSB_API int bgsb_get_param(bgsb_ctx *ctx, const char *key, double *value);
  *   bg         : h x w 8UC3, may be NULL (background model not wanted)
  *   *fg_valid  : 0 reproduces "output left untouched" (FD frame 0, WMV frames 0-1:
  *                FrameDifferenceBGS.cpp:39-43, WeightedMovingVarianceBGS.cpp:40-51)
- *   *bg_valid  : 0 for FD / WMV, which never write img_bgmodel
+ *   *bg_valid  : 0 for FD / WMV, which never write img_bgmodel (StaticFD / WMM / ABL / MOG2 do)
  * For a stream group the buffers hold nstreams images back to back (stride * h bytes each). */
 BGSB_API int bgsb_process(bgsb_ctx *ctx, const uint8_t *bgr, int w, int h, size_t stride,
                           uint8_t *fg, size_t fg_stride, uint8_t *bg, size_t bg_stride,

@@ -82,6 +82,51 @@ ORC_API void orc_fd(const uint8_t *prev, const uint8_t *cur, int npx,
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* StaticFrameDifference (package_bgs/StaticFrameDifferenceBGS.cpp:29-57): the background is   */
+/* the first frame, frozen (:34-35); fg = thr(gray(absdiff(in, bg))) (:42-48).                 */
+/* Same arithmetic as orc_fd with prev := the frozen background.                               */
+/* ------------------------------------------------------------------------------------ */
+ORC_API void orc_sfd(const uint8_t *bg, const uint8_t *cur, int npx, int enable_thr, int thr,
+                     int gray_variant, uint8_t *fg)
+{
+    orc_fd(bg, cur, npx, enable_thr, thr, gray_variant, fg);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* WeightedMovingMean (package_bgs/WeightedMovingMeanBGS.cpp:30-103)                           */
+/*   bg_f = 0.5 x0 + 0.3 x1 + 0.2 x2 (:61-62; addWeighted then scaleAdd, as in WMV) or          */
+/*          (x0 + x1 + x2)/3.0 (:64): MatExpr lowers it to cv::add(x0,x1) then                   */
+/*          addWeighted(t, 1/3., x2, 1/3.) [upstream matop.cpp MatOp_AddEx]                      */
+/*   bg8 = sat_u8(rint(bg_f*255)) (:70); fg = thr(gray(absdiff(in, bg8))) (:76-82)               */
+/* ------------------------------------------------------------------------------------ */
+ORC_API void orc_wmm(const uint8_t *cur, const uint8_t *p1, const uint8_t *p2, int npx,
+                     int enable_weight, int enable_thr, int thr, int gray_variant, uint8_t *fg, uint8_t *bgout)
+{
+    const float s = (float)(1. / 255.);
+    for (int i = 0; i < npx; i++) {
+        unsigned d[3];
+        for (int c = 0; c < 3; c++) {
+            float x0 = (float)cur[3 * i + c] * s;
+            float x1 = (float)p1[3 * i + c] * s;
+            float x2 = (float)p2[3 * i + c] * s;
+            float m;
+            if (enable_weight) {
+                float m01 = (float)((double)x0 * 0.5 + (double)x1 * 0.3);
+                m = fmaf(x2, (float)0.2, m01);
+            } else {
+                float t = x0 + x1;
+                m = (float)((double)t * (1. / 3.0) + (double)x2 * (1. / 3.0));
+            }
+            uint8_t b8 = sat_u8_rint(m * 255.f);
+            bgout[3 * i + c] = b8;
+            int a = cur[3 * i + c];
+            d[c] = (unsigned)(a > b8 ? a - b8 : b8 - a);
+        }
+        fg[i] = thr_u8(gray_bgr(d[0], d[1], d[2], gray_variant), enable_thr, thr);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* AdaptiveBackgroundLearning (package_bgs/AdaptiveBackgroundLearning.cpp:43-71)          */
 /*   bg is the 8-bit model state (img_background), updated in place and is also the       */
 /*   img_bgmodel output (:80).                                                            */

@@ -50,6 +50,61 @@ class FrameDifferenceBGS:
         return fg, None
 
 
+class StaticFrameDifferenceBGS:
+    """package_bgs/StaticFrameDifferenceBGS.cpp:29-57."""
+
+    def __init__(self, enableThreshold=True, threshold=15):
+        self.enableThreshold, self.threshold = enableThreshold, threshold
+        self.bg = None
+
+    def process(self, img):
+        if img is None or img.size == 0:
+            return None, None
+        if self.bg is None:                        # :34-35
+            self.bg = img.copy()
+        fg = cv2.absdiff(img, self.bg)             # :42
+        if fg.ndim == 3 and fg.shape[2] == 3:
+            fg = cv2.cvtColor(fg, cv2.COLOR_BGR2GRAY)        # :44-45
+        fg = _thr(fg, self.enableThreshold, self.threshold)  # :47-48
+        return fg, self.bg.copy()                  # :53-54
+
+
+class WeightedMovingMeanBGS:
+    """package_bgs/WeightedMovingMeanBGS.cpp:30-103."""
+
+    def __init__(self, enableWeight=True, enableThreshold=True, threshold=15):
+        self.enableWeight, self.enableThreshold, self.threshold = enableWeight, enableThreshold, threshold
+        self.p1 = None
+        self.p2 = None
+
+    def process(self, img):
+        if img is None or img.size == 0:
+            return None, None
+        if self.p1 is None:                        # :40-44
+            self.p1 = img.copy()
+            return None, None
+        if self.p2 is None:                        # :46-51
+            self.p2 = self.p1.copy()
+            self.p1 = img.copy()
+            return None, None
+        s = np.float32(1.0 / 255.0)
+        x0 = img.astype(np.float32) * s            # :53-60
+        x1 = self.p1.astype(np.float32) * s
+        x2 = self.p2.astype(np.float32) * s
+        if self.enableWeight:                      # :61-62  (A*.5 + B*.3) -> addWeighted, + C*.2 -> scaleAdd
+            bg_f = cv2.scaleAdd(x2, 0.2, cv2.addWeighted(x0, 0.5, x1, 0.3, 0))
+        else:                                      # :64     (A + B) -> add, (t + C)/3.0 -> addWeighted(t,1/3.,C,1/3.)
+            bg_f = cv2.addWeighted(cv2.add(x0, x1), 1. / 3.0, x2, 1. / 3.0, 0)
+        bg = _to_u8(bg_f)                          # :70
+        fg = cv2.absdiff(img, bg)                  # :76
+        if fg.ndim == 3 and fg.shape[2] == 3:
+            fg = cv2.cvtColor(fg, cv2.COLOR_BGR2GRAY)        # :78-79
+        fg = _thr(fg, self.enableThreshold, self.threshold)  # :81-82
+        self.p2 = self.p1                          # :90-91
+        self.p1 = img.copy()
+        return fg, bg
+
+
 class AdaptiveBackgroundLearning:
     """package_bgs/AdaptiveBackgroundLearning.cpp:30-83 (limit == -1 branch; the limit>0
     branch is dead because `counter` only advances inside it, :52,60-61)."""
@@ -149,6 +204,8 @@ class MixtureOfGaussianV2BGS:
 
 ALGOS = {
     0: FrameDifferenceBGS,            # ustc_src/ustc_bgs.cpp:8
+    1: StaticFrameDifferenceBGS,      # ustc_src/ustc_bgs.cpp:9   (sibling plugin)
+    2: WeightedMovingMeanBGS,         # ustc_src/ustc_bgs.cpp:10  (sibling plugin)
     3: WeightedMovingVarianceBGS,     # ustc_src/ustc_bgs.cpp:11
     5: MixtureOfGaussianV2BGS,        # ustc_src/ustc_bgs.cpp:13
     6: AdaptiveBackgroundLearning,    # ustc_src/ustc_bgs.cpp:14

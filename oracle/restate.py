@@ -42,6 +42,8 @@ def lib():
         u8p, f32p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_int32)
         L.orc_gray_bgr.argtypes = [u8p, C.c_int, C.c_int, u8p]
         L.orc_fd.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
+        L.orc_sfd.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
+        L.orc_wmm.argtypes = [u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, u8p]
         L.orc_abl.argtypes = [u8p, u8p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, u8p]
         L.orc_wmv.argtypes = [u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
         L.orc_mog2_default_params.argtypes = [C.POINTER(Mog2Params)]
@@ -97,6 +99,54 @@ class FrameDifferenceBGS:
                      self.gray_variant, _u8(fg))
         self.prev = img.copy()
         return fg, None
+
+
+class StaticFrameDifferenceBGS:
+    """package_bgs/StaticFrameDifferenceBGS.cpp:29-57 (sibling plugin)."""
+
+    def __init__(self, enableThreshold=True, threshold=15, gray_variant=0):
+        self.enableThreshold, self.threshold, self.gray_variant = enableThreshold, threshold, gray_variant
+        self.bg = None
+
+    def process(self, img):
+        if img is None or img.size == 0:
+            return None, None
+        img = _dense(img)
+        if self.bg is None:
+            self.bg = img.copy()
+        fg = np.empty(img.shape[:2], np.uint8)
+        lib().orc_sfd(_u8(self.bg), _u8(img), fg.size, int(self.enableThreshold), self.threshold,
+                      self.gray_variant, _u8(fg))
+        return fg, self.bg.copy()
+
+
+class WeightedMovingMeanBGS:
+    """package_bgs/WeightedMovingMeanBGS.cpp:30-103 (sibling plugin)."""
+
+    def __init__(self, enableWeight=True, enableThreshold=True, threshold=15, gray_variant=0):
+        self.enableWeight, self.enableThreshold, self.threshold = enableWeight, enableThreshold, threshold
+        self.gray_variant = gray_variant
+        self.p1 = None
+        self.p2 = None
+
+    def process(self, img):
+        if img is None or img.size == 0:
+            return None, None
+        img = _dense(img)
+        if self.p1 is None:
+            self.p1 = img.copy()
+            return None, None
+        if self.p2 is None:
+            self.p2 = self.p1
+            self.p1 = img.copy()
+            return None, None
+        fg = np.empty(img.shape[:2], np.uint8)
+        bg = np.empty(img.shape, np.uint8)
+        lib().orc_wmm(_u8(img), _u8(self.p1), _u8(self.p2), fg.size, int(self.enableWeight),
+                      int(self.enableThreshold), self.threshold, self.gray_variant, _u8(fg), _u8(bg))
+        self.p2 = self.p1
+        self.p1 = img.copy()
+        return fg, bg
 
 
 class AdaptiveBackgroundLearning:
@@ -185,7 +235,8 @@ class MixtureOfGaussianV2BGS:
         return fg, bg
 
 
-ALGOS = {0: FrameDifferenceBGS, 3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS,
+ALGOS = {0: FrameDifferenceBGS, 1: StaticFrameDifferenceBGS, 2: WeightedMovingMeanBGS,
+         3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS,
          6: AdaptiveBackgroundLearning}          # ids of ustc_src/ustc_bgs.cpp:8-14
 
 

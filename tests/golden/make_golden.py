@@ -29,8 +29,8 @@ from oracle import cv2_chain as ref          # noqa: E402
 from oracle import blobdetect as ref_bd      # noqa: E402
 
 REF = "/root/reference"
-NAMES = {0: "FrameDifferenceBGS", 3: "WeightedMovingVarianceBGS", 5: "MixtureOfGaussianV2BGS",
-         6: "AdaptiveBackgroundLearning"}
+NAMES = {0: "FrameDifferenceBGS", 1: "StaticFrameDifferenceBGS", 2: "WeightedMovingMeanBGS",
+         3: "WeightedMovingVarianceBGS", 5: "MixtureOfGaussianV2BGS", 6: "AdaptiveBackgroundLearning"}
 
 
 def sha(arrs):

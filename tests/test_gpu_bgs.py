@@ -8,8 +8,8 @@ from conftest import stress_sequence
 
 pytestmark = pytest.mark.gpu
 
-NAMES = {0: "FrameDifferenceBGS", 3: "WeightedMovingVarianceBGS", 5: "MixtureOfGaussianV2BGS",
-         6: "AdaptiveBackgroundLearning"}
+NAMES = {0: "FrameDifferenceBGS", 1: "StaticFrameDifferenceBGS", 2: "WeightedMovingMeanBGS",
+         3: "WeightedMovingVarianceBGS", 5: "MixtureOfGaussianV2BGS", 6: "AdaptiveBackgroundLearning"}
 # north_star tolerances: FD bit-exact; MOG2/ABL/WMV masks <= 0.1 % disagreement, bg <= 1e-4 relative.
 # The kernels are in fact bit-exact on every fixture, so the tests assert 0 mismatches and would
 # start failing long before the contractual tolerance is reached.
@@ -43,7 +43,7 @@ def assert_same(a, b, what):
 
 
 @pytest.mark.parametrize("seq", ["video_clip", "png_clip"])
-@pytest.mark.parametrize("aid", [0, 3, 5, 6])
+@pytest.mark.parametrize("aid", [0, 1, 2, 3, 5, 6])
 @pytest.mark.parametrize("thr", [True, False])
 def test_host_path_matches_golden_and_oracle(oracle, clips, golden, seq, aid, thr):
     import tracking_b200 as tb
@@ -169,6 +169,22 @@ def test_abl_exhaustive_byte_pairs(oracle):
         assert np.array_equal(fa, fb) and np.array_equal(ba, bb)
 
 
+def test_wmm_unweighted_and_raw(oracle):
+    """WeightedMovingMean sibling plugin: (x0+x1+x2)/3.0 branch and un-thresholded output."""
+    import tracking_b200 as tb
+    rng = np.random.default_rng(12)
+    frames = [rng.integers(0, 256, (131, 177, 3), dtype=np.uint8) for _ in range(6)]
+    for ew, thr in ((1, 1), (0, 1), (1, 0), (0, 0)):
+        p = tb.WeightedMovingMeanBGS(enableWeight=ew, enableThreshold=thr)
+        o = oracle.WeightedMovingMeanBGS(enableWeight=bool(ew), enableThreshold=bool(thr))
+        for f in frames:
+            fa, ba = p.process(f)
+            fb, bb = o.process(f)
+            assert (fa is None) == (fb is None) and (ba is None) == (bb is None)
+            if fa is not None:
+                assert np.array_equal(fa, fb) and np.array_equal(ba, bb)
+
+
 def test_wmv_exhaustive_triples_sample(oracle):
     """Random byte triples incl. unweighted variant and raw (un-thresholded) output."""
     import tracking_b200 as tb
@@ -186,7 +202,7 @@ def test_wmv_exhaustive_triples_sample(oracle):
                     assert np.array_equal(fa, fb)
 
 
-@pytest.mark.parametrize("aid", [0, 3, 5, 6])
+@pytest.mark.parametrize("aid", [0, 1, 2, 3, 5, 6])
 def test_gray_variant_24_constants(oracle, clips, aid):
     import tracking_b200 as tb
     if aid == 5:
@@ -199,7 +215,7 @@ def test_gray_variant_24_constants(oracle, clips, aid):
     assert_same(a, b, "gray 2.4")
 
 
-@pytest.mark.parametrize("aid", [0, 3, 5, 6])
+@pytest.mark.parametrize("aid", [0, 1, 2, 3, 5, 6])
 @pytest.mark.parametrize("T", [1, 3, 8])
 def test_device_batch_and_stream_group(oracle, clips, aid, T):
     """Temporal batches of T frames and a group of 3 streams advanced by one launch equal the
@@ -213,7 +229,7 @@ def test_device_batch_and_stream_group(oracle, clips, aid, T):
     h, w = clip.shape[1:3]
     p = tb.ALGOS[aid](nstreams=S)
     oracles = [oracle.ALGOS[aid]() for _ in range(S)]
-    has_bg = aid in (5, 6)
+    has_bg = aid in (1, 2, 5, 6)
     for t0 in range(0, n, T):
         host = np.stack([np.stack([streams[s][t0 + t] for t in range(T)]) for s in range(S)])   # S,T,h,w,3
         d_in = torch.from_numpy(host).cuda()
@@ -223,7 +239,7 @@ def test_device_batch_and_stream_group(oracle, clips, aid, T):
                                          stream=torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         fg, bg = d_fg.cpu().numpy(), d_bg.cpu().numpy()
-        assert bgv == has_bg
+        assert bgv == (has_bg and first < T)
         for s in range(S):
             for t in range(T):
                 ofg, obg = oracles[s].process(streams[s][t0 + t])

@@ -13,8 +13,8 @@ import pytest
 
 from conftest import REFERENCE_DIR, stress_sequence
 
-NAMES = {0: "FrameDifferenceBGS", 3: "WeightedMovingVarianceBGS", 5: "MixtureOfGaussianV2BGS",
-         6: "AdaptiveBackgroundLearning"}
+NAMES = {0: "FrameDifferenceBGS", 1: "StaticFrameDifferenceBGS", 2: "WeightedMovingMeanBGS",
+         3: "WeightedMovingVarianceBGS", 5: "MixtureOfGaussianV2BGS", 6: "AdaptiveBackgroundLearning"}
 
 
 def sha(arrs):
@@ -37,7 +37,7 @@ def run(algo_cls, frames, **kw):
 
 
 @pytest.mark.parametrize("seq", ["video_clip", "png_clip"])
-@pytest.mark.parametrize("aid", [0, 3, 5, 6])
+@pytest.mark.parametrize("aid", [0, 1, 2, 3, 5, 6])
 @pytest.mark.parametrize("thr", [True, False])
 def test_c_oracle_matches_golden_hashes(oracle, clips, golden, seq, aid, thr):
     frames = list(clips[seq])
@@ -52,7 +52,7 @@ def test_c_oracle_matches_golden_hashes(oracle, clips, golden, seq, aid, thr):
         assert sha(bgs) == exp["bg_sha256"]                   # byte-exact background model
 
 
-@pytest.mark.parametrize("aid", [0, 3, 5, 6])
+@pytest.mark.parametrize("aid", [0, 1, 2, 3, 5, 6])
 def test_c_oracle_matches_opencv_live(oracle, clips, aid):
     """Same comparison against cv2 running live (the image on the GPU box has cv2 too)."""
     from oracle import cv2_chain
@@ -65,7 +65,7 @@ def test_c_oracle_matches_opencv_live(oracle, clips, aid):
 
 
 @pytest.mark.skipif(not os.path.exists(REFERENCE_DIR), reason="reference data only exists in the build container")
-@pytest.mark.parametrize("aid", [0, 3, 5, 6])
+@pytest.mark.parametrize("aid", [0, 1, 2, 3, 5, 6])
 def test_c_oracle_full_reference_sequences(oracle, golden, aid):
     """All 374 frames of dataset/video.avi and all 51 frames/N.png (BASELINE config 1 inputs)."""
     import cv2

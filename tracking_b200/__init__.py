@@ -6,8 +6,9 @@ Python host-side mirror of the reference's plugin interface; the C++ drop-in ada
 tracking_b200/adapters/.  There is no CPU fallback.
 """
 from .bgs import (ALGOS, USTC_BGS, AdaptiveBackgroundLearning, FrameDifferenceBGS,  # noqa: F401
-                  MixtureOfGaussianV2BGS, WeightedMovingVarianceBGS)
+                  MixtureOfGaussianV2BGS, StaticFrameDifferenceBGS, WeightedMovingMeanBGS,
+                  WeightedMovingVarianceBGS)
 from .capi import BgsbError, kernel_launch_count  # noqa: F401
 
-__all__ = ["FrameDifferenceBGS", "WeightedMovingVarianceBGS", "AdaptiveBackgroundLearning",
+__all__ = ["FrameDifferenceBGS", "StaticFrameDifferenceBGS", "WeightedMovingMeanBGS", "WeightedMovingVarianceBGS", "AdaptiveBackgroundLearning",
            "MixtureOfGaussianV2BGS", "USTC_BGS", "ALGOS", "BgsbError", "kernel_launch_count"]

@@ -1,4 +1,4 @@
-// Drop-in replacements for four plugins of the reference, same class names, same public shape, same
+// Drop-in replacements for four plugins of the reference (plus two siblings of the same family), same class names, same public shape, same
 // XML keys and files, same stdout banners and imshow windows -- the arithmetic runs on a B200 through
 // the C ABI of include/bgsb200.h (libbgsb200.so).  Header-only; link with -lbgsb200.
 //
@@ -103,6 +103,114 @@ private:
     threshold = cvReadIntByName(fs, 0, "threshold", 15);
     showOutput = cvReadIntByName(fs, 0, "showOutput", true);
     cvReleaseFileStorage(&fs);
+    set("enableThreshold", enableThreshold);
+    set("threshold", threshold);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sibling plugins, same wrapper pattern.
+class StaticFrameDifferenceBGS : public bgsb_adapter::PluginBase
+{
+private:
+  bool enableThreshold;
+  int threshold;
+  bool showOutput;
+
+public:
+  StaticFrameDifferenceBGS() : PluginBase(BGSB_ALGO_STATIC_FRAME_DIFFERENCE), enableThreshold(true), threshold(15), showOutput(true)
+  {
+    std::cout << "StaticFrameDifferenceBGS()" << std::endl;
+  }
+  ~StaticFrameDifferenceBGS() { std::cout << "~StaticFrameDifferenceBGS()" << std::endl; }
+
+  void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
+  {
+    if (img_input.empty()) return;
+    loadConfig();
+    if (firstTime) saveConfig();
+    bool fg, bg;
+    run(img_input, fg, bg, true);
+    if (showOutput) cv::imshow("Static Frame Difference", img_foreground);
+    img_foreground.copyTo(img_output);       // StaticFrameDifferenceBGS.cpp:53-54
+    img_background.copyTo(img_bgmodel);
+    firstTime = false;
+  }
+
+private:
+  void saveConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/StaticFrameDifferenceBGS.xml", 0, CV_STORAGE_WRITE);
+    cvWriteInt(fs, "enableThreshold", enableThreshold);
+    cvWriteInt(fs, "threshold", threshold);
+    cvWriteInt(fs, "showOutput", showOutput);
+    cvReleaseFileStorage(&fs);
+  }
+  void loadConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/StaticFrameDifferenceBGS.xml", 0, CV_STORAGE_READ);
+    enableThreshold = cvReadIntByName(fs, 0, "enableThreshold", true);
+    threshold = cvReadIntByName(fs, 0, "threshold", 15);
+    showOutput = cvReadIntByName(fs, 0, "showOutput", true);
+    cvReleaseFileStorage(&fs);
+    set("enableThreshold", enableThreshold);
+    set("threshold", threshold);
+  }
+};
+
+class WeightedMovingMeanBGS : public bgsb_adapter::PluginBase
+{
+private:
+  bool enableWeight;
+  bool enableThreshold;
+  int threshold;
+  bool showOutput;
+  bool showBackground;
+
+public:
+  WeightedMovingMeanBGS() : PluginBase(BGSB_ALGO_WEIGHTED_MOVING_MEAN), enableWeight(true), enableThreshold(true),
+    threshold(15), showOutput(true), showBackground(false)
+  {
+    std::cout << "WeightedMovingMeanBGS()" << std::endl;
+  }
+  ~WeightedMovingMeanBGS() { std::cout << "~WeightedMovingMeanBGS()" << std::endl; }
+
+  void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
+  {
+    if (img_input.empty()) return;
+    loadConfig();
+    if (firstTime) saveConfig();
+    bool fg, bg;
+    run(img_input, fg, bg, true);
+    if (!fg) return;                         // first two frames fill the history (WeightedMovingMeanBGS.cpp:40-51)
+    if (showBackground) cv::imshow("W Moving Mean BG Model", img_background);
+    if (showOutput) cv::imshow("W Moving Mean FG Mask", img_foreground);
+    img_foreground.copyTo(img_output);       // :87-88
+    img_background.copyTo(img_bgmodel);
+    firstTime = false;
+  }
+
+private:
+  void saveConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/WeightedMovingMeanBGS.xml", 0, CV_STORAGE_WRITE);
+    cvWriteInt(fs, "enableWeight", enableWeight);
+    cvWriteInt(fs, "enableThreshold", enableThreshold);
+    cvWriteInt(fs, "threshold", threshold);
+    cvWriteInt(fs, "showOutput", showOutput);
+    cvWriteInt(fs, "showBackground", showBackground);
+    cvReleaseFileStorage(&fs);
+  }
+  void loadConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/WeightedMovingMeanBGS.xml", 0, CV_STORAGE_READ);
+    enableWeight = cvReadIntByName(fs, 0, "enableWeight", true);
+    enableThreshold = cvReadIntByName(fs, 0, "enableThreshold", true);
+    threshold = cvReadIntByName(fs, 0, "threshold", 15);
+    showOutput = cvReadIntByName(fs, 0, "showOutput", true);
+    showBackground = cvReadIntByName(fs, 0, "showBackground", false);
+    cvReleaseFileStorage(&fs);
+    set("enableWeight", enableWeight);
     set("enableThreshold", enableThreshold);
     set("threshold", threshold);
   }

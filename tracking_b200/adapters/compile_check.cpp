@@ -4,10 +4,10 @@
 int compile_check_calls()
 {
     // FrameProcessor.cpp:40-59,157-167 pattern
-    IBGS *plugins[4] = {new FrameDifferenceBGS, new WeightedMovingVarianceBGS, new MixtureOfGaussianV2BGS,
-                        new AdaptiveBackgroundLearning};
+    IBGS *plugins[6] = {new FrameDifferenceBGS, new WeightedMovingVarianceBGS, new MixtureOfGaussianV2BGS,
+                        new AdaptiveBackgroundLearning, new StaticFrameDifferenceBGS, new WeightedMovingMeanBGS};
     cv::Mat img_input, img_bgs, img_bkgmodel;
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < 6; i++) {
         plugins[i]->process(img_input, img_bgs, img_bkgmodel);
         delete plugins[i];
     }

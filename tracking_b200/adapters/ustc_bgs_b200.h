@@ -31,10 +31,12 @@ public:
         CV_Assert(type >= 0 && type <= 37);                 // ustc_bgs.cpp:6
         switch (type) {
         case 0: bgs = new FrameDifferenceBGS; break;        // ustc_bgs.cpp:8
+        case 1: bgs = new StaticFrameDifferenceBGS; break;  // :9
+        case 2: bgs = new WeightedMovingMeanBGS; break;     // :10
         case 3: bgs = new WeightedMovingVarianceBGS; break; // :11
         case 5: bgs = new MixtureOfGaussianV2BGS; break;    // :13
         case 6: bgs = new AdaptiveBackgroundLearning; break;// :14
-        default: CV_Assert(!"this plugin id is not on the B200 hot path (0 FD, 3 WMV, 5 MOG2, 6 ABL)");
+        default: CV_Assert(!"this plugin id is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL)");
         }
     }
     ~USTC_BGS() {}

@@ -117,6 +117,16 @@ class FrameDifferenceBGS(_Plugin):
     ALGO = capi.ALGO_FRAME_DIFFERENCE
 
 
+class StaticFrameDifferenceBGS(_Plugin):
+    """package_bgs/StaticFrameDifferenceBGS.cpp (sibling plugin); keys enableThreshold, threshold."""
+    ALGO = capi.ALGO_STATIC_FRAME_DIFFERENCE
+
+
+class WeightedMovingMeanBGS(_Plugin):
+    """package_bgs/WeightedMovingMeanBGS.cpp (sibling plugin); keys enableWeight, enableThreshold, threshold."""
+    ALGO = capi.ALGO_WEIGHTED_MOVING_MEAN
+
+
 class WeightedMovingVarianceBGS(_Plugin):
     """package_bgs/WeightedMovingVarianceBGS.cpp; keys enableWeight, enableThreshold, threshold (:155-158)."""
     ALGO = capi.ALGO_WEIGHTED_MOVING_VARIANCE
@@ -148,8 +158,8 @@ class MixtureOfGaussianV2BGS(_Plugin):
 
 
 # integer ids of the USTC_BGS factory (ustc_src/ustc_bgs.cpp:8-14)
-ALGOS = {0: FrameDifferenceBGS, 3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS,
-         6: AdaptiveBackgroundLearning}
+ALGOS = {0: FrameDifferenceBGS, 1: StaticFrameDifferenceBGS, 2: WeightedMovingMeanBGS,
+         3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS, 6: AdaptiveBackgroundLearning}
 
 
 class USTC_BGS:
@@ -157,7 +167,7 @@ class USTC_BGS:
 
     def __init__(self, type, device=0):
         if type not in ALGOS:                   # CV_Assert(type>=0 && type<=37), .cpp:6
-            raise ValueError("USTC_BGS type %r is not on the B200 hot path (0 FD, 3 WMV, 5 MOG2, 6 ABL)" % type)
+            raise ValueError("USTC_BGS type %r is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL)" % type)
         self.bgs = ALGOS[type](device=device)
         self.frameNum = 0
         self.img_mask = None

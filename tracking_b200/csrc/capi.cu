@@ -91,7 +91,7 @@ static int ensure_geometry(bgsb_ctx *c, int w, int h)
         BGSB_CUDA(cudaMemsetAsync(c->d_nmodes, 0, S * c->pstride, c->stream));
         BGSB_CUDA(cudaStreamSynchronize(c->stream));
     } else {
-        int nh = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE) ? 2 : 1;
+        int nh = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE || c->algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN) ? 2 : 1;
         for (int i = 0; i < nh; i++) BGSB_CUDA(cudaMalloc(&c->d_hist[i], S * c->npx * 3));
     }
     return BGSB_OK;
@@ -101,12 +101,13 @@ static int ensure_host_staging(bgsb_ctx *c)
 {
     const size_t S = (size_t)c->nstreams;
     if (!c->d_ring[0]) {
-        int nr = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE) ? 3 : (c->algo == BGSB_ALGO_FRAME_DIFFERENCE ? 2 : 1);
+        const bool two = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE || c->algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN);
+        int nr = two ? 3 : (c->algo == BGSB_ALGO_FRAME_DIFFERENCE ? 2 : 1);
         for (int i = 0; i < nr; i++) BGSB_CUDA(cudaMalloc(&c->d_ring[i], S * c->npx * 3));
         c->ring_pos = 0;
     }
     if (!c->d_fg) BGSB_CUDA(cudaMalloc(&c->d_fg, S * c->npx));
-    if (!c->d_bg && (c->algo == BGSB_ALGO_MOG2 || c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING))
+    if (!c->d_bg && c->algo != BGSB_ALGO_FRAME_DIFFERENCE && c->algo != BGSB_ALGO_WEIGHTED_MOVING_VARIANCE)
         BGSB_CUDA(cudaMalloc(&c->d_bg, S * c->npx * 3));
     return BGSB_OK;
 }
@@ -122,7 +123,26 @@ static cudaError_t copy_rows(void *dst, size_t dpitch, const void *src, size_t s
 
 static int warmup_frames(int algo)
 {
-    return algo == BGSB_ALGO_FRAME_DIFFERENCE ? 1 : (algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE ? 2 : 0);
+    if (algo == BGSB_ALGO_FRAME_DIFFERENCE) return 1;
+    if (algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN) return 2;
+    return 0;
+}
+// history images a plugin keeps: FD 1 (previous frame), WMV/WMM 2, ABL/StaticFD 1 (8-bit background)
+static int history_images(int algo)
+{
+    if (algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN) return 2;
+    return algo == BGSB_ALGO_MOG2 ? 0 : 1;
+}
+// FD / WMV / WMM: the history is the previous input frame(s) -> on the host path it lives in the upload ring
+static bool ring_history(int algo)
+{
+    return algo == BGSB_ALGO_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE ||
+           algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN;
+}
+static bool writes_background(int algo)
+{
+    return algo == BGSB_ALGO_MOG2 || algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING ||
+           algo == BGSB_ALGO_STATIC_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN;
 }
 
 // Advance the model by T frames that sit in device memory.  `own_history`: write FD/WMV history
@@ -164,7 +184,9 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
         L.hist1 = c->hist_ptr[1] ? c->hist_ptr[1] + p0 * 3 : nullptr;
         L.hist0_out = (own_history && c->d_hist[0]) ? c->d_hist[0] + p0 * 3 : nullptr;
         L.hist1_out = (own_history && c->d_hist[1]) ? c->d_hist[1] + p0 * 3 : nullptr;
-        if (c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING) { L.hist0 = c->d_hist[0] + p0 * 3; L.hist0_out = c->d_hist[0] + p0 * 3; }
+        if (c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING || c->algo == BGSB_ALGO_STATIC_FRAME_DIFFERENCE) {
+            L.hist0 = c->d_hist[0] + p0 * 3; L.hist0_out = c->d_hist[0] + p0 * 3;    // the 8-bit background model
+        }
         L.npx = pcount; L.T = T; L.have_hist = c->have_hist; L.bg_last_only = bg_last_only;
         L.enable_thr = c->enable_thr; L.thr = c->thr; L.gray_variant = c->gray_variant;
         L.alpha = c->alpha;
@@ -181,7 +203,7 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
 static void advance(bgsb_ctx *c, int T, bool own_history)
 {
     if (c->algo != BGSB_ALGO_MOG2 && own_history) {
-        int need = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE) ? 2 : 1;
+        int need = history_images(c->algo);
         c->have_hist = (int)std::min<int64_t>(need, (int64_t)c->have_hist + T);
         c->hist_ptr[0] = c->d_hist[0]; c->hist_ptr[1] = c->d_hist[1];
     }
@@ -216,8 +238,9 @@ int bgsb_create_group(bgsb_ctx **out, int algo, int device, int nstreams)
 {
     BGSB_REQUIRE(out, "null out");
     BGSB_REQUIRE(algo == BGSB_ALGO_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE ||
-                 algo == BGSB_ALGO_MOG2 || algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING,
-                 "unknown algorithm id (USTC_BGS ids: 0 FD, 3 WMV, 5 MOG2, 6 ABL)");
+                 algo == BGSB_ALGO_MOG2 || algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING ||
+                 algo == BGSB_ALGO_STATIC_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN,
+                 "unknown algorithm id (USTC_BGS ids: 0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL)");
     BGSB_REQUIRE(nstreams >= 1 && nstreams <= 65535, "nstreams out of range");
     BGSB_CUDA(cudaSetDevice(device));
     bgsb_ctx *c = new bgsb_ctx();
@@ -321,7 +344,7 @@ int bgsb_state_bytes(bgsb_ctx *c, size_t *bytes)
 {
     BGSB_REQUIRE(c && bytes, "null");
     if (c->algo == BGSB_ALGO_MOG2) *bytes = (size_t)c->npx * (MOG2_PLANES * 4 + 1);
-    else if (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE) *bytes = (size_t)c->npx * 6;
+    else if (history_images(c->algo) == 2) *bytes = (size_t)c->npx * 6;
     else *bytes = (size_t)c->npx * 3;
     return BGSB_OK;
 }
@@ -337,8 +360,9 @@ int bgsb_process_batch_dev(bgsb_ctx *c, const uint8_t *d_frames, int T, int w, i
     int warm = warmup_frames(c->algo);
     int64_t first = std::max<int64_t>(0, warm - c->nframes);
     if (first_fg_valid) *first_fg_valid = (int)std::min<int64_t>(first, T);
-    if (bg_valid) *bg_valid = (c->algo == BGSB_ALGO_MOG2 || c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING) && d_bg;
-    bool has_bg = (c->algo == BGSB_ALGO_MOG2 || c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING);
+    bool has_bg = writes_background(c->algo);
+    // WMM writes its background only from the third frame on (WeightedMovingMeanBGS.cpp:40-51)
+    if (bg_valid) *bg_valid = has_bg && d_bg && (first < T);
     return run_frames(c, d_frames, T, d_fg, has_bg ? d_bg : nullptr, bg_last_only, true, (cudaStream_t)stream);
 }
 
@@ -363,12 +387,12 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
     rc = ensure_host_staging(c);
     if (rc) return rc;
     const size_t rows = (size_t)h * c->nstreams;
-    const bool fdlike = (c->algo == BGSB_ALGO_FRAME_DIFFERENCE || c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE);
-    const int nring = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE) ? 3 : 2;
+    const bool fdlike = ring_history(c->algo);
+    const int nring = history_images(c->algo) + 1;
     uint8_t *d_in = fdlike ? c->d_ring[c->ring_pos] : c->d_ring[0];
     const int warm = warmup_frames(c->algo);
     const bool out_fg = c->nframes >= warm;
-    const bool has_bg = (c->algo == BGSB_ALGO_MOG2 || c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING);
+    const bool has_bg = writes_background(c->algo);
     const bool want_bg = has_bg && bg;
     // FD / WMV: history = the previous upload(s) in the ring -- no copy, the frame is read once
     const bool own_hist = !fdlike;
@@ -430,7 +454,7 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
         c->ring_pos = (c->ring_pos + 1) % nring;
     }
     if (fg_valid) *fg_valid = out_fg;
-    if (bg_valid) *bg_valid = want_bg ? 1 : 0;
+    if (bg_valid) *bg_valid = (want_bg && out_fg) ? 1 : 0;
     return BGSB_OK;
 }
 
