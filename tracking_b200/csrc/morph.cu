@@ -217,25 +217,41 @@ int bgsb_morph_dev(const uint8_t *d_mask, int w, int h, int nimages, const int *
     return launch_morph_chain(d_mask, d_out, w, h, nimages, ops, nops, (cudaStream_t)stream);
 }
 
+// Host-buffer convenience call (cvErode(mask, mask, NULL, n) pattern).  The two device staging buffers are cached
+// per host thread and device (grow-only) so that a per-frame caller does not pay cudaMalloc/cudaFree every call.
+namespace {
+struct MorphScratch {
+    uint8_t *a = nullptr, *b = nullptr;
+    size_t cap = 0;
+    int device = -1;
+    ~MorphScratch() { if (a) cudaFree(a); if (b) cudaFree(b); }
+};
+thread_local MorphScratch g_morph_scratch;
+}  // namespace
+
 int bgsb_morph(const uint8_t *mask, int w, int h, size_t stride, const int *ops, int nops, uint8_t *out,
                size_t out_stride)
 {
     BGSB_REQUIRE(mask && out, "null");
     BGSB_REQUIRE(w > 0 && h > 0, "empty image");
     BGSB_REQUIRE(stride >= (size_t)w && out_stride >= (size_t)w, "stride smaller than a row");
-    uint8_t *d_a = nullptr, *d_b = nullptr;
     const size_t bytes = (size_t)w * h;
-    BGSB_CUDA(cudaMalloc(&d_a, bytes));
-    if (cudaMalloc(&d_b, bytes) != cudaSuccess) { cudaFree(d_a); set_error("cudaMalloc failed"); return BGSB_ERR_CUDA; }
-    int rc = BGSB_OK;
-    cudaError_t e = cudaMemcpy2D(d_a, w, mask, stride, w, h, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        rc = launch_morph_chain(d_a, d_b, w, h, 1, ops, nops, nullptr);
-        if (rc == BGSB_OK) e = cudaMemcpy2D(out, out_stride, d_b, w, w, h, cudaMemcpyDeviceToHost);
+    int dev = 0;
+    BGSB_CUDA(cudaGetDevice(&dev));
+    MorphScratch &S = g_morph_scratch;
+    if (S.device != dev || S.cap < bytes) {
+        if (S.a) cudaFree(S.a);
+        if (S.b) cudaFree(S.b);
+        S.a = S.b = nullptr; S.cap = 0; S.device = dev;
+        BGSB_CUDA(cudaMalloc(&S.a, bytes));
+        BGSB_CUDA(cudaMalloc(&S.b, bytes));
+        S.cap = bytes;
     }
-    cudaFree(d_a); cudaFree(d_b);
-    if (e != cudaSuccess) { set_error("bgsb_morph: %s", cudaGetErrorString(e)); return BGSB_ERR_CUDA; }
-    return rc;
+    BGSB_CUDA(cudaMemcpy2D(S.a, w, mask, stride, w, h, cudaMemcpyHostToDevice));
+    int rc = launch_morph_chain(S.a, S.b, w, h, 1, ops, nops, nullptr);
+    if (rc) return rc;
+    BGSB_CUDA(cudaMemcpy2D(out, out_stride, S.b, w, w, h, cudaMemcpyDeviceToHost));
+    return BGSB_OK;
 }
 
 }  // extern "C"
