@@ -94,7 +94,8 @@ BGSB_API int bgsb_reset(bgsb_ctx *ctx);
  * "complexityReductionThreshold" 0.05, "detectShadows" 1, "shadowValue" 127,
  * "shadowThreshold" 0.5; and "grayVariant": 0 = OpenCV 4.x BGR2GRAY constants, 1 = 2.4.x;
  * "kernelVariant" (MOG2): 0 = production kernels, 1 = straight restatement kernel, 2 / 3 = earlier
- * generations of the fast kernel -- identical results, kept for A/B measurements. */
+ * generations of the fast kernel -- identical results, kept for A/B measurements;
+ * "hostBands" (default 4, 1..8): row bands of the upload / kernel / download pipeline inside bgsb_process. */
 BGSB_API int bgsb_set_param(bgsb_ctx *ctx, const char *key, double value);
 BGSB_API int bgsb_get_param(bgsb_ctx *ctx, const char *key, double *value);
 

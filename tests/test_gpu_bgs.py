@@ -301,6 +301,30 @@ def test_strided_host_input_and_reset(oracle):
     assert (fg == 255).all() and np.array_equal(bg, f2)
 
 
+@pytest.mark.parametrize("aid", [0, 2, 5, 6])
+def test_host_path_band_pipeline_large_frames(oracle, aid):
+    """bgsb_process on frames >= 1 MB cuts the image into row bands (upload / kernel / download overlap);
+    results must not depend on the band count (incl. history kept in the upload ring for FD / WMM)."""
+    import tracking_b200 as tb
+    from tracking_b200 import synth
+    w, h = 1280, 720
+    frames = [synth.frame(w, h, t) for t in range(5)]
+    ref = None
+    for bands in (1, 4, 7):
+        p = tb.ALGOS[aid](hostBands=bands)
+        outs = [p.process(f) for f in frames]
+        if ref is None:
+            o = oracle.ALGOS[aid]()
+            ref = [o.process(f) for f in frames]
+        for (fa, ba), (fb, bb) in zip(outs, ref):
+            assert (fa is None) == (fb is None) and (ba is None) == (bb is None)
+            if fa is not None:
+                assert np.array_equal(fa, fb)
+            if ba is not None:
+                assert np.array_equal(ba, bb)
+        p.close()
+
+
 def test_mog2_state_export_import_roundtrip(clips):
     import tracking_b200 as tb
     clip = clips["video_clip"]

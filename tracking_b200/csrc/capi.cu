@@ -39,6 +39,7 @@ struct bgsb_ctx {
     int history = 500;
     float Tb = 16.f, Tg = 9.f, TB = 0.9f, varInit = 15.f, varMin = 4.f, varMax = 75.f, CT = 0.05f, tau = 0.5f;
     int detect_shadows = 1, shadow_value = 127;
+    int host_bands = 4;        // row bands of the host-path upload/compute/download pipeline (1 = no overlap)
     int mog2_variant = 0;      // see launch_mog2 (mog2.cu): 0 production, 1 straight restatement, 2/3 earlier generations
     // geometry / counters
     int w = 0, h = 0, npx = 0;
@@ -300,6 +301,7 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     else if (k == "detectShadows") c->detect_shadows = (v != 0);
     else if (k == "shadowValue") c->shadow_value = (int)v;
     else if (k == "shadowThreshold") c->tau = (float)v;
+    else if (k == "hostBands") { BGSB_REQUIRE(v >= 1 && v <= 8, "hostBands in [1,8]"); c->host_bands = (int)v; }
     else if (k == "kernelVariant") { BGSB_REQUIRE(v >= 0 && v <= 3 && v == (int)v, "kernelVariant is 0..3"); c->mog2_variant = (int)v; }
     else if (k == "showOutput" || k == "showForeground" || k == "showBackground") { /* GUI only */ }
     else { set_error("bgsb_set_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
@@ -329,6 +331,7 @@ int bgsb_get_param(bgsb_ctx *c, const char *key, double *v)
     else if (k == "shadowValue") *v = c->shadow_value;
     else if (k == "shadowThreshold") *v = c->tau;
     else if (k == "kernelVariant") *v = c->mog2_variant;
+    else if (k == "hostBands") *v = c->host_bands;
     else { set_error("bgsb_get_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
     return BGSB_OK;
 }
@@ -401,8 +404,8 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
     // kernel on band i and the download of band i-1 overlap on three streams (pixels are independent),
     // so a synchronous IBGS::process costs ~max(H2D, D2H) instead of H2D + kernel + D2H.
     int nchunks = 1, band = h;
-    if (c->nstreams == 1 && (size_t)w * h * 3 >= (1u << 20) && out_fg) {
-        band = ((h + 3) / 4 + 31) / 32 * 32;
+    if (c->nstreams == 1 && c->host_bands > 1 && (size_t)w * h * 3 >= (1u << 20) && out_fg) {
+        band = ((h + c->host_bands - 1) / c->host_bands + 31) / 32 * 32;
         nchunks = (h + band - 1) / band;
         if (nchunks > 8) { nchunks = 1; band = h; }
     }
