@@ -80,6 +80,8 @@ static int ensure_geometry(bgsb_ctx *c, int w, int h)
     if (c->w == w && c->h == h) return BGSB_OK;
     BGSB_REQUIRE(w > 0 && h > 0, "empty frame");
     BGSB_REQUIRE((long long)w * h < (1LL << 30), "frame too large");
+    // MOG2 kernels address plane q of a stream with a 32-bit element offset q*pstride (q < 25)
+    BGSB_REQUIRE(c->algo != BGSB_ALGO_MOG2 || (long long)w * h <= (1LL << 27), "MOG2 frames are limited to 2^27 pixels");
     free_buffers(c);
     c->w = w; c->h = h; c->npx = w * h;
     c->pstride = ((size_t)c->npx + 31) / 32 * 32;
