@@ -395,3 +395,45 @@ def test_full_size_1080p_mog2_parity_and_launch_counter(oracle):
     torch.cuda.synchronize()
     assert not d_fg.any().item()
     assert torch.equal(d_bg, d[0, 0])
+
+
+def test_max_size_2160p_parity(oracle):
+    """BASELINE config 5 geometry (3840x2160): MOG2 (T = 1 and a temporal batch) and FD against the C oracle."""
+    import torch
+    import tracking_b200 as tb
+    from tracking_b200 import synth
+    w, h, n = 3840, 2160, 4
+    d = torch.zeros((1, n, h, w, 3), dtype=torch.uint8, device="cuda")
+    synth.frames_dev(d.data_ptr(), 1, n, w, h, t0=3)
+    torch.cuda.synchronize()
+    frames = d.cpu().numpy()[0]
+    assert np.array_equal(frames[1], synth.frame(w, h, 4))          # the 2x-scaled rectangles of the 2160p generator
+    d_fg = torch.zeros((n, h, w), dtype=torch.uint8, device="cuda")
+    d_bg = torch.zeros((n, h, w, 3), dtype=torch.uint8, device="cuda")
+    exp = []
+    o = oracle.MixtureOfGaussianV2BGS()
+    for t in range(n):
+        exp.append(o.process(frames[t]))
+    # frame by frame
+    p = tb.MixtureOfGaussianV2BGS()
+    for t in range(n):
+        p.process_dev(d[0, t].data_ptr(), w, h, d_fg[t].data_ptr(), d_bg[t].data_ptr())
+    torch.cuda.synchronize()
+    for t in range(n):
+        assert np.array_equal(d_fg[t].cpu().numpy(), exp[t][0]) and np.array_equal(d_bg[t].cpu().numpy(), exp[t][1]), t
+    # one temporal batch of all 4 frames
+    q = tb.MixtureOfGaussianV2BGS()
+    d_fg.zero_(); d_bg.zero_()
+    q.process_batch_dev(d.data_ptr(), n, w, h, d_fg.data_ptr(), d_bg.data_ptr())
+    torch.cuda.synchronize()
+    for t in range(n):
+        assert np.array_equal(d_fg[t].cpu().numpy(), exp[t][0]) and np.array_equal(d_bg[t].cpu().numpy(), exp[t][1]), t
+    # FD
+    fd, ofd = tb.FrameDifferenceBGS(), oracle.FrameDifferenceBGS()
+    first, _ = fd.process_batch_dev(d.data_ptr(), n, w, h, d_fg.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert first == 1
+    for t in range(n):
+        e, _ = ofd.process(frames[t])
+        if e is not None:
+            assert np.array_equal(d_fg[t].cpu().numpy(), e), t
