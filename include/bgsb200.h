@@ -66,6 +66,11 @@ typedef struct bgsb_ctx bgsb_ctx;
 BGSB_API const char *bgsb_last_error(void);          /* thread-local text of the last failure */
 BGSB_API const char *bgsb_version(void);
 BGSB_API int bgsb_device_count(int *count);
+/* Page-locked host memory for frame staging (the capture side of the boundary): uploads from
+ * pinned buffers are true DMA.  write_combined != 0 allocates write-combined memory (fast for the CPU to
+ * fill sequentially and for the GPU to read, slow for the CPU to read back: use it for INPUT frames only). */
+BGSB_API int bgsb_host_alloc(void **ptr, size_t bytes, int write_combined);
+BGSB_API void bgsb_host_free(void *ptr);
 /* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
 BGSB_API uint64_t bgsb_kernel_launch_count(void);
 
@@ -93,8 +98,8 @@ BGSB_API int bgsb_reset(bgsb_ctx *ctx);
  * "varThresholdGen" 9, "backgroundRatio" 0.9, "varInit" 15, "varMin" 4, "varMax" 75,
  * "complexityReductionThreshold" 0.05, "detectShadows" 1, "shadowValue" 127,
  * "shadowThreshold" 0.5; and "grayVariant": 0 = OpenCV 4.x BGR2GRAY constants, 1 = 2.4.x;
- * "kernelVariant" (MOG2): 0 = production kernels, 1 = straight restatement kernel, 2 / 3 = earlier
- * generations of the fast kernel -- identical results, kept for A/B measurements;
+ * "kernelVariant" (MOG2): 0 = production kernels, 1 = straight restatement kernel, 3 = production T=1
+ * kernel with 4 px/thread -- identical results, kept for A/B measurements;
  * "hostBands" (default 4, 1..8): row bands of the upload / kernel / download pipeline inside bgsb_process. */
 BGSB_API int bgsb_set_param(bgsb_ctx *ctx, const char *key, double value);
 BGSB_API int bgsb_get_param(bgsb_ctx *ctx, const char *key, double *value);

@@ -43,6 +43,8 @@ SIGNATURES = {
     "bgsb_version": (C.c_char_p, []),
     "bgsb_device_count": (C.c_int, [intp]),
     "bgsb_kernel_launch_count": (C.c_uint64, []),
+    "bgsb_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t, C.c_int]),
+    "bgsb_host_free": (None, [vp]),
     "bgsb_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int]),
     "bgsb_create_group": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int]),
     "bgsb_destroy": (None, [vp]),

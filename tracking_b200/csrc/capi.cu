@@ -230,6 +230,18 @@ const char *bgsb_last_error(void) { return bgsb::g_err; }
 const char *bgsb_version(void) { return "bgsb200 0.1 (sm_100a)"; }
 uint64_t bgsb_kernel_launch_count(void) { return bgsb::g_launches.load(); }
 
+int bgsb_host_alloc(void **ptr, size_t bytes, int write_combined)
+{
+    BGSB_REQUIRE(ptr && bytes > 0, "bad args");
+    BGSB_CUDA(cudaHostAlloc(ptr, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+    return BGSB_OK;
+}
+
+void bgsb_host_free(void *ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
+}
+
 int bgsb_device_count(int *count)
 {
     BGSB_REQUIRE(count, "null");
@@ -304,7 +316,7 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     else if (k == "shadowValue") c->shadow_value = (int)v;
     else if (k == "shadowThreshold") c->tau = (float)v;
     else if (k == "hostBands") { BGSB_REQUIRE(v >= 1 && v <= 8, "hostBands in [1,8]"); c->host_bands = (int)v; }
-    else if (k == "kernelVariant") { BGSB_REQUIRE(v >= 0 && v <= 3 && v == (int)v, "kernelVariant is 0..3"); c->mog2_variant = (int)v; }
+    else if (k == "kernelVariant") { BGSB_REQUIRE(v == 0 || v == 1 || v == 3, "kernelVariant is 0, 1 or 3"); c->mog2_variant = (int)v; }
     else if (k == "showOutput" || k == "showForeground" || k == "showBackground") { /* GUI only */ }
     else { set_error("bgsb_set_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
     return BGSB_OK;

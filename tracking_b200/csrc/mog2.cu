@@ -142,17 +142,16 @@ mog2_kernel(const __grid_constant__ Mog2Launch L)
     st_stream_u32(nmp, (unsigned)n[0] | ((unsigned)n[1] << 8) | ((unsigned)n[2] << 16) | ((unsigned)n[3] << 24));
 }
 
-int launch_mog2_fast(const Mog2Launch &L, int nstreams, cudaStream_t stream);
 int launch_mog2_t1v4(const Mog2Launch &L, int nstreams, int px, cudaStream_t stream);
 int launch_mog2_fused(const Mog2Launch &L, int nstreams, cudaStream_t stream);
 
-// variant: 0 production (T==1: generation-4 kernel, 2 px/thread; T>1: temporal-fusion kernel), 1 straight restatement,
-//          2 generation-3 T==1 kernel (4 px/thread, mog2_fast.cu), 3 generation-4 with 4 px/thread
+// variant: 0 production (T == 1: two-phase kernel, 2 px/thread; T > 1: temporal-fusion kernel; csrc/mog2_t1.cu)
+//          1 straight restatement (this file) -- the reference point of profiles/r1_mog2_kernel_history.md
+//          3 production T == 1 kernel instantiated with 4 px/thread (A/B)
 int launch_mog2(const Mog2Launch &L, int nstreams, int variant, cudaStream_t stream)
 {
     if (variant == 0) return L.T == 1 ? launch_mog2_t1v4(L, nstreams, 2, stream) : launch_mog2_fused(L, nstreams, stream);
-    if (variant == 2) return launch_mog2_fast(L, nstreams, stream);
-    if (variant == 3) return L.T == 1 ? launch_mog2_t1v4(L, nstreams, 4, stream) : launch_mog2_fast(L, nstreams, stream);
+    if (variant == 3) return L.T == 1 ? launch_mog2_t1v4(L, nstreams, 4, stream) : launch_mog2_fused(L, nstreams, stream);
     const int threads = 128;
     long long nthreads = ((long long)L.npx + PX - 1) / PX;
     dim3 grid((unsigned)((nthreads + threads - 1) / threads), (unsigned)nstreams);

@@ -1,5 +1,5 @@
 // Generic per-pixel MOG2 update (one pixel, one frame, every case of the algorithm), shared by the
-// straight kernel (mog2.cu) and by the slow path of the production kernel (mog2_fast.cu).
+// straight kernel (mog2.cu) and by the generic phase of the production kernels (mog2_t1.cu).
 // Restates cv::BackgroundSubtractorMOG2's MOG2Invoker loop body + detectShadowGMM +
 // getBackgroundImage (bgfg_gaussmix2.cpp; reference call sites package_bgs/MixtureOfGaussianV2BGS.cpp:56,59),
 // spec SURVEY.md Appendix A.4.  All register indices are compile-time (fully unrolled).
