@@ -1,0 +1,34 @@
+"""Which pixels leave the MOG2 fast path?  Classifies the pixels of frame NF+1 against the model exported after NF
+frames (numpy restatement of the match test only; GPU box, measurement tooling)."""
+import os, sys
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import tracking_b200 as tb
+from tracking_b200 import synth
+W, H, NF = 1920, 1080, int(sys.argv[1]) if len(sys.argv) > 1 else 128
+st = torch.cuda.current_stream().cuda_stream
+d = torch.empty((NF + 1, H, W, 3), dtype=torch.uint8, device="cuda")
+synth.frames_dev(d.data_ptr(), 1, NF + 1, W, H, stream=st)
+fg = torch.empty((H, W), dtype=torch.uint8, device="cuda"); bg = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+p = tb.MixtureOfGaussianV2BGS()
+for t in range(NF):
+    p.process_dev(d[t].data_ptr(), W, H, fg.data_ptr(), bg.data_ptr(), stream=st)
+torch.cuda.synchronize()
+planes, nm = p.export_state()
+x = d[NF].cpu().numpy().reshape(-1, 3).astype(np.float32)
+npx = W * H
+Tg = 9.0
+fit = np.full(npx, -1, np.int32)
+for m in range(5):
+    w, v, b, g, r = planes[m * 5:(m + 1) * 5]
+    d2 = (b - x[:, 0]) ** 2 + (g - x[:, 1]) ** 2 + (r - x[:, 2]) ** 2
+    ok = (m < nm) & (d2 < Tg * v) & (fit < 0)
+    fit[ok] = m
+print("frames", NF, "mean modes", nm.mean(), "hist n", np.bincount(nm, minlength=6) / npx)
+print("no fit             ", (fit < 0).mean())
+for n in range(1, 6):
+    for f in range(n):
+        print("n=%d fit slot %d     " % (n, f), ((nm == n) & (fit == f)).mean())
+for n in range(1, 6):
+    print("n=%d no fit         " % n, ((nm == n) & (fit < 0)).mean())

@@ -24,41 +24,57 @@ __device__ __forceinline__ unsigned mog2_pixel(Mode (&md)[K], int &n, float x0, 
     float tw = 0.f;
     const float nprune = -prune;
 
+    // Walk the live modes: decay every weight, find the first mode that explains the pixel (its update is
+    // deferred to one block below -- the walk itself stays short), prune.
+    float wcmp = 0.f, wfin = 0.f;                      // matched mode: weight before / after the prune test
+    float fb = 0.f, fg_ = 0.f, fr = 0.f, fvar = 0.f, fd0 = 0.f, fd1 = 0.f, fd2 = 0.f, fdist2 = 0.f;
+    int f = -1;
 #pragma unroll
     for (int m = 0; m < K; m++) {
         if (m < n) {                                   // LIVE bound: pruning below shortens the walk
             float wt = a1 * md[m].w + prune;
-            int pos = m;
+            bool here = false;
             if (!fits) {
                 float var = md[m].v;
                 float d0 = md[m].b - x0, d1 = md[m].g - x1, d2 = md[m].r - x2;
                 float dist2 = d0 * d0 + d1 * d1 + d2 * d2;
                 if (tw < L.TB && dist2 < L.Tb * var) bgflag = true;
                 if (dist2 < L.Tg * var) {
-                    fits = true;
+                    fits = true; here = true; f = m;
                     wt += aT;
-                    float k = aT / wt;
-                    float nb = md[m].b - k * d0, ng = md[m].g - k * d1, nr = md[m].r - k * d2;
-                    float vn = var + k * (dist2 - var);
-                    vn = fmaxf(vn, L.varMin);
-                    vn = fminf(vn, L.varMax);
-                    // keep the list sorted by weight: bubble the matched mode up past every
-                    // predecessor whose (already updated) weight is not larger
-#pragma unroll
-                    for (int i = m; i > 0; i--) {
-                        if (pos == i && !(wt < md[i - 1].w)) { md[i] = md[i - 1]; pos = i - 1; }
-                    }
-#pragma unroll
-                    for (int i = 0; i <= m; i++)
-                        if (pos == i) { md[i].v = vn; md[i].b = nb; md[i].g = ng; md[i].r = nr; }
+                    wcmp = wt;                         // the sort compares the weight before the prune test
+                    fb = md[m].b; fg_ = md[m].g; fr = md[m].r; fvar = var;
+                    fd0 = d0; fd1 = d1; fd2 = d2; fdist2 = dist2;
                 }
             }
             if (wt < nprune) { wt = 0.f; n--; }
-#pragma unroll
-            for (int i = 0; i <= m; i++)
-                if (pos == i) md[i].w = wt;
+            if (here) wfin = wt;
+            md[m].w = wt;
             tw += wt;
         }
+    }
+    if (fits) {
+        Mode upd;
+        const float k = aT / wcmp;
+        upd.w = wfin;
+        upd.b = fb - k * fd0; upd.g = fg_ - k * fd1; upd.r = fr - k * fd2;
+        float vn = fvar + k * (fdist2 - fvar);
+        vn = fmaxf(vn, L.varMin);
+        upd.v = fminf(vn, L.varMax);
+        // keep the list sorted by weight: the matched mode moves up past every predecessor whose (already
+        // decayed) weight is not larger.  Written as a shift of the predecessors with the mode carried in
+        // registers -- no position variable indexes the list, so every index stays a constant and the list
+        // stays in registers (a tracked position turns into a dynamically indexed array in local memory).
+        // Slots above f are untouched by the sort, so running it after the walk changes nothing.
+        bool placed = false;
+#pragma unroll
+        for (int i = K - 1; i > 0; i--) {
+            if (i <= f && !placed) {
+                if (!(wcmp < md[i - 1].w)) md[i] = md[i - 1];
+                else { md[i] = upd; placed = true; }
+            }
+        }
+        if (!placed) md[0] = upd;
     }
 
     // renormalise
@@ -71,22 +87,25 @@ __device__ __forceinline__ unsigned mog2_pixel(Mode (&md)[K], int &n, float x0, 
     // no mode explains the pixel: insert a new one (replace the weakest if the list is full)
     if (!fits && aT > 0.f) {
         if (n < K) n++;
-        int pos = n - 1;
-        float wn;
-        if (n == 1) wn = 1.f;
+        Mode ins;
+        ins.v = L.varInit; ins.b = x0; ins.g = x1; ins.r = x2;
+        if (n == 1) ins.w = 1.f;
         else {
-            wn = aT;
+            ins.w = aT;
 #pragma unroll
             for (int i = 0; i < K - 1; i++)
                 if (i < n - 1) md[i].w *= a1;
         }
+        // the new mode starts in slot n-1 and moves up like a matched one (constant indices only, see above)
+        bool placed = false;
 #pragma unroll
         for (int i = K - 1; i > 0; i--) {
-            if (pos == i && !(aT < md[i - 1].w)) { md[i] = md[i - 1]; pos = i - 1; }
+            if (i <= n - 1 && !placed) {
+                if (!(aT < md[i - 1].w)) md[i] = md[i - 1];
+                else { md[i] = ins; placed = true; }
+            }
         }
-#pragma unroll
-        for (int i = 0; i < K; i++)
-            if (pos == i) { md[i].w = wn; md[i].v = L.varInit; md[i].b = x0; md[i].g = x1; md[i].r = x2; }
+        if (!placed) md[0] = ins;
     }
 
     // classification
