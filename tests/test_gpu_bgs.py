@@ -86,7 +86,7 @@ def test_warmup_contract_outputs_untouched():
     assert fd.frame_count == 2
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("variant", [0, 1])
 def test_mog2_stress_sequence_state_bit_exact(oracle, variant):
     """Mode churn (prune / replace / re-sort paths) incl. the exported mixture state."""
     import tracking_b200 as tb
@@ -111,7 +111,7 @@ def test_mog2_stress_sequence_state_bit_exact(oracle, variant):
         p.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("variant", [0, 1])
 def test_mog2_variants_on_reference_clip_temporal_batches(oracle, clips, variant):
     """Both kernels, T in {1, 5, 32}, raw {0,127,255} output (shadow path) on the reference video clip."""
     import torch

@@ -40,7 +40,7 @@ struct bgsb_ctx {
     float Tb = 16.f, Tg = 9.f, TB = 0.9f, varInit = 15.f, varMin = 4.f, varMax = 75.f, CT = 0.05f, tau = 0.5f;
     int detect_shadows = 1, shadow_value = 127;
     int host_bands = 4;        // row bands of the host-path upload/compute/download pipeline (1 = no overlap)
-    int mog2_variant = 0;      // see launch_mog2 (mog2.cu): 0 production, 1 straight restatement, 2/3 earlier generations
+    int mog2_variant = 0;      // see launch_mog2 (mog2.cu): 0 production, 1 straight restatement, 8/9 timing instruments
     // geometry / counters
     int w = 0, h = 0, npx = 0;
     size_t pstride = 0;
@@ -80,11 +80,10 @@ static int ensure_geometry(bgsb_ctx *c, int w, int h)
     if (c->w == w && c->h == h) return BGSB_OK;
     BGSB_REQUIRE(w > 0 && h > 0, "empty frame");
     BGSB_REQUIRE((long long)w * h < (1LL << 30), "frame too large");
-    // MOG2 kernels address plane q of a stream with a 32-bit element offset q*pstride (q < 25)
     BGSB_REQUIRE(c->algo != BGSB_ALGO_MOG2 || (long long)w * h <= (1LL << 27), "MOG2 frames are limited to 2^27 pixels");
     free_buffers(c);
     c->w = w; c->h = h; c->npx = w * h;
-    c->pstride = ((size_t)c->npx + 31) / 32 * 32;
+    c->pstride = ((size_t)c->npx + MOG2_TILE - 1) / MOG2_TILE * MOG2_TILE;       // whole state tiles
     const size_t S = (size_t)c->nstreams;
     if (c->algo == BGSB_ALGO_MOG2) {
         size_t fb = S * MOG2_PLANES * c->pstride * sizeof(float);
@@ -150,7 +149,7 @@ static bool writes_background(int algo)
 
 // Advance the model by T frames that sit in device memory.  `own_history`: write FD/WMV history
 // into the context's own buffers (caller's frame buffers may be reused after the call).
-// Launch the kernel for pixels [p0, p0+pcount) of the frame(s); p0 must be a multiple of 32.
+// Launch the kernel for pixels [p0, p0+pcount) of the frame(s); p0 must be a multiple of 64 (a MOG2 state tile).
 // A sub-range is only used for single-stream, single-frame calls (host-path chunk pipelining).
 static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_fg, uint8_t *d_bg,
                         int bg_last_only, bool own_history, cudaStream_t stream, size_t p0, int pcount)
@@ -160,7 +159,7 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
         Mog2Launch L;
         memset(&L, 0, sizeof(L));
         L.frames = d_frames + p0 * 3; L.fg = d_fg + p0; L.bg = d_bg ? d_bg + p0 * 3 : nullptr;
-        L.state = c->d_state + p0; L.nmodes = c->d_nmodes + p0; L.pstride = c->pstride;
+        L.state = c->d_state + p0 * MOG2_PLANES; L.nmodes = c->d_nmodes + p0; L.pstride = c->pstride;   // p0 % 64 == 0
         L.npx = pcount; L.T = T; L.bg_last_only = bg_last_only;
         L.fresh = (c->nframes == 0);
         L.fast_ok = 1;
@@ -316,7 +315,7 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     else if (k == "shadowValue") c->shadow_value = (int)v;
     else if (k == "shadowThreshold") c->tau = (float)v;
     else if (k == "hostBands") { BGSB_REQUIRE(v >= 1 && v <= 8, "hostBands in [1,8]"); c->host_bands = (int)v; }
-    else if (k == "kernelVariant") { BGSB_REQUIRE(v == 0 || v == 1 || v == 3, "kernelVariant is 0, 1 or 3"); c->mog2_variant = (int)v; }
+    else if (k == "kernelVariant") { BGSB_REQUIRE(v == 0 || v == 1 || v == 8 || v == 9, "kernelVariant is 0 or 1 (8, 9: timing instruments)"); c->mog2_variant = (int)v; }
     else if (k == "showOutput" || k == "showForeground" || k == "showBackground") { /* GUI only */ }
     else { set_error("bgsb_set_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
     return BGSB_OK;
@@ -420,6 +419,7 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
     int nchunks = 1, band = h;
     if (c->nstreams == 1 && c->host_bands > 1 && (size_t)w * h * 3 >= (1u << 20) && out_fg) {
         band = ((h + c->host_bands - 1) / c->host_bands + 31) / 32 * 32;
+        if (((size_t)band * w) % MOG2_TILE) band += 32;          // bands start on a state tile
         nchunks = (h + band - 1) / band;
         if (nchunks > 8) { nchunks = 1; band = h; }
     }
@@ -483,8 +483,15 @@ int bgsb_mog2_export_state(bgsb_ctx *c, int si, float *planes, uint8_t *nmodes)
     BGSB_CUDA(cudaSetDevice(c->device));
     BGSB_CUDA(cudaDeviceSynchronize());
     const float *src = c->d_state + (size_t)si * MOG2_PLANES * c->pstride;
-    BGSB_CUDA(cudaMemcpy2D(planes, (size_t)c->npx * 4, src, c->pstride * 4, (size_t)c->npx * 4, MOG2_PLANES,
-                           cudaMemcpyDeviceToHost));
+    // device tiles [tile][25][64] -> whole-frame planes [25][npx]
+    const size_t nt = (size_t)c->npx / MOG2_TILE, rem = (size_t)c->npx % MOG2_TILE;
+    for (int q = 0; q < MOG2_PLANES; q++) {
+        float *hp = planes + (size_t)q * c->npx;
+        if (nt) BGSB_CUDA(cudaMemcpy2D(hp, MOG2_TILE * 4, src + q * MOG2_TILE, MOG2_TILE_FLOATS * 4, MOG2_TILE * 4, nt,
+                                       cudaMemcpyDeviceToHost));
+        if (rem) BGSB_CUDA(cudaMemcpy(hp + nt * MOG2_TILE, src + nt * MOG2_TILE_FLOATS + q * MOG2_TILE, rem * 4,
+                                      cudaMemcpyDeviceToHost));
+    }
     BGSB_CUDA(cudaMemcpy(nmodes, c->d_nmodes + (size_t)si * c->pstride, c->npx, cudaMemcpyDeviceToHost));
     if (c->nframes == 0) memset(nmodes, 0, c->npx);
     return BGSB_OK;
@@ -502,8 +509,14 @@ int bgsb_mog2_import_state(bgsb_ctx *c, int si, int w, int h, int64_t nframes, c
     if (rc) return rc;
     BGSB_CUDA(cudaDeviceSynchronize());
     float *dst = c->d_state + (size_t)si * MOG2_PLANES * c->pstride;
-    BGSB_CUDA(cudaMemcpy2D(dst, c->pstride * 4, planes, (size_t)c->npx * 4, (size_t)c->npx * 4, MOG2_PLANES,
-                           cudaMemcpyHostToDevice));
+    const size_t nt = (size_t)c->npx / MOG2_TILE, rem = (size_t)c->npx % MOG2_TILE;
+    for (int q = 0; q < MOG2_PLANES; q++) {
+        const float *hp = planes + (size_t)q * c->npx;
+        if (nt) BGSB_CUDA(cudaMemcpy2D(dst + q * MOG2_TILE, MOG2_TILE_FLOATS * 4, hp, MOG2_TILE * 4, MOG2_TILE * 4, nt,
+                                       cudaMemcpyHostToDevice));
+        if (rem) BGSB_CUDA(cudaMemcpy(dst + nt * MOG2_TILE_FLOATS + q * MOG2_TILE, hp + nt * MOG2_TILE, rem * 4,
+                                      cudaMemcpyHostToDevice));
+    }
     BGSB_CUDA(cudaMemcpy(c->d_nmodes + (size_t)si * c->pstride, nmodes, c->npx, cudaMemcpyHostToDevice));
     c->nframes = nframes;
     return BGSB_OK;

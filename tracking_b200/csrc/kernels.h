@@ -28,14 +28,21 @@ int launch_simple(int algo, const SimpleLaunch &L, int nstreams, cudaStream_t st
 constexpr int MOG2_K = 5;             // nmixtures of the default-constructed cv::BackgroundSubtractorMOG2
 constexpr int MOG2_PLANES = 5 * MOG2_K;   // per mode: weight, variance, mean B, G, R
 constexpr int MOG2_TMAX = 32;         // frames per temporal batch launch
+// Model state layout: tiles of 64 consecutive pixels; inside a tile the 25 planes are rows of 64 floats
+// (plane q = mode*5 + {0 weight, 1 variance, 2 muB, 3 muG, 4 muR}).  A pixel's plane q sits q*64 floats
+// after its plane 0 -- a compile-time offset -- and a warp that owns one tile reads / writes each plane as one
+// contiguous 256-byte row.  Per pixel the footprint is the same 100 bytes as whole-frame planes.
+constexpr int MOG2_TILE = 64;
+constexpr int MOG2_TILE_FLOATS = MOG2_PLANES * MOG2_TILE;
+__host__ __device__ inline size_t mog2_tile_off(size_t p) { return (p >> 6) * (size_t)MOG2_TILE_FLOATS + (p & 63); }
 
 struct Mog2Launch {
     const uint8_t *frames;   // [S][T][npx*3]
     uint8_t *fg;             // [S][T][npx]
     uint8_t *bg;             // [S][T][npx*3] | [S][npx*3] | null
-    float *state;            // [S][25][pstride]  plane q = mode*5 + {0:w,1:var,2:muB,3:muG,4:muR}
+    float *state;            // [S][pstride/64 tiles][25][64]  (mog2_tile_off)
     uint8_t *nmodes;         // [S][pstride]
-    size_t pstride;          // plane stride in elements (npx rounded up to 32)
+    size_t pstride;          // pixels per stream rounded up to whole tiles (64)
     int npx, T;
     int bg_last_only;
     int fresh;               // 1: state is uninitialised -> treat nmodes as 0 (first frame after create/reset)

@@ -7,7 +7,8 @@
 // member `mog` at package_bgs/MixtureOfGaussianV2BGS.h:30); spec = SURVEY.md Appendix A.4.
 //
 // Data layout in HBM (structure of arrays, per camera stream):
-//   state  : 25 fp32 planes [q][pstride], q = mode*5 + {0 weight, 1 variance, 2 muB, 3 muG, 4 muR}
+//   state  : tiles of 64 pixels x 25 fp32 planes (kernels.h: mog2_tile_off), plane q = mode*5 +
+//            {0 weight, 1 variance, 2 muB, 3 muG, 4 muR}
 //   nmodes : 1 u8 plane
 //   = 101 B/px, read once and written once per launch (per T frames with temporal batching).
 // A thread owns 4 consecutive pixels: every plane access is one 128-bit load/store and a warp
@@ -41,7 +42,7 @@ mog2_kernel(const __grid_constant__ Mog2Launch L)
     const long long px0 = g * PX;
     if (px0 >= L.npx) return;
     const int s = blockIdx.y;
-    float *state = L.state + (size_t)s * MOG2_PLANES * L.pstride + px0;
+    float *state = L.state + (size_t)s * MOG2_PLANES * L.pstride + mog2_tile_off((size_t)px0);   // 4 | 64: one tile
     uint8_t *nmp = L.nmodes + (size_t)s * L.pstride + px0;
     const uint8_t *frames = L.frames + (size_t)s * L.T * L.npx * 3;
     uint8_t *fg = L.fg + (size_t)s * L.T * L.npx;
@@ -60,7 +61,7 @@ mog2_kernel(const __grid_constant__ Mog2Launch L)
     for (int m = 0; m < K; m++) {
         if (m < nmax) {
 #pragma unroll
-            for (int f = 0; f < 5; f++) P[m * 5 + f] = ld_stream_f4(state + (size_t)(m * 5 + f) * L.pstride);
+            for (int f = 0; f < 5; f++) P[m * 5 + f] = ld_stream_f4(state + (m * 5 + f) * MOG2_TILE);
         } else {
 #pragma unroll
             for (int f = 0; f < 5; f++) P[m * 5 + f] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -136,22 +137,23 @@ mog2_kernel(const __grid_constant__ Mog2Launch L)
     for (int m = 0; m < K; m++) {
         if (m < nmax2) {
 #pragma unroll
-            for (int f = 0; f < 5; f++) st_stream_f4(state + (size_t)(m * 5 + f) * L.pstride, P[m * 5 + f]);
+            for (int f = 0; f < 5; f++) st_stream_f4(state + (m * 5 + f) * MOG2_TILE, P[m * 5 + f]);
         }
     }
     st_stream_u32(nmp, (unsigned)n[0] | ((unsigned)n[1] << 8) | ((unsigned)n[2] << 16) | ((unsigned)n[3] << 24));
 }
 
-int launch_mog2_t1v4(const Mog2Launch &L, int nstreams, int px, cudaStream_t stream);
+int launch_mog2_t1(const Mog2Launch &L, int nstreams, int mode, cudaStream_t stream);
 int launch_mog2_fused(const Mog2Launch &L, int nstreams, cudaStream_t stream);
 
-// variant: 0 production (T == 1: two-phase kernel, 2 px/thread; T > 1: temporal-fusion kernel; csrc/mog2_t1.cu)
+// variant: 0 production (T == 1: two-phase kernel; T > 1: temporal-fusion kernel; csrc/mog2_t1.cu)
 //          1 straight restatement (this file) -- the reference point of profiles/r1_mog2_kernel_history.md
-//          3 production T == 1 kernel instantiated with 4 px/thread (A/B)
+//          8, 9 timing instruments with wrong results: T == 1 kernel without its generic phase / without arithmetic
 int launch_mog2(const Mog2Launch &L, int nstreams, int variant, cudaStream_t stream)
 {
-    if (variant == 0) return L.T == 1 ? launch_mog2_t1v4(L, nstreams, 2, stream) : launch_mog2_fused(L, nstreams, stream);
-    if (variant == 3) return L.T == 1 ? launch_mog2_t1v4(L, nstreams, 4, stream) : launch_mog2_fused(L, nstreams, stream);
+    if (variant == 0) return L.T == 1 ? launch_mog2_t1(L, nstreams, 0, stream) : launch_mog2_fused(L, nstreams, stream);
+    if (variant == 9) return launch_mog2_t1(L, nstreams, 1, stream);
+    if (variant == 8) return launch_mog2_t1(L, nstreams, 2, stream);
     const int threads = 128;
     long long nthreads = ((long long)L.npx + PX - 1) / PX;
     dim3 grid((unsigned)((nthreads + threads - 1) / threads), (unsigned)nstreams);
