@@ -156,28 +156,41 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
 {
     if (c->algo == BGSB_ALGO_MOG2) {
         BGSB_REQUIRE(T <= MOG2_TMAX, "temporal batch too long (max 32)");
-        Mog2Launch L;
-        memset(&L, 0, sizeof(L));
-        L.frames = d_frames + p0 * 3; L.fg = d_fg + p0; L.bg = d_bg ? d_bg + p0 * 3 : nullptr;
-        L.state = c->d_state + p0 * MOG2_PLANES; L.nmodes = c->d_nmodes + p0; L.pstride = c->pstride;   // p0 % 64 == 0
-        L.npx = pcount; L.T = T; L.bg_last_only = bg_last_only;
-        L.fresh = (c->nframes == 0);
-        L.fast_ok = 1;
-        L.enable_thr = c->enable_thr; L.thr = c->thr;
-        L.detect_shadows = c->detect_shadows; L.shadow_value = c->shadow_value;
-        L.Tb = c->Tb; L.Tg = c->Tg; L.TB = c->TB; L.varInit = c->varInit; L.varMin = c->varMin;
-        L.varMax = c->varMax; L.tau = c->tau;
-        for (int t = 0; t < T; t++) {
-            // operator(): ++nframes; learningRate = alpha>=0 && nframes>1 ? alpha : 1./min(2*nframes, history)
-            int64_t nf = c->nframes + t + 1;
-            double lr = (c->alpha >= 0 && nf > 1) ? c->alpha : 1. / (double)std::min<int64_t>(2 * nf, c->history);
-            L.alphaT[t] = (float)lr;
-            L.alpha1[t] = 1.f - L.alphaT[t];
-            L.prune[t] = (float)(-lr * (double)c->CT);
-            if (!(L.alphaT[t] >= 1e-4f && L.alphaT[t] <= 1.f)) L.fast_ok = 0;
+        // Short batches of one stream run frame by frame: the T == 1 kernel costs less per frame than the
+        // temporal-fusion kernel's fixed state load/store until about six frames share it (profiles/).
+        const bool per_frame = T > 1 && T < 6 && c->nstreams == 1 && c->mog2_variant == 0;
+        const int nlaunch = per_frame ? T : 1, Tl = per_frame ? 1 : T;
+        for (int i = 0; i < nlaunch; i++) {
+            Mog2Launch L;
+            memset(&L, 0, sizeof(L));
+            const size_t f0 = (size_t)i * c->npx;                  // first pixel of frame i in the batch buffers
+            L.frames = d_frames + (f0 + p0) * 3; L.fg = d_fg + f0 + p0;
+            L.bg = nullptr;
+            if (d_bg) {
+                if (!per_frame) L.bg = d_bg + p0 * 3;
+                else if (!bg_last_only) L.bg = d_bg + (f0 + p0) * 3;
+                else if (i == T - 1) L.bg = d_bg + p0 * 3;
+            }
+            L.state = c->d_state + p0 * MOG2_PLANES; L.nmodes = c->d_nmodes + p0; L.pstride = c->pstride;   // p0 % 64 == 0
+            L.npx = pcount; L.T = Tl; L.bg_last_only = per_frame ? 0 : bg_last_only;
+            L.fresh = (c->nframes + i == 0);
+            L.fast_ok = 1;
+            L.enable_thr = c->enable_thr; L.thr = c->thr;
+            L.detect_shadows = c->detect_shadows; L.shadow_value = c->shadow_value;
+            L.Tb = c->Tb; L.Tg = c->Tg; L.TB = c->TB; L.varInit = c->varInit; L.varMin = c->varMin;
+            L.varMax = c->varMax; L.tau = c->tau;
+            for (int t = 0; t < Tl; t++) {
+                // operator(): ++nframes; learningRate = alpha>=0 && nframes>1 ? alpha : 1./min(2*nframes, history)
+                int64_t nf = c->nframes + i + t + 1;
+                double lr = (c->alpha >= 0 && nf > 1) ? c->alpha : 1. / (double)std::min<int64_t>(2 * nf, c->history);
+                L.alphaT[t] = (float)lr;
+                L.alpha1[t] = 1.f - L.alphaT[t];
+                L.prune[t] = (float)(-lr * (double)c->CT);
+                if (!(L.alphaT[t] >= 1e-4f && L.alphaT[t] <= 1.f)) L.fast_ok = 0;
+            }
+            int rc = launch_mog2(L, c->nstreams, c->mog2_variant, stream);
+            if (rc) return rc;
         }
-        int rc = launch_mog2(L, c->nstreams, c->mog2_variant, stream);
-        if (rc) return rc;
     } else {
         SimpleLaunch L;
         memset(&L, 0, sizeof(L));
