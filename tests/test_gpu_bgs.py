@@ -156,16 +156,24 @@ def test_mog2_auto_learning_rate_and_params(oracle):
         assert np.array_equal(fg, ofg) and np.array_equal(bg, obg), i
 
 
-def test_abl_exhaustive_byte_pairs(oracle):
+@pytest.mark.parametrize("table", [1, 0])
+def test_abl_exhaustive_byte_pairs(oracle, table):
+    """Every (input, background) byte pair, lookup-table kernel and arithmetic kernel; alpha changes mid-stream
+    (the table is rebuilt)."""
     import tracking_b200 as tb
     inp, bg = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8))
     f0 = np.repeat(bg[:, :, None], 3, 2).copy()
     f1 = np.repeat(inp[:, :, None], 3, 2).copy()
     for alpha in (0.05, 0.3, 0.001):
-        p, o = tb.AdaptiveBackgroundLearning(alpha=alpha), oracle.AdaptiveBackgroundLearning(alpha=alpha)
+        p = tb.AdaptiveBackgroundLearning(alpha=alpha, ablTable=table)
+        o = oracle.AdaptiveBackgroundLearning(alpha=alpha)
         for f in (f0, f1):
             fa, ba = p.process(f)
             fb, bb = o.process(f)
+        assert np.array_equal(fa, fb) and np.array_equal(ba, bb)
+        p.set("alpha", 0.5); o.alpha = 0.5
+        fa, ba = p.process(f0)
+        fb, bb = o.process(f0)
         assert np.array_equal(fa, fb) and np.array_equal(ba, bb)
 
 

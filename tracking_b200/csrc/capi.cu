@@ -40,6 +40,7 @@ struct bgsb_ctx {
     float Tb = 16.f, Tg = 9.f, TB = 0.9f, varInit = 15.f, varMin = 4.f, varMax = 75.f, CT = 0.05f, tau = 0.5f;
     int detect_shadows = 1, shadow_value = 127;
     int host_bands = 4;        // row bands of the host-path upload/compute/download pipeline (1 = no overlap)
+    int abl_table = 1;         // ABL: 1 = lookup-table kernel, 0 = arithmetic kernel (A/B, identical results)
     int mog2_variant = 0;      // see launch_mog2 (mog2.cu): 0 production, 1 straight restatement, 8/9 timing instruments
     // geometry / counters
     int w = 0, h = 0, npx = 0;
@@ -48,6 +49,8 @@ struct bgsb_ctx {
     // device state
     float *d_state = nullptr;
     uint8_t *d_nmodes = nullptr;
+    uint8_t *d_abl_lut = nullptr;         // ABL: 64 KB blend table for lut_alpha (simple_bgs.cu)
+    double lut_alpha = -1.;
     uint8_t *d_hist[2] = {nullptr, nullptr};
     const uint8_t *hist_ptr[2] = {nullptr, nullptr};
     int have_hist = 0;
@@ -65,6 +68,7 @@ static void free_buffers(bgsb_ctx *c)
 {
     cudaFree(c->d_state); c->d_state = nullptr;
     cudaFree(c->d_nmodes); c->d_nmodes = nullptr;
+    cudaFree(c->d_abl_lut); c->d_abl_lut = nullptr; c->lut_alpha = -1.;
     for (int i = 0; i < 2; i++) { cudaFree(c->d_hist[i]); c->d_hist[i] = nullptr; c->hist_ptr[i] = nullptr; }
     for (int i = 0; i < 3; i++) { cudaFree(c->d_ring[i]); c->d_ring[i] = nullptr; }
     cudaFree(c->d_fg); c->d_fg = nullptr;
@@ -205,6 +209,15 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
         L.npx = pcount; L.T = T; L.have_hist = c->have_hist; L.bg_last_only = bg_last_only;
         L.enable_thr = c->enable_thr; L.thr = c->thr; L.gray_variant = c->gray_variant;
         L.alpha = c->alpha;
+        if (c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING && c->abl_table) {
+            if (!c->d_abl_lut) BGSB_CUDA(cudaMalloc(&c->d_abl_lut, 65536));
+            if (c->lut_alpha != c->alpha) {                 // stream-ordered before the kernel that reads it
+                int rcl = launch_abl_lut_build(c->d_abl_lut, c->alpha, stream);
+                if (rcl) return rcl;
+                c->lut_alpha = c->alpha;
+            }
+            L.abl_lut = c->d_abl_lut;
+        }
         L.abl_update = (c->limit == -1);   // the limit>0 branch never fires: counter stays 0 (.cpp:52,60-61)
         if (c->enable_weight) { L.w0 = 0.5; L.w1 = 0.3; L.w2 = 0.2; }      // WeightedMovingVarianceBGS.cpp:67-68
         else { L.w0 = 0.3; L.w1 = 0.3; L.w2 = 0.3; }                          // :70
@@ -329,6 +342,7 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     else if (k == "shadowThreshold") c->tau = (float)v;
     else if (k == "hostBands") { BGSB_REQUIRE(v >= 1 && v <= 8, "hostBands in [1,8]"); c->host_bands = (int)v; }
     else if (k == "kernelVariant") { BGSB_REQUIRE(v == 0 || v == 1 || v == 8 || v == 9, "kernelVariant is 0 or 1 (8, 9: timing instruments)"); c->mog2_variant = (int)v; }
+    else if (k == "ablTable") { BGSB_REQUIRE(v == 0 || v == 1, "ablTable is 0 or 1"); c->abl_table = (int)v; }
     else if (k == "showOutput" || k == "showForeground" || k == "showBackground") { /* GUI only */ }
     else { set_error("bgsb_set_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
     return BGSB_OK;
@@ -358,6 +372,7 @@ int bgsb_get_param(bgsb_ctx *c, const char *key, double *v)
     else if (k == "shadowThreshold") *v = c->tau;
     else if (k == "kernelVariant") *v = c->mog2_variant;
     else if (k == "hostBands") *v = c->host_bands;
+    else if (k == "ablTable") *v = c->abl_table;
     else { set_error("bgsb_get_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
     return BGSB_OK;
 }

@@ -20,9 +20,12 @@ struct SimpleLaunch {
     int enable_thr, thr, gray_variant;
     double alpha;            // ABL
     int abl_update;          // ABL: limit == -1 (AdaptiveBackgroundLearning.cpp:52); 0 freezes the model
+    const uint8_t *abl_lut;  // ABL: 64 KB table of the blend for this alpha (abl_lut_index), null = arithmetic kernel
     double w0, w1, w2;       // WMV weights (0.5,0.3,0.2 | 0.3,0.3,0.3)
 };
 int launch_simple(int algo, const SimpleLaunch &L, int nstreams, cudaStream_t stream);
+// Fill the 64 KB ABL table for `alpha` with the arithmetic kernel's own blend (bit-exact by construction).
+int launch_abl_lut_build(uint8_t *d_lut, double alpha, cudaStream_t stream);
 
 // ---- MOG2 -------------------------------------------------------------------------------------
 constexpr int MOG2_K = 5;             // nmixtures of the default-constructed cv::BackgroundSubtractorMOG2
