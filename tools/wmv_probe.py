@@ -1,0 +1,25 @@
+"""WMV: 16 streams of 1080p, us per step (GPU box, measurement tooling)."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import tracking_b200 as tb
+from tracking_b200 import synth
+w, h, NT = 1920, 1080, 6
+st = torch.cuda.current_stream().cuda_stream
+for S in (1, 16):
+    frames = torch.empty((NT, S, h, w, 3), dtype=torch.uint8, device="cuda")
+    for t in range(NT):
+        synth.frames_dev(frames[t].data_ptr(), S, 1, w, h, t0=t, stream=st)
+    fg = torch.empty((S, h, w), dtype=torch.uint8, device="cuda")
+    p = tb.WeightedMovingVarianceBGS(nstreams=S)
+    k = [0]
+    def run(n):
+        for _ in range(n):
+            p.process_dev(frames[k[0] % NT].data_ptr(), w, h, fg.data_ptr(), None, stream=st); k[0] += 1
+    run(8)
+    torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 40
+    e0.record(); run(n); e1.record(); torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) / n * 1e-3
+    print("S=%d  %.1f us/step  %.0f GB/s (16 B/px)  checksum %d" % (S, dt * 1e6, S * w * h * 16 / dt / 1e9, int(fg.long().sum())))
+    p.close()

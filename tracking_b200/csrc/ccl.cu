@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(256)
 ccl_pack_kernel(const uint8_t *__restrict__ mask, unsigned *__restrict__ bits, int w, int h, int wpr, int zero_border,
                 size_t img_px, size_t img_words)
 {
+    pdl_entry();
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= h * wpr) return;
     mask += blockIdx.y * img_px; bits += blockIdx.y * img_words;
@@ -122,6 +123,7 @@ ccl_init_kernel(const unsigned *__restrict__ bits, int *__restrict__ parent, uin
                 int *__restrict__ blockcount, const int *__restrict__ need_bg, int w, int h, int wpr, size_t img_px,
                 size_t img_words, int nblocks)
 {
+    pdl_entry();
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
     if (BG) { if (!need_bg[blockIdx.y]) return; }
     else if (threadIdx.x == 0) {
@@ -178,6 +180,7 @@ __global__ void __launch_bounds__(256)
 ccl_merge_kernel(const unsigned *__restrict__ bits, int *parent, const int *__restrict__ need_bg, int w, int h, int wpr,
                  size_t img_px, size_t img_words)
 {
+    pdl_entry();
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
     if (BG && !need_bg[blockIdx.y]) return;
     if (wi >= h * wpr) return;
@@ -210,6 +213,7 @@ ccl_flatten_kernel(const unsigned *__restrict__ bits, int *parent, uint8_t *oute
                    int *__restrict__ blockcount, const int *__restrict__ need_bg, int w, int h, int wpr, size_t img_px,
                    size_t img_words, int nblocks)
 {
+    pdl_entry();
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
     if (BG && !need_bg[blockIdx.y]) return;
     if (wi >= h * wpr) return;
@@ -252,6 +256,7 @@ struct CompRaw { int label, first_index, xmin, ymin, xmax, ymax, area, external;
 __global__ void __launch_bounds__(1024)
 ccl_blockscan_kernel(int *blockcount, int nblocks, int *ncomp)
 {
+    pdl_entry();
     __shared__ int sums[1024];
     int *bc = blockcount + blockIdx.x * (size_t)(nblocks + 1);
     const int tid = threadIdx.x;
@@ -277,6 +282,7 @@ __global__ void __launch_bounds__(256)
 ccl_rank_kernel(const unsigned *__restrict__ rootbits, int *__restrict__ wordrank, const int *__restrict__ blockcount,
                 CompRaw *comp, int cap, int w, int h, int wpr, size_t img_words, int nblocks)
 {
+    pdl_entry();
     __shared__ int wsum[8];
     rootbits += blockIdx.y * img_words; wordrank += blockIdx.y * img_words;
     blockcount += blockIdx.y * (size_t)(nblocks + 1); comp += blockIdx.y * (size_t)cap;
@@ -316,6 +322,7 @@ ccl_label_kernel(const unsigned *__restrict__ bits, const int *__restrict__ pare
                  const unsigned *__restrict__ rootbits, const int *__restrict__ wordrank, CompRaw *comp, int cap,
                  int *__restrict__ labels, int w, int h, int wpr, size_t img_px, size_t img_words)
 {
+    pdl_entry();
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
     if (wi >= h * wpr) return;
     bits += blockIdx.y * img_words; parent += blockIdx.y * img_px; outer += blockIdx.y * img_px;
@@ -374,6 +381,7 @@ ccl_label_kernel(const unsigned *__restrict__ bits, const int *__restrict__ pare
 __global__ void __launch_bounds__(256)
 ccl_nest_kernel(const CompRaw *__restrict__ comp, const int *__restrict__ ncomp, int cap, int *__restrict__ need_bg)
 {
+    pdl_entry();
     __shared__ int4 box[256];
     const int img = blockIdx.y;
     const int n = ncomp[img];
@@ -406,6 +414,7 @@ ccl_resolve_external_kernel(const unsigned *__restrict__ bits, const int *__rest
                             const uint8_t *__restrict__ outer, CompRaw *comp, const int *__restrict__ ncomp, int cap,
                             const int *__restrict__ need_bg, int w, int wpr, size_t img_px, size_t img_words)
 {
+    pdl_entry();
     const int img = blockIdx.y;
     if (!need_bg[img]) return;
     const int n = min(ncomp[img], cap);
@@ -430,6 +439,7 @@ __global__ void __launch_bounds__(256)
 rect_moments_kernel(const uint8_t *__restrict__ mask, int w, int h, const int *__restrict__ rects,
                     unsigned long long *out)
 {
+    pdl_entry();
     const int ri = blockIdx.x;
     const int rx = rects[4 * ri], ry = rects[4 * ri + 1], rw = rects[4 * ri + 2], rh = rects[4 * ri + 3];
     unsigned long long m[6] = {0, 0, 0, 0, 0, 0};
@@ -552,22 +562,22 @@ int bgsb_ccl_label_batch_dev(bgsb_ccl *c, const uint8_t *d_masks, int w, int h, 
     const int threads = 256, nblocks = (nwords + threads - 1) / threads;
     const size_t ipx = (size_t)w * h, iw = (size_t)nwords;       // dense per-image strides for this geometry
     dim3 grid(nblocks, nimages);
-    ccl_pack_kernel<<<grid, threads, 0, stream>>>(d_masks, c->d_bits, w, h, wpr, zero_border, ipx, iw);
+    launch_pdl(ccl_pack_kernel, dim3(grid), dim3(threads), 0, stream, d_masks, c->d_bits, w, h, wpr, zero_border, ipx, iw);
     BGSB_LAUNCH_CHECK();
-    ccl_init_kernel<false><<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_blockcount, c->d_need_bg,
+    launch_pdl(ccl_init_kernel<false>, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_blockcount, c->d_need_bg,
                                                         w, h, wpr, ipx, iw, nblocks);
     BGSB_LAUNCH_CHECK();
-    ccl_merge_kernel<false><<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_need_bg, w, h, wpr, ipx, iw);
+    launch_pdl(ccl_merge_kernel<false>, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_need_bg, w, h, wpr, ipx, iw);
     BGSB_LAUNCH_CHECK();
-    ccl_flatten_kernel<false><<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_rootbits,
+    launch_pdl(ccl_flatten_kernel<false>, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_rootbits,
                                                            c->d_blockcount, c->d_need_bg, w, h, wpr, ipx, iw, nblocks);
     BGSB_LAUNCH_CHECK();
-    ccl_blockscan_kernel<<<nimages, 1024, 0, stream>>>(c->d_blockcount, nblocks, c->d_ncomp);
+    launch_pdl(ccl_blockscan_kernel, dim3(nimages), dim3(1024), 0, stream, c->d_blockcount, nblocks, c->d_ncomp);
     BGSB_LAUNCH_CHECK();
-    ccl_rank_kernel<<<grid, threads, 0, stream>>>(c->d_rootbits, c->d_wordrank, c->d_blockcount, c->d_comp, c->cap, w, h, wpr,
+    launch_pdl(ccl_rank_kernel, dim3(grid), dim3(threads), 0, stream, c->d_rootbits, c->d_wordrank, c->d_blockcount, c->d_comp, c->cap, w, h, wpr,
                                                   iw, nblocks);
     BGSB_LAUNCH_CHECK();
-    ccl_label_kernel<<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_rootbits, c->d_wordrank,
+    launch_pdl(ccl_label_kernel, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_rootbits, c->d_wordrank,
                                                    c->d_comp, c->cap, d_labels, w, h, wpr, ipx, iw);
     BGSB_LAUNCH_CHECK();
     // RETR_EXTERNAL: background pass only for images where a bounding box lies strictly inside another
@@ -576,22 +586,22 @@ int bgsb_ccl_label_batch_dev(bgsb_ccl *c, const uint8_t *d_masks, int w, int h, 
         BGSB_CUDA(cudaMemcpyAsync(c->d_need_bg, ones.data(), nimages * sizeof(int), cudaMemcpyHostToDevice, stream));
         BGSB_CUDA(cudaStreamSynchronize(stream));
     } else {
-        ccl_nest_kernel<<<dim3(16, nimages), 256, 0, stream>>>(c->d_comp, c->d_ncomp, c->cap, c->d_need_bg);
+        launch_pdl(ccl_nest_kernel, dim3(dim3(16, nimages)), dim3(256), 0, stream, c->d_comp, c->d_ncomp, c->cap, c->d_need_bg);
         BGSB_LAUNCH_CHECK();
     }
-    ccl_init_kernel<true><<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_blockcount, c->d_need_bg,
+    launch_pdl(ccl_init_kernel<true>, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_blockcount, c->d_need_bg,
                                                        w, h, wpr, ipx, iw, nblocks);
     BGSB_LAUNCH_CHECK();
-    ccl_merge_kernel<true><<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_need_bg, w, h, wpr, ipx, iw);
+    launch_pdl(ccl_merge_kernel<true>, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_need_bg, w, h, wpr, ipx, iw);
     BGSB_LAUNCH_CHECK();
-    ccl_flatten_kernel<true><<<grid, threads, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_rootbits,
+    launch_pdl(ccl_flatten_kernel<true>, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_rootbits,
                                                           c->d_blockcount, c->d_need_bg, w, h, wpr, ipx, iw, nblocks);
     BGSB_LAUNCH_CHECK();
     {
         // at most cap components per image; the kernel exits early past the real count
         const int maxc = std::min(c->cap, (int)(((size_t)w * h + 3) / 4 + 1));
         dim3 rgrid((maxc + 255) / 256, nimages);
-        ccl_resolve_external_kernel<<<rgrid, 256, 0, stream>>>(c->d_bits, c->d_parent, c->d_outer, c->d_comp, c->d_ncomp,
+        launch_pdl(ccl_resolve_external_kernel, dim3(rgrid), dim3(256), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_comp, c->d_ncomp,
                                                                c->cap, c->d_need_bg, w, wpr, ipx, iw);
         BGSB_LAUNCH_CHECK();
     }
@@ -655,7 +665,7 @@ int bgsb_ccl_rect_moments(bgsb_ccl *c, const int32_t *rects, int nrects, uint64_
     BGSB_CUDA(cudaMemcpyAsync(d_rects, rects, (size_t)nrects * 16, cudaMemcpyHostToDevice, st));
     BGSB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nrects * 48, st));
     dim3 grid(nrects, 16);
-    rect_moments_kernel<<<grid, 256, 0, st>>>(c->last_mask, c->w, c->h, d_rects, d_out);
+    launch_pdl(rect_moments_kernel, dim3(grid), dim3(256), 0, st, c->last_mask, c->w, c->h, d_rects, d_out);
     BGSB_LAUNCH_CHECK();
     BGSB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)nrects * 48, cudaMemcpyDeviceToHost, st));
     BGSB_CUDA(cudaStreamSynchronize(st));

@@ -35,6 +35,33 @@ extern std::atomic<uint64_t> g_launches;
         }                                                                                    \
     } while (0)
 
+// ---- programmatic dependent launch -----------------------------------------------------------------
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute and starts with
+// pdl_entry(): its grid may become resident while the previous kernel of the stream drains, and waits there
+// until that kernel has completed and flushed.  This hides the launch ramp between the small dependent kernels
+// of a stream (one MOG2 kernel per frame, the 12-kernel labelling chain).  Rules: pdl_entry() is the first
+// statement, executed by every thread before any memory access or exit -- a grid whose CTAs left without waiting
+// would complete early and release ITS successor before the predecessor's data is visible.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_entry()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);    // errors surface in BGSB_LAUNCH_CHECK
+}
+#endif
+
 #define BGSB_REQUIRE(cond, msg)                                                              \
     do {                                                                                     \
         if (!(cond)) {                                                                       \

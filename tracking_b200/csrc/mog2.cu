@@ -38,6 +38,7 @@ template <bool SHADOWS>
 __global__ void __launch_bounds__(128)
 mog2_kernel(const __grid_constant__ Mog2Launch L)
 {
+    pdl_entry();
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long px0 = g * PX;
     if (px0 >= L.npx) return;
@@ -159,8 +160,8 @@ int launch_mog2(const Mog2Launch &L, int nstreams, int variant, cudaStream_t str
     dim3 grid((unsigned)((nthreads + threads - 1) / threads), (unsigned)nstreams);
     // the shadow test only changes the output when 127 survives the wrapper's threshold
     const bool shadows = L.detect_shadows && !(L.enable_thr && (L.thr < L.shadow_value || L.thr >= 255));
-    if (shadows) mog2_kernel<true><<<grid, threads, 0, stream>>>(L);
-    else mog2_kernel<false><<<grid, threads, 0, stream>>>(L);
+    if (shadows) launch_pdl(mog2_kernel<true>, dim3(grid), dim3(threads), 0, stream, L);
+    else launch_pdl(mog2_kernel<false>, dim3(grid), dim3(threads), 0, stream, L);
     BGSB_LAUNCH_CHECK();
     return BGSB_OK;
 }

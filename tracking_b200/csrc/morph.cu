@@ -40,6 +40,7 @@ __device__ __forceinline__ unsigned inside_mask(int y, int k, int w, int h, int 
 __global__ void __launch_bounds__(256)
 morph_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, int h, int wpr, MorphChain chain, int R)
 {
+    pdl_entry();
     __shared__ unsigned buf[2][MORPH_ROWS][MORPH_SW];
     const int img = blockIdx.z;
     const size_t npx = (size_t)w * h;
@@ -193,7 +194,7 @@ int launch_morph_chain(const uint8_t *d_in, uint8_t *d_out, int w, int h, int ni
             ch.op[ch.n] = (signed char)items[i].op; ch.iters[ch.n] = (signed char)items[i].iters; ch.n++;
             R += items[i].iters;
         }
-        morph_kernel<<<grid, 256, 0, stream>>>(src, dst, w, h, wpr, ch, R);
+        launch_pdl(morph_kernel, dim3(grid), dim3(256), 0, stream, src, dst, w, h, wpr, ch, R);
         BGSB_LAUNCH_CHECK();
         src = dst;
     }
