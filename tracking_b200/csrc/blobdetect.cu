@@ -48,18 +48,30 @@ inline bool rects_close(const Rect &ra, const Rect &rb)
 }
 
 // cvSeqPartition: transitive closure of the predicate; classes numbered by first appearance.
+// cvSeqPartition itself tests all n(n-1)/2 pairs.  The predicate needs the x-extents to overlap (dx < 0), so
+// only pairs whose integer x-ranges come within one pixel of each other can satisfy it: a sweep over the
+// rectangles sorted by x hands exactly those pairs to the exact float predicate.  The partition and its
+// numbering (first member of each class in index order) do not depend on the order the pairs are visited in.
 int partition_rects(const std::vector<Rect> &r, std::vector<int> &cls)
 {
     const int n = (int)r.size();
     std::vector<int> parent(n);
     for (int i = 0; i < n; i++) parent[i] = i;
     auto find = [&](int a) { while (parent[a] != a) { parent[a] = parent[parent[a]]; a = parent[a]; } return a; };
-    for (int i = 0; i < n; i++)
-        for (int j = i + 1; j < n; j++)
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return r[a].x < r[b].x; });
+    for (int u = 0; u < n; u++) {
+        const int i = order[u];
+        const int xend = r[i].x + r[i].w + 1;
+        for (int v = u + 1; v < n && r[order[v]].x <= xend; v++) {
+            const int j = order[v];
             if (rects_close(r[i], r[j])) {
                 int a = find(i), b = find(j);
                 if (a != b) parent[std::max(a, b)] = std::min(a, b);
             }
+        }
+    }
     cls.assign(n, -1);
     std::vector<int> id(n, -1);
     int ncls = 0;
