@@ -211,7 +211,7 @@ def run_ours(args):
     total_px = world * K * F * NPX
     value = total_px / (ms_max * 1e-3) / 1e6
 
-    # ---- roofline of the dominant kernel (mog2_t1v4_kernel, csrc/mog2_t1.cu): per-launch figures, this rank ----
+    # ---- roofline of the dominant kernel (mog2_t1_kernel, csrc/mog2_t1.cu): per-launch figures, this rank ----
     # Algorithmic bytes: SURVEY 8(d) quotes 209 B/px for a DENSE model (all K=5 modes live).  Like the
     # reference's CPU loop (`for mode < nmodes`), the kernel only touches LIVE modes, so the bytes the
     # algorithm has to move depend on the stream: 9 + 40 * (mean live modes per pixel).  `achieved` uses
@@ -309,7 +309,7 @@ def finish(args, rank, world, value, K, Wm, ms_max, F, clocks, e2e, launches, ac
                 "e2e": e2e,
                 "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "kernel": "mog2_t1v4_kernel<SHADOWS,2>", "peak_source": peak_src,
+                             "traffic": traffic, "kernel": "mog2_t1_kernel<SHADOWS,0,GROUP>", "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
                              "frac_of_8TBs_nominal": achieved / 8000.0, **extra},
                 "cpu_baseline": cpu}

@@ -9,6 +9,7 @@
 #include <string.h>
 #include <algorithm>
 
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -248,6 +249,14 @@ static int run_frames(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_fg
     advance(c, T, own_history);
     return BGSB_OK;
 }
+
+namespace bgsb {
+bool pdl_enabled()
+{
+    static const bool on = [] { const char *e = getenv("BGSB_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+}  // namespace bgsb
 
 extern "C" {
 
