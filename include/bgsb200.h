@@ -117,6 +117,18 @@ BGSB_API int bgsb_process(bgsb_ctx *ctx, const uint8_t *bgr, int w, int h, size_
                           uint8_t *fg, size_t fg_stride, uint8_t *bg, size_t bg_stride,
                           int *fg_valid, int *bg_valid);
 
+/* FrameProcessor::process (FrameProcessor.cpp:169-215) runs every enabled plugin back to back on the same
+ * prepared frame.  Fan-out does that with ONE upload: the frame goes to the device once (in row bands), the n
+ * contexts' kernels run on it concurrently, and each plugin's outputs come back as in bgsb_process.
+ * Results and per-context state are identical to calling bgsb_process on each context.
+ *   ctxs[n]      : single-stream contexts on one device (any mix of algorithms), n <= 16
+ *   fg[n], bg[n] : per-context output buffers (bg or bg[k] may be NULL), with their row strides
+ *   fg_valid[n], bg_valid[n] : as in bgsb_process, may be NULL */
+BGSB_API int bgsb_process_fanout(bgsb_ctx *const *ctxs, int n, const uint8_t *bgr, int w, int h, size_t stride,
+                                 uint8_t *const *fg, const size_t *fg_stride,
+                                 uint8_t *const *bg, const size_t *bg_stride,
+                                 int *fg_valid, int *bg_valid);
+
 /* Same, DEVICE buffers, dense rows (stride == 3*w / w), asynchronous on `stream`
  * (a cudaStream_t; NULL = legacy default stream).  d_bg may be NULL. */
 BGSB_API int bgsb_process_dev(bgsb_ctx *ctx, const uint8_t *d_bgr, int w, int h,

@@ -333,6 +333,43 @@ def test_host_path_band_pipeline_large_frames(oracle, aid):
         p.close()
 
 
+@pytest.mark.parametrize("shape", [(97, 131), (600, 700)])
+def test_fanout_one_upload_matches_separate_plugins(oracle, shape):
+    """FrameProcessor-style fan-out (FrameProcessor.cpp:169-215): FD, StaticFD, WMM, WMV, MOG2, ABL on one uploaded
+    frame == the oracle's plugins run one by one, incl. warm-up frames; (600, 700) takes the row-band pipeline.
+    Afterwards every context continues correctly through its own process()."""
+    import tracking_b200 as tb
+    h, w = shape
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    frames = [np.clip(base.astype(np.int16) + rng.integers(-12, 13, (h, w, 3)), 0, 255).astype(np.uint8) for _ in range(7)]
+    frames[4][h // 4:h // 2, w // 4:w // 2] = 255 - frames[4][h // 4:h // 2, w // 4:w // 2]
+    names = ["FrameDifferenceBGS", "StaticFrameDifferenceBGS", "WeightedMovingMeanBGS", "WeightedMovingVarianceBGS",
+             "MixtureOfGaussianV2BGS", "AdaptiveBackgroundLearning"]
+    ps = [getattr(tb, nm)() for nm in names]
+    os_ = [getattr(oracle, nm)() for nm in names]
+    for i, f in enumerate(frames[:6]):
+        outs = tb.process_fanout(ps, f)
+        for nm, (fa, ba), o in zip(names, outs, os_):
+            fb, bb = o.process(f)
+            assert (fa is None) == (fb is None), (nm, i)
+            assert (ba is None) == (bb is None), (nm, i)
+            if fa is not None:
+                assert np.array_equal(fa, fb), (nm, i)
+            if ba is not None:
+                assert np.array_equal(ba, bb), (nm, i)
+    for nm, p, o in zip(names, ps, os_):               # the per-context state is the ordinary one
+        fa, ba = p.process(frames[6])
+        fb, bb = o.process(frames[6])
+        assert np.array_equal(fa, fb), nm
+        if bb is not None:
+            assert np.array_equal(ba, bb), nm
+        p.close()
+    with pytest.raises(tb.BgsbError):
+        q = tb.FrameDifferenceBGS()
+        tb.process_fanout([q, q], frames[0])
+
+
 def test_mog2_state_export_import_roundtrip(clips):
     import tracking_b200 as tb
     clip = clips["video_clip"]

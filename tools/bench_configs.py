@@ -17,6 +17,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 import tracking_b200 as tb                      # noqa: E402
 from tracking_b200 import blobs, capi, synth    # noqa: E402
 
@@ -208,6 +209,8 @@ def main():
     simple_streams(tb.AdaptiveBackgroundLearning, "ABL", 10)
     simple_streams(tb.WeightedMovingVarianceBGS, "WMV", 10 + 6)  # device path writes both history images
     ccl_kernel_probe()
+    import fanout_probe                                   # tools/fanout_probe.py: FrameProcessor fan-out vs four uploads
+    fanout_probe.main()
     pipeline(S=16 if quick else 64)
     mog2_batches(1, 1920, 1080, [1, 2, 4, 8, 16], "2-T")
     mog2_batches(16, 1920, 1080, [1, 4, 16], "16x1080p-T")

@@ -14,6 +14,7 @@
 #pragma once
 #include <iostream>
 #include <string>
+#include <vector>
 
 #include <opencv2/opencv.hpp>
 
@@ -22,14 +23,21 @@
 
 namespace bgsb_adapter {
 
+class FanOut;
+
 class PluginBase : public IBGS
 {
+  friend class FanOut;
+
 protected:
   bgsb_ctx *ctx;
   bool firstTime;
   cv::Mat img_foreground, img_background;   // members of the reference classes; own the outputs
+  // set by FanOut::process: this frame's outputs are already in img_foreground / img_background
+  const unsigned char *pre_frame;
+  bool pre_fg, pre_bg;
 
-  explicit PluginBase(int algo) : ctx(0), firstTime(true)
+  explicit PluginBase(int algo) : ctx(0), firstTime(true), pre_frame(0), pre_fg(false), pre_bg(false)
   {
     int rc = bgsb_create(&ctx, algo, 0);
     if (rc != BGSB_OK) std::cerr << "bgsb200: " << bgsb_last_error() << std::endl;
@@ -43,6 +51,13 @@ protected:
   void run(const cv::Mat &img_input, bool &fg_valid, bool &bg_valid, bool want_bg)
   {
     CV_Assert(img_input.type() == CV_8UC3);     // PreProcessor.cpp:56 hands BGR 8UC3 frames to every plugin
+    if (pre_frame && pre_frame == img_input.data) {   // FanOut already ran this frame through this plugin
+      fg_valid = pre_fg;
+      bg_valid = pre_bg && want_bg;
+      pre_frame = 0;
+      return;
+    }
+    pre_frame = 0;
     img_foreground.create(img_input.rows, img_input.cols, CV_8UC1);
     if (want_bg) img_background.create(img_input.rows, img_input.cols, CV_8UC3);
     int fv = 0, bv = 0;
@@ -53,6 +68,51 @@ protected:
     CV_Assert(rc == BGSB_OK);
     fg_valid = fv != 0;
     bg_valid = bv != 0;
+  }
+};
+
+// FrameProcessor::process (FrameProcessor.cpp:169-215) hands the same img_prep to every enabled plugin, each of which
+// would upload it again.  With one added line in front of those calls --
+//     fanout.process(img_prep);          // FanOut fanout; fanout.add(frameDifference); fanout.add(mixtureOfGaussianV2BGS); ...
+// -- the frame crosses PCIe once (bgsb_process_fanout) and the unchanged `plugin->process(img_prep, fg, bg)` calls that
+// follow find their outputs ready.  Parameters re-read by a plugin's loadConfig() apply from the next frame on.
+class FanOut
+{
+  std::vector<PluginBase *> plugins;
+
+public:
+  void add(IBGS *p)
+  {
+    PluginBase *b = dynamic_cast<PluginBase *>(p);
+    CV_Assert(b != 0);
+    plugins.push_back(b);
+  }
+  void process(const cv::Mat &img_input)
+  {
+    if (img_input.empty() || plugins.empty()) return;
+    CV_Assert(img_input.type() == CV_8UC3);
+    const size_t n = plugins.size();
+    std::vector<bgsb_ctx *> ctxs(n);
+    std::vector<uint8_t *> fg(n), bg(n);
+    std::vector<size_t> fgs(n), bgs(n);
+    std::vector<int> fv(n), bv(n);
+    for (size_t k = 0; k < n; k++) {
+      PluginBase *p = plugins[k];
+      p->img_foreground.create(img_input.rows, img_input.cols, CV_8UC1);
+      p->img_background.create(img_input.rows, img_input.cols, CV_8UC3);
+      ctxs[k] = p->ctx;
+      fg[k] = p->img_foreground.data; fgs[k] = (size_t)p->img_foreground.step;
+      bg[k] = p->img_background.data; bgs[k] = (size_t)p->img_background.step;
+    }
+    int rc = bgsb_process_fanout(&ctxs[0], (int)n, img_input.data, img_input.cols, img_input.rows, (size_t)img_input.step,
+                                 &fg[0], &fgs[0], &bg[0], &bgs[0], &fv[0], &bv[0]);
+    if (rc != BGSB_OK) std::cerr << "bgsb200: " << bgsb_last_error() << std::endl;
+    CV_Assert(rc == BGSB_OK);
+    for (size_t k = 0; k < n; k++) {
+      plugins[k]->pre_frame = img_input.data;
+      plugins[k]->pre_fg = fv[k] != 0;
+      plugins[k]->pre_bg = bv[k] != 0;
+    }
   }
 };
 

@@ -7,6 +7,10 @@ int compile_check_calls()
     IBGS *plugins[6] = {new FrameDifferenceBGS, new WeightedMovingVarianceBGS, new MixtureOfGaussianV2BGS,
                         new AdaptiveBackgroundLearning, new StaticFrameDifferenceBGS, new WeightedMovingMeanBGS};
     cv::Mat img_input, img_bgs, img_bkgmodel;
+    // FrameProcessor.cpp:169-215 with the one added line: a single upload feeds all enabled plugins
+    bgsb_adapter::FanOut fanout;
+    for (int i = 0; i < 6; i++) fanout.add(plugins[i]);
+    fanout.process(img_input);
     for (int i = 0; i < 6; i++) {
         plugins[i]->process(img_input, img_bgs, img_bkgmodel);
         delete plugins[i];

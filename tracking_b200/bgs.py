@@ -157,6 +157,30 @@ class MixtureOfGaussianV2BGS(_Plugin):
                                                      planes.ctypes.data_as(capi.f32p), nmodes.ctypes.data_as(capi.u8p)))
 
 
+def process_fanout(plugins, img_input, want_bg=True):
+    """FrameProcessor::process (FrameProcessor.cpp:169-215): every plugin on the same frame, one upload.
+    Returns [(img_output | None, img_bgmodel | None), ...] exactly as plugin.process(img_input) would for each."""
+    if img_input is None or img_input.size == 0:
+        return [(None, None) for _ in plugins]
+    img = np.asarray(img_input)
+    if img.dtype != np.uint8 or img.ndim != 3 or img.shape[-1] != 3:
+        raise ValueError("fan-out takes one BGR 8UC3 frame")
+    if img.strides[-1] != 1 or img.strides[-2] != 3:
+        img = np.ascontiguousarray(img)
+    h, w = img.shape[:2]
+    n = len(plugins)
+    fgs = [np.empty((h, w), np.uint8) for _ in plugins]
+    bgs = [np.empty((h, w, 3), np.uint8) if want_bg else None for _ in plugins]
+    ctxs = (C.c_void_p * n)(*[p._h for p in plugins])
+    fgp = (C.c_void_p * n)(*[f.ctypes.data for f in fgs])
+    fgst = (C.c_size_t * n)(*[w] * n)
+    bgp = (C.c_void_p * n)(*[(b.ctypes.data if b is not None else None) for b in bgs])
+    bgst = (C.c_size_t * n)(*[3 * w] * n)
+    fv, bv = (C.c_int * n)(), (C.c_int * n)()
+    capi.check(capi.lib().bgsb_process_fanout(ctxs, n, _ptr(img), w, h, img.strides[0], fgp, fgst, bgp, bgst, fv, bv))
+    return [((fgs[k] if fv[k] else None), (bgs[k] if bv[k] else None)) for k in range(n)]
+
+
 # integer ids of the USTC_BGS factory (ustc_src/ustc_bgs.cpp:8-14)
 ALGOS = {0: FrameDifferenceBGS, 1: StaticFrameDifferenceBGS, 2: WeightedMovingMeanBGS,
          3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS, 6: AdaptiveBackgroundLearning}

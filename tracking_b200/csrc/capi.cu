@@ -59,6 +59,8 @@ struct bgsb_ctx {
     uint8_t *d_ring[3] = {nullptr, nullptr, nullptr};
     int ring_pos = 0;
     uint8_t *d_fg = nullptr, *d_bg = nullptr;
+    uint8_t *d_fan = nullptr;             // bgsb_process_fanout: the shared uploaded frame (owned by the first context)
+    size_t d_fan_bytes = 0;
     cudaStream_t stream = nullptr;
     // host-path chunk pipeline: upload / compute / download overlap inside one synchronous call
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -74,6 +76,7 @@ static void free_buffers(bgsb_ctx *c)
     for (int i = 0; i < 3; i++) { cudaFree(c->d_ring[i]); c->d_ring[i] = nullptr; }
     cudaFree(c->d_fg); c->d_fg = nullptr;
     cudaFree(c->d_bg); c->d_bg = nullptr;
+    cudaFree(c->d_fan); c->d_fan = nullptr; c->d_fan_bytes = 0;
     c->w = c->h = c->npx = 0; c->pstride = 0;
     c->nframes = 0; c->have_hist = 0; c->ring_pos = 0;
 }
@@ -257,6 +260,19 @@ bool pdl_enabled()
     return on;
 }
 }  // namespace bgsb
+
+// copy streams and per-band events of the upload / kernel / download pipelines
+static int ensure_pipe_streams(bgsb_ctx *c)
+{
+    if (c->s_h2d) return BGSB_OK;
+    BGSB_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    BGSB_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) {
+        BGSB_CUDA(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
+        BGSB_CUDA(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+    }
+    return BGSB_OK;
+}
 
 extern "C" {
 
@@ -460,13 +476,9 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
         nchunks = (h + band - 1) / band;
         if (nchunks > 8) { nchunks = 1; band = h; }
     }
-    if (nchunks > 1 && !c->s_h2d) {
-        BGSB_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
-        BGSB_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
-        for (int i = 0; i < 8; i++) {
-            BGSB_CUDA(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
-            BGSB_CUDA(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
-        }
+    if (nchunks > 1) {
+        rc = ensure_pipe_streams(c);
+        if (rc) return rc;
     }
     if (nchunks == 1) {
         BGSB_CUDA(copy_rows(d_in, (size_t)w * 3, bgr, stride, (size_t)w * 3, rows, cudaMemcpyHostToDevice, c->stream));
@@ -509,6 +521,83 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
     }
     if (fg_valid) *fg_valid = out_fg;
     if (bg_valid) *bg_valid = (want_bg && out_fg) ? 1 : 0;
+    return BGSB_OK;
+}
+
+int bgsb_process_fanout(bgsb_ctx *const *ctxs, int n, const uint8_t *bgr, int w, int h, size_t stride,
+                        uint8_t *const *fg, const size_t *fg_stride, uint8_t *const *bg, const size_t *bg_stride,
+                        int *fg_valid, int *bg_valid)
+{
+    BGSB_REQUIRE(ctxs && bgr && fg && fg_stride && n >= 1 && n <= 16, "bad args");
+    BGSB_REQUIRE(stride >= (size_t)w * 3, "stride smaller than a row");
+    bgsb_ctx *c0 = ctxs[0];
+    for (int k = 0; k < n; k++) {
+        BGSB_REQUIRE(ctxs[k] && fg[k], "null context or mask buffer");
+        BGSB_REQUIRE(ctxs[k]->device == c0->device && ctxs[k]->nstreams == 1, "fan-out takes single-stream contexts of one device");
+        BGSB_REQUIRE(fg_stride[k] >= (size_t)w, "fg stride smaller than a row");
+        BGSB_REQUIRE(!(bg && bg[k]) || (bg_stride && bg_stride[k] >= (size_t)w * 3), "bg stride smaller than a row");
+        for (int j = 0; j < k; j++) BGSB_REQUIRE(ctxs[j] != ctxs[k], "the same context twice");
+    }
+    BGSB_CUDA(cudaSetDevice(c0->device));
+    for (int k = 0; k < n; k++) {
+        int rc = ensure_geometry(ctxs[k], w, h);
+        if (rc) return rc;
+        rc = ensure_host_staging(ctxs[k]);
+        if (rc) return rc;
+        rc = ensure_pipe_streams(ctxs[k]);
+        if (rc) return rc;
+    }
+    const size_t fbytes = (size_t)w * h * 3;
+    if (c0->d_fan_bytes < fbytes) {
+        cudaFree(c0->d_fan); c0->d_fan = nullptr; c0->d_fan_bytes = 0;
+        BGSB_CUDA(cudaMalloc(&c0->d_fan, fbytes));
+        c0->d_fan_bytes = fbytes;
+    }
+    // row bands as in bgsb_process: the upload of band i+1 overlaps the n kernels on band i (each on its own
+    // context's stream) and the downloads of band i-1
+    int nchunks = 1, band = h;
+    if (c0->host_bands > 1 && fbytes >= (1u << 20)) {
+        band = ((h + c0->host_bands - 1) / c0->host_bands + 31) / 32 * 32;
+        if (((size_t)band * w) % MOG2_TILE) band += 32;
+        nchunks = (h + band - 1) / band;
+        if (nchunks > 8) { nchunks = 1; band = h; }
+    }
+    bool fgv[16], bgv[16];
+    for (int k = 0; k < n; k++) {
+        bgsb_ctx *c = ctxs[k];
+        fgv[k] = c->nframes >= warmup_frames(c->algo);
+        bgv[k] = writes_background(c->algo) && bg && bg[k] && fgv[k];
+    }
+    for (int i = 0; i < nchunks; i++) {
+        const int r0 = i * band, nr = std::min(band, h - r0);
+        const size_t p0 = (size_t)r0 * w;
+        BGSB_CUDA(copy_rows(c0->d_fan + p0 * 3, (size_t)w * 3, bgr + (size_t)r0 * stride, stride, (size_t)w * 3, nr,
+                            cudaMemcpyHostToDevice, c0->s_h2d));
+        BGSB_CUDA(cudaEventRecord(c0->ev_up[i], c0->s_h2d));
+        for (int k = 0; k < n; k++) {
+            bgsb_ctx *c = ctxs[k];
+            BGSB_CUDA(cudaStreamWaitEvent(c->stream, c0->ev_up[i], 0));
+            // the frame buffer is shared, so every plugin keeps its own history (FD / WMV copy the frame)
+            int rc = launch_range(c, c0->d_fan, 1, c->d_fg, writes_background(c->algo) ? c->d_bg : nullptr, 0, true,
+                                  c->stream, p0, nr * w);
+            if (rc) return rc;
+            BGSB_CUDA(cudaEventRecord(c->ev_k[i], c->stream));
+            BGSB_CUDA(cudaStreamWaitEvent(c0->s_d2h, c->ev_k[i], 0));
+            if (fgv[k])
+                BGSB_CUDA(copy_rows(fg[k] + (size_t)r0 * fg_stride[k], fg_stride[k], c->d_fg + p0, (size_t)w, (size_t)w, nr,
+                                    cudaMemcpyDeviceToHost, c0->s_d2h));
+            if (bgv[k])
+                BGSB_CUDA(copy_rows(bg[k] + (size_t)r0 * bg_stride[k], bg_stride[k], c->d_bg + p0 * 3, (size_t)w * 3,
+                                    (size_t)w * 3, nr, cudaMemcpyDeviceToHost, c0->s_d2h));
+        }
+    }
+    BGSB_CUDA(cudaStreamSynchronize(c0->s_d2h));
+    for (int k = 0; k < n; k++) {
+        BGSB_CUDA(cudaStreamSynchronize(ctxs[k]->stream));
+        advance(ctxs[k], 1, true);
+        if (fg_valid) fg_valid[k] = fgv[k];
+        if (bg_valid) bg_valid[k] = bgv[k];
+    }
     return BGSB_OK;
 }
 
