@@ -193,6 +193,34 @@ def test_wmm_unweighted_and_raw(oracle):
                 assert np.array_equal(fa, fb) and np.array_equal(ba, bb)
 
 
+def test_wmv_small_differences_and_weight_change(oracle):
+    """Frames that differ by camera-noise amounts (many exact rounding ties: equal previous frames and an odd
+    difference give 255*sd = k + 0.5) with a moving high-contrast patch, both weightings, raw and thresholded
+    output, and a weighting change mid-stream."""
+    import tracking_b200 as tb
+    rng = np.random.default_rng(21)
+    h, w = 203, 317
+    base = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    frames = []
+    for t in range(9):
+        f = np.clip(base.astype(np.int16) + rng.integers(-14, 15, (h, w, 3)), 0, 255).astype(np.uint8)
+        f[20 + 9 * t:60 + 9 * t, 30 + 11 * t:90 + 11 * t] = (255 * (t & 1), 128, 255 - 255 * (t & 1))
+        frames.append(f)
+    for ew in (1, 0):
+        for thr in (1, 0):
+            p = tb.WeightedMovingVarianceBGS(enableWeight=ew, enableThreshold=thr)
+            o = oracle.WeightedMovingVarianceBGS(enableWeight=bool(ew), enableThreshold=bool(thr))
+            for i, f in enumerate(frames):
+                if i == 6:
+                    p.set("enableWeight", 1 - ew); o.enableWeight = not bool(ew)
+                fa, _ = p.process(f)
+                fb, _ = o.process(f)
+                assert (fa is None) == (fb is None)
+                if fa is not None:
+                    assert np.array_equal(fa, fb), (ew, thr, i)
+            p.close()
+
+
 def test_wmv_exhaustive_triples_sample(oracle):
     """Random byte triples incl. unweighted variant and raw (un-thresholded) output."""
     import tracking_b200 as tb
