@@ -100,7 +100,8 @@ BGSB_API int bgsb_reset(bgsb_ctx *ctx);
  * "shadowThreshold" 0.5; and "grayVariant": 0 = OpenCV 4.x BGR2GRAY constants, 1 = 2.4.x;
  * "kernelVariant" (MOG2): 0 = production kernels, 1 = straight restatement kernel (identical results, kept for
  * A/B measurements); 8, 9 = timing instruments with WRONG results (tools/floor_probe.py);
- * "ablTable" (AdaptiveBackgroundLearning): 1 = lookup-table kernel (default), 0 = arithmetic kernel, identical results;
+ * "ablTable" (AdaptiveBackgroundLearning): 1 = lookup-table kernels (default), 2 = only the per-thread table kernel,
+ * 0 = arithmetic kernel -- identical results;
  * "hostBands" (default 4, 1..8): row bands of the upload / kernel / download pipeline inside bgsb_process. */
 BGSB_API int bgsb_set_param(bgsb_ctx *ctx, const char *key, double value);
 BGSB_API int bgsb_get_param(bgsb_ctx *ctx, const char *key, double *value);

@@ -13,7 +13,7 @@ for S in (1, 16):
     fg = torch.empty((S, h, w), dtype=torch.uint8, device="cuda")
     bg = torch.empty((S, h, w, 3), dtype=torch.uint8, device="cuda")
     ref = None
-    for table in (1, 0):
+    for table in (1, 2, 0):
         p = tb.AdaptiveBackgroundLearning(nstreams=S, ablTable=table)
         k = [0]
         def run(n):

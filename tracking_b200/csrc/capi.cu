@@ -221,6 +221,7 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
                 c->lut_alpha = c->alpha;
             }
             L.abl_lut = c->d_abl_lut;
+            L.abl_lut_mode = c->abl_table == 2 ? 1 : 0;
         }
         L.abl_update = (c->limit == -1);   // the limit>0 branch never fires: counter stays 0 (.cpp:52,60-61)
         if (c->enable_weight) { L.w0 = 0.5; L.w1 = 0.3; L.w2 = 0.2; }      // WeightedMovingVarianceBGS.cpp:67-68
@@ -367,7 +368,7 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     else if (k == "shadowThreshold") c->tau = (float)v;
     else if (k == "hostBands") { BGSB_REQUIRE(v >= 1 && v <= 8, "hostBands in [1,8]"); c->host_bands = (int)v; }
     else if (k == "kernelVariant") { BGSB_REQUIRE(v == 0 || v == 1 || v == 8 || v == 9, "kernelVariant is 0 or 1 (8, 9: timing instruments)"); c->mog2_variant = (int)v; }
-    else if (k == "ablTable") { BGSB_REQUIRE(v == 0 || v == 1, "ablTable is 0 or 1"); c->abl_table = (int)v; }
+    else if (k == "ablTable") { BGSB_REQUIRE(v == 0 || v == 1 || v == 2, "ablTable is 0, 1 or 2"); c->abl_table = (int)v; }
     else if (k == "showOutput" || k == "showForeground" || k == "showBackground") { /* GUI only */ }
     else { set_error("bgsb_set_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
     return BGSB_OK;

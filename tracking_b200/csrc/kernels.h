@@ -21,6 +21,7 @@ struct SimpleLaunch {
     double alpha;            // ABL
     int abl_update;          // ABL: limit == -1 (AdaptiveBackgroundLearning.cpp:52); 0 freezes the model
     const uint8_t *abl_lut;  // ABL: 64 KB table of the blend for this alpha (abl_lut_index), null = arithmetic kernel
+    int abl_lut_mode;        // ABL table kernels: 0 = warp-coalesced where the alignment allows, 1 = per-thread groups
     double w0, w1, w2;       // WMV weights (0.5,0.3,0.2 | 0.3,0.3,0.3)
 };
 int launch_simple(int algo, const SimpleLaunch &L, int nstreams, cudaStream_t stream);
