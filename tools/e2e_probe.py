@@ -26,7 +26,7 @@ for name, src in (("pinned", [h_in[i].data_ptr() for i in range(NF)]), ("write-c
     t0 = time.perf_counter(); run(256); dt = (time.perf_counter() - t0) / 256
     print(name, "input: us/frame %.1f  Gpx/s %.2f" % (dt * 1e6, W * H / dt / 1e9), flush=True)
     p.close()
-for bands in (4,):
+for bands in (1, 2, 3, 4, 6, 8):
     for want_bg in (1, 0):
         p = tb.MixtureOfGaussianV2BGS(hostBands=bands)
         fv, bv = C.c_int(0), C.c_int(0)
