@@ -317,6 +317,7 @@ ccl_rank_kernel(const unsigned *__restrict__ rootbits, int *__restrict__ wordran
     }
 }
 
+template <bool LABELS>       // LABELS = false: component table only (no 32-register label row per thread)
 __global__ void __launch_bounds__(256)
 ccl_label_kernel(const unsigned *__restrict__ bits, const int *__restrict__ parent, const uint8_t *__restrict__ outer,
                  const unsigned *__restrict__ rootbits, const int *__restrict__ wordrank, CompRaw *comp, int cap,
@@ -327,13 +328,13 @@ ccl_label_kernel(const unsigned *__restrict__ bits, const int *__restrict__ pare
     if (wi >= h * wpr) return;
     bits += blockIdx.y * img_words; parent += blockIdx.y * img_px; outer += blockIdx.y * img_px;
     rootbits += blockIdx.y * img_words; wordrank += blockIdx.y * img_words; comp += blockIdx.y * (size_t)cap;
-    if (labels) labels += blockIdx.y * img_px;
+    if (LABELS) labels += blockIdx.y * img_px;
     int y = wi / wpr, k = wi - y * wpr;
     unsigned v = bits[wi];
     int base = y * w + k * 32;
     int nvalid = min(32, w - k * 32);
-    int lab[32];
-    if (labels) {
+    int lab[LABELS ? 32 : 1];
+    if (LABELS) {
 #pragma unroll
         for (int i = 0; i < 32; i++) lab[i] = 0;
     }
@@ -347,7 +348,7 @@ ccl_label_kernel(const unsigned *__restrict__ bits, const int *__restrict__ pare
         int rank = wordrank[rwi] + __popc(rootbits[rwi] & ((rx & 31) ? (0xffffffffu >> (32 - (rx & 31))) : 0u));
         unsigned rest = ~(v >> b);
         int len = rest ? __ffs(rest) - 1 : 32 - b;
-        if (labels) {
+        if (LABELS) {
 #pragma unroll
             for (int i = 0; i < 32; i++)
                 if (i >= b && i < b + len) lab[i] = rank + 1;
@@ -361,7 +362,7 @@ ccl_label_kernel(const unsigned *__restrict__ bits, const int *__restrict__ pare
             if (r == p) c->external = 1;           // provisional; nested components are found by the bg pass
         }
     }
-    if (labels) {
+    if (LABELS) {
         int *o = labels + base;
         if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
@@ -418,20 +419,21 @@ ccl_resolve_external_kernel(const unsigned *__restrict__ bits, const int *__rest
     const int img = blockIdx.y;
     if (!need_bg[img]) return;
     const int n = min(ncomp[img], cap);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     bits += img * img_words; parent += img * img_px; outer += img * img_px;
-    CompRaw *c = comp + (size_t)img * cap + i;
-    const int r = c->first_index;
-    const int ry = r / w, rx = r - ry * w;
-    int ext = 1;
-    if (rx > 0) {
-        const int lk = (rx - 1) >> 5, lb = (rx - 1) & 31;
-        const unsigned lv = ~bits[ry * wpr + lk] & in_mask(lk, w, wpr);
-        const int node = ry * w + lk * 32 + run_start(lv, lb);
-        ext = outer[parent[node]];
+    // the component count is only known on the device: a small grid strides over the table
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        CompRaw *c = comp + (size_t)img * cap + i;
+        const int r = c->first_index;
+        const int ry = r / w, rx = r - ry * w;
+        int ext = 1;
+        if (rx > 0) {
+            const int lk = (rx - 1) >> 5, lb = (rx - 1) & 31;
+            const unsigned lv = ~bits[ry * wpr + lk] & in_mask(lk, w, wpr);
+            const int node = ry * w + lk * 32 + run_start(lv, lb);
+            ext = outer[parent[node]];
+        }
+        c->external = ext;
     }
-    c->external = ext;
 }
 
 // cvMoments(ROI, binary=0): pixel-value weighted raw moments, ROI-relative coordinates.
@@ -577,8 +579,12 @@ int bgsb_ccl_label_batch_dev(bgsb_ccl *c, const uint8_t *d_masks, int w, int h, 
     launch_pdl(ccl_rank_kernel, dim3(grid), dim3(threads), 0, stream, c->d_rootbits, c->d_wordrank, c->d_blockcount, c->d_comp, c->cap, w, h, wpr,
                                                   iw, nblocks);
     BGSB_LAUNCH_CHECK();
-    launch_pdl(ccl_label_kernel, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_rootbits, c->d_wordrank,
-                                                   c->d_comp, c->cap, d_labels, w, h, wpr, ipx, iw);
+    if (d_labels)
+        launch_pdl(ccl_label_kernel<true>, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_rootbits,
+                   c->d_wordrank, c->d_comp, c->cap, d_labels, w, h, wpr, ipx, iw);
+    else
+        launch_pdl(ccl_label_kernel<false>, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_rootbits,
+                   c->d_wordrank, c->d_comp, c->cap, d_labels, w, h, wpr, ipx, iw);
     BGSB_LAUNCH_CHECK();
     // RETR_EXTERNAL: background pass only for images where a bounding box lies strictly inside another
     if (c->force_bg) {
@@ -600,7 +606,7 @@ int bgsb_ccl_label_batch_dev(bgsb_ccl *c, const uint8_t *d_masks, int w, int h, 
     {
         // at most cap components per image; the kernel exits early past the real count
         const int maxc = std::min(c->cap, (int)(((size_t)w * h + 3) / 4 + 1));
-        dim3 rgrid((maxc + 255) / 256, nimages);
+        dim3 rgrid(std::min((maxc + 255) / 256, 16), nimages);
         launch_pdl(ccl_resolve_external_kernel, dim3(rgrid), dim3(256), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_comp, c->d_ncomp,
                                                                c->cap, c->d_need_bg, w, wpr, ipx, iw);
         BGSB_LAUNCH_CHECK();
