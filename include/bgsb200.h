@@ -55,7 +55,8 @@ enum {
     BGSB_ALGO_WEIGHTED_MOVING_MEAN = 2,       /* ustc_bgs.cpp:10  sibling plugin */
     BGSB_ALGO_WEIGHTED_MOVING_VARIANCE = 3,   /* ustc_bgs.cpp:11 */
     BGSB_ALGO_MOG2 = 5,                       /* ustc_bgs.cpp:13 */
-    BGSB_ALGO_ADAPTIVE_BG_LEARNING = 6        /* ustc_bgs.cpp:14 */
+    BGSB_ALGO_ADAPTIVE_BG_LEARNING = 6,       /* ustc_bgs.cpp:14 */
+    BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING = 7  /* ustc_bgs.cpp:15  sibling plugin; gray 1-channel bg image */
 };
 
 typedef struct bgsb_ctx bgsb_ctx;
@@ -92,6 +93,8 @@ BGSB_API int bgsb_reset(bgsb_ctx *ctx);
  *   all      : "enableThreshold" (1), "threshold" (15)
  *   MOG2     : "alpha" (0.05)             MixtureOfGaussianV2BGS.cpp:92-95
  *   ABL      : "alpha" (0.05), "limit" (-1; only -1 updates the model, .cpp:52)
+ *   ASBL     : "learningFrames" (90), "alphaLearn" (0.05), "alphaDetection" (0.05), "threshold" (25)
+ *              AdaptiveSelectiveBackgroundLearning.cpp:108-126 (the defaults its loadConfig applies)
  *   WMV, WMM : "enableWeight" (1)         WeightedMovingVarianceBGS.cpp:155-158, WeightedMovingMeanBGS.cpp
  * plus the cv::BackgroundSubtractorMOG2 properties of the default-constructed member
  * (MixtureOfGaussianV2BGS.h:30): "history" 500, "nmixtures" 5 (fixed), "varThreshold" 16,
@@ -109,7 +112,7 @@ BGSB_API int bgsb_get_param(bgsb_ctx *ctx, const char *key, double *value);
 /* IBGS::process with HOST buffers, synchronous (outputs complete on return).
  *   bgr        : h rows of w BGR pixels, `stride` bytes between rows (cv::Mat::step)
  *   fg         : h x w 8UC1, fg_stride bytes between rows
- *   bg         : h x w 8UC3, may be NULL (background model not wanted)
+ *   bg         : h x w 8UC3 (8UC1 for BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING, whose model is gray), may be NULL
  *   *fg_valid  : 0 reproduces "output left untouched" (FD frame 0, WMV frames 0-1:
  *                FrameDifferenceBGS.cpp:39-43, WeightedMovingVarianceBGS.cpp:40-51)
  *   *bg_valid  : 0 for FD / WMV, which never write img_bgmodel (StaticFD / WMM / ABL / MOG2 do)

@@ -153,6 +153,46 @@ ORC_API void orc_abl(const uint8_t *in, uint8_t *bg, int npx, double alpha,
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* AdaptiveSelectiveBackgroundLearning (package_bgs/AdaptiveSelectiveBackgroundLearning.cpp:30-105)  */
+/*   gray input, 8-bit gray background model `bg` (updated in place), thresholded |in - bg| mask, */
+/*   3x3 median (cv::medianBlur replicates the border), then either the adaptive update of every   */
+/*   pixel (learning phase, :65-71) or the update of the pixels the mask calls background (:72-90). */
+/* ------------------------------------------------------------------------------------ */
+ORC_API void orc_asbl(const uint8_t *in_bgr, uint8_t *bg, int w, int h, double alpha, int selective,
+                      int thr, int gray_variant, uint8_t *fg, uint8_t *scratch /* 2*w*h */)
+{
+    const float s = (float)(1. / 255.);
+    const double beta = 1 - alpha;
+    const int npx = w * h;
+    uint8_t *gray = scratch, *raw = scratch + npx;
+    for (int i = 0; i < npx; i++) {
+        gray[i] = gray_bgr(in_bgr[3 * i], in_bgr[3 * i + 1], in_bgr[3 * i + 2], gray_variant);   /* :36-37 */
+        float x = (float)gray[i] * s, y = (float)bg[i] * s;                  /* :50-54 */
+        float d = fabsf(x - y);                                              /* :56-57 */
+        uint8_t d8 = sat_u8_rint(d * 255.f + -0.f);                          /* :59-60 */
+        raw[i] = d8 > thr ? 255 : 0;                                         /* :62 */
+    }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {                                        /* :63, BORDER_REPLICATE */
+            int cnt = 0;
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    int yy = y + dy < 0 ? 0 : (y + dy >= h ? h - 1 : y + dy);
+                    int xx = x + dx < 0 ? 0 : (x + dx >= w ? w - 1 : x + dx);
+                    cnt += raw[yy * w + xx] != 0;
+                }
+            fg[y * w + x] = cnt >= 5 ? 255 : 0;
+        }
+    for (int i = 0; i < npx; i++) {
+        float x = (float)gray[i] * s, y = (float)bg[i] * s;
+        float nb = y;
+        if (!selective || fg[i] == 0)                                        /* :68 / :82-85 */
+            nb = (float)((double)x * alpha + (double)y * beta);
+        bg[i] = sat_u8_rint(nb * 255.f + -0.f);                              /* :92-94 */
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* WeightedMovingVariance (package_bgs/WeightedMovingVarianceBGS.cpp:53-106,126-138)       */
 /* ------------------------------------------------------------------------------------ */
 ORC_API void orc_wmv(const uint8_t *cur, const uint8_t *p1, const uint8_t *p2, int npx,

@@ -132,6 +132,41 @@ class AdaptiveBackgroundLearning:
         return fg, self.bg.copy()                              # :79-80
 
 
+class AdaptiveSelectiveBackgroundLearning:
+    """package_bgs/AdaptiveSelectiveBackgroundLearning.cpp:30-105 (USTC_BGS type 7, ustc_src/ustc_bgs.cpp:15).
+    Defaults are those of loadConfig() (:121-125), which runs before the first saveConfig (:43-46) and
+    therefore overrides the constructor's threshold 15 / learningFrames -1."""
+
+    def __init__(self, learningFrames=90, alphaLearn=0.05, alphaDetection=0.05, threshold=25):
+        self.learningFrames, self.alphaLearn, self.alphaDetection = learningFrames, alphaLearn, alphaDetection
+        self.threshold = threshold
+        self.counter = 0
+        self.bg = None
+
+    def process(self, img):
+        if img is None or img.size == 0:
+            return None, None
+        gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY) if img.ndim == 3 else img.copy()   # :36-39
+        if self.bg is None:                                    # :47-48
+            self.bg = gray.copy()
+        s = 1.0 / 255.0
+        in_f = gray.astype(np.float32) * np.float32(s)         # :50-51
+        bg_f = self.bg.astype(np.float32) * np.float32(s)      # :53-54
+        diff_f = cv2.absdiff(in_f, bg_f)                       # :56-57
+        fg = _to_u8(diff_f)                                    # :59-60  (255/(maxVal-minVal) = 255, -minVal = -0)
+        _, fg = cv2.threshold(fg, self.threshold, 255, cv2.THRESH_BINARY)   # :62
+        fg = cv2.medianBlur(fg, 3)                             # :63
+        if self.learningFrames > 0 and self.counter <= self.learningFrames:   # :65-71
+            bg_f = cv2.addWeighted(in_f, self.alphaLearn, bg_f, 1 - self.alphaLearn, 0)
+            self.counter += 1
+        else:                                                  # :72-90: double arithmetic, stored to float
+            a = float(self.alphaDetection)
+            upd = (a * in_f.astype(np.float64) + (1 - a) * bg_f.astype(np.float64)).astype(np.float32)
+            bg_f = np.where(fg == 0, upd, bg_f)
+        self.bg = _to_u8(bg_f)                                 # :92-94
+        return fg, self.bg.copy()                              # :102-103 (single-channel background model)
+
+
 def _to_u8(img_f):
     """Mat::convertTo(CV_8U, 255.0, 0): saturate_cast<uchar>(x*255) with round-half-even."""
     # cv2 does not expose Mat::convertTo directly; cv2.convertScaleAbs computes

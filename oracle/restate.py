@@ -45,6 +45,7 @@ def lib():
         L.orc_sfd.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
         L.orc_wmm.argtypes = [u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, u8p]
         L.orc_abl.argtypes = [u8p, u8p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, u8p]
+        L.orc_asbl.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, u8p, u8p]
         L.orc_wmv.argtypes = [u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
         L.orc_mog2_default_params.argtypes = [C.POINTER(Mog2Params)]
         L.orc_mog2_learning_rate.argtypes = [C.c_double, C.c_int, C.c_int]
@@ -164,6 +165,33 @@ class AdaptiveBackgroundLearning:
         fg = np.empty(img.shape[:2], np.uint8)
         lib().orc_abl(_u8(img), _u8(self.bg), fg.size, float(self.alpha), int(self.enableThreshold),
                       self.threshold, self.gray_variant, _u8(fg))
+        return fg, self.bg.copy()
+
+
+class AdaptiveSelectiveBackgroundLearning:
+    """USTC_BGS type 7; defaults = loadConfig()'s (AdaptiveSelectiveBackgroundLearning.cpp:121-125)."""
+
+    def __init__(self, learningFrames=90, alphaLearn=0.05, alphaDetection=0.05, threshold=25, gray_variant=0):
+        self.learningFrames, self.alphaLearn, self.alphaDetection = learningFrames, alphaLearn, alphaDetection
+        self.threshold, self.gray_variant = threshold, gray_variant
+        self.counter = 0
+        self.bg = None
+
+    def process(self, img):
+        if img is None or img.size == 0:
+            return None, None
+        img = _dense(img)
+        h, w = img.shape[:2]
+        if self.bg is None:
+            self.bg = np.empty((h, w), np.uint8)
+            lib().orc_gray_bgr(_u8(img), h * w, self.gray_variant, _u8(self.bg))
+        learning = self.learningFrames > 0 and self.counter <= self.learningFrames
+        if learning:
+            self.counter += 1
+        fg = np.empty((h, w), np.uint8)
+        scratch = np.empty(2 * h * w, np.uint8)
+        lib().orc_asbl(_u8(img), _u8(self.bg), w, h, float(self.alphaLearn if learning else self.alphaDetection),
+                       0 if learning else 1, int(self.threshold), self.gray_variant, _u8(fg), _u8(scratch))
         return fg, self.bg.copy()
 
 

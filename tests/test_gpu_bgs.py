@@ -398,6 +398,81 @@ def test_fanout_one_upload_matches_separate_plugins(oracle, shape):
         tb.process_fanout([q, q], frames[0])
 
 
+def _asbl_frames(h, w, n, seed):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    frames = []
+    for t in range(n):
+        f = np.clip(base.astype(np.int16) + rng.integers(-30, 31, (h, w, 3)), 0, 255).astype(np.uint8)
+        f[10 + 4 * t:40 + 4 * t, 20 + 5 * t:60 + 5 * t] = 255 - base[10 + 4 * t:40 + 4 * t, 20 + 5 * t:60 + 5 * t]
+        frames.append(f)
+    return frames
+
+
+@pytest.mark.parametrize("kw", [{}, {"learningFrames": 3}, {"learningFrames": -1, "alphaDetection": 0.3, "threshold": 10},
+                                {"learningFrames": 5, "alphaLearn": 0.5, "threshold": 40}])
+def test_asbl_sibling_plugin(oracle, kw):
+    """AdaptiveSelectiveBackgroundLearning (USTC_BGS type 7): gray model, 3x3 median with replicated border, learning
+    phase then selective update; single-channel background image; host path, device path and reset."""
+    import torch
+    import tracking_b200 as tb
+    for (h, w) in ((97, 131), (600, 700)):
+        frames = _asbl_frames(h, w, 12, 3)
+        p, o = tb.AdaptiveSelectiveBackgroundLearning(**kw), oracle.AdaptiveSelectiveBackgroundLearning(**kw)
+        for i, f in enumerate(frames[:8]):
+            fa, ba = p.process(f)
+            fb, bb = o.process(f)
+            assert ba.shape == (h, w)
+            assert np.array_equal(fa, fb) and np.array_equal(ba, bb), (h, w, i)
+        d_fg = torch.zeros((h, w), dtype=torch.uint8, device="cuda")
+        d_bg = torch.zeros((h, w), dtype=torch.uint8, device="cuda")
+        for i, f in enumerate(frames[8:]):                       # device buffers continue the same model
+            d_in = torch.from_numpy(f).cuda()
+            fv, bv = p.process_dev(d_in.data_ptr(), w, h, d_fg.data_ptr(), d_bg.data_ptr())
+            torch.cuda.synchronize()
+            fb, bb = o.process(f)
+            assert fv and bv
+            assert np.array_equal(d_fg.cpu().numpy(), fb) and np.array_equal(d_bg.cpu().numpy(), bb), (h, w, i)
+        p.reset()
+        o2 = oracle.AdaptiveSelectiveBackgroundLearning(**kw)
+        fa, ba = p.process(frames[0]); fb, bb = o2.process(frames[0])
+        assert np.array_equal(fa, fb) and np.array_equal(ba, bb)
+        p.close()
+    u = tb.USTC_BGS(7)
+    u.Process(frames[0]); u.Process(frames[1])
+    assert u.GetMask().shape == (h, w)
+    u.Release()
+
+
+def test_asbl_stream_group_and_fanout(oracle):
+    """Two streams advanced by one launch pair, and ASBL next to banded plugins in a fan-out (it runs once on the
+    whole frame after the last band)."""
+    import tracking_b200 as tb
+    h, w = 600, 700
+    fa_ = _asbl_frames(h, w, 5, 7); fb_ = _asbl_frames(h, w, 5, 8)
+    g = tb.AdaptiveSelectiveBackgroundLearning(nstreams=2, learningFrames=2)
+    oa, ob = oracle.AdaptiveSelectiveBackgroundLearning(learningFrames=2), oracle.AdaptiveSelectiveBackgroundLearning(learningFrames=2)
+    for i in range(5):
+        fg, bg = g.process(np.stack([fa_[i], fb_[i]]))
+        ra, rb = oa.process(fa_[i]), ob.process(fb_[i])
+        assert np.array_equal(fg[0], ra[0]) and np.array_equal(fg[1], rb[0]), i
+        assert np.array_equal(bg[0], ra[1]) and np.array_equal(bg[1], rb[1]), i
+    g.close()
+    ps = [tb.FrameDifferenceBGS(), tb.AdaptiveSelectiveBackgroundLearning(), tb.MixtureOfGaussianV2BGS()]
+    os_ = [oracle.FrameDifferenceBGS(), oracle.AdaptiveSelectiveBackgroundLearning(), oracle.MixtureOfGaussianV2BGS()]
+    for i in range(5):
+        outs = tb.process_fanout(ps, fa_[i])
+        for k, o in enumerate(os_):
+            fb, bb = o.process(fa_[i])
+            assert (outs[k][0] is None) == (fb is None), (k, i)
+            if fb is not None:
+                assert np.array_equal(outs[k][0], fb), (k, i)
+            if bb is not None:
+                assert np.array_equal(outs[k][1], bb), (k, i)
+    for p in ps:
+        p.close()
+
+
 def test_mog2_state_export_import_roundtrip(clips):
     import tracking_b200 as tb
     clip = clips["video_clip"]

@@ -111,6 +111,31 @@ def test_abl_exhaustive_pairs_against_opencv(oracle):
     assert np.array_equal(fa, fb) and np.array_equal(ba, bb)
 
 
+@pytest.mark.parametrize("kw", [{}, {"learningFrames": 3}, {"learningFrames": -1, "alphaDetection": 0.3, "threshold": 10},
+                                {"learningFrames": 5, "alphaLearn": 0.5, "threshold": 40}])
+def test_asbl_restatement_against_opencv(oracle, clips, kw):
+    """AdaptiveSelectiveBackgroundLearning (USTC_BGS type 7): the C restatement vs the OpenCV call chain
+    (cvtColor, absdiff, convertScaleAbs, threshold, medianBlur, addWeighted) on the reference clip, on a
+    noisy moving scene, and on every (gray input, model) byte pair."""
+    from oracle import cv2_chain
+    rng = np.random.default_rng(3)
+    h, w = 97, 131
+    base = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    moving = []
+    for t in range(14):
+        f = np.clip(base.astype(np.int16) + rng.integers(-30, 31, (h, w, 3)), 0, 255).astype(np.uint8)
+        f[10 + 4 * t:40 + 4 * t, 20 + 5 * t:60 + 5 * t] = 255 - base[10 + 4 * t:40 + 4 * t, 20 + 5 * t:60 + 5 * t]
+        moving.append(f)
+    inp, bg = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8))
+    pairs = [np.repeat(bg[:, :, None], 3, 2).copy(), np.repeat(inp[:, :, None], 3, 2).copy()]   # gray(v,v,v) == v
+    for frames in (list(clips["video_clip"]), moving, pairs):
+        a, b = cv2_chain.AdaptiveSelectiveBackgroundLearning(**kw), oracle.AdaptiveSelectiveBackgroundLearning(**kw)
+        for i, f in enumerate(frames):
+            fa, ba = a.process(f)
+            fb, bb = b.process(f)
+            assert np.array_equal(fa, fb) and np.array_equal(ba, bb), i
+
+
 def test_morph_and_ccl_against_opencv(oracle):
     from oracle import cv2_chain
     rng = np.random.default_rng(3)

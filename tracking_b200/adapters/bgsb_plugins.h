@@ -36,8 +36,9 @@ protected:
   // set by FanOut::process: this frame's outputs are already in img_foreground / img_background
   const unsigned char *pre_frame;
   bool pre_fg, pre_bg;
+  int bg_type;                              // CV_8UC3; CV_8UC1 for the gray model of AdaptiveSelectiveBackgroundLearning
 
-  explicit PluginBase(int algo) : ctx(0), firstTime(true), pre_frame(0), pre_fg(false), pre_bg(false)
+  explicit PluginBase(int algo) : ctx(0), firstTime(true), pre_frame(0), pre_fg(false), pre_bg(false), bg_type(CV_8UC3)
   {
     int rc = bgsb_create(&ctx, algo, 0);
     if (rc != BGSB_OK) std::cerr << "bgsb200: " << bgsb_last_error() << std::endl;
@@ -59,7 +60,7 @@ protected:
     }
     pre_frame = 0;
     img_foreground.create(img_input.rows, img_input.cols, CV_8UC1);
-    if (want_bg) img_background.create(img_input.rows, img_input.cols, CV_8UC3);
+    if (want_bg) img_background.create(img_input.rows, img_input.cols, bg_type);
     int fv = 0, bv = 0;
     int rc = bgsb_process(ctx, img_input.data, img_input.cols, img_input.rows, (size_t)img_input.step,
                           img_foreground.data, (size_t)img_foreground.step,
@@ -99,7 +100,7 @@ public:
     for (size_t k = 0; k < n; k++) {
       PluginBase *p = plugins[k];
       p->img_foreground.create(img_input.rows, img_input.cols, CV_8UC1);
-      p->img_background.create(img_input.rows, img_input.cols, CV_8UC3);
+      p->img_background.create(img_input.rows, img_input.cols, p->bg_type);
       ctxs[k] = p->ctx;
       fg[k] = p->img_foreground.data; fgs[k] = (size_t)p->img_foreground.step;
       bg[k] = p->img_background.data; bgs[k] = (size_t)p->img_background.step;
@@ -389,6 +390,69 @@ private:
     set("alpha", alpha);
     set("limit", (double)limit);
     set("enableThreshold", enableThreshold);
+    set("threshold", threshold);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sibling plugin, USTC_BGS type 7 (ustc_src/ustc_bgs.cpp:15).
+class AdaptiveSelectiveBackgroundLearning : public bgsb_adapter::PluginBase
+{
+private:
+  double alphaLearn;
+  double alphaDetection;
+  long learningFrames;
+  int threshold;
+  bool showOutput;
+
+public:
+  AdaptiveSelectiveBackgroundLearning() : PluginBase(BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING), alphaLearn(0.05),
+    alphaDetection(0.05), learningFrames(-1), threshold(15), showOutput(true)
+  {
+    bg_type = CV_8UC1;                       // the model is the gray image (.cpp:103)
+    std::cout << "AdaptiveSelectiveBackgroundLearning()" << std::endl;
+  }
+  ~AdaptiveSelectiveBackgroundLearning() { std::cout << "~AdaptiveSelectiveBackgroundLearning()" << std::endl; }
+
+  void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
+  {
+    if (img_input.empty()) return;
+    loadConfig();                            // before saveConfig, as in the reference (.cpp:41-46): the file's
+    if (firstTime) saveConfig();             // defaults (90 frames, threshold 25) replace the constructor's
+    bool fg, bg;
+    run(img_input, fg, bg, true);
+    if (showOutput) {
+      cv::imshow("AS-Learning FG", img_foreground);
+      cv::imshow("AS-Learning BG", img_background);
+    }
+    img_foreground.copyTo(img_output);       // .cpp:102-103
+    img_background.copyTo(img_bgmodel);
+    firstTime = false;
+  }
+
+private:
+  void saveConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/AdaptiveSelectiveBackgroundLearning.xml", 0, CV_STORAGE_WRITE);
+    cvWriteInt(fs, "learningFrames", learningFrames);
+    cvWriteReal(fs, "alphaLearn", alphaLearn);
+    cvWriteReal(fs, "alphaDetection", alphaDetection);
+    cvWriteInt(fs, "threshold", threshold);
+    cvWriteInt(fs, "showOutput", showOutput);
+    cvReleaseFileStorage(&fs);
+  }
+  void loadConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/AdaptiveSelectiveBackgroundLearning.xml", 0, CV_STORAGE_READ);
+    learningFrames = cvReadIntByName(fs, 0, "learningFrames", 90);
+    alphaLearn = cvReadRealByName(fs, 0, "alphaLearn", 0.05);
+    alphaDetection = cvReadRealByName(fs, 0, "alphaDetection", 0.05);
+    threshold = cvReadIntByName(fs, 0, "threshold", 25);
+    showOutput = cvReadIntByName(fs, 0, "showOutput", true);
+    cvReleaseFileStorage(&fs);
+    set("learningFrames", (double)learningFrames);
+    set("alphaLearn", alphaLearn);
+    set("alphaDetection", alphaDetection);
     set("threshold", threshold);
   }
 };

@@ -27,6 +27,7 @@ def _ptr(a):
 class _Plugin:
     ALGO = None
     PARAMS = ()
+    BG_CHANNELS = 3            # channels of img_bgmodel (AdaptiveSelectiveBackgroundLearning: 1)
 
     def __init__(self, device=0, nstreams=1, **params):
         self._h = C.c_void_p()
@@ -84,10 +85,11 @@ class _Plugin:
         stride = img.strides[-3]
         lead = (self.nstreams,) if grouped else ()
         fg = np.empty(lead + (h, w), np.uint8)
-        bg = np.empty(lead + (h, w, 3), np.uint8) if want_bg else None
+        bgshape = (h, w, 3) if self.BG_CHANNELS == 3 else (h, w)
+        bg = np.empty(lead + bgshape, np.uint8) if want_bg else None
         fv, bv = C.c_int(0), C.c_int(0)
         capi.check(capi.lib().bgsb_process(self._h, _ptr(img), w, h, stride, _ptr(fg), w,
-                                           _ptr(bg) if bg is not None else None, 3 * w,
+                                           _ptr(bg) if bg is not None else None, self.BG_CHANNELS * w,
                                            C.byref(fv), C.byref(bv)))
         return (fg if fv.value else None), (bg if bv.value else None)
 
@@ -137,6 +139,13 @@ class AdaptiveBackgroundLearning(_Plugin):
     ALGO = capi.ALGO_ADAPTIVE_BG_LEARNING
 
 
+class AdaptiveSelectiveBackgroundLearning(_Plugin):
+    """package_bgs/AdaptiveSelectiveBackgroundLearning.cpp (USTC_BGS type 7); keys learningFrames, alphaLearn,
+    alphaDetection, threshold (:108-126).  Gray model: img_bgmodel is single-channel."""
+    ALGO = capi.ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING
+    BG_CHANNELS = 1
+
+
 class MixtureOfGaussianV2BGS(_Plugin):
     """package_bgs/MixtureOfGaussianV2BGS.cpp; keys alpha, enableThreshold, threshold (:92-95)."""
     ALGO = capi.ALGO_MOG2
@@ -170,12 +179,12 @@ def process_fanout(plugins, img_input, want_bg=True):
     h, w = img.shape[:2]
     n = len(plugins)
     fgs = [np.empty((h, w), np.uint8) for _ in plugins]
-    bgs = [np.empty((h, w, 3), np.uint8) if want_bg else None for _ in plugins]
+    bgs = [np.empty((h, w, 3) if p.BG_CHANNELS == 3 else (h, w), np.uint8) if want_bg else None for p in plugins]
     ctxs = (C.c_void_p * n)(*[p._h for p in plugins])
     fgp = (C.c_void_p * n)(*[f.ctypes.data for f in fgs])
     fgst = (C.c_size_t * n)(*[w] * n)
     bgp = (C.c_void_p * n)(*[(b.ctypes.data if b is not None else None) for b in bgs])
-    bgst = (C.c_size_t * n)(*[3 * w] * n)
+    bgst = (C.c_size_t * n)(*[p.BG_CHANNELS * w for p in plugins])
     fv, bv = (C.c_int * n)(), (C.c_int * n)()
     capi.check(capi.lib().bgsb_process_fanout(ctxs, n, _ptr(img), w, h, img.strides[0], fgp, fgst, bgp, bgst, fv, bv))
     return [((fgs[k] if fv[k] else None), (bgs[k] if bv[k] else None)) for k in range(n)]
@@ -183,7 +192,8 @@ def process_fanout(plugins, img_input, want_bg=True):
 
 # integer ids of the USTC_BGS factory (ustc_src/ustc_bgs.cpp:8-14)
 ALGOS = {0: FrameDifferenceBGS, 1: StaticFrameDifferenceBGS, 2: WeightedMovingMeanBGS,
-         3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS, 6: AdaptiveBackgroundLearning}
+         3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS, 6: AdaptiveBackgroundLearning,
+         7: AdaptiveSelectiveBackgroundLearning}
 
 
 class USTC_BGS:
@@ -191,7 +201,7 @@ class USTC_BGS:
 
     def __init__(self, type, device=0):
         if type not in ALGOS:                   # CV_Assert(type>=0 && type<=37), .cpp:6
-            raise ValueError("USTC_BGS type %r is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL)" % type)
+            raise ValueError("USTC_BGS type %r is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL)" % type)
         self.bgs = ALGOS[type](device=device)
         self.frameNum = 0
         self.img_mask = None

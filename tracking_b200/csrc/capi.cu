@@ -41,6 +41,9 @@ struct bgsb_ctx {
     float Tb = 16.f, Tg = 9.f, TB = 0.9f, varInit = 15.f, varMin = 4.f, varMax = 75.f, CT = 0.05f, tau = 0.5f;
     int detect_shadows = 1, shadow_value = 127;
     int host_bands = 4;        // row bands of the host-path upload/compute/download pipeline (1 = no overlap)
+    // AdaptiveSelectiveBackgroundLearning (defaults of its loadConfig, .cpp:121-125)
+    int learning_frames = 90, asbl_counter = 0;
+    double alpha_learn = 0.05, alpha_detection = 0.05;
     int abl_table = 1;         // ABL: 1 = lookup-table kernel, 0 = arithmetic kernel (A/B, identical results)
     int mog2_variant = 0;      // see launch_mog2 (mog2.cu): 0 production, 1 straight restatement, 8/9 timing instruments
     // geometry / counters
@@ -101,7 +104,9 @@ static int ensure_geometry(bgsb_ctx *c, int w, int h)
         BGSB_CUDA(cudaMemsetAsync(c->d_nmodes, 0, S * c->pstride, c->stream));
         BGSB_CUDA(cudaStreamSynchronize(c->stream));
     } else {
-        int nh = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE || c->algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN) ? 2 : 1;
+        // ASBL: d_hist[0] = gray model, d_hist[1] = scratch (gray input + pre-median mask)
+        int nh = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE || c->algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN ||
+                  c->algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) ? 2 : 1;
         for (int i = 0; i < nh; i++) BGSB_CUDA(cudaMalloc(&c->d_hist[i], S * c->npx * 3));
     }
     return BGSB_OK;
@@ -149,9 +154,13 @@ static bool ring_history(int algo)
     return algo == BGSB_ALGO_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE ||
            algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN;
 }
+// channels of img_bgmodel: ASBL's model is the gray image (AdaptiveSelectiveBackgroundLearning.cpp:103)
+static int bg_channels(int algo) { return algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING ? 1 : 3; }
+// the mask depends on neighbouring pixels (3x3 median): no row-band sub-launches
+static bool stencil_algo(int algo) { return algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING; }
 static bool writes_background(int algo)
 {
-    return algo == BGSB_ALGO_MOG2 || algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING ||
+    return algo == BGSB_ALGO_MOG2 || algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING || algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING ||
            algo == BGSB_ALGO_STATIC_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN;
 }
 
@@ -198,6 +207,32 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
             }
             int rc = launch_mog2(L, c->nstreams, c->mog2_variant, stream);
             if (rc) return rc;
+        }
+    } else if (c->algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) {
+        BGSB_REQUIRE(p0 == 0 && pcount == c->npx, "ASBL works on whole frames (3x3 median)");
+        const size_t npx = (size_t)c->npx;
+        for (int t = 0; t < T; t++) {
+            AsblLaunch L;
+            memset(&L, 0, sizeof(L));
+            // batch layouts: frames [S][T][npx*3], masks [S][T][npx], model images [S][T][npx] or [S][npx]
+            L.frame = d_frames + (size_t)t * npx * 3; L.frame_stride = (size_t)T * npx * 3;
+            L.fg = d_fg + (size_t)t * npx; L.fg_stride = (size_t)T * npx;
+            if (d_bg && (!bg_last_only || t == T - 1)) {
+                L.bgout = bg_last_only ? d_bg : d_bg + (size_t)t * npx;
+                L.bg_stride = bg_last_only ? npx : (size_t)T * npx;
+            }
+            L.model = c->d_hist[0]; L.gray = c->d_hist[1]; L.raw = c->d_hist[1] + (size_t)c->nstreams * npx;
+            L.w = c->w; L.h = c->h;
+            L.first = (c->have_hist == 0 && t == 0);
+            // learning phase: `learningFrames > 0 && counter <= learningFrames`, counter++ (.cpp:65-71)
+            const bool learning = c->learning_frames > 0 && c->asbl_counter <= c->learning_frames;
+            if (learning) c->asbl_counter++;
+            L.selective = learning ? 0 : 1;
+            L.alpha = learning ? c->alpha_learn : c->alpha_detection;
+            L.thr = c->thr; L.gray_variant = c->gray_variant;
+            int rc = launch_asbl(L, c->nstreams, stream);
+            if (rc) return rc;
+            if (t == 0 && c->have_hist == 0) c->have_hist = 1;   // the model exists from the first frame on
         }
     } else {
         SimpleLaunch L;
@@ -305,12 +340,13 @@ int bgsb_create_group(bgsb_ctx **out, int algo, int device, int nstreams)
     BGSB_REQUIRE(out, "null out");
     BGSB_REQUIRE(algo == BGSB_ALGO_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE ||
                  algo == BGSB_ALGO_MOG2 || algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING ||
-                 algo == BGSB_ALGO_STATIC_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN,
-                 "unknown algorithm id (USTC_BGS ids: 0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL)");
+                 algo == BGSB_ALGO_STATIC_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN || algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING,
+                 "unknown algorithm id (USTC_BGS ids: 0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL)");
     BGSB_REQUIRE(nstreams >= 1 && nstreams <= 65535, "nstreams out of range");
     BGSB_CUDA(cudaSetDevice(device));
     bgsb_ctx *c = new bgsb_ctx();
     c->algo = algo; c->device = device; c->nstreams = nstreams;
+    if (algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) c->thr = 25;        // loadConfig default (.cpp:124)
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         set_error("cudaStreamCreate -> %s", cudaGetErrorString(e));
@@ -339,7 +375,7 @@ void bgsb_destroy(bgsb_ctx *c)
 int bgsb_reset(bgsb_ctx *c)
 {
     BGSB_REQUIRE(c, "null ctx");
-    c->nframes = 0; c->have_hist = 0;
+    c->nframes = 0; c->have_hist = 0; c->asbl_counter = 0;
     c->hist_ptr[0] = c->hist_ptr[1] = nullptr;
     return BGSB_OK;
 }
@@ -350,6 +386,9 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     std::string k(key);
     if (k == "alpha") c->alpha = v;
     else if (k == "limit") c->limit = (int)v;
+    else if (k == "learningFrames") c->learning_frames = (int)v;
+    else if (k == "alphaLearn") c->alpha_learn = v;
+    else if (k == "alphaDetection") c->alpha_detection = v;
     else if (k == "enableThreshold") c->enable_thr = (v != 0);
     else if (k == "threshold") c->thr = (int)v;
     else if (k == "enableWeight") c->enable_weight = (v != 0);
@@ -380,6 +419,9 @@ int bgsb_get_param(bgsb_ctx *c, const char *key, double *v)
     std::string k(key);
     if (k == "alpha") *v = c->alpha;
     else if (k == "limit") *v = c->limit;
+    else if (k == "learningFrames") *v = c->learning_frames;
+    else if (k == "alphaLearn") *v = c->alpha_learn;
+    else if (k == "alphaDetection") *v = c->alpha_detection;
     else if (k == "enableThreshold") *v = c->enable_thr;
     else if (k == "threshold") *v = c->thr;
     else if (k == "enableWeight") *v = c->enable_weight;
@@ -414,6 +456,7 @@ int bgsb_state_bytes(bgsb_ctx *c, size_t *bytes)
 {
     BGSB_REQUIRE(c && bytes, "null");
     if (c->algo == BGSB_ALGO_MOG2) *bytes = (size_t)c->npx * (MOG2_PLANES * 4 + 1);
+    else if (c->algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) *bytes = (size_t)c->npx;
     else if (history_images(c->algo) == 2) *bytes = (size_t)c->npx * 6;
     else *bytes = (size_t)c->npx * 3;
     return BGSB_OK;
@@ -450,7 +493,8 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
 {
     BGSB_REQUIRE(c && bgr && fg, "null");
     BGSB_REQUIRE(stride >= (size_t)w * 3 && fg_stride >= (size_t)w, "stride smaller than a row");
-    BGSB_REQUIRE(!bg || bg_stride >= (size_t)w * 3, "bg stride smaller than a row");
+    const size_t bgw = (size_t)w * bg_channels(c ? c->algo : 0);          // bytes per row of img_bgmodel
+    BGSB_REQUIRE(!bg || bg_stride >= bgw, "bg stride smaller than a row");
     BGSB_CUDA(cudaSetDevice(c->device));
     int rc = ensure_geometry(c, w, h);
     if (rc) return rc;
@@ -471,7 +515,7 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
     // kernel on band i and the download of band i-1 overlap on three streams (pixels are independent),
     // so a synchronous IBGS::process costs ~max(H2D, D2H) instead of H2D + kernel + D2H.
     int nchunks = 1, band = h;
-    if (c->nstreams == 1 && c->host_bands > 1 && (size_t)w * h * 3 >= (1u << 20) && out_fg) {
+    if (c->nstreams == 1 && c->host_bands > 1 && (size_t)w * h * 3 >= (1u << 20) && out_fg && !stencil_algo(c->algo)) {
         band = ((h + c->host_bands - 1) / c->host_bands + 31) / 32 * 32;
         if (((size_t)band * w) % MOG2_TILE) band += 32;          // bands start on a state tile
         nchunks = (h + band - 1) / band;
@@ -488,7 +532,7 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
             if (rc) return rc;
             BGSB_CUDA(copy_rows(fg, fg_stride, c->d_fg, (size_t)w, (size_t)w, rows, cudaMemcpyDeviceToHost, c->stream));
             if (want_bg)
-                BGSB_CUDA(copy_rows(bg, bg_stride, c->d_bg, (size_t)w * 3, (size_t)w * 3, rows, cudaMemcpyDeviceToHost, c->stream));
+                BGSB_CUDA(copy_rows(bg, bg_stride, c->d_bg, bgw, bgw, rows, cudaMemcpyDeviceToHost, c->stream));
         }
         BGSB_CUDA(cudaStreamSynchronize(c->stream));
     } else {
@@ -506,8 +550,8 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
             BGSB_CUDA(copy_rows(fg + (size_t)r0 * fg_stride, fg_stride, c->d_fg + p0, (size_t)w, (size_t)w, nr,
                                         cudaMemcpyDeviceToHost, c->s_d2h));
             if (want_bg)
-                BGSB_CUDA(copy_rows(bg + (size_t)r0 * bg_stride, bg_stride, c->d_bg + p0 * 3, (size_t)w * 3,
-                                            (size_t)w * 3, nr, cudaMemcpyDeviceToHost, c->s_d2h));
+                BGSB_CUDA(copy_rows(bg + (size_t)r0 * bg_stride, bg_stride, c->d_bg + p0 * 3, bgw, bgw, nr,
+                                            cudaMemcpyDeviceToHost, c->s_d2h));
         }
         BGSB_CUDA(cudaStreamSynchronize(c->s_d2h));
         BGSB_CUDA(cudaStreamSynchronize(c->stream));
@@ -536,7 +580,8 @@ int bgsb_process_fanout(bgsb_ctx *const *ctxs, int n, const uint8_t *bgr, int w,
         BGSB_REQUIRE(ctxs[k] && fg[k], "null context or mask buffer");
         BGSB_REQUIRE(ctxs[k]->device == c0->device && ctxs[k]->nstreams == 1, "fan-out takes single-stream contexts of one device");
         BGSB_REQUIRE(fg_stride[k] >= (size_t)w, "fg stride smaller than a row");
-        BGSB_REQUIRE(!(bg && bg[k]) || (bg_stride && bg_stride[k] >= (size_t)w * 3), "bg stride smaller than a row");
+        BGSB_REQUIRE(!(bg && bg[k]) || (bg_stride && bg_stride[k] >= (size_t)w * bg_channels(ctxs[k]->algo)),
+                     "bg stride smaller than a row");
         for (int j = 0; j < k; j++) BGSB_REQUIRE(ctxs[j] != ctxs[k], "the same context twice");
     }
     BGSB_CUDA(cudaSetDevice(c0->device));
@@ -578,18 +623,25 @@ int bgsb_process_fanout(bgsb_ctx *const *ctxs, int n, const uint8_t *bgr, int w,
         for (int k = 0; k < n; k++) {
             bgsb_ctx *c = ctxs[k];
             BGSB_CUDA(cudaStreamWaitEvent(c->stream, c0->ev_up[i], 0));
+            // a plugin whose mask needs neighbouring pixels (3x3 median) runs once, on the whole frame, after the
+            // last band has arrived
+            const bool whole = stencil_algo(c->algo);
+            if (whole && i != nchunks - 1) continue;
+            const size_t q0 = whole ? 0 : p0;
+            const int qr0 = whole ? 0 : r0, qnr = whole ? h : nr;
+            const size_t bgw = (size_t)w * bg_channels(c->algo);
             // the frame buffer is shared, so every plugin keeps its own history (FD / WMV copy the frame)
             int rc = launch_range(c, c0->d_fan, 1, c->d_fg, writes_background(c->algo) ? c->d_bg : nullptr, 0, true,
-                                  c->stream, p0, nr * w);
+                                  c->stream, q0, qnr * w);
             if (rc) return rc;
             BGSB_CUDA(cudaEventRecord(c->ev_k[i], c->stream));
             BGSB_CUDA(cudaStreamWaitEvent(c0->s_d2h, c->ev_k[i], 0));
             if (fgv[k])
-                BGSB_CUDA(copy_rows(fg[k] + (size_t)r0 * fg_stride[k], fg_stride[k], c->d_fg + p0, (size_t)w, (size_t)w, nr,
+                BGSB_CUDA(copy_rows(fg[k] + (size_t)qr0 * fg_stride[k], fg_stride[k], c->d_fg + q0, (size_t)w, (size_t)w, qnr,
                                     cudaMemcpyDeviceToHost, c0->s_d2h));
             if (bgv[k])
-                BGSB_CUDA(copy_rows(bg[k] + (size_t)r0 * bg_stride[k], bg_stride[k], c->d_bg + p0 * 3, (size_t)w * 3,
-                                    (size_t)w * 3, nr, cudaMemcpyDeviceToHost, c0->s_d2h));
+                BGSB_CUDA(copy_rows(bg[k] + (size_t)qr0 * bg_stride[k], bg_stride[k], c->d_bg + q0 * 3, bgw, bgw, qnr,
+                                    cudaMemcpyDeviceToHost, c0->s_d2h));
         }
     }
     BGSB_CUDA(cudaStreamSynchronize(c0->s_d2h));

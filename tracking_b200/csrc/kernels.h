@@ -28,6 +28,22 @@ int launch_simple(int algo, const SimpleLaunch &L, int nstreams, cudaStream_t st
 // Fill the 64 KB ABL table for `alpha` with the arithmetic kernel's own blend (bit-exact by construction).
 int launch_abl_lut_build(uint8_t *d_lut, double alpha, cudaStream_t stream);
 
+// ---- AdaptiveSelectiveBackgroundLearning (single-channel model; one frame per launch pair) --------
+struct AsblLaunch {
+    const uint8_t *frame;    // [S] BGR frames, frame_stride bytes apart
+    uint8_t *fg;             // [S] masks, fg_stride bytes apart
+    uint8_t *bgout;          // [S] gray background images, bg_stride bytes apart, nullable
+    uint8_t *model;          // [S][npx] 8-bit gray background model
+    uint8_t *gray, *raw;     // [S][npx] scratch: gray input, thresholded difference before the median
+    size_t frame_stride, fg_stride, bg_stride;
+    int w, h;
+    int first;               // no model yet: it starts as the gray input (AdaptiveSelectiveBackgroundLearning.cpp:47-48)
+    int selective;           // 0: learning phase, every pixel is blended (:65-71); 1: only background pixels (:72-90)
+    double alpha;            // alphaLearn or alphaDetection
+    int thr, gray_variant;
+};
+int launch_asbl(const AsblLaunch &L, int nstreams, cudaStream_t stream);
+
 // ---- MOG2 -------------------------------------------------------------------------------------
 constexpr int MOG2_K = 5;             // nmixtures of the default-constructed cv::BackgroundSubtractorMOG2
 constexpr int MOG2_PLANES = 5 * MOG2_K;   // per mode: weight, variance, mean B, G, R
