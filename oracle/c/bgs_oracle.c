@@ -193,6 +193,90 @@ ORC_API void orc_asbl(const uint8_t *in_bgr, uint8_t *bg, int w, int h, double a
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* DPZivkovicAGMMBGS (USTC_BGS type 11): package_bgs/dp/ZivkovicAGMM.cpp:98-372 (SubtractPixel), */
+/* called per pixel by Subtract (:382-407); wrapper package_bgs/dp/DPZivkovicAGMMBGS.cpp:32-84.  */
+/* The plugin's output is the HIGH-threshold mask (high = 2 * threshold, :60); img_bgmodel is    */
+/* never written.  State per pixel: K modes {weight, sigma, mu0, mu1, mu2} + the mode count.     */
+/* modes[(i*K + m)*5 + {0 weight, 1 sigma, 2 mu0, 3 mu1, 4 mu2}].  Pinned against a build of the  */
+/* reference's own sources (oracle/_ref/libdp_ref.so, `make ref`).                               */
+/* ------------------------------------------------------------------------------------ */
+ORC_API void orc_dpz_apply(const uint8_t *in, int npx, int K, double threshold, double alpha_d,
+                           float *modes, uint8_t *nmodes, uint8_t *fg)
+{
+    const float low_thr = (float)threshold;                   /* params.LowThreshold() = threshold :59 */
+    const float high_thr = 2 * low_thr;                       /* :60 */
+    const float alpha = (float)alpha_d;                       /* params.Alpha() = alpha :61 (float member) */
+    const float bg_threshold = 0.75f, variance = 36.0f, complexity_prior = 0.05f;   /* ZivkovicAGMM.cpp:64-67 */
+    for (int i = 0; i < npx; i++) {
+        float *md = modes + (size_t)i * K * 5;
+        const float p0 = (float)in[3 * i], p1 = (float)in[3 * i + 1], p2 = (float)in[3 * i + 2];
+        int fits = 0, bg_high = 0;
+        const float one_min_alpha = 1 - alpha;                /* :108 */
+        const float prune = -alpha * complexity_prior;        /* :110 */
+        int n = nmodes[i];
+        float total = 0.0f;
+        int bg_gauss = 0;                                     /* :116-128 */
+        double sum = 0.0;
+        for (int m = 0; m < n; m++) {
+            if (sum < bg_threshold) { bg_gauss++; sum += md[m * 5]; }
+            else break;
+        }
+        for (int m = 0; m < n; m++) {                         /* :131-254, n shrinks on prune */
+            float *c = md + m * 5;
+            float weight = c[0];
+            if (!fits) {
+                float var = c[1];
+                float d0 = c[2] - p0, d1 = c[3] - p1, d2 = c[4] - p2;
+                float dist = (d0 * d0 + d1 * d1 + d2 * d2);
+                if (dist < high_thr * var && m < bg_gauss) bg_high = 1;            /* :153-154 */
+                if (dist < low_thr * var) {                   /* :157 */
+                    fits = 1;
+                    float k = alpha / weight;                 /* :168, the OLD weight */
+                    weight = one_min_alpha * weight + prune;
+                    weight += alpha;
+                    c[0] = weight;
+                    c[2] = c[2] - k * d0; c[3] = c[3] - k * d1; c[4] = c[4] - k * d2;
+                    float sigmanew = var + k * (dist - var);  /* :183 */
+                    c[1] = sigmanew < 4 ? 4 : sigmanew > 5 * variance ? 5 * variance : sigmanew;   /* :186 */
+                    for (int l = m; l > 0; l--) {             /* :212-227 */
+                        float *a = md + l * 5, *b = md + (l - 1) * 5;
+                        if (a[0] > b[0]) { for (int q = 0; q < 5; q++) { float t = a[q]; a[q] = b[q]; b[q] = t; } }
+                        else break;
+                    }
+                } else {
+                    weight = one_min_alpha * weight + prune;  /* :231-238 */
+                    if (weight < -prune) { weight = 0.0; n--; }
+                    c[0] = weight;
+                }
+            } else {
+                weight = one_min_alpha * weight + prune;      /* :245-252 */
+                if (weight < -prune) { weight = 0.0; n--; }
+                c[0] = weight;
+            }
+            total += weight;
+        }
+        for (int m = 0; m < n; m++) md[m * 5] = md[m * 5] / total;                   /* :257-260 */
+        if (!fits) {                                          /* :263-345 */
+            if (n != K) n++;
+            float *c = md + (n - 1) * 5;
+            c[0] = (n == 1) ? 1 : alpha;
+            float s2 = 0.0;
+            for (int m = 0; m < n; m++) s2 += md[m * 5];
+            float inv = 1.0f / s2;
+            for (int m = 0; m < n; m++) md[m * 5] *= inv;
+            c[2] = p0; c[3] = p1; c[4] = p2; c[1] = variance;
+            for (int l = n - 1; l > 0; l--) {
+                float *a = md + l * 5, *b = md + (l - 1) * 5;
+                if (a[0] > b[0]) { for (int q = 0; q < 5; q++) { float t = a[q]; a[q] = b[q]; b[q] = t; } }
+                else break;
+            }
+        }
+        nmodes[i] = (uint8_t)n;
+        fg[i] = bg_high ? 0 : 255;                            /* :360-367, Bgs.h:41-42 */
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* WeightedMovingVariance (package_bgs/WeightedMovingVarianceBGS.cpp:53-106,126-138)       */
 /* ------------------------------------------------------------------------------------ */
 ORC_API void orc_wmv(const uint8_t *cur, const uint8_t *p1, const uint8_t *p2, int npx,

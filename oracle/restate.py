@@ -46,6 +46,7 @@ def lib():
         L.orc_wmm.argtypes = [u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, u8p]
         L.orc_abl.argtypes = [u8p, u8p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, u8p]
         L.orc_asbl.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, u8p, u8p]
+        L.orc_dpz_apply.argtypes = [u8p, C.c_int, C.c_int, C.c_double, C.c_double, f32p, u8p, u8p]
         L.orc_wmv.argtypes = [u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
         L.orc_mog2_default_params.argtypes = [C.POINTER(Mog2Params)]
         L.orc_mog2_learning_rate.argtypes = [C.c_double, C.c_int, C.c_int]
@@ -193,6 +194,57 @@ class AdaptiveSelectiveBackgroundLearning:
         lib().orc_asbl(_u8(img), _u8(self.bg), w, h, float(self.alphaLearn if learning else self.alphaDetection),
                        0 if learning else 1, int(self.threshold), self.gray_variant, _u8(fg), _u8(scratch))
         return fg, self.bg.copy()
+
+
+class DPZivkovicAGMMBGS:
+    """USTC_BGS type 11 (package_bgs/dp/DPZivkovicAGMMBGS.cpp); defaults of its loadConfig (:97-100).
+    Never writes img_bgmodel."""
+
+    def __init__(self, threshold=25.0, alpha=0.001, gaussians=3):
+        self.threshold, self.alpha, self.gaussians = threshold, alpha, gaussians
+        self.modes = None
+        self.nmodes = None
+
+    def process(self, img):
+        if img is None or img.size == 0:
+            return None, None
+        img = _dense(img)
+        h, w = img.shape[:2]
+        if self.modes is None:                               # InitModel: everything zero (ZivkovicAGMM.cpp:77-91)
+            self.modes = np.zeros((h * w, self.gaussians, 5), np.float32)
+            self.nmodes = np.zeros(h * w, np.uint8)
+        fg = np.empty((h, w), np.uint8)
+        lib().orc_dpz_apply(_u8(img), h * w, self.gaussians, float(self.threshold), float(self.alpha),
+                            self.modes.ctypes.data_as(C.POINTER(C.c_float)), _u8(self.nmodes), _u8(fg))
+        return fg, None
+
+
+class ReferenceDPZivkovic:
+    """The reference's own ZivkovicAGMM class, compiled from /root/reference by `make -C oracle ref`
+    (oracle/_ref/libdp_ref.so).  Raises FileNotFoundError when that build is absent."""
+
+    def __init__(self, w, h, threshold=25.0, alpha=0.001, gaussians=3):
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libdp_ref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.L = C.CDLL(path)
+        self.L.dpz_ref_create.restype = C.c_void_p
+        self.L.dpz_ref_create.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
+        self.L.dpz_ref_process.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]
+        self.L.dpz_ref_destroy.argtypes = [C.c_void_p]
+        self.w, self.h = w, h
+        self.p = self.L.dpz_ref_create(w, h, float(threshold), float(alpha), int(gaussians))
+
+    def process(self, img):
+        img = _dense(img)
+        fg = np.empty((self.h, self.w), np.uint8)
+        self.L.dpz_ref_process(self.p, _u8(img), _u8(fg))
+        return fg, None
+
+    def close(self):
+        if self.p:
+            self.L.dpz_ref_destroy(self.p)
+            self.p = None
 
 
 class WeightedMovingVarianceBGS:
