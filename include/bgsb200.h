@@ -56,7 +56,8 @@ enum {
     BGSB_ALGO_WEIGHTED_MOVING_VARIANCE = 3,   /* ustc_bgs.cpp:11 */
     BGSB_ALGO_MOG2 = 5,                       /* ustc_bgs.cpp:13 */
     BGSB_ALGO_ADAPTIVE_BG_LEARNING = 6,       /* ustc_bgs.cpp:14 */
-    BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING = 7  /* ustc_bgs.cpp:15  sibling plugin; gray 1-channel bg image */
+    BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING = 7, /* ustc_bgs.cpp:15  sibling plugin; gray 1-channel bg image */
+    BGSB_ALGO_DP_ZIVKOVIC_AGMM = 11               /* ustc_bgs.cpp:21  sibling plugin; never writes img_bgmodel */
 };
 
 typedef struct bgsb_ctx bgsb_ctx;
@@ -93,6 +94,7 @@ BGSB_API int bgsb_reset(bgsb_ctx *ctx);
  *   all      : "enableThreshold" (1), "threshold" (15)
  *   MOG2     : "alpha" (0.05)             MixtureOfGaussianV2BGS.cpp:92-95
  *   ABL      : "alpha" (0.05), "limit" (-1; only -1 updates the model, .cpp:52)
+ *   DPZivkovicAGMM : "threshold" (25.0), "alpha" (0.001), "gaussians" (3, at most 5)   DPZivkovicAGMMBGS.cpp:86-100
  *   ASBL     : "learningFrames" (90), "alphaLearn" (0.05), "alphaDetection" (0.05), "threshold" (25)
  *              AdaptiveSelectiveBackgroundLearning.cpp:108-126 (the defaults its loadConfig applies)
  *   WMV, WMM : "enableWeight" (1)         WeightedMovingVarianceBGS.cpp:155-158, WeightedMovingMeanBGS.cpp

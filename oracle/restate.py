@@ -34,6 +34,15 @@ class Mog2Params(C.Structure):
                 ("shadow_value", C.c_int), ("history", C.c_int)]
 
 
+def build_ref(reference="/root/reference"):
+    """Compile the reference's own DP Zivkovic sources into oracle/_ref/libdp_ref.so (`make ref`) when the
+    reference tree is there; returns True if the library exists afterwards."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    if os.path.exists(os.path.join(reference, "package_bgs", "dp", "ZivkovicAGMM.cpp")):
+        subprocess.run(["make", "-C", here, "ref", "REFERENCE=" + reference], check=True, stdout=subprocess.DEVNULL)
+    return os.path.exists(os.path.join(here, "_ref", "libdp_ref.so"))
+
+
 def lib():
     global _lib
     if _lib is None:

@@ -473,6 +473,44 @@ def test_asbl_stream_group_and_fanout(oracle):
         p.close()
 
 
+@pytest.mark.parametrize("kw", [{}, {"alpha": 0.05, "threshold": 9.0, "gaussians": 5}, {"alpha": 0.3, "gaussians": 2},
+                                {"alpha": 0.01, "threshold": 12.5, "gaussians": 4}])
+def test_dpzivkovic_sibling_plugin(oracle, clips, kw):
+    """DPZivkovicAGMMBGS (USTC_BGS type 11): bit-exact masks against the restatement that is pinned to a build of the
+    reference's own sources; reference clip, mode-churn stress sequence, large frame through the row-band host path,
+    device path, two-stream group; img_bgmodel is never produced."""
+    import torch
+    import tracking_b200 as tb
+    rng = np.random.default_rng(5)
+    big = rng.integers(0, 256, (600, 700, 3), dtype=np.uint8)
+    bigs = []
+    for t in range(10):
+        f = np.clip(big.astype(np.int16) + rng.integers(-8, 9, big.shape), 0, 255).astype(np.uint8)
+        f[50 + 10 * t:200 + 10 * t, 100 + 20 * t:300 + 20 * t] = rng.integers(0, 256, 3)
+        bigs.append(f)
+    for frames in (list(clips["video_clip"]), stress_sequence(120, 40, 52), bigs):
+        p, o = tb.DPZivkovicAGMMBGS(**kw), oracle.DPZivkovicAGMMBGS(**kw)
+        for i, f in enumerate(frames):
+            fa, ba = p.process(f)
+            fb, _ = o.process(f)
+            assert ba is None
+            assert np.array_equal(fa, fb), i
+        p.close()
+    # device path + stream group
+    h, w = bigs[0].shape[:2]
+    g = tb.DPZivkovicAGMMBGS(nstreams=2, **kw)
+    oa, ob = oracle.DPZivkovicAGMMBGS(**kw), oracle.DPZivkovicAGMMBGS(**kw)
+    d_fg = torch.zeros((2, h, w), dtype=torch.uint8, device="cuda")
+    for i in range(6):
+        d_in = torch.from_numpy(np.stack([bigs[i], bigs[9 - i]])).cuda()
+        fv, bv = g.process_dev(d_in.data_ptr(), w, h, d_fg.data_ptr(), None)
+        torch.cuda.synchronize()
+        assert fv and not bv
+        out = d_fg.cpu().numpy()
+        assert np.array_equal(out[0], oa.process(bigs[i])[0]) and np.array_equal(out[1], ob.process(bigs[9 - i])[0]), i
+    g.close()
+
+
 def test_mog2_state_export_import_roundtrip(clips):
     import tracking_b200 as tb
     clip = clips["video_clip"]

@@ -136,6 +136,52 @@ def test_asbl_restatement_against_opencv(oracle, clips, kw):
             assert np.array_equal(fa, fb) and np.array_equal(ba, bb), i
 
 
+DPZ_PARAMS = [{}, {"alpha": 0.05, "threshold": 9.0, "gaussians": 5}, {"alpha": 0.3, "gaussians": 2},
+              {"alpha": 0.01, "threshold": 12.5, "gaussians": 4}]
+
+
+@pytest.mark.parametrize("kw", DPZ_PARAMS)
+def test_dpzivkovic_restatement_matches_reference_golden(oracle, clips, kw):
+    """orc_dpz_apply vs the masks a build of the reference's OWN ZivkovicAGMM sources produced
+    (tests/golden/golden_dpz.json, written by make_golden_dpz.py from oracle/_ref/libdp_ref.so)."""
+    import hashlib
+    import json
+    import os
+    from conftest import stress_sequence
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_dpz.json")))
+    seqs = {"video_clip": list(clips["video_clip"]), "png_clip": list(clips["png_clip"]),
+            "stress_120x40x52": stress_sequence(120, 40, 52)}
+    for name, frames in seqs.items():
+        o = oracle.DPZivkovicAGMMBGS(**kw)
+        hs = hashlib.sha256()
+        for f in frames:
+            fg, bg = o.process(f)
+            assert bg is None
+            hs.update(fg.tobytes())
+        assert hs.hexdigest() == g["sequences"][name]["params"][json.dumps(kw, sort_keys=True)]["masks_sha256"], name
+
+
+@pytest.mark.parametrize("kw", DPZ_PARAMS)
+def test_dpzivkovic_restatement_matches_reference_build_live(oracle, kw):
+    """The same, frame by frame against the compiled reference itself, on a sequence the golden file does not hold.
+    Skipped where oracle/_ref/libdp_ref.so has not been built (`make -C oracle ref` needs /root/reference)."""
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 256, (57, 83, 3), dtype=np.uint8)
+    frames = []
+    for t in range(60):
+        f = np.clip(base.astype(np.int16) + rng.integers(-8, 9, base.shape), 0, 255).astype(np.uint8)
+        f[5 + t // 2:25 + t // 2, 10 + t:40 + t] = rng.integers(0, 256, 3)
+        frames.append(f)
+    try:
+        ref = oracle.ReferenceDPZivkovic(83, 57, **kw)
+    except FileNotFoundError:
+        pytest.skip("oracle/_ref/libdp_ref.so not built")
+    o = oracle.DPZivkovicAGMMBGS(**kw)
+    for i, f in enumerate(frames):
+        assert np.array_equal(o.process(f)[0], ref.process(f)[0]), i
+    ref.close()
+
+
 def test_morph_and_ccl_against_opencv(oracle):
     from oracle import cv2_chain
     rng = np.random.default_rng(3)

@@ -458,6 +458,62 @@ private:
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// Sibling plugin, USTC_BGS type 11 (ustc_src/ustc_bgs.cpp:21): package_bgs/dp/DPZivkovicAGMMBGS.{h,cpp}.
+class DPZivkovicAGMMBGS : public bgsb_adapter::PluginBase
+{
+private:
+  double threshold;
+  double alpha;
+  int gaussians;
+  bool showOutput;
+
+public:
+  DPZivkovicAGMMBGS() : PluginBase(BGSB_ALGO_DP_ZIVKOVIC_AGMM), threshold(25.0f), alpha(0.001f), gaussians(3), showOutput(true)
+  {
+    std::cout << "DPZivkovicAGMMBGS()" << std::endl;
+  }
+  ~DPZivkovicAGMMBGS() { std::cout << "~DPZivkovicAGMMBGS()" << std::endl; }
+
+  void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
+  {
+    (void)img_bgmodel;                       // never written (DPZivkovicAGMMBGS.cpp:32-84)
+    if (img_input.empty()) return;
+    loadConfig();
+    if (firstTime) {                         // the reference hands the parameters over once, on the first frame (:58-65)
+      saveConfig();
+      set("threshold", threshold);
+      set("alpha", alpha);
+      set("gaussians", gaussians);
+    }
+    bool fg, bg;
+    run(img_input, fg, bg, false);
+    if (showOutput) cv::imshow("Gaussian Mixture Model (Zivkovic)", img_foreground);
+    img_foreground.copyTo(img_output);       // :78
+    firstTime = false;
+  }
+
+private:
+  void saveConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/DPZivkovicAGMMBGS.xml", 0, CV_STORAGE_WRITE);
+    cvWriteReal(fs, "threshold", threshold);
+    cvWriteReal(fs, "alpha", alpha);
+    cvWriteInt(fs, "gaussians", gaussians);
+    cvWriteInt(fs, "showOutput", showOutput);
+    cvReleaseFileStorage(&fs);
+  }
+  void loadConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/DPZivkovicAGMMBGS.xml", 0, CV_STORAGE_READ);
+    threshold = cvReadRealByName(fs, 0, "threshold", 25.0f);
+    alpha = cvReadRealByName(fs, 0, "alpha", 0.001f);
+    gaussians = cvReadIntByName(fs, 0, "gaussians", 3);
+    showOutput = cvReadIntByName(fs, 0, "showOutput", true);
+    cvReleaseFileStorage(&fs);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 class MixtureOfGaussianV2BGS : public bgsb_adapter::PluginBase
 {
 private:

@@ -4,15 +4,15 @@
 int compile_check_calls()
 {
     // FrameProcessor.cpp:40-59,157-167 pattern
-    IBGS *plugins[7] = {new FrameDifferenceBGS, new WeightedMovingVarianceBGS, new MixtureOfGaussianV2BGS,
+    IBGS *plugins[8] = {new FrameDifferenceBGS, new WeightedMovingVarianceBGS, new MixtureOfGaussianV2BGS,
                         new AdaptiveBackgroundLearning, new StaticFrameDifferenceBGS, new WeightedMovingMeanBGS,
-                        new AdaptiveSelectiveBackgroundLearning};
+                        new AdaptiveSelectiveBackgroundLearning, new DPZivkovicAGMMBGS};
     cv::Mat img_input, img_bgs, img_bkgmodel;
     // FrameProcessor.cpp:169-215 with the one added line: a single upload feeds all enabled plugins
     bgsb_adapter::FanOut fanout;
-    for (int i = 0; i < 7; i++) fanout.add(plugins[i]);
+    for (int i = 0; i < 8; i++) fanout.add(plugins[i]);
     fanout.process(img_input);
-    for (int i = 0; i < 7; i++) {
+    for (int i = 0; i < 8; i++) {
         plugins[i]->process(img_input, img_bgs, img_bkgmodel);
         delete plugins[i];
     }

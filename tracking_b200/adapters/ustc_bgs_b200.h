@@ -37,7 +37,8 @@ public:
         case 5: bgs = new MixtureOfGaussianV2BGS; break;    // :13
         case 6: bgs = new AdaptiveBackgroundLearning; break;// :14
         case 7: bgs = new AdaptiveSelectiveBackgroundLearning; break;   // :15
-        default: CV_Assert(!"this plugin id is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL)");
+        case 11: bgs = new DPZivkovicAGMMBGS; break;        // :21
+        default: CV_Assert(!"this plugin id is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL, 11 DPZivkovicAGMM)");
         }
     }
     ~USTC_BGS() {}

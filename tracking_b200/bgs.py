@@ -146,6 +146,12 @@ class AdaptiveSelectiveBackgroundLearning(_Plugin):
     BG_CHANNELS = 1
 
 
+class DPZivkovicAGMMBGS(_Plugin):
+    """package_bgs/dp/DPZivkovicAGMMBGS.cpp (USTC_BGS type 11): the reference's own Zivkovic adaptive GMM; keys
+    threshold, alpha, gaussians (:86-100).  Never writes img_bgmodel."""
+    ALGO = capi.ALGO_DP_ZIVKOVIC_AGMM
+
+
 class MixtureOfGaussianV2BGS(_Plugin):
     """package_bgs/MixtureOfGaussianV2BGS.cpp; keys alpha, enableThreshold, threshold (:92-95)."""
     ALGO = capi.ALGO_MOG2
@@ -193,7 +199,7 @@ def process_fanout(plugins, img_input, want_bg=True):
 # integer ids of the USTC_BGS factory (ustc_src/ustc_bgs.cpp:8-14)
 ALGOS = {0: FrameDifferenceBGS, 1: StaticFrameDifferenceBGS, 2: WeightedMovingMeanBGS,
          3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS, 6: AdaptiveBackgroundLearning,
-         7: AdaptiveSelectiveBackgroundLearning}
+         7: AdaptiveSelectiveBackgroundLearning, 11: DPZivkovicAGMMBGS}
 
 
 class USTC_BGS:
@@ -201,7 +207,7 @@ class USTC_BGS:
 
     def __init__(self, type, device=0):
         if type not in ALGOS:                   # CV_Assert(type>=0 && type<=37), .cpp:6
-            raise ValueError("USTC_BGS type %r is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL)" % type)
+            raise ValueError("USTC_BGS type %r is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL, 11 DPZivkovicAGMM)" % type)
         self.bgs = ALGOS[type](device=device)
         self.frameNum = 0
         self.img_mask = None

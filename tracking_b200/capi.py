@@ -14,6 +14,7 @@ OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_CAPACITY = 0, 1, 2, 3, 4
 ALGO_FRAME_DIFFERENCE, ALGO_WEIGHTED_MOVING_VARIANCE, ALGO_MOG2, ALGO_ADAPTIVE_BG_LEARNING = 0, 3, 5, 6
 ALGO_STATIC_FRAME_DIFFERENCE, ALGO_WEIGHTED_MOVING_MEAN = 1, 2        # sibling plugins
 ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING = 7
+ALGO_DP_ZIVKOVIC_AGMM = 11
 MORPH_ERODE, MORPH_DILATE = 0, 1
 
 

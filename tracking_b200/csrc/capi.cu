@@ -44,6 +44,9 @@ struct bgsb_ctx {
     // AdaptiveSelectiveBackgroundLearning (defaults of its loadConfig, .cpp:121-125)
     int learning_frames = 90, asbl_counter = 0;
     double alpha_learn = 0.05, alpha_detection = 0.05;
+    // DPZivkovicAGMMBGS (defaults of its loadConfig, DPZivkovicAGMMBGS.cpp:97-100); its alpha default is set at create
+    double dpz_threshold = 25.0;
+    int gaussians = 3;
     int abl_table = 1;         // ABL: 1 = lookup-table kernel, 0 = arithmetic kernel (A/B, identical results)
     int mog2_variant = 0;      // see launch_mog2 (mog2.cu): 0 production, 1 straight restatement, 8/9 timing instruments
     // geometry / counters
@@ -70,6 +73,7 @@ struct bgsb_ctx {
     cudaEvent_t ev_up[8] = {}, ev_k[8] = {};
 };
 
+static bool gmm_state(int algo);
 static void free_buffers(bgsb_ctx *c)
 {
     cudaFree(c->d_state); c->d_state = nullptr;
@@ -91,12 +95,12 @@ static int ensure_geometry(bgsb_ctx *c, int w, int h)
     if (c->w == w && c->h == h) return BGSB_OK;
     BGSB_REQUIRE(w > 0 && h > 0, "empty frame");
     BGSB_REQUIRE((long long)w * h < (1LL << 30), "frame too large");
-    BGSB_REQUIRE(c->algo != BGSB_ALGO_MOG2 || (long long)w * h <= (1LL << 27), "MOG2 frames are limited to 2^27 pixels");
+    BGSB_REQUIRE(!gmm_state(c->algo) || (long long)w * h <= (1LL << 27), "mixture-model frames are limited to 2^27 pixels");
     free_buffers(c);
     c->w = w; c->h = h; c->npx = w * h;
     c->pstride = ((size_t)c->npx + MOG2_TILE - 1) / MOG2_TILE * MOG2_TILE;       // whole state tiles
     const size_t S = (size_t)c->nstreams;
-    if (c->algo == BGSB_ALGO_MOG2) {
+    if (gmm_state(c->algo)) {
         size_t fb = S * MOG2_PLANES * c->pstride * sizeof(float);
         BGSB_CUDA(cudaMalloc(&c->d_state, fb));
         BGSB_CUDA(cudaMalloc(&c->d_nmodes, S * c->pstride));
@@ -146,7 +150,7 @@ static int warmup_frames(int algo)
 static int history_images(int algo)
 {
     if (algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN) return 2;
-    return algo == BGSB_ALGO_MOG2 ? 0 : 1;
+    return gmm_state(algo) ? 0 : 1;
 }
 // FD / WMV / WMM: the history is the previous input frame(s) -> on the host path it lives in the upload ring
 static bool ring_history(int algo)
@@ -154,6 +158,8 @@ static bool ring_history(int algo)
     return algo == BGSB_ALGO_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE ||
            algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN;
 }
+// per-pixel mixture state in the MOG2 tile layout (d_state / d_nmodes)
+static bool gmm_state(int algo) { return algo == BGSB_ALGO_MOG2 || algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM; }
 // channels of img_bgmodel: ASBL's model is the gray image (AdaptiveSelectiveBackgroundLearning.cpp:103)
 static int bg_channels(int algo) { return algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING ? 1 : 3; }
 // the mask depends on neighbouring pixels (3x3 median): no row-band sub-launches
@@ -206,6 +212,20 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
                 if (!(L.alphaT[t] >= 1e-4f && L.alphaT[t] <= 1.f)) L.fast_ok = 0;
             }
             int rc = launch_mog2(L, c->nstreams, c->mog2_variant, stream);
+            if (rc) return rc;
+        }
+    } else if (c->algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM) {
+        for (int t = 0; t < T; t++) {
+            DpzLaunch L;
+            memset(&L, 0, sizeof(L));
+            // batch layouts: frames [S][T][npx*3], masks [S][T][npx]; pixels [p0, p0+pcount), p0 on a state tile
+            L.frame = d_frames + ((size_t)t * c->npx + p0) * 3; L.frame_stride = (size_t)T * c->npx * 3;
+            L.fg = d_fg + (size_t)t * c->npx + p0; L.fg_stride = (size_t)T * c->npx;
+            L.state = c->d_state + p0 * MOG2_PLANES; L.nmodes = c->d_nmodes + p0; L.pstride = c->pstride;
+            L.npx = pcount; L.K = c->gaussians;
+            L.fresh = (c->nframes + t == 0);
+            L.low_thr = (float)c->dpz_threshold; L.alpha = (float)c->alpha;
+            int rc = launch_dpz(L, c->nstreams, stream);
             if (rc) return rc;
         }
     } else if (c->algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) {
@@ -340,13 +360,15 @@ int bgsb_create_group(bgsb_ctx **out, int algo, int device, int nstreams)
     BGSB_REQUIRE(out, "null out");
     BGSB_REQUIRE(algo == BGSB_ALGO_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE ||
                  algo == BGSB_ALGO_MOG2 || algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING ||
-                 algo == BGSB_ALGO_STATIC_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN || algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING,
-                 "unknown algorithm id (USTC_BGS ids: 0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL)");
+                 algo == BGSB_ALGO_STATIC_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN || algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING ||
+                 algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM,
+                 "unknown algorithm id (USTC_BGS ids: 0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL, 11 DPZivkovicAGMM)");
     BGSB_REQUIRE(nstreams >= 1 && nstreams <= 65535, "nstreams out of range");
     BGSB_CUDA(cudaSetDevice(device));
     bgsb_ctx *c = new bgsb_ctx();
     c->algo = algo; c->device = device; c->nstreams = nstreams;
     if (algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) c->thr = 25;        // loadConfig default (.cpp:124)
+    if (algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM) c->alpha = 0.001;                        // DPZivkovicAGMMBGS.cpp:98
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         set_error("cudaStreamCreate -> %s", cudaGetErrorString(e));
@@ -390,7 +412,8 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     else if (k == "alphaLearn") c->alpha_learn = v;
     else if (k == "alphaDetection") c->alpha_detection = v;
     else if (k == "enableThreshold") c->enable_thr = (v != 0);
-    else if (k == "threshold") c->thr = (int)v;
+    else if (k == "threshold") { c->thr = (int)v; c->dpz_threshold = v; }      // DPZivkovicAGMM keeps the real value
+    else if (k == "gaussians") { BGSB_REQUIRE(v >= 1 && v <= MOG2_K, "gaussians in [1,5]"); c->gaussians = (int)v; }
     else if (k == "enableWeight") c->enable_weight = (v != 0);
     else if (k == "grayVariant") { BGSB_REQUIRE(v == 0 || v == 1, "grayVariant is 0 or 1"); c->gray_variant = (int)v; }
     else if (k == "history") { BGSB_REQUIRE(v >= 1, "history >= 1"); c->history = (int)v; }
@@ -423,7 +446,8 @@ int bgsb_get_param(bgsb_ctx *c, const char *key, double *v)
     else if (k == "alphaLearn") *v = c->alpha_learn;
     else if (k == "alphaDetection") *v = c->alpha_detection;
     else if (k == "enableThreshold") *v = c->enable_thr;
-    else if (k == "threshold") *v = c->thr;
+    else if (k == "threshold") *v = c->algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM ? c->dpz_threshold : c->thr;
+    else if (k == "gaussians") *v = c->gaussians;
     else if (k == "enableWeight") *v = c->enable_weight;
     else if (k == "grayVariant") *v = c->gray_variant;
     else if (k == "history") *v = c->history;
@@ -456,6 +480,7 @@ int bgsb_state_bytes(bgsb_ctx *c, size_t *bytes)
 {
     BGSB_REQUIRE(c && bytes, "null");
     if (c->algo == BGSB_ALGO_MOG2) *bytes = (size_t)c->npx * (MOG2_PLANES * 4 + 1);
+    else if (c->algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM) *bytes = (size_t)c->npx * (c->gaussians * 20 + 1);
     else if (c->algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) *bytes = (size_t)c->npx;
     else if (history_images(c->algo) == 2) *bytes = (size_t)c->npx * 6;
     else *bytes = (size_t)c->npx * 3;

@@ -76,6 +76,19 @@ struct Mog2Launch {
 };
 int launch_mog2(const Mog2Launch &L, int nstreams, int variant, cudaStream_t stream);
 
+// ---- DPZivkovicAGMMBGS (the reference's own adaptive GMM; state in the MOG2 tile layout, K <= 5) ----
+struct DpzLaunch {
+    const uint8_t *frame;    // [S] BGR frames, frame_stride bytes apart
+    uint8_t *fg;             // [S] high-threshold masks, fg_stride bytes apart
+    float *state;            // [S][pstride/64 tiles][25][64]
+    uint8_t *nmodes;         // [S][pstride]
+    size_t pstride, frame_stride, fg_stride;
+    int npx, K;
+    int fresh;               // InitModel: no modes yet
+    float low_thr, alpha;    // params.LowThreshold() / Alpha() are floats (ZivkovicAGMM.h)
+};
+int launch_dpz(const DpzLaunch &L, int nstreams, cudaStream_t stream);
+
 // ---- morphology -------------------------------------------------------------------------------
 int launch_morph_chain(const uint8_t *d_in, uint8_t *d_out, int w, int h, int nimages, const int *ops, int nops,
                        cudaStream_t stream);
