@@ -60,7 +60,7 @@ def simple_streams(algo_cls, name, bpp, S=16, w=1920, h=1080, NT=6, iters=40):
         k[0] += 1
     dt = timed(step, iters, warm=4)
     px = S * w * h
-    out(config="3" if name != "FD" else "fd", algo=name, streams=S, resolution=[w, h], ms_per_step=dt * 1e3,
+    out(config={"FD": "fd", "ABL": "3", "WMV": "3"}.get(name, "sibling"), algo=name, streams=S, resolution=[w, h], ms_per_step=dt * 1e3,
         mpixel_s=px / dt / 1e6, algorithmic_bytes_per_px=bpp, achieved_gbs=px * bpp / dt / 1e9,
         frac_of_measured_peak=px * bpp / dt / 1e9 / PEAK)
     p.close()
@@ -208,6 +208,8 @@ def main():
     simple_streams(tb.FrameDifferenceBGS, "FD", 7 + 3)        # device path also writes the 3 B/px history
     simple_streams(tb.AdaptiveBackgroundLearning, "ABL", 10)
     simple_streams(tb.WeightedMovingVarianceBGS, "WMV", 10 + 6)  # device path writes both history images
+    simple_streams(tb.AdaptiveSelectiveBackgroundLearning, "ASBL", 3 + 2 + 1 + 1)   # in, gray model r/w, mask, gray bg image
+    simple_streams(tb.DPZivkovicAGMMBGS, "DPZivkovicAGMM (3 modes; bytes = 3 in + 1 mask + 2 counts + 40 per live mode, 1.4 live modes assumed)", 62)
     ccl_kernel_probe()
     import fanout_probe                                   # tools/fanout_probe.py: FrameProcessor fan-out vs four uploads
     fanout_probe.main()
