@@ -164,6 +164,9 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL's version banner goes to stdout; rank 0's stdout is the ONE JSON line of the contract
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
