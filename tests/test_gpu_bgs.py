@@ -177,6 +177,42 @@ def test_abl_exhaustive_byte_pairs(oracle, table):
         assert np.array_equal(fa, fb) and np.array_equal(ba, bb)
 
 
+@pytest.mark.parametrize("shape", [(64, 512), (96, 1024), (37, 53)])
+def test_fd_coalesced_and_per_thread_kernels(oracle, shape):
+    """FrameDifference: frames whose pixel count is a multiple of 512 take the warp-coalesced kernel (device path,
+    single stream, two-stream group, temporal batch), anything else the per-thread one; raw and thresholded."""
+    import torch
+    import tracking_b200 as tb
+    h, w = shape
+    rng = np.random.default_rng(17)
+    frames = [rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8) for _ in range(7)]
+    for thr in (1, 0):
+        g = tb.FrameDifferenceBGS(nstreams=2, enableThreshold=thr)
+        oa, ob = oracle.FrameDifferenceBGS(enableThreshold=bool(thr)), oracle.FrameDifferenceBGS(enableThreshold=bool(thr))
+        d_fg = torch.zeros((2, h, w), dtype=torch.uint8, device="cuda")
+        for i, f in enumerate(frames[:4]):
+            d_in = torch.from_numpy(f).cuda()
+            fv, _ = g.process_dev(d_in.data_ptr(), w, h, d_fg.data_ptr(), None)
+            torch.cuda.synchronize()
+            ra, rb = oa.process(f[0])[0], ob.process(f[1])[0]
+            assert fv == (ra is not None), i
+            if ra is not None:
+                out = d_fg.cpu().numpy()
+                assert np.array_equal(out[0], ra) and np.array_equal(out[1], rb), i
+        # temporal batch of 3 frames per stream: [S][T][h][w][3]
+        batch = np.stack([np.stack([frames[4 + t][s_] for t in range(3)]) for s_ in range(2)])
+        d_b = torch.from_numpy(batch).cuda()
+        d_fgb = torch.zeros((2, 3, h, w), dtype=torch.uint8, device="cuda")
+        first, _ = g.process_batch_dev(d_b.data_ptr(), 3, w, h, d_fgb.data_ptr())
+        torch.cuda.synchronize()
+        assert first == 0
+        out = d_fgb.cpu().numpy()
+        for t in range(3):
+            assert np.array_equal(out[0, t], oa.process(frames[4 + t][0])[0]), t
+            assert np.array_equal(out[1, t], ob.process(frames[4 + t][1])[0]), t
+        g.close()
+
+
 def test_wmm_unweighted_and_raw(oracle):
     """WeightedMovingMean sibling plugin: (x0+x1+x2)/3.0 branch and un-thresholded output."""
     import tracking_b200 as tb
