@@ -257,6 +257,54 @@ def test_wmv_small_differences_and_weight_change(oracle):
             p.close()
 
 
+@pytest.mark.parametrize("ew", [1, 0])
+def test_wmv_all_byte_triples(oracle, ew):
+    """Every (current, previous, previous-previous) byte triple, both weightings: 4096 x 4096 pixels whose three
+    channels carry the same triple, raw output (gray(v, v, v) == v, so the mask byte IS the per-channel value)."""
+    import torch
+    import tracking_b200 as tb
+    n = 4096
+    idx = np.arange(n * n, dtype=np.uint32).reshape(n, n)
+    planes = [(idx & 0xff).astype(np.uint8), ((idx >> 8) & 0xff).astype(np.uint8), ((idx >> 16) & 0xff).astype(np.uint8)]
+    frames = [np.repeat(pl[:, :, None], 3, 2) for pl in (planes[2], planes[1], planes[0])]      # oldest first
+    p = tb.WeightedMovingVarianceBGS(enableWeight=ew, enableThreshold=0)
+    o = oracle.WeightedMovingVarianceBGS(enableWeight=bool(ew), enableThreshold=False)
+    d_fg = torch.zeros((n, n), dtype=torch.uint8, device="cuda")
+    for f in frames:
+        d_in = torch.from_numpy(f).cuda()
+        fv, _ = p.process_dev(d_in.data_ptr(), n, n, d_fg.data_ptr(), None)
+        torch.cuda.synchronize()
+        ofg, _ = o.process(f)
+    assert fv and ofg is not None
+    got = d_fg.cpu().numpy()
+    bad = int((got != ofg).sum())
+    assert bad == 0, "%d of 16.7 M triples differ" % bad
+    p.close()
+
+
+@pytest.mark.parametrize("ew", [1, 0])
+def test_wmm_all_byte_triples(oracle, ew):
+    """WeightedMovingMean: every byte triple, both weightings; the background image carries the per-channel mean."""
+    import torch
+    import tracking_b200 as tb
+    n = 4096
+    idx = np.arange(n * n, dtype=np.uint32).reshape(n, n)
+    planes = [(idx & 0xff).astype(np.uint8), ((idx >> 8) & 0xff).astype(np.uint8), ((idx >> 16) & 0xff).astype(np.uint8)]
+    frames = [np.repeat(pl[:, :, None], 3, 2) for pl in (planes[2], planes[1], planes[0])]
+    p = tb.WeightedMovingMeanBGS(enableWeight=ew, enableThreshold=0)
+    o = oracle.WeightedMovingMeanBGS(enableWeight=bool(ew), enableThreshold=False)
+    d_fg = torch.zeros((n, n), dtype=torch.uint8, device="cuda")
+    d_bg = torch.zeros((n, n, 3), dtype=torch.uint8, device="cuda")
+    for f in frames:
+        d_in = torch.from_numpy(f).cuda()
+        fv, bv = p.process_dev(d_in.data_ptr(), n, n, d_fg.data_ptr(), d_bg.data_ptr())
+        torch.cuda.synchronize()
+        ofg, obg = o.process(f)
+    assert fv and bv and obg is not None
+    assert int((d_bg.cpu().numpy() != obg).sum()) == 0 and int((d_fg.cpu().numpy() != ofg).sum()) == 0
+    p.close()
+
+
 def test_wmv_exhaustive_triples_sample(oracle):
     """Random byte triples incl. unweighted variant and raw (un-thresholded) output."""
     import tracking_b200 as tb
