@@ -326,7 +326,8 @@ class MixtureOfGaussianV2BGS:
 
 ALGOS = {0: FrameDifferenceBGS, 1: StaticFrameDifferenceBGS, 2: WeightedMovingMeanBGS,
          3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS,
-         6: AdaptiveBackgroundLearning}          # ids of ustc_src/ustc_bgs.cpp:8-14
+         6: AdaptiveBackgroundLearning, 7: AdaptiveSelectiveBackgroundLearning,
+         11: DPZivkovicAGMMBGS}                  # ids of ustc_src/ustc_bgs.cpp:8-21
 
 
 def morph(mask, op, iterations=1):
