@@ -10,7 +10,9 @@
 //   5    drop small blobs and blobs overlapping tracked ones
 //   6    insertion sort by w*h (descending), keep 10
 //   7    track lists over the last `Latency` frames, uniform-motion test, emit best new blob
+#include <chrono>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -121,16 +123,26 @@ static int detect_impl(bgsb_blobdetector *bd, const uint8_t *d_mask, int w, int 
                        bgsb_blob *frame_blobs, int frame_cap, int *n_frame, cudaStream_t stream)
 {
     const int SEQ_SIZE = bd->latency;
+    static const bool trace = getenv("BGSB_TRACE_DETECT") != nullptr;     // stage times on stderr (debugging aid)
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    const auto t0 = now();
     int rc = ensure_ccl(bd, w, h);
     if (rc) return rc;
     rc = bgsb_ccl_label_dev(bd->ccl, d_mask, w, h, bd->zero_border, nullptr, stream);
     if (rc) return rc;
+    const auto t1 = now();
     int ncomp = 0;
-    rc = bgsb_ccl_components(bd->ccl, nullptr, 0, &ncomp);
-    if (rc) return rc;
-    bd->comps.resize(std::max(ncomp, 1));
+    if (bd->comps.size() < 2048) bd->comps.resize(2048);     // one round trip in the common case
     rc = bgsb_ccl_components(bd->ccl, bd->comps.data(), (int)bd->comps.size(), &ncomp);
+    if (rc == BGSB_ERR_CAPACITY && ncomp > (int)bd->comps.size()) {
+        bd->comps.resize(ncomp);
+        rc = bgsb_ccl_components(bd->ccl, bd->comps.data(), (int)bd->comps.size(), &ncomp);
+    }
     if (rc) return rc;
+    const auto t2 = now();
 
     // cvFindContours(RETR_EXTERNAL) lists outer contours in REVERSE raster order of their first pixels
     std::vector<Rect> rects;
@@ -167,6 +179,7 @@ static int detect_impl(bgsb_blobdetector *bd, const uint8_t *d_mask, int w, int 
             qrects.push_back(r);
         }
     }
+    const auto t3 = now();
     std::vector<uint64_t> mom(qrects.size() * 6 + 6);
     if (!qrects.empty()) {
         std::vector<int32_t> flat(qrects.size() * 4);
@@ -176,6 +189,9 @@ static int detect_impl(bgsb_blobdetector *bd, const uint8_t *d_mask, int w, int 
         rc = bgsb_ccl_rect_moments(bd->ccl, flat.data(), (int)qrects.size(), mom.data());
         if (rc) return rc;
     }
+    if (trace)
+        fprintf(stderr, "detect: launch %.0f us, components(%d) %.0f us, clustering(%zu rects) %.0f us, moments(%zu) %.0f us\n",
+                us(t0, t1), ncomp, us(t1, t2), rects.size(), us(t2, t3), qrects.size(), us(t3, now()));
     for (size_t i = 0; i < qrects.size(); i++) {
         const Rect &R = qrects[i];
         double X, Y, XX, YY;

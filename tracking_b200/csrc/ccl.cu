@@ -495,6 +495,13 @@ struct bgsb_ccl {
     cudaStream_t last_stream = nullptr;
     cudaStream_t own_stream = nullptr;
     bool labelled = false;
+    // host round trips of the per-frame path: pinned staging (count + the first PIN_COMPS table rows, or moments) and
+    // device buffers for the rectangle queries that live as long as the context (no allocator calls per frame)
+    static constexpr int PIN_COMPS = 2048;
+    uint8_t *h_pin = nullptr;               // 64 + PIN_COMPS * sizeof(CompRaw) bytes
+    int *d_rects = nullptr;
+    unsigned long long *d_mom = nullptr;
+    int rect_cap = 0;
 };
 
 extern "C" {
@@ -547,6 +554,8 @@ void bgsb_ccl_destroy(bgsb_ccl *c)
     cudaFree(c->d_bits); cudaFree(c->d_rootbits); cudaFree(c->d_wordrank); cudaFree(c->d_parent);
     cudaFree(c->d_outer); cudaFree(c->d_mask_own); cudaFree(c->d_comp); cudaFree(c->d_ncomp);
     cudaFree(c->d_blockcount); cudaFree(c->d_need_bg); cudaFree(c->d_labels_own);
+    cudaFree(c->d_rects); cudaFree(c->d_mom);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -639,16 +648,25 @@ int bgsb_ccl_components_of(bgsb_ccl *c, int image, bgsb_component *out, int capa
     if (!c->labelled) { set_error("bgsb_ccl_components: nothing labelled yet"); return BGSB_ERR_STATE; }
     BGSB_REQUIRE(image >= 0 && image < c->nimages, "image index");
     BGSB_CUDA(cudaSetDevice(c->device));
+    // one round trip: the count and the first PIN_COMPS rows come back together through pinned memory
+    if (!c->h_pin) BGSB_CUDA(cudaMallocHost(&c->h_pin, 64 + (size_t)bgsb_ccl::PIN_COMPS * sizeof(CompRaw)));
+    static_assert(sizeof(CompRaw) == sizeof(bgsb_component), "layout");
+    const int want = (out && capacity > 0) ? std::min(std::min(capacity, c->cap), (int)bgsb_ccl::PIN_COMPS) : 0;
+    BGSB_CUDA(cudaMemcpyAsync(c->h_pin, c->d_ncomp + image, sizeof(int), cudaMemcpyDeviceToHost, c->last_stream));
+    if (want)
+        BGSB_CUDA(cudaMemcpyAsync(c->h_pin + 64, c->d_comp + (size_t)image * c->cap, (size_t)want * sizeof(CompRaw),
+                                  cudaMemcpyDeviceToHost, c->last_stream));
     BGSB_CUDA(cudaStreamSynchronize(c->last_stream));
-    int cnt = 0;
-    BGSB_CUDA(cudaMemcpy(&cnt, c->d_ncomp + image, sizeof(int), cudaMemcpyDeviceToHost));
+    const int cnt = *reinterpret_cast<const int *>(c->h_pin);
     *n = cnt;
     if (cnt > c->cap) { set_error("component table overflow (%d > %d)", cnt, c->cap); return BGSB_ERR_CAPACITY; }
     if (!out || capacity <= 0) return BGSB_OK;
     if (cnt > capacity) { set_error("caller table too small (%d > %d)", cnt, capacity); return BGSB_ERR_CAPACITY; }
     if (cnt == 0) return BGSB_OK;
-    static_assert(sizeof(CompRaw) == sizeof(bgsb_component), "layout");
-    BGSB_CUDA(cudaMemcpy(out, c->d_comp + (size_t)image * c->cap, (size_t)cnt * sizeof(CompRaw), cudaMemcpyDeviceToHost));
+    memcpy(out, c->h_pin + 64, (size_t)std::min(cnt, want) * sizeof(CompRaw));
+    if (cnt > want)
+        BGSB_CUDA(cudaMemcpy(out + want, c->d_comp + (size_t)image * c->cap + want, (size_t)(cnt - want) * sizeof(CompRaw),
+                             cudaMemcpyDeviceToHost));
     for (int i = 0; i < cnt; i++) {       // (xmin,ymin,xmax,ymax) -> (x,y,w,h)
         out[i].w = out[i].w - out[i].x + 1;
         out[i].h = out[i].h - out[i].y + 1;
@@ -667,20 +685,26 @@ int bgsb_ccl_rect_moments(bgsb_ccl *c, const int32_t *rects, int nrects, uint64_
     if (!c->labelled) { set_error("bgsb_ccl_rect_moments: nothing labelled yet"); return BGSB_ERR_STATE; }
     if (nrects == 0) return BGSB_OK;
     BGSB_CUDA(cudaSetDevice(c->device));
-    int *d_rects = nullptr;
-    unsigned long long *d_out = nullptr;
     cudaStream_t st = c->last_stream;
-    BGSB_CUDA(cudaMallocAsync(&d_rects, (size_t)nrects * 16, st));
-    BGSB_CUDA(cudaMallocAsync(&d_out, (size_t)nrects * 48, st));
-    BGSB_CUDA(cudaMemcpyAsync(d_rects, rects, (size_t)nrects * 16, cudaMemcpyHostToDevice, st));
-    BGSB_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nrects * 48, st));
+    if (nrects > c->rect_cap) {                              // grows rarely; no allocator calls on the per-frame path
+        cudaFree(c->d_rects); cudaFree(c->d_mom); c->d_rects = nullptr; c->d_mom = nullptr; c->rect_cap = 0;
+        const int cap = std::max(1024, nrects * 2);
+        BGSB_CUDA(cudaMalloc(&c->d_rects, (size_t)cap * 16));
+        BGSB_CUDA(cudaMalloc(&c->d_mom, (size_t)cap * 48));
+        c->rect_cap = cap;
+    }
+    if (!c->h_pin) BGSB_CUDA(cudaMallocHost(&c->h_pin, 64 + (size_t)bgsb_ccl::PIN_COMPS * sizeof(CompRaw)));
+    const size_t pin_bytes = (size_t)bgsb_ccl::PIN_COMPS * sizeof(CompRaw);
+    const bool staged = (size_t)nrects * 48 <= pin_bytes;     // moments come back through pinned memory when they fit
+    BGSB_CUDA(cudaMemcpyAsync(c->d_rects, rects, (size_t)nrects * 16, cudaMemcpyHostToDevice, st));
+    BGSB_CUDA(cudaMemsetAsync(c->d_mom, 0, (size_t)nrects * 48, st));
     dim3 grid(nrects, 16);
-    launch_pdl(rect_moments_kernel, dim3(grid), dim3(256), 0, st, c->last_mask, c->w, c->h, d_rects, d_out);
+    launch_pdl(rect_moments_kernel, dim3(grid), dim3(256), 0, st, c->last_mask, c->w, c->h, c->d_rects, c->d_mom);
     BGSB_LAUNCH_CHECK();
-    BGSB_CUDA(cudaMemcpyAsync(out, d_out, (size_t)nrects * 48, cudaMemcpyDeviceToHost, st));
+    BGSB_CUDA(cudaMemcpyAsync(staged ? (void *)(c->h_pin + 64) : (void *)out, c->d_mom, (size_t)nrects * 48,
+                              cudaMemcpyDeviceToHost, st));
     BGSB_CUDA(cudaStreamSynchronize(st));
-    BGSB_CUDA(cudaFreeAsync(d_rects, st));
-    BGSB_CUDA(cudaFreeAsync(d_out, st));
+    if (staged) memcpy(out, c->h_pin + 64, (size_t)nrects * 48);
     return BGSB_OK;
 }
 
