@@ -12,6 +12,7 @@
 // runs every pass of the chain there (ping-pong buffers, one __syncthreads per pass; each pass
 // is 3 shifted ANDs/ORs per word and per row), and unpacks the interior back to bytes.  HBM
 // traffic is one byte read and one byte written per pixel for the whole chain.
+#include <string.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -225,7 +226,12 @@ struct MorphScratch {
     uint8_t *a = nullptr, *b = nullptr;
     size_t cap = 0;
     int device = -1;
-    ~MorphScratch() { if (a) cudaFree(a); if (b) cudaFree(b); }
+    // small masks (the reference's 320x240 class) go through pinned staging on a private stream: two short
+    // asynchronous copies and one synchronisation instead of two blocking pageable copies on the legacy stream
+    static constexpr size_t PIN_MAX = 512 * 1024;
+    uint8_t *pin = nullptr;
+    cudaStream_t stream = nullptr;
+    ~MorphScratch() { if (a) cudaFree(a); if (b) cudaFree(b); if (pin) cudaFreeHost(pin); if (stream) cudaStreamDestroy(stream); }
 };
 thread_local MorphScratch g_morph_scratch;
 }  // namespace
@@ -248,10 +254,24 @@ int bgsb_morph(const uint8_t *mask, int w, int h, size_t stride, const int *ops,
         BGSB_CUDA(cudaMalloc(&S.b, bytes));
         S.cap = bytes;
     }
-    BGSB_CUDA(cudaMemcpy2D(S.a, w, mask, stride, w, h, cudaMemcpyHostToDevice));
-    int rc = launch_morph_chain(S.a, S.b, w, h, 1, ops, nops, nullptr);
+    if (!S.stream) BGSB_CUDA(cudaStreamCreateWithFlags(&S.stream, cudaStreamNonBlocking));
+    if (bytes <= MorphScratch::PIN_MAX) {
+        if (!S.pin) BGSB_CUDA(cudaMallocHost(&S.pin, 2 * MorphScratch::PIN_MAX));
+        for (int y = 0; y < h; y++) memcpy(S.pin + (size_t)y * w, mask + (size_t)y * stride, (size_t)w);
+        BGSB_CUDA(cudaMemcpyAsync(S.a, S.pin, bytes, cudaMemcpyHostToDevice, S.stream));
+        int rc = launch_morph_chain(S.a, S.b, w, h, 1, ops, nops, S.stream);
+        if (rc) return rc;
+        uint8_t *back = S.pin + MorphScratch::PIN_MAX;
+        BGSB_CUDA(cudaMemcpyAsync(back, S.b, bytes, cudaMemcpyDeviceToHost, S.stream));
+        BGSB_CUDA(cudaStreamSynchronize(S.stream));
+        for (int y = 0; y < h; y++) memcpy(out + (size_t)y * out_stride, back + (size_t)y * w, (size_t)w);
+        return BGSB_OK;
+    }
+    BGSB_CUDA(cudaMemcpy2DAsync(S.a, w, mask, stride, w, h, cudaMemcpyHostToDevice, S.stream));
+    int rc = launch_morph_chain(S.a, S.b, w, h, 1, ops, nops, S.stream);
     if (rc) return rc;
-    BGSB_CUDA(cudaMemcpy2D(out, out_stride, S.b, w, w, h, cudaMemcpyDeviceToHost));
+    BGSB_CUDA(cudaMemcpy2DAsync(out, out_stride, S.b, w, w, h, cudaMemcpyDeviceToHost, S.stream));
+    BGSB_CUDA(cudaStreamSynchronize(S.stream));
     return BGSB_OK;
 }
 
