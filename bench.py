@@ -295,7 +295,7 @@ def run_e2e(args, tb, capi, frames, F, K, world, local, barrier):
     return {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": F * NPX * 3, "d2h_bytes_per_step": F * NPX * 4,
             "steps": Ke,
             "note": "bgsb_process (IBGS::process boundary): pinned host BGR frame in, mask + background image out, "
-                    "synchronous per frame; upload/kernel/download of 4 row bands overlap inside the call"}
+                    "synchronous per frame; upload/kernel/download of 2 row bands overlap inside the call"}
 
 
 def finish(args, rank, world, value, K, Wm, ms_max, F, clocks, e2e, launches, achieved, peak, traffic, peak_src,

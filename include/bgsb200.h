@@ -107,7 +107,7 @@ BGSB_API int bgsb_reset(bgsb_ctx *ctx);
  * A/B measurements); 8, 9 = timing instruments with WRONG results (tools/floor_probe.py);
  * "ablTable" (AdaptiveBackgroundLearning): 1 = lookup-table kernels (default), 2 = only the per-thread table kernel,
  * 0 = arithmetic kernel -- identical results;
- * "hostBands" (default 4, 1..8): row bands of the upload / kernel / download pipeline inside bgsb_process. */
+ * "hostBands" (default 2, 1..8): row bands of the upload / kernel / download pipeline inside bgsb_process. */
 BGSB_API int bgsb_set_param(bgsb_ctx *ctx, const char *key, double value);
 BGSB_API int bgsb_get_param(bgsb_ctx *ctx, const char *key, double *value);
 
