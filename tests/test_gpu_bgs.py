@@ -595,6 +595,29 @@ def test_dpzivkovic_sibling_plugin(oracle, clips, kw):
     g.close()
 
 
+def test_second_device_in_one_process(oracle, clips):
+    """Contexts on two devices of one process (per-device function attributes, stream and buffer ownership).
+    Skipped on single-GPU boxes."""
+    import torch
+    import tracking_b200 as tb
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    frames = _asbl_frames(600, 700, 4, 11)
+    for aid in (6, 5, 3, 0, 7, 11):
+        p0, p1 = tb.ALGOS[aid](device=0), tb.ALGOS[aid](device=1)
+        o = oracle.ALGOS[aid]()
+        for f in frames:
+            a, b = p0.process(f), p1.process(f)
+            r = o.process(f)
+            for got in (a, b):
+                assert (got[0] is None) == (r[0] is None)
+                if r[0] is not None:
+                    assert np.array_equal(got[0], r[0]), aid
+                if r[1] is not None:
+                    assert np.array_equal(got[1], r[1]), aid
+        p0.close(); p1.close()
+
+
 def test_mog2_state_export_import_roundtrip(clips):
     import tracking_b200 as tb
     clip = clips["video_clip"]
