@@ -249,6 +249,7 @@ int bgsb_morph(const uint8_t *mask, int w, int h, size_t stride, const int *ops,
     if (S.device != dev || S.cap < bytes) {
         if (S.a) cudaFree(S.a);
         if (S.b) cudaFree(S.b);
+        if (S.device != dev && S.stream) { cudaStreamDestroy(S.stream); S.stream = nullptr; }   // a stream belongs to its device
         S.a = S.b = nullptr; S.cap = 0; S.device = dev;
         BGSB_CUDA(cudaMalloc(&S.a, bytes));
         BGSB_CUDA(cudaMalloc(&S.b, bytes));
