@@ -32,3 +32,16 @@ for n in range(1, 6):
         print("n=%d fit slot %d     " % (n, f), ((nm == n) & (fit == f)).mean())
 for n in range(1, 6):
     print("n=%d no fit         " % n, ((nm == n) & (fit < 0)).mean())
+# --- of the pixels that match slot 0: how many need three or more modes for the background image? ---
+aT = np.float32(p.get("alpha")); a1 = np.float32(1) - aT; prune = np.float32(-float(aT) * 0.05)
+w = [planes[m * 5].astype(np.float32) for m in range(5)]
+wt = [a1 * w[m] + prune for m in range(5)]
+wt[0] = wt[0] + aT
+live = [(nm > m) for m in range(5)]
+tw = sum(np.where(live[m], wt[m], 0) for m in range(5))
+wn = [np.where(live[m], wt[m] / tw, 0) for m in range(5)]
+fit0 = (fit == 0)
+need3 = fit0 & (nm >= 3) & ((wn[0] + wn[1]) <= np.float32(0.9))
+pruned = fit0 & np.any([live[m] & (wt[m] < -prune) for m in range(1, 5)], axis=0)
+print("fit slot 0 and background image needs >= 3 modes:", need3.mean())
+print("fit slot 0 and some weight pruned this frame     :", pruned.mean())
