@@ -38,6 +38,28 @@ __device__ __forceinline__ unsigned inside_mask(int y, int k, int w, int h, int 
     return (1u << (w & 31)) - 1u;
 }
 
+// 32 mask bytes (as eight words) -> one word of "byte is non-zero" bits.  Per word: bit 7 of every byte says
+// non-zero, and one multiply gathers the four flags into a nibble (the partial products land on distinct bits).
+__device__ __forceinline__ unsigned pack32(const unsigned (&ws)[8])
+{
+    unsigned word = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const unsigned v = ws[i];
+        const unsigned f = ((((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u) >> 7;    // 0x01 per non-zero byte
+        word |= ((f * 0x01020408u) >> 24 & 0xfu) << (4 * i);
+    }
+    return word;
+}
+
+// nibble -> four {0,255} bytes: one multiply spreads the bits to the byte positions, one more fills the bytes
+__device__ __forceinline__ unsigned unpack4(unsigned nib)
+{
+    return ((nib * 0x00204081u) & 0x01010101u) * 0xffu;
+}
+
+// Thread (tx, ty) = (tid & 63, tid >> 6) owns shared-memory column tx and rows ty, ty+4, ...: the column's
+// in-image masks are computed once, and no index is divided.
 __global__ void __launch_bounds__(256)
 morph_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, int h, int wpr, MorphChain chain, int R)
 {
@@ -50,31 +72,37 @@ morph_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, i
     const int y0 = blockIdx.y * MORPH_TH - R;          // image row of smem row 0 (halo)
     const int rows = MORPH_TH + 2 * R;
     const int tw = min(MORPH_TW, wpr - blockIdx.x * MORPH_TW) + 2;   // smem columns in use
+    const int c = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int k = k0 + c;
+    const bool col_used = c < tw;
+    // in-image bits of this column and of its neighbours (row validity is added per row)
+    auto colmask = [&](int kk) -> unsigned {
+        if (kk < 0 || kk >= wpr) return 0u;
+        if (kk < wpr - 1 || (w & 31) == 0) return 0xffffffffu;
+        return (1u << (w & 31)) - 1u;
+    };
+    const unsigned cm = colmask(k), cl = colmask(k - 1), cr = colmask(k + 1);
+    const bool vec = cm == 0xffffffffu && ((reinterpret_cast<uintptr_t>(in) | (size_t)w) & 15) == 0;   // 32 whole, aligned bytes
 
     // ---- pack: bytes -> bits (bit i of word k = pixel 32k+i is set) ----
-    for (int idx = threadIdx.x; idx < rows * tw; idx += blockDim.x) {
-        int r = idx / tw, c = idx - r * tw;
-        int y = y0 + r, k = k0 + c;
-        unsigned word = 0;
-        if (y >= 0 && y < h && k >= 0 && k < wpr) {
-            const uint8_t *p = in + (size_t)y * w + (size_t)k * 32;
-            int nvalid = min(32, w - k * 32);
-            if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
-                const uint4 *q = reinterpret_cast<const uint4 *>(p);
-                uint4 a = __ldg(q), b = __ldg(q + 1);
-                unsigned ws[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    unsigned v = ws[i];
-                    unsigned nz = ((v & 0xffu) ? 1u : 0u) | ((v & 0xff00u) ? 2u : 0u) |
-                                  ((v & 0xff0000u) ? 4u : 0u) | ((v & 0xff000000u) ? 8u : 0u);
-                    word |= nz << (4 * i);
+    if (col_used) {
+        for (int r = ty; r < rows; r += 4) {
+            const int y = y0 + r;
+            unsigned word = 0;
+            if (y >= 0 && y < h && cm) {
+                const uint8_t *p = in + (size_t)y * w + (size_t)k * 32;
+                if (vec) {
+                    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+                    const uint4 a = __ldg(q), b = __ldg(q + 1);
+                    const unsigned ws[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    word = pack32(ws);
+                } else {
+                    const int nvalid = min(32, w - k * 32);
+                    for (int i = 0; i < nvalid; i++) word |= (p[i] ? 1u : 0u) << i;
                 }
-            } else {
-                for (int i = 0; i < nvalid; i++) word |= (p[i] ? 1u : 0u) << i;
             }
+            buf[0][r][c] = word;
         }
-        buf[0][r][c] = word;
     }
     __syncthreads();
 
@@ -83,30 +111,32 @@ morph_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, i
     for (int o = 0; o < chain.n; o++) {
         const bool dil = chain.op[o] == BGSB_MORPH_DILATE;
         for (int it = 0; it < chain.iters[o]; it++) {
-            for (int idx = threadIdx.x; idx < rows * tw; idx += blockDim.x) {
-                int r = idx / tw, c = idx - r * tw;
-                int y = y0 + r, k = k0 + c;
-                unsigned acc = dil ? 0u : 0xffffffffu;
+            if (col_used) {
+                for (int r = ty; r < rows; r += 4) {
+                    const int y = y0 + r;
+                    unsigned acc = dil ? 0u : 0xffffffffu;
 #pragma unroll
-                for (int dr = -1; dr <= 1; dr++) {
-                    int rr = r + dr;
-                    unsigned L = 0, M = 0, Rt = 0;
-                    if (rr >= 0 && rr < rows) {
-                        M = buf[cur][rr][c];
-                        if (c > 0) L = buf[cur][rr][c - 1];
-                        if (c + 1 < tw) Rt = buf[cur][rr][c + 1];
+                    for (int dr = -1; dr <= 1; dr++) {
+                        const int rr = r + dr;
+                        unsigned L = 0, M = 0, Rt = 0;
+                        if (rr >= 0 && rr < rows) {
+                            M = buf[cur][rr][c];
+                            if (c > 0) L = buf[cur][rr][c - 1];
+                            if (c + 1 < tw) Rt = buf[cur][rr][c + 1];
+                        }
+                        if (!dil) {   // outside-image pixels are neutral (all ones) for erosion
+                            const bool rowin = (y + dr >= 0 && y + dr < h);
+                            M |= rowin ? ~cm : 0xffffffffu;
+                            L |= rowin ? ~cl : 0xffffffffu;
+                            Rt |= rowin ? ~cr : 0xffffffffu;
+                        }
+                        const unsigned left = (M << 1) | (L >> 31);      // neighbour x-1
+                        const unsigned right = (M >> 1) | (Rt << 31);    // neighbour x+1
+                        if (dil) acc |= M | left | right;
+                        else acc &= M & left & right;
                     }
-                    if (!dil) {   // outside-image pixels are neutral (all ones) for erosion
-                        M |= ~inside_mask(y + dr, k, w, h, wpr);
-                        L |= ~inside_mask(y + dr, k - 1, w, h, wpr);
-                        Rt |= ~inside_mask(y + dr, k + 1, w, h, wpr);
-                    }
-                    unsigned left = (M << 1) | (L >> 31);      // neighbour x-1
-                    unsigned right = (M >> 1) | (Rt << 31);    // neighbour x+1
-                    if (dil) acc |= M | left | right;
-                    else acc &= M & left & right;
+                    buf[cur ^ 1][r][c] = (y >= 0 && y < h) ? (acc & cm) : 0u;
                 }
-                buf[cur ^ 1][r][c] = acc & inside_mask(y, k, w, h, wpr);
             }
             __syncthreads();
             cur ^= 1;
@@ -114,27 +144,22 @@ morph_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, i
     }
 
     // ---- unpack the interior: bits -> {0,255} bytes ----
-    const int itw = tw - 2;
-    for (int idx = threadIdx.x; idx < MORPH_TH * itw; idx += blockDim.x) {
-        int r = idx / itw, c = idx - r * itw;
-        int y = blockIdx.y * MORPH_TH + r, k = k0 + 1 + c;
-        if (y >= h) continue;
-        unsigned word = buf[cur][r + R][c + 1];
-        uint8_t *p = out + (size_t)y * w + (size_t)k * 32;
-        int nvalid = min(32, w - k * 32);
-        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
-            unsigned ws[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                unsigned nib = (word >> (4 * i)) & 0xfu;
-                ws[i] = ((nib & 1u) ? 0xffu : 0u) | ((nib & 2u) ? 0xff00u : 0u) |
-                        ((nib & 4u) ? 0xff0000u : 0u) | ((nib & 8u) ? 0xff000000u : 0u);
+    if (c >= 1 && c < tw - 1) {
+        for (int r = ty; r < MORPH_TH; r += 4) {
+            const int y = blockIdx.y * MORPH_TH + r;
+            if (y >= h) break;
+            const unsigned word = buf[cur][r + R][c];
+            uint8_t *p = out + (size_t)y * w + (size_t)k * 32;
+            if (cm == 0xffffffffu && ((reinterpret_cast<uintptr_t>(out) | (size_t)w) & 15) == 0) {
+                uint4 *q = reinterpret_cast<uint4 *>(p);
+                q[0] = make_uint4(unpack4(word & 0xfu), unpack4((word >> 4) & 0xfu), unpack4((word >> 8) & 0xfu),
+                                  unpack4((word >> 12) & 0xfu));
+                q[1] = make_uint4(unpack4((word >> 16) & 0xfu), unpack4((word >> 20) & 0xfu), unpack4((word >> 24) & 0xfu),
+                                  unpack4(word >> 28));
+            } else {
+                const int nvalid = min(32, w - k * 32);
+                for (int i = 0; i < nvalid; i++) p[i] = ((word >> i) & 1u) ? 255 : 0;
             }
-            uint4 *q = reinterpret_cast<uint4 *>(p);
-            q[0] = make_uint4(ws[0], ws[1], ws[2], ws[3]);
-            q[1] = make_uint4(ws[4], ws[5], ws[6], ws[7]);
-        } else {
-            for (int i = 0; i < nvalid; i++) p[i] = ((word >> i) & 1u) ? 255 : 0;
         }
     }
 }
