@@ -82,14 +82,21 @@ __device__ __forceinline__ void unite(int *parent, int a, int b)
     }
 }
 
+// pack + foreground init in one pass: a word's run starts become their own union-find roots right away (the
+// init step only needs the word itself), and the per-block root counters / background-pass flag are cleared.
 __global__ void __launch_bounds__(256)
-ccl_pack_kernel(const uint8_t *__restrict__ mask, unsigned *__restrict__ bits, int w, int h, int wpr, int zero_border,
+ccl_pack_kernel(const uint8_t *__restrict__ mask, unsigned *__restrict__ bits, int *__restrict__ parent,
+                int *__restrict__ blockcount, int *__restrict__ need_bg, int nblocks, int w, int h, int wpr, int zero_border,
                 size_t img_px, size_t img_words)
 {
     pdl_entry();
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (threadIdx.x == 0) {
+        blockcount[blockIdx.y * (size_t)(nblocks + 1) + blockIdx.x] = 0;
+        if (blockIdx.x == 0) need_bg[blockIdx.y] = 0;
+    }
     if (wi >= h * wpr) return;
-    mask += blockIdx.y * img_px; bits += blockIdx.y * img_words;
+    mask += blockIdx.y * img_px; bits += blockIdx.y * img_words; parent += blockIdx.y * img_px;
     int y = wi / wpr, k = wi - y * wpr;
     const uint8_t *p = mask + (size_t)y * w + (size_t)k * 32;
     int nvalid = min(32, w - k * 32);
@@ -114,6 +121,12 @@ ccl_pack_kernel(const uint8_t *__restrict__ mask, unsigned *__restrict__ bits, i
         if (k == wpr - 1) word &= ~(1u << ((w - 1) & 31));
     }
     bits[wi] = word;
+    const int base = y * w + k * 32;
+    unsigned s = word & ~(word << 1);                  // run starts inside the word
+    while (s) {
+        const int b = __ffs(s) - 1; s &= s - 1;
+        parent[base + b] = base + b;
+    }
 }
 
 // BG = false: foreground runs;  BG = true: background runs (only for images flagged by the nest check)
@@ -378,7 +391,7 @@ ccl_label_kernel(const unsigned *__restrict__ bits, const int *__restrict__ pare
 
 // Does any component's bounding box lie strictly inside another's?  (Necessary for a component to sit in a
 // hole of another one.)  grid = (16 tiles of 256 components, images); the j-loop runs over shared-memory tiles.
-// More than 4096 components: not worth checking, run the bg pass.  need_bg[] was zeroed by ccl_init_kernel<false>.
+// More than 4096 components: not worth checking, run the bg pass.  need_bg[] was zeroed by ccl_pack_kernel.
 __global__ void __launch_bounds__(256)
 ccl_nest_kernel(const CompRaw *__restrict__ comp, const int *__restrict__ ncomp, int cap, int *__restrict__ need_bg)
 {
@@ -573,10 +586,8 @@ int bgsb_ccl_label_batch_dev(bgsb_ccl *c, const uint8_t *d_masks, int w, int h, 
     const int threads = 256, nblocks = (nwords + threads - 1) / threads;
     const size_t ipx = (size_t)w * h, iw = (size_t)nwords;       // dense per-image strides for this geometry
     dim3 grid(nblocks, nimages);
-    launch_pdl(ccl_pack_kernel, dim3(grid), dim3(threads), 0, stream, d_masks, c->d_bits, w, h, wpr, zero_border, ipx, iw);
-    BGSB_LAUNCH_CHECK();
-    launch_pdl(ccl_init_kernel<false>, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_blockcount, c->d_need_bg,
-                                                        w, h, wpr, ipx, iw, nblocks);
+    launch_pdl(ccl_pack_kernel, dim3(grid), dim3(threads), 0, stream, d_masks, c->d_bits, c->d_parent, c->d_blockcount, c->d_need_bg,
+               nblocks, w, h, wpr, zero_border, ipx, iw);
     BGSB_LAUNCH_CHECK();
     launch_pdl(ccl_merge_kernel<false>, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_need_bg, w, h, wpr, ipx, iw);
     BGSB_LAUNCH_CHECK();
