@@ -198,6 +198,7 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
             L.npx = pcount; L.T = Tl; L.bg_last_only = per_frame ? 0 : bg_last_only;
             L.fresh = (c->nframes + i == 0);
             L.fast_ok = 1;
+            L.one = 1.f;
             L.enable_thr = c->enable_thr; L.thr = c->thr;
             L.detect_shadows = c->detect_shadows; L.shadow_value = c->shadow_value;
             L.Tb = c->Tb; L.Tg = c->Tg; L.TB = c->TB; L.varInit = c->varInit; L.varMin = c->varMin;

@@ -66,6 +66,8 @@ struct Mog2Launch {
     int npx, T;
     int bg_last_only;
     int fresh;               // 1: state is uninitialised -> treat nmodes as 0 (first frame after create/reset)
+    float one;               // 1.0f, opaque to the compiler: packed adds of products go through fma(p, one, b) because ptxas
+                             // contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 whatever -fmad says (mog2_fastmath.cuh)
     int fast_ok;             // learning rates are inside the range the fast path's unguarded division is exact for
     int enable_thr, thr;
     int detect_shadows, shadow_value;
