@@ -123,6 +123,20 @@ BGSB_API int bgsb_process(bgsb_ctx *ctx, const uint8_t *bgr, int w, int h, size_
                           uint8_t *fg, size_t fg_stride, uint8_t *bg, size_t bg_stride,
                           int *fg_valid, int *bg_valid);
 
+/* Pipelined ingest for the capture loop (VideoCapture.cpp:151-239 reads a frame and calls FrameProcessor::process;
+ * ustc_src/trackingMain.cpp:161-166 does the same with cvQueryFrame + USTC_BGS::Process): bgsb_process, queued.
+ * bgsb_submit returns once the frame's upload, kernel and downloads are enqueued; the upload of the next frame then
+ * overlaps the download of this one (a synchronous call cannot use both PCIe directions at once).  The model
+ * advances in submission order: results are those of the same sequence of bgsb_process calls.  Arguments as in
+ * bgsb_process; bgr / fg / bg must stay valid and untouched until bgsb_wait returns and should be page-locked
+ * (bgsb_host_alloc).  *fg_valid / *bg_valid are known at submission.  Any number of frames may be queued; every other
+ * entry point taking this context waits for them first.
+ * bgsb_wait: all submitted frames' outputs are in their host buffers. */
+BGSB_API int bgsb_submit(bgsb_ctx *ctx, const uint8_t *bgr, int w, int h, size_t stride,
+                         uint8_t *fg, size_t fg_stride, uint8_t *bg, size_t bg_stride,
+                         int *fg_valid, int *bg_valid);
+BGSB_API int bgsb_wait(bgsb_ctx *ctx);
+
 /* FrameProcessor::process (FrameProcessor.cpp:169-215) runs every enabled plugin back to back on the same
  * prepared frame.  Fan-out does that with ONE upload: the frame goes to the device once (in row bands), the n
  * contexts' kernels run on it concurrently, and each plugin's outputs come back as in bgsb_process.

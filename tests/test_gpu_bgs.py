@@ -482,6 +482,71 @@ def test_fanout_one_upload_matches_separate_plugins(oracle, shape):
         tb.process_fanout([q, q], frames[0])
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_submit_wait_pipeline_matches_oracle(oracle, pinned):
+    """Pipelined ingest (bgsb_submit / bgsb_wait): nine queued frames per plugin give exactly the
+    outputs the oracle's plugins give frame by frame -- warm-up frames leave their buffers untouched -- and the model
+    continues correctly through a synchronous process() (which drains the queue first) and through reset()."""
+    import tracking_b200 as tb
+    h, w = 203, 311
+    rng = np.random.default_rng(11)
+    base = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    frames = [np.clip(base.astype(np.int16) + rng.integers(-12, 13, (h, w, 3)), 0, 255).astype(np.uint8) for _ in range(10)]
+    frames[5][h // 4:h // 2, w // 4:w // 2] = 255 - frames[5][h // 4:h // 2, w // 4:w // 2]
+    alloc = tb.pinned_empty if pinned else (lambda shape: np.empty(shape, np.uint8))
+    names = ["FrameDifferenceBGS", "StaticFrameDifferenceBGS", "WeightedMovingMeanBGS", "WeightedMovingVarianceBGS",
+             "MixtureOfGaussianV2BGS", "AdaptiveBackgroundLearning", "AdaptiveSelectiveBackgroundLearning",
+             "DPZivkovicAGMMBGS"]
+    for nm in names:
+        p, o = getattr(tb, nm)(), getattr(oracle, nm)()
+        bgshape = (h, w, 3) if p.BG_CHANNELS == 3 else (h, w)
+        ins, fgs, bgs, flags = [], [], [], []
+        for f in frames[:9]:
+            a = alloc((h, w, 3)); a[...] = f
+            fg = alloc((h, w)); fg[...] = 77
+            bg = alloc(bgshape); bg[...] = 77
+            flags.append(p.submit(a, fg, bg))
+            ins.append(a); fgs.append(fg); bgs.append(bg)
+        p.wait()
+        for i, f in enumerate(frames[:9]):
+            fb, bb = o.process(f)
+            assert flags[i] == (fb is not None, bb is not None), (nm, i)
+            assert np.array_equal(fgs[i], fb) if fb is not None else (fgs[i] == 77).all(), (nm, i)
+            assert np.array_equal(bgs[i], bb) if bb is not None else (bgs[i] == 77).all(), (nm, i)
+        # queue two more and go straight into a synchronous call: it waits for the queue
+        a = alloc((h, w, 3)); a[...] = frames[9]
+        fg = alloc((h, w)); bg = alloc(bgshape)
+        p.submit(a, fg, bg)
+        fa, ba = p.process(frames[3])
+        fb, bb = o.process(frames[9])
+        assert np.array_equal(fg, fb), nm
+        fb, bb = o.process(frames[3])
+        assert np.array_equal(fa, fb), nm
+        if bb is not None:
+            assert np.array_equal(ba, bb), nm
+        p.wait()                                         # nothing queued: returns at once
+        p.close()
+
+
+def test_submit_geometry_change_and_errors():
+    """A new frame size re-initialises the model exactly as process() does; bad buffers are refused."""
+    import tracking_b200 as tb
+    rng = np.random.default_rng(3)
+    p, q = tb.MixtureOfGaussianV2BGS(), tb.MixtureOfGaussianV2BGS()
+    for (h, w) in [(64, 80), (64, 80), (50, 33), (50, 33)]:
+        f = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        fg, bg = np.empty((h, w), np.uint8), np.empty((h, w, 3), np.uint8)
+        p.submit(f, fg, bg)
+        p.wait()
+        fb, bb = q.process(f)
+        assert np.array_equal(fg, fb) and np.array_equal(bg, bb)
+    with pytest.raises(ValueError):
+        p.submit(f, np.empty((5, 5), np.uint8))
+    with pytest.raises(ValueError):
+        p.submit(f[:, ::2], np.empty((50, 17), np.uint8))
+    p.close(); q.close()
+
+
 def _asbl_frames(h, w, n, seed):
     rng = np.random.default_rng(seed)
     base = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)

@@ -7,8 +7,8 @@ tracking_b200/adapters/.  There is no CPU fallback.
 """
 from .bgs import (ALGOS, USTC_BGS, AdaptiveBackgroundLearning, AdaptiveSelectiveBackgroundLearning, DPZivkovicAGMMBGS, FrameDifferenceBGS,  # noqa: F401
                   MixtureOfGaussianV2BGS, StaticFrameDifferenceBGS, WeightedMovingMeanBGS,
-                  WeightedMovingVarianceBGS, process_fanout)
+                  WeightedMovingVarianceBGS, pinned_empty, process_fanout)
 from .capi import BgsbError, kernel_launch_count  # noqa: F401
 
 __all__ = ["FrameDifferenceBGS", "StaticFrameDifferenceBGS", "WeightedMovingMeanBGS", "WeightedMovingVarianceBGS", "AdaptiveBackgroundLearning", "AdaptiveSelectiveBackgroundLearning", "DPZivkovicAGMMBGS",
-           "MixtureOfGaussianV2BGS", "USTC_BGS", "ALGOS", "process_fanout", "BgsbError", "kernel_launch_count"]
+           "MixtureOfGaussianV2BGS", "USTC_BGS", "ALGOS", "process_fanout", "pinned_empty", "BgsbError", "kernel_launch_count"]

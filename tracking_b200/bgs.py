@@ -93,6 +93,34 @@ class _Plugin:
                                            C.byref(fv), C.byref(bv)))
         return (fg if fv.value else None), (bg if bv.value else None)
 
+    # -- pipelined ingest (capture loop) ----------------------------------------------------------
+    def submit(self, img_input, fg_out, bg_out=None):
+        """Queue one frame (bgsb_submit): like process(), but returns once the work is enqueued; the upload of the
+        next frame overlaps this frame's download.  img_input / fg_out / bg_out are caller-owned C-contiguous uint8
+        arrays (page-locked ones from pinned_empty() to really overlap) that must stay untouched until wait().
+        Returns (fg_valid, bg_valid): whether fg_out / bg_out will be written for this frame."""
+        img = np.asarray(img_input)
+        if img.dtype != np.uint8 or img.ndim != 3 or img.shape[-1] != 3 or not img.flags.c_contiguous:
+            raise ValueError("submit takes one C-contiguous BGR 8UC3 frame")
+        h, w = img.shape[:2]
+        if fg_out.dtype != np.uint8 or fg_out.shape != (h, w) or not fg_out.flags.c_contiguous:
+            raise ValueError("fg_out must be a C-contiguous HxW uint8 array")
+        bgshape = (h, w, 3) if self.BG_CHANNELS == 3 else (h, w)
+        if bg_out is not None and (bg_out.dtype != np.uint8 or bg_out.shape != bgshape or not bg_out.flags.c_contiguous):
+            raise ValueError("bg_out must be a C-contiguous uint8 array of shape %r" % (bgshape,))
+        fv, bv = C.c_int(0), C.c_int(0)
+        capi.check(capi.lib().bgsb_submit(self._h, _ptr(img), w, h, w * 3, _ptr(fg_out), w,
+                                          _ptr(bg_out) if bg_out is not None else None, self.BG_CHANNELS * w,
+                                          C.byref(fv), C.byref(bv)))
+        self._keep = getattr(self, "_keep", [])
+        self._keep.append((img, fg_out, bg_out))          # the arrays outlive the queued copies
+        return bool(fv.value), bool(bv.value)
+
+    def wait(self):
+        """All submitted frames' outputs are in their arrays (bgsb_wait)."""
+        capi.check(capi.lib().bgsb_wait(self._h))
+        self._keep = []
+
     # -- device buffers (torch tensors or raw pointers) -----------------------------------------
     def process_dev(self, d_bgr, w, h, d_fg, d_bg=None, stream=0):
         fv, bv = C.c_int(0), C.c_int(0)
@@ -170,6 +198,29 @@ class MixtureOfGaussianV2BGS(_Plugin):
         nmodes = np.ascontiguousarray(nmodes, np.uint8)
         capi.check(capi.lib().bgsb_mog2_import_state(self._h, stream_index, w, h, nframes,
                                                      planes.ctypes.data_as(capi.f32p), nmodes.ctypes.data_as(capi.u8p)))
+
+
+class _PinnedOwner:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            capi.lib().bgsb_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, write_combined=False):
+    """uint8 numpy array on page-locked host memory (bgsb_host_alloc); freed with the array."""
+    n = int(np.prod(shape))
+    p = C.c_void_p()
+    capi.check(capi.lib().bgsb_host_alloc(C.byref(p), max(n, 1), int(write_combined)))
+    owner = _PinnedOwner(p)
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    buf._owner = owner
+    arr = np.frombuffer(buf, dtype=np.uint8, count=n).reshape(shape)
+    return arr
 
 
 def process_fanout(plugins, img_input, want_bg=True):

@@ -54,6 +54,8 @@ SIGNATURES = {
     "bgsb_set_param": (C.c_int, [vp, C.c_char_p, C.c_double]),
     "bgsb_get_param": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_double)]),
     "bgsb_process": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t, intp, intp]),
+    "bgsb_submit": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_size_t, vp, C.c_size_t, vp, C.c_size_t, intp, intp]),
+    "bgsb_wait": (C.c_int, [vp]),
     "bgsb_process_fanout": (C.c_int, [C.POINTER(vp), C.c_int, vp, C.c_int, C.c_int, C.c_size_t, C.POINTER(vp),
                                       C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(C.c_size_t), intp, intp]),
     "bgsb_process_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, intp, intp, vp]),

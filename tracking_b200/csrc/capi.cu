@@ -71,6 +71,11 @@ struct bgsb_ctx {
     // host-path chunk pipeline: upload / compute / download overlap inside one synchronous call
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_up[8] = {}, ev_k[8] = {};
+    // bgsb_submit / bgsb_wait: frames in flight, second output slot, download-complete events per slot
+    uint8_t *d_fg2 = nullptr, *d_bg2 = nullptr;
+    cudaEvent_t ev_dn[2] = {};
+    uint64_t seq = 0;
+    bool inflight = false;
 };
 
 static bool gmm_state(int algo);
@@ -83,6 +88,8 @@ static void free_buffers(bgsb_ctx *c)
     for (int i = 0; i < 3; i++) { cudaFree(c->d_ring[i]); c->d_ring[i] = nullptr; }
     cudaFree(c->d_fg); c->d_fg = nullptr;
     cudaFree(c->d_bg); c->d_bg = nullptr;
+    cudaFree(c->d_fg2); c->d_fg2 = nullptr;
+    cudaFree(c->d_bg2); c->d_bg2 = nullptr;
     cudaFree(c->d_fan); c->d_fan = nullptr; c->d_fan_bytes = 0;
     c->w = c->h = c->npx = 0; c->pstride = 0;
     c->nframes = 0; c->have_hist = 0; c->ring_pos = 0;
@@ -328,6 +335,20 @@ static int ensure_pipe_streams(bgsb_ctx *c)
         BGSB_CUDA(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
         BGSB_CUDA(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < 2; i++) BGSB_CUDA(cudaEventCreateWithFlags(&c->ev_dn[i], cudaEventDisableTiming));
+    return BGSB_OK;
+}
+
+// Frames queued by bgsb_submit: every other entry point that touches the model or the staging buffers first waits
+// for them (results are then in the host buffers given to bgsb_submit).
+static int drain(bgsb_ctx *c)
+{
+    if (!c->inflight) return BGSB_OK;
+    BGSB_CUDA(cudaSetDevice(c->device));
+    BGSB_CUDA(cudaStreamSynchronize(c->s_h2d));
+    BGSB_CUDA(cudaStreamSynchronize(c->stream));
+    BGSB_CUDA(cudaStreamSynchronize(c->s_d2h));
+    c->inflight = false;
     return BGSB_OK;
 }
 
@@ -386,18 +407,22 @@ void bgsb_destroy(bgsb_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    drain(c);
     if (c->stream) { cudaStreamSynchronize(c->stream); }
     free_buffers(c);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     for (int i = 0; i < 8; i++) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]); }
+    for (int i = 0; i < 2; i++) if (c->ev_dn[i]) cudaEventDestroy(c->ev_dn[i]);
     delete c;
 }
 
 int bgsb_reset(bgsb_ctx *c)
 {
     BGSB_REQUIRE(c, "null ctx");
+    int rc = drain(c);
+    if (rc) return rc;
     c->nframes = 0; c->have_hist = 0; c->asbl_counter = 0;
     c->hist_ptr[0] = c->hist_ptr[1] = nullptr;
     return BGSB_OK;
@@ -492,6 +517,7 @@ int bgsb_process_batch_dev(bgsb_ctx *c, const uint8_t *d_frames, int T, int w, i
                            uint8_t *d_bg, int bg_last_only, int *first_fg_valid, int *bg_valid, void *stream)
 {
     BGSB_REQUIRE(c && d_frames && d_fg, "null");
+    if (int drc = drain(c)) return drc;
     BGSB_REQUIRE(T >= 1, "T >= 1");
     BGSB_CUDA(cudaSetDevice(c->device));
     int rc = ensure_geometry(c, w, h);
@@ -522,7 +548,9 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
     const size_t bgw = (size_t)w * bg_channels(c ? c->algo : 0);          // bytes per row of img_bgmodel
     BGSB_REQUIRE(!bg || bg_stride >= bgw, "bg stride smaller than a row");
     BGSB_CUDA(cudaSetDevice(c->device));
-    int rc = ensure_geometry(c, w, h);
+    int rc = drain(c);
+    if (rc) return rc;
+    rc = ensure_geometry(c, w, h);
     if (rc) return rc;
     rc = ensure_host_staging(c);
     if (rc) return rc;
@@ -595,6 +623,85 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
     return BGSB_OK;
 }
 
+// Pipelined ingest (the capture loop VideoCapture.cpp:151-239 / ustc_src/trackingMain.cpp:161-166):
+// the same work as bgsb_process, queued.  The call returns as soon as the upload, the kernel and the downloads of this
+// frame are enqueued on three streams; the upload of frame t+1 overlaps the download of frame t (PCIe is full duplex),
+// which a synchronous IBGS::process cannot do.  The model advances in submission order, so the results are the ones a
+// sequence of bgsb_process calls gives.  bgr / fg / bg must stay valid and untouched until bgsb_wait returns, and
+// should be page-locked (bgsb_host_alloc) -- pageable buffers work but serialise.  Output slots alternate between two
+// device buffers; the kernel of frame t+2 waits for the download of frame t.
+int bgsb_submit(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, uint8_t *fg, size_t fg_stride,
+                uint8_t *bg, size_t bg_stride, int *fg_valid, int *bg_valid)
+{
+    BGSB_REQUIRE(c && bgr && fg, "null");
+    BGSB_REQUIRE(stride >= (size_t)w * 3 && fg_stride >= (size_t)w, "stride smaller than a row");
+    const size_t bgw = (size_t)w * bg_channels(c->algo);
+    BGSB_REQUIRE(!bg || bg_stride >= bgw, "bg stride smaller than a row");
+    BGSB_CUDA(cudaSetDevice(c->device));
+    int rc;
+    if (c->w != w || c->h != h) {                                  // geometry change: nothing may be in flight
+        rc = drain(c);
+        if (rc) return rc;
+    }
+    rc = ensure_geometry(c, w, h);
+    if (rc) return rc;
+    rc = ensure_host_staging(c);
+    if (rc) return rc;
+    rc = ensure_pipe_streams(c);
+    if (rc) return rc;
+    const size_t S = (size_t)c->nstreams;
+    if (!c->d_fg2) BGSB_CUDA(cudaMalloc(&c->d_fg2, S * c->npx));
+    if (!c->d_bg2 && c->d_bg) BGSB_CUDA(cudaMalloc(&c->d_bg2, S * c->npx * 3));
+    const size_t rows = (size_t)h * c->nstreams;
+    const bool fdlike = ring_history(c->algo);
+    const int nring = history_images(c->algo) + 1;
+    uint8_t *d_in = fdlike ? c->d_ring[c->ring_pos] : c->d_ring[0];
+    const int warm = warmup_frames(c->algo);
+    const bool out_fg = c->nframes >= warm;
+    const bool want_bg = writes_background(c->algo) && bg;
+    const bool own_hist = !fdlike;
+    const int slot = (int)(c->seq & 1);
+    uint8_t *o_fg = slot ? c->d_fg2 : c->d_fg, *o_bg = slot ? c->d_bg2 : c->d_bg;
+
+    // the input buffer (ring slot) was last read by the previous frame's kernel
+    if (c->seq > 0) BGSB_CUDA(cudaStreamWaitEvent(c->s_h2d, c->ev_k[slot ^ 1], 0));
+    BGSB_CUDA(copy_rows(d_in, (size_t)w * 3, bgr, stride, (size_t)w * 3, rows, cudaMemcpyHostToDevice, c->s_h2d));
+    BGSB_CUDA(cudaEventRecord(c->ev_up[slot], c->s_h2d));
+    BGSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up[slot], 0));
+    if (out_fg) {
+        BGSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_dn[slot], 0));       // output slot free (no-op until recorded)
+        rc = launch_range(c, d_in, 1, o_fg, want_bg ? o_bg : nullptr, 0, own_hist, c->stream, 0, c->npx);
+        if (rc) return rc;
+    }
+    BGSB_CUDA(cudaEventRecord(c->ev_k[slot], c->stream));
+    if (out_fg) {
+        BGSB_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_k[slot], 0));
+        BGSB_CUDA(copy_rows(fg, fg_stride, o_fg, (size_t)w, (size_t)w, rows, cudaMemcpyDeviceToHost, c->s_d2h));
+        if (want_bg) BGSB_CUDA(copy_rows(bg, bg_stride, o_bg, bgw, bgw, rows, cudaMemcpyDeviceToHost, c->s_d2h));
+        BGSB_CUDA(cudaEventRecord(c->ev_dn[slot], c->s_d2h));
+        advance(c, 1, own_hist);
+    } else {
+        c->nframes += 1;
+    }
+    if (fdlike) {
+        c->hist_ptr[1] = c->hist_ptr[0];
+        c->hist_ptr[0] = d_in;
+        c->have_hist = std::min(warm, c->have_hist + 1);
+        c->ring_pos = (c->ring_pos + 1) % nring;
+    }
+    c->seq += 1;
+    c->inflight = true;
+    if (fg_valid) *fg_valid = out_fg;
+    if (bg_valid) *bg_valid = (want_bg && out_fg) ? 1 : 0;
+    return BGSB_OK;
+}
+
+int bgsb_wait(bgsb_ctx *c)
+{
+    BGSB_REQUIRE(c, "null ctx");
+    return drain(c);
+}
+
 int bgsb_process_fanout(bgsb_ctx *const *ctxs, int n, const uint8_t *bgr, int w, int h, size_t stride,
                         uint8_t *const *fg, const size_t *fg_stride, uint8_t *const *bg, const size_t *bg_stride,
                         int *fg_valid, int *bg_valid)
@@ -602,6 +709,7 @@ int bgsb_process_fanout(bgsb_ctx *const *ctxs, int n, const uint8_t *bgr, int w,
     BGSB_REQUIRE(ctxs && bgr && fg && fg_stride && n >= 1 && n <= 16, "bad args");
     BGSB_REQUIRE(stride >= (size_t)w * 3, "stride smaller than a row");
     bgsb_ctx *c0 = ctxs[0];
+    for (int k = 0; k < n; k++) { BGSB_REQUIRE(ctxs[k], "null ctx"); if (int drc = drain(ctxs[k])) return drc; }
     for (int k = 0; k < n; k++) {
         BGSB_REQUIRE(ctxs[k] && fg[k], "null context or mask buffer");
         BGSB_REQUIRE(ctxs[k]->device == c0->device && ctxs[k]->nstreams == 1, "fan-out takes single-stream contexts of one device");
@@ -683,6 +791,7 @@ int bgsb_process_fanout(bgsb_ctx *const *ctxs, int n, const uint8_t *bgr, int w,
 int bgsb_mog2_export_state(bgsb_ctx *c, int si, float *planes, uint8_t *nmodes)
 {
     BGSB_REQUIRE(c && planes && nmodes, "null");
+    if (int drc = drain(c)) return drc;
     BGSB_REQUIRE(c->algo == BGSB_ALGO_MOG2 && c->d_state, "no MOG2 state");
     BGSB_REQUIRE(si >= 0 && si < c->nstreams, "stream index");
     BGSB_CUDA(cudaSetDevice(c->device));
@@ -706,6 +815,7 @@ int bgsb_mog2_import_state(bgsb_ctx *c, int si, int w, int h, int64_t nframes, c
                            const uint8_t *nmodes)
 {
     BGSB_REQUIRE(c && planes && nmodes, "null");
+    if (int drc = drain(c)) return drc;
     BGSB_REQUIRE(c->algo == BGSB_ALGO_MOG2, "not a MOG2 context");
     BGSB_REQUIRE(si >= 0 && si < c->nstreams, "stream index");
     BGSB_REQUIRE(nframes >= 1, "nframes >= 1");
