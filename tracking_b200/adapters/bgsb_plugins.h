@@ -48,6 +48,33 @@ protected:
 
   void set(const char *key, double v) { CV_Assert(bgsb_set_param(ctx, key, v) == BGSB_OK); }
 
+public:
+  virtual void configure() = 0;
+
+  // Queued form of process() for a capture loop (VideoCapture.cpp:151-239): returns once the frame's upload, kernel and
+  // downloads are enqueued (bgsb_submit), so the next frame's upload overlaps this frame's download.  img_output /
+  // img_bgmodel are the caller's Mats (created here if empty; give preallocated page-locked ones -- bgsb_host_alloc --
+  // for the copies to overlap); they and img_input must stay untouched until wait().  No imshow on this path.
+  void submit(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel, bool *fg_valid = 0, bool *bg_valid = 0)
+  {
+    if (img_input.empty()) return;
+    CV_Assert(img_input.type() == CV_8UC3);
+    configure();
+    img_output.create(img_input.rows, img_input.cols, CV_8UC1);
+    img_bgmodel.create(img_input.rows, img_input.cols, bg_type);
+    int fv = 0, bv = 0;
+    int rc = bgsb_submit(ctx, img_input.data, img_input.cols, img_input.rows, (size_t)img_input.step, img_output.data,
+                         (size_t)img_output.step, img_bgmodel.data, (size_t)img_bgmodel.step, &fv, &bv);
+    if (rc != BGSB_OK) std::cerr << "bgsb200: " << bgsb_last_error() << std::endl;
+    CV_Assert(rc == BGSB_OK);
+    if (fg_valid) *fg_valid = fv != 0;
+    if (bg_valid) *bg_valid = bv != 0;
+    firstTime = false;
+  }
+  void wait() { CV_Assert(bgsb_wait(ctx) == BGSB_OK); }
+
+protected:
+
   // Runs one frame; returns which outputs were produced (reference early returns leave them untouched).
   void run(const cv::Mat &img_input, bool &fg_valid, bool &bg_valid, bool want_bg)
   {
@@ -134,12 +161,18 @@ public:
   }
   ~FrameDifferenceBGS() { std::cout << "~FrameDifferenceBGS()" << std::endl; }
 
+  // the configuration preamble of process() (also run by the queued submit())
+  void configure()
+  {
+    loadConfig();
+    if (firstTime) saveConfig();
+  }
+
   void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
   {
     (void)img_bgmodel;                       // never written (FrameDifferenceBGS.cpp:29-61)
     if (img_input.empty()) return;
-    loadConfig();
-    if (firstTime) saveConfig();
+    configure();
     bool fg, bg;
     run(img_input, fg, bg, false);
     if (!fg) return;                         // first frame: only remembered (.cpp:39-43)
@@ -185,11 +218,17 @@ public:
   }
   ~StaticFrameDifferenceBGS() { std::cout << "~StaticFrameDifferenceBGS()" << std::endl; }
 
+  // the configuration preamble of process() (also run by the queued submit())
+  void configure()
+  {
+    loadConfig();
+    if (firstTime) saveConfig();
+  }
+
   void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
   {
     if (img_input.empty()) return;
-    loadConfig();
-    if (firstTime) saveConfig();
+    configure();
     bool fg, bg;
     run(img_input, fg, bg, true);
     if (showOutput) cv::imshow("Static Frame Difference", img_foreground);
@@ -236,11 +275,17 @@ public:
   }
   ~WeightedMovingMeanBGS() { std::cout << "~WeightedMovingMeanBGS()" << std::endl; }
 
+  // the configuration preamble of process() (also run by the queued submit())
+  void configure()
+  {
+    loadConfig();
+    if (firstTime) saveConfig();
+  }
+
   void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
   {
     if (img_input.empty()) return;
-    loadConfig();
-    if (firstTime) saveConfig();
+    configure();
     bool fg, bg;
     run(img_input, fg, bg, true);
     if (!fg) return;                         // first two frames fill the history (WeightedMovingMeanBGS.cpp:40-51)
@@ -294,12 +339,18 @@ public:
   }
   ~WeightedMovingVarianceBGS() { std::cout << "~WeightedMovingVarianceBGS()" << std::endl; }
 
+  // the configuration preamble of process() (also run by the queued submit())
+  void configure()
+  {
+    loadConfig();
+    if (firstTime) saveConfig();
+  }
+
   void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
   {
     (void)img_bgmodel;                       // never written (WeightedMovingVarianceBGS.cpp:30-117)
     if (img_input.empty()) return;
-    loadConfig();
-    if (firstTime) saveConfig();
+    configure();
     bool fg, bg;
     run(img_input, fg, bg, false);
     if (!fg) return;                         // first two frames fill the history (.cpp:40-51)
@@ -351,11 +402,17 @@ public:
   }
   ~AdaptiveBackgroundLearning() { std::cout << "~AdaptiveBackgroundLearning()" << std::endl; }
 
+  // the configuration preamble of process() (also run by the queued submit())
+  void configure()
+  {
+    loadConfig();
+    if (firstTime) saveConfig();
+  }
+
   void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
   {
     if (img_input.empty()) return;
-    loadConfig();
-    if (firstTime) saveConfig();
+    configure();
     bool fg, bg;
     run(img_input, fg, bg, true);
     if (showForeground) cv::imshow("A-Learning FG", img_foreground);
@@ -414,11 +471,17 @@ public:
   }
   ~AdaptiveSelectiveBackgroundLearning() { std::cout << "~AdaptiveSelectiveBackgroundLearning()" << std::endl; }
 
+  // the configuration preamble of process() (also run by the queued submit())
+  void configure()
+  {
+    loadConfig();                            // before saveConfig, as in the reference (.cpp:41-46): the file's
+    if (firstTime) saveConfig();             // defaults (90 frames, threshold 25) replace the constructor's
+  }
+
   void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
   {
     if (img_input.empty()) return;
-    loadConfig();                            // before saveConfig, as in the reference (.cpp:41-46): the file's
-    if (firstTime) saveConfig();             // defaults (90 frames, threshold 25) replace the constructor's
+    configure();
     bool fg, bg;
     run(img_input, fg, bg, true);
     if (showOutput) {
@@ -474,10 +537,9 @@ public:
   }
   ~DPZivkovicAGMMBGS() { std::cout << "~DPZivkovicAGMMBGS()" << std::endl; }
 
-  void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
+  // the configuration preamble of process() (also run by the queued submit())
+  void configure()
   {
-    (void)img_bgmodel;                       // never written (DPZivkovicAGMMBGS.cpp:32-84)
-    if (img_input.empty()) return;
     loadConfig();
     if (firstTime) {                         // the reference hands the parameters over once, on the first frame (:58-65)
       saveConfig();
@@ -485,6 +547,13 @@ public:
       set("alpha", alpha);
       set("gaussians", gaussians);
     }
+  }
+
+  void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
+  {
+    (void)img_bgmodel;                       // never written (DPZivkovicAGMMBGS.cpp:32-84)
+    if (img_input.empty()) return;
+    configure();
     bool fg, bg;
     run(img_input, fg, bg, false);
     if (showOutput) cv::imshow("Gaussian Mixture Model (Zivkovic)", img_foreground);
@@ -529,11 +598,17 @@ public:
   }
   ~MixtureOfGaussianV2BGS() { std::cout << "~MixtureOfGaussianV2BGS()" << std::endl; }
 
+  // the configuration preamble of process() (also run by the queued submit())
+  void configure()
+  {
+    loadConfig();
+    if (firstTime) saveConfig();
+  }
+
   void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
   {
     if (img_input.empty()) return;
-    loadConfig();
-    if (firstTime) saveConfig();
+    configure();
     bool fg, bg;
     run(img_input, fg, bg, true);            // mog(in, fg, alpha) + getBackgroundImage + threshold, one kernel
     if (showOutput)

@@ -14,6 +14,11 @@ int compile_check_calls()
     fanout.process(img_input);
     for (int i = 0; i < 8; i++) {
         plugins[i]->process(img_input, img_bgs, img_bkgmodel);
+        // capture-loop form (VideoCapture.cpp:151-239): queue the frame, collect later
+        bgsb_adapter::PluginBase *q = dynamic_cast<bgsb_adapter::PluginBase *>(plugins[i]);
+        bool fgv = false, bgv = false;
+        q->submit(img_input, img_bgs, img_bkgmodel, &fgv, &bgv);
+        q->wait();
         delete plugins[i];
     }
     // ustc_src/trackingMain.cpp:33-35,613-615 pattern
