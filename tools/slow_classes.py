@@ -45,3 +45,14 @@ need3 = fit0 & (nm >= 3) & ((wn[0] + wn[1]) <= np.float32(0.9))
 pruned = fit0 & np.any([live[m] & (wt[m] < -prune) for m in range(1, 5)], axis=0)
 print("fit slot 0 and background image needs >= 3 modes:", need3.mean())
 print("fit slot 0 and some weight pruned this frame     :", pruned.mean())
+# --- how are the ineligible pixels spread over the 64-pixel state tiles (= warps of the T == 1 kernel)? ---
+slowpx = ~fit0 | need3 | pruned
+ntile = npx // 64
+per_tile = slowpx[:ntile * 64].reshape(ntile, 64).sum(1)
+print("ineligible (approx.):", slowpx.mean(), " tiles with none: %.3f" % (per_tile == 0).mean())
+print("tiles by count 1-4 / 5-16 / 17-32 / 33-64: %.3f %.3f %.3f %.3f" % (
+    ((per_tile >= 1) & (per_tile <= 4)).mean(), ((per_tile >= 5) & (per_tile <= 16)).mean(),
+    ((per_tile >= 17) & (per_tile <= 32)).mean(), (per_tile >= 33).mean()))
+print("share of ineligible pixels in tiles with > 16 of them: %.3f" % (per_tile[per_tile > 16].sum() / max(1, per_tile.sum())))
+per_cta = slowpx[:(npx // 256) * 256].reshape(-1, 256).sum(1)
+print("per 256-px CTA: mean %.1f, none %.3f, > 32: %.3f, > 64: %.3f" % (per_cta.mean(), (per_cta == 0).mean(), (per_cta > 32).mean(), (per_cta > 64).mean()))
