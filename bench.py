@@ -48,6 +48,18 @@ UNIT = "Mpixel/s"
 WORKLOAD = "MixtureOfGaussianV2 (MOG2, K=5) on one synthetic 1920x1080 BGR stream per GPU, T=1"
 
 
+_STDOUT_FD = None
+
+
+def emit(text):
+    """The contract's one line, on the process's original stdout."""
+    sys.stdout.flush()
+    if _STDOUT_FD is None:
+        print(text, flush=True)
+    else:
+        os.write(_STDOUT_FD, (text + "\n").encode())
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -145,7 +157,7 @@ def run_reference(args):
                                        % (fps, args.steps, __import__("cv2").__version__, cores)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(json.dumps(line))
     return 0
 
 
@@ -164,9 +176,12 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL's version banner goes to stdout; rank 0's stdout is the ONE JSON line of the contract
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL prints its version banner on stdout at communicator creation, and rank 0's stdout is the ONE JSON line
+        # of the contract: from here on file descriptor 1 is stderr, the line goes to the saved descriptor (emit()).
+        global _STDOUT_FD
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -347,7 +362,7 @@ def finish(args, rank, world, value, K, Wm, ms_max, F, clocks, e2e, launches, ac
                              "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
                              "frac_of_8TBs_nominal": achieved / 8000.0, **extra},
                 "cpu_baseline": cpu}
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
