@@ -528,6 +528,38 @@ def test_submit_wait_pipeline_matches_oracle(oracle, pinned):
         p.close()
 
 
+@pytest.mark.parametrize("shape", [(1, 1), (1, 67), (3, 2), (2, 33), (65, 1), (5, 129)])
+def test_tiny_and_ragged_frames_all_plugins(oracle, shape):
+    """Degenerate geometries (one pixel, one row, one column, widths that are not multiples of any vector or tile
+    size): every plugin, synchronous and queued host calls, against the oracle."""
+    import tracking_b200 as tb
+    h, w = shape
+    rng = np.random.default_rng(h * 1000 + w)
+    base = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    frames = [np.clip(base.astype(np.int16) + rng.integers(-20, 21, (h, w, 3)), 0, 255).astype(np.uint8) for _ in range(6)]
+    frames[3] = 255 - frames[3]
+    for nm in ["FrameDifferenceBGS", "StaticFrameDifferenceBGS", "WeightedMovingMeanBGS", "WeightedMovingVarianceBGS",
+               "MixtureOfGaussianV2BGS", "AdaptiveBackgroundLearning", "AdaptiveSelectiveBackgroundLearning",
+               "DPZivkovicAGMMBGS"]:
+        p, q, o = getattr(tb, nm)(), getattr(tb, nm)(), getattr(oracle, nm)()
+        bgshape = (h, w, 3) if q.BG_CHANNELS == 3 else (h, w)
+        outs = []
+        for f in frames:
+            fg, bg = np.full((h, w), 77, np.uint8), np.full(bgshape, 77, np.uint8)
+            q.submit(np.ascontiguousarray(f), fg, bg)
+            outs.append((fg, bg))
+        q.wait()
+        for i, f in enumerate(frames):
+            fa, ba = p.process(f)
+            fb, bb = o.process(f)
+            assert (fa is None) == (fb is None) and (ba is None) == (bb is None), (nm, i)
+            if fb is not None:
+                assert np.array_equal(fa, fb) and np.array_equal(outs[i][0], fb), (nm, i)
+            if bb is not None:
+                assert np.array_equal(ba, bb) and np.array_equal(outs[i][1], bb), (nm, i)
+        p.close(); q.close()
+
+
 def test_submit_geometry_change_and_errors():
     """A new frame size re-initialises the model exactly as process() does; bad buffers are refused."""
     import tracking_b200 as tb
