@@ -597,7 +597,8 @@ def test_asbl_sibling_plugin(oracle, kw):
     phase then selective update; single-channel background image; host path, device path and reset."""
     import torch
     import tracking_b200 as tb
-    for (h, w) in ((97, 131), (600, 700)):
+    # (600, 700) and the two small multiples of 4 take the single-pass tile kernel (partial and exact tiles)
+    for (h, w) in ((97, 131), (600, 700), (64, 256), (35, 132)):
         frames = _asbl_frames(h, w, 12, 3)
         p, o = tb.AdaptiveSelectiveBackgroundLearning(**kw), oracle.AdaptiveSelectiveBackgroundLearning(**kw)
         for i, f in enumerate(frames[:8]):

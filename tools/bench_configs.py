@@ -202,6 +202,9 @@ def ccl_kernel_probe(w=1920, h=1080):
 def main():
     quick = "--quick" in sys.argv
     torch.cuda.set_device(0)
+    if "--asbl" in sys.argv:                                  # just the ASBL line
+        simple_streams(tb.AdaptiveSelectiveBackgroundLearning, "ASBL", 3 + 2 + 1 + 1)
+        return
     z = np.load(os.path.join(ROOT, "tests", "golden", "clips.npz"))
     config1(z["video_clip"])
     pcie_probe()

@@ -43,6 +43,7 @@ struct bgsb_ctx {
     int host_bands = 2;        // row bands of the host-path upload/compute/download pipeline (1 = no overlap); 2 measured best at 1080p (277 vs 289 us with 4: each band costs ~8 host API calls)
     // AdaptiveSelectiveBackgroundLearning (defaults of its loadConfig, .cpp:121-125)
     int learning_frames = 90, asbl_counter = 0;
+    int asbl_cur = 0;          // which of the two ASBL model buffers holds the model
     double alpha_learn = 0.05, alpha_detection = 0.05;
     // DPZivkovicAGMMBGS (defaults of its loadConfig, DPZivkovicAGMMBGS.cpp:97-100); its alpha default is set at create
     double dpz_threshold = 25.0;
@@ -249,7 +250,10 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
                 L.bgout = bg_last_only ? d_bg : d_bg + (size_t)t * npx;
                 L.bg_stride = bg_last_only ? npx : (size_t)T * npx;
             }
-            L.model = c->d_hist[0]; L.gray = c->d_hist[1]; L.raw = c->d_hist[1] + (size_t)c->nstreams * npx;
+            // d_hist[1] (3 bytes per pixel) = gray scratch | pre-median mask scratch | second model buffer
+            uint8_t *const mbuf[2] = {c->d_hist[0], c->d_hist[1] + 2 * (size_t)c->nstreams * npx};
+            L.model = mbuf[c->asbl_cur]; L.model_out = mbuf[c->asbl_cur ^ 1];
+            L.gray = c->d_hist[1]; L.raw = c->d_hist[1] + (size_t)c->nstreams * npx;
             L.w = c->w; L.h = c->h;
             L.first = (c->have_hist == 0 && t == 0);
             // learning phase: `learningFrames > 0 && counter <= learningFrames`, counter++ (.cpp:65-71)
@@ -258,8 +262,19 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
             L.selective = learning ? 0 : 1;
             L.alpha = learning ? c->alpha_learn : c->alpha_detection;
             L.thr = c->thr; L.gray_variant = c->gray_variant;
-            int rc = launch_asbl(L, c->nstreams, stream);
+            // the blend of two bytes as a 64 KB table (ABL's, simple_bgs.cu): rebuilt when alpha changes, i.e. once at
+            // the end of the learning phase; stream-ordered before the kernel that reads it
+            if (!c->d_abl_lut) BGSB_CUDA(cudaMalloc(&c->d_abl_lut, 65536));
+            if (c->lut_alpha != L.alpha) {
+                int rcl = launch_abl_lut_build(c->d_abl_lut, L.alpha, stream);
+                if (rcl) return rcl;
+                c->lut_alpha = L.alpha;
+            }
+            L.lut = c->d_abl_lut;
+            int swapped = 0;
+            int rc = launch_asbl(L, c->nstreams, stream, &swapped);
             if (rc) return rc;
+            c->asbl_cur ^= swapped;
             if (t == 0 && c->have_hist == 0) c->have_hist = 1;   // the model exists from the first frame on
         }
     } else {

@@ -34,15 +34,18 @@ struct AsblLaunch {
     uint8_t *fg;             // [S] masks, fg_stride bytes apart
     uint8_t *bgout;          // [S] gray background images, bg_stride bytes apart, nullable
     uint8_t *model;          // [S][npx] 8-bit gray background model
+    uint8_t *model_out;      // [S][npx] second model buffer: the single-pass kernel reads `model` and writes this one
     uint8_t *gray, *raw;     // [S][npx] scratch: gray input, thresholded difference before the median
     size_t frame_stride, fg_stride, bg_stride;
     int w, h;
     int first;               // no model yet: it starts as the gray input (AdaptiveSelectiveBackgroundLearning.cpp:47-48)
     int selective;           // 0: learning phase, every pixel is blended (:65-71); 1: only background pixels (:72-90)
     double alpha;            // alphaLearn or alphaDetection
+    const uint8_t *lut;      // 64 KB blend table for alpha (launch_abl_lut_build), nullable: blend in arithmetic
     int thr, gray_variant;
 };
-int launch_asbl(const AsblLaunch &L, int nstreams, cudaStream_t stream);
+// *swapped = 1: the new model is in model_out (the caller exchanges the two buffers), 0: updated in place
+int launch_asbl(const AsblLaunch &L, int nstreams, cudaStream_t stream, int *swapped);
 
 // ---- MOG2 -------------------------------------------------------------------------------------
 constexpr int MOG2_K = 5;             // nmixtures of the default-constructed cv::BackgroundSubtractorMOG2
