@@ -202,6 +202,9 @@ def ccl_kernel_probe(w=1920, h=1080):
 def main():
     quick = "--quick" in sys.argv
     torch.cuda.set_device(0)
+    if "--wmv" in sys.argv:                                   # just the WMV line
+        simple_streams(tb.WeightedMovingVarianceBGS, "WMV", 10 + 6)
+        return
     if "--asbl" in sys.argv:                                  # just the ASBL line
         simple_streams(tb.AdaptiveSelectiveBackgroundLearning, "ASBL", 3 + 2 + 1 + 1)
         return

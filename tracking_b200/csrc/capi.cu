@@ -280,6 +280,7 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
     } else {
         SimpleLaunch L;
         memset(&L, 0, sizeof(L));
+        L.one = 1.f;
         L.frames = d_frames + p0 * 3; L.fg = d_fg + p0; L.bg = d_bg ? d_bg + p0 * 3 : nullptr;
         L.hist0 = c->hist_ptr[0] ? c->hist_ptr[0] + p0 * 3 : nullptr;
         L.hist1 = c->hist_ptr[1] ? c->hist_ptr[1] + p0 * 3 : nullptr;

@@ -23,6 +23,7 @@ struct SimpleLaunch {
     const uint8_t *abl_lut;  // ABL: 64 KB table of the blend for this alpha (abl_lut_index), null = arithmetic kernel
     int abl_lut_mode;        // ABL table kernels: 0 = warp-coalesced where the alignment allows, 1 = per-thread groups
     double w0, w1, w2;       // WMV weights (0.5,0.3,0.2 | 0.3,0.3,0.3)
+    float one;               // 1.0f at run time: keeps ptxas from contracting packed mul + add (mog2_fastmath.cuh)
 };
 int launch_simple(int algo, const SimpleLaunch &L, int nstreams, cudaStream_t stream);
 // Fill the 64 KB ABL table for `alpha` with the arithmetic kernel's own blend (bit-exact by construction).
