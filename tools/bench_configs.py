@@ -205,6 +205,9 @@ def main():
     if "--wmv" in sys.argv:                                   # just the WMV line
         simple_streams(tb.WeightedMovingVarianceBGS, "WMV", 10 + 6)
         return
+    if "--wmm" in sys.argv:                                   # just the WMM line
+        simple_streams(tb.WeightedMovingMeanBGS, "WMM", 10 + 6 + 3)
+        return
     if "--asbl" in sys.argv:                                  # just the ASBL line
         simple_streams(tb.AdaptiveSelectiveBackgroundLearning, "ASBL", 3 + 2 + 1 + 1)
         return
