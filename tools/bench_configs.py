@@ -202,6 +202,11 @@ def ccl_kernel_probe(w=1920, h=1080):
 def main():
     quick = "--quick" in sys.argv
     torch.cuda.set_device(0)
+    if "--mog2t" in sys.argv:                                 # just the temporal-batch lines
+        mog2_batches(1, 1920, 1080, [1, 8, 16], "2-T")
+        mog2_batches(16, 1920, 1080, [1, 16], "16x1080p-T")
+        mog2_batches(4, 3840, 2160, [1, 16], "5", NF=16)
+        return
     if "--wmv" in sys.argv:                                   # just the WMV line
         simple_streams(tb.WeightedMovingVarianceBGS, "WMV", 10 + 6)
         return
