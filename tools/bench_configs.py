@@ -207,6 +207,9 @@ def main():
         mog2_batches(16, 1920, 1080, [1, 16], "16x1080p-T")
         mog2_batches(4, 3840, 2160, [1, 16], "5", NF=16)
         return
+    if "--pipeline" in sys.argv:                              # just config 4 (16 streams): ncu launch-list target
+        pipeline(S=16)
+        return
     if "--abl" in sys.argv:
         simple_streams(tb.AdaptiveBackgroundLearning, "ABL", 10)
         return
