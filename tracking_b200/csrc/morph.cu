@@ -38,24 +38,29 @@ __device__ __forceinline__ unsigned inside_mask(int y, int k, int w, int h, int 
     return (1u << (w & 31)) - 1u;
 }
 
-// 32 mask bytes (as eight words) -> one word of "byte is non-zero" bits.  Per word: bit 7 of every byte says
-// non-zero, and one multiply gathers the four flags into a nibble (the partial products land on distinct bits).
+// 32 mask bytes (as eight words) -> one word of "byte is non-zero" bits.  Per word, bit 7 of every byte says
+// non-zero; the flags of two words (the first shifted down by 4: bits 3, 11, 19, 27 and 7, 15, 23, 31) go through ONE
+// multiply by 2^0 + 2^7 + 2^14 + 2^21, which lands them on bits 24..31 in pixel order -- the other partial products
+// fall on distinct bits below 24 or above 31, so nothing carries.
+__device__ __forceinline__ unsigned nz_flags(unsigned v) { return (((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u; }
 __device__ __forceinline__ unsigned pack32(const unsigned (&ws)[8])
 {
     unsigned word = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const unsigned v = ws[i];
-        const unsigned f = ((((v & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v) & 0x80808080u) >> 7;    // 0x01 per non-zero byte
-        word |= ((f * 0x01020408u) >> 24 & 0xfu) << (4 * i);
+    for (int i = 0; i < 4; i++) {
+        const unsigned g = (nz_flags(ws[2 * i]) >> 4) | nz_flags(ws[2 * i + 1]);
+        word |= ((g * 0x00204081u) >> 24) << (8 * i);
     }
     return word;
 }
 
-// nibble -> four {0,255} bytes: one multiply spreads the bits to the byte positions, one more fills the bytes
+// nibble -> four {0,255} bytes: one multiply puts bit j of the nibble on bit 7 of byte j, PRMT in its
+// sign-replicating mode fills the bytes
 __device__ __forceinline__ unsigned unpack4(unsigned nib)
 {
-    return ((nib * 0x00204081u) & 0x01010101u) * 0xffu;
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(nib * 0x10204080u), "r"(0u), "r"(0xBA98u));   // selector bit 3: replicate the msb
+    return d;
 }
 
 // Thread (tx, ty) = (tid & 63, tid >> 6) owns shared-memory column tx and rows ty, ty+4, ...: the column's
@@ -71,6 +76,7 @@ morph_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, i
     const int k0 = blockIdx.x * MORPH_TW - 1;          // word index of smem column 0 (halo)
     const int y0 = blockIdx.y * MORPH_TH - R;          // image row of smem row 0 (halo)
     const int rows = MORPH_TH + 2 * R;
+    const int rblock = (rows + 3) >> 2;                 // consecutive rows per thread in the passes (4 row groups)
     const int tw = min(MORPH_TW, wpr - blockIdx.x * MORPH_TW) + 2;   // smem columns in use
     const int c = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int k = k0 + c;
@@ -111,31 +117,35 @@ morph_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, i
     for (int o = 0; o < chain.n; o++) {
         const bool dil = chain.op[o] == BGSB_MORPH_DILATE;
         for (int it = 0; it < chain.iters[o]; it++) {
-            if (col_used) {
-                for (int r = ty; r < rows; r += 4) {
-                    const int y = y0 + r;
-                    unsigned acc = dil ? 0u : 0xffffffffu;
-#pragma unroll
-                    for (int dr = -1; dr <= 1; dr++) {
-                        const int rr = r + dr;
-                        unsigned L = 0, M = 0, Rt = 0;
-                        if (rr >= 0 && rr < rows) {
-                            M = buf[cur][rr][c];
-                            if (c > 0) L = buf[cur][rr][c - 1];
-                            if (c + 1 < tw) Rt = buf[cur][rr][c + 1];
-                        }
-                        if (!dil) {   // outside-image pixels are neutral (all ones) for erosion
-                            const bool rowin = (y + dr >= 0 && y + dr < h);
-                            M |= rowin ? ~cm : 0xffffffffu;
-                            L |= rowin ? ~cl : 0xffffffffu;
-                            Rt |= rowin ? ~cr : 0xffffffffu;
-                        }
-                        const unsigned left = (M << 1) | (L >> 31);      // neighbour x-1
-                        const unsigned right = (M >> 1) | (Rt << 31);    // neighbour x+1
-                        if (dil) acc |= M | left | right;
-                        else acc &= M & left & right;
+            // The 3x3 rectangle is separable: h(row) = the row combined with its two horizontal neighbours, and the
+            // result is h(r-1) op h(r) op h(r+1).  A thread owns a block of consecutive rows of its column and slides
+            // the three h values through registers: three shared-memory loads per output word instead of nine.
+            const int r0 = ty * rblock, r1 = min(rows, r0 + rblock);
+            if (col_used && r0 < r1) {
+                auto hrow = [&](int rr) -> unsigned {
+                    unsigned L = 0, M = 0, Rt = 0;
+                    if (rr >= 0 && rr < rows) {
+                        M = buf[cur][rr][c];
+                        if (c > 0) L = buf[cur][rr][c - 1];
+                        if (c + 1 < tw) Rt = buf[cur][rr][c + 1];
                     }
+                    if (!dil) {   // outside-image pixels are neutral (all ones) for erosion
+                        const bool rowin = (y0 + rr >= 0 && y0 + rr < h);
+                        M |= rowin ? ~cm : 0xffffffffu;
+                        L |= rowin ? ~cl : 0xffffffffu;
+                        Rt |= rowin ? ~cr : 0xffffffffu;
+                    }
+                    const unsigned left = (M << 1) | (L >> 31);      // neighbour x-1
+                    const unsigned right = (M >> 1) | (Rt << 31);    // neighbour x+1
+                    return dil ? (M | left | right) : (M & left & right);
+                };
+                unsigned hp = hrow(r0 - 1), hc = hrow(r0);
+                for (int r = r0; r < r1; r++) {
+                    const unsigned hn = hrow(r + 1);
+                    const unsigned acc = dil ? (hp | hc | hn) : (hp & hc & hn);
+                    const int y = y0 + r;
                     buf[cur ^ 1][r][c] = (y >= 0 && y < h) ? (acc & cm) : 0u;
+                    hp = hc; hc = hn;
                 }
             }
             __syncthreads();
