@@ -216,6 +216,9 @@ def main():
     if "--wmv" in sys.argv:                                   # just the WMV line
         simple_streams(tb.WeightedMovingVarianceBGS, "WMV", 10 + 6)
         return
+    if "--sfd" in sys.argv:                                   # StaticFD: 3 in + 3 bg read + 1 mask + 3 bg image
+        simple_streams(tb.StaticFrameDifferenceBGS, "StaticFD", 10)
+        return
     if "--wmm" in sys.argv:                                   # just the WMM line
         simple_streams(tb.WeightedMovingMeanBGS, "WMM", 10 + 6 + 3)
         return
