@@ -95,6 +95,8 @@ BGSB_API int bgsb_reset(bgsb_ctx *ctx);
  *   MOG2     : "alpha" (0.05)             MixtureOfGaussianV2BGS.cpp:92-95
  *   ABL      : "alpha" (0.05), "limit" (-1; only -1 updates the model, .cpp:52)
  *   DPZivkovicAGMM : "threshold" (25.0), "alpha" (0.001), "gaussians" (3, at most 5)   DPZivkovicAGMMBGS.cpp:86-100
+ *              (latched at the first frame like the reference's params hand-over, .cpp:58-65: a later change takes
+ *              effect after bgsb_reset)
  *   ASBL     : "learningFrames" (90), "alphaLearn" (0.05), "alphaDetection" (0.05), "threshold" (25)
  *              AdaptiveSelectiveBackgroundLearning.cpp:108-126 (the defaults its loadConfig applies)
  *   WMV, WMM : "enableWeight" (1)         WeightedMovingVarianceBGS.cpp:155-158, WeightedMovingMeanBGS.cpp
@@ -104,10 +106,19 @@ BGSB_API int bgsb_reset(bgsb_ctx *ctx);
  * "complexityReductionThreshold" 0.05, "detectShadows" 1, "shadowValue" 127,
  * "shadowThreshold" 0.5; and "grayVariant": 0 = OpenCV 4.x BGR2GRAY constants, 1 = 2.4.x;
  * "kernelVariant" (MOG2): 0 = production kernels, 1 = straight restatement kernel (identical results, kept for
- * A/B measurements); 8, 9 = timing instruments with WRONG results (tools/floor_probe.py);
+ * A/B measurements).  (8, 9 = timing instruments with WRONG results exist only in a library built with
+ * -DBGSB_INSTRUMENT for tools/floor_probe.py; the shipped library rejects them);
  * "ablTable" (AdaptiveBackgroundLearning): 1 = lookup-table kernels (default), 2 = only the per-thread table kernel,
  * 0 = arithmetic kernel -- identical results;
- * "hostBands" (default 2, 1..8): row bands of the upload / kernel / download pipeline inside bgsb_process. */
+ * "ablBlend" (AdaptiveBackgroundLearning): 0 = cv::addWeighted as OpenCV 4.x computes it (double precision; pinned
+ * against cv2 4.13, default), 1 = as OpenCV 2.4 does (fp32 arithmetic, scalars cast to float; SURVEY Appendix B --
+ * "parity unpinned": no OpenCV 2.4 in the build image), table kernels only;
+ * "hostBands" (default 2, 1..8): row bands of the upload / kernel / download pipeline inside bgsb_process;
+ * "retainInput" (default 0; FrameDifference, WeightedMovingVariance, WeightedMovingMean on the *_dev entry points):
+ * 1 = the caller promises that the device frame given to a call stays valid and unmodified until the next call (FD)
+ * / the next two calls (WMV, WMM) have completed, so the previous-frame history is read from those buffers and never
+ * copied (the reference's img_input_prev members, FrameDifferenceBGS.cpp:58, WeightedMovingVarianceBGS.cpp:113-114):
+ * FD moves 7 B/px instead of 10, WMV 10 instead of 16.  Single frames, or batches on a single-stream context. */
 BGSB_API int bgsb_set_param(bgsb_ctx *ctx, const char *key, double value);
 BGSB_API int bgsb_get_param(bgsb_ctx *ctx, const char *key, double *value);
 

@@ -1,5 +1,6 @@
 """Where the MOG2 frame time goes: production kernel vs two timing instruments on the same warmed 1080p model
-(kernelVariant 9: same loads/stores, no arithmetic; 8: no generic phase).  GPU box, measurement tooling."""
+(kernelVariant 9: same loads/stores, no arithmetic; 8: no generic phase).  GPU box, measurement tooling.
+Needs an instrumented library: `python -m tracking_b200._build --force --instrument` first (the shipped build rejects 8 / 9)."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

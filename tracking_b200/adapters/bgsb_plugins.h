@@ -33,16 +33,27 @@ protected:
   bgsb_ctx *ctx;
   bool firstTime;
   cv::Mat img_foreground, img_background;   // members of the reference classes; own the outputs
-  // set by FanOut::process: this frame's outputs are already in img_foreground / img_background
-  const unsigned char *pre_frame;
+  // set by FanOut::process: the next process() call finds this frame's outputs in img_foreground / img_background
+  // (one-shot: consumed by that call, dropped by the next FanOut::process -- capture loops reuse one buffer, so the
+  // frame's address says nothing about its identity)
+  bool pre_valid;
   bool pre_fg, pre_bg;
   int bg_type;                              // CV_8UC3; CV_8UC1 for the gray model of AdaptiveSelectiveBackgroundLearning
 
-  explicit PluginBase(int algo) : ctx(0), firstTime(true), pre_frame(0), pre_fg(false), pre_bg(false), bg_type(CV_8UC3)
+  explicit PluginBase(int algo) : ctx(0), firstTime(true), pre_valid(false), pre_fg(false), pre_bg(false), bg_type(CV_8UC3)
   {
     int rc = bgsb_create(&ctx, algo, 0);
     if (rc != BGSB_OK) std::cerr << "bgsb200: " << bgsb_last_error() << std::endl;
     CV_Assert(rc == BGSB_OK);
+    // The arithmetic of the OpenCV this translation unit is compiled against: the reference only
+    // builds with 2.4 (legacy blob tracking, CvFileStorage), whose BGR2GRAY constants and fp32 addWeighted differ from
+    // 3.x / 4.x in the last bit.  BgsbBlobDetectorCC picks cvFindContours' border behaviour the same way.
+#if defined(CV_MAJOR_VERSION) && CV_MAJOR_VERSION >= 3
+    set("grayVariant", 0);
+#else
+    set("grayVariant", 1);
+    if (algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING) set("ablBlend", 1);
+#endif
   }
   virtual ~PluginBase() { bgsb_destroy(ctx); }
 
@@ -79,13 +90,12 @@ protected:
   void run(const cv::Mat &img_input, bool &fg_valid, bool &bg_valid, bool want_bg)
   {
     CV_Assert(img_input.type() == CV_8UC3);     // PreProcessor.cpp:56 hands BGR 8UC3 frames to every plugin
-    if (pre_frame && pre_frame == img_input.data) {   // FanOut already ran this frame through this plugin
+    if (pre_valid) {                            // FanOut already ran this frame through this plugin
       fg_valid = pre_fg;
       bg_valid = pre_bg && want_bg;
-      pre_frame = 0;
+      pre_valid = false;
       return;
     }
-    pre_frame = 0;
     img_foreground.create(img_input.rows, img_input.cols, CV_8UC1);
     if (want_bg) img_background.create(img_input.rows, img_input.cols, bg_type);
     int fv = 0, bv = 0;
@@ -103,7 +113,8 @@ protected:
 // would upload it again.  With one added line in front of those calls --
 //     fanout.process(img_prep);          // FanOut fanout; fanout.add(frameDifference); fanout.add(mixtureOfGaussianV2BGS); ...
 // -- the frame crosses PCIe once (bgsb_process_fanout) and the unchanged `plugin->process(img_prep, fg, bg)` calls that
-// follow find their outputs ready.  Parameters re-read by a plugin's loadConfig() apply from the next frame on.
+// follow find their outputs ready (each plugin's next process() call consumes them; it must be given the same frame).
+// Parameters re-read by a plugin's loadConfig() apply from the next frame on.
 class FanOut
 {
   std::vector<PluginBase *> plugins;
@@ -137,7 +148,7 @@ public:
     if (rc != BGSB_OK) std::cerr << "bgsb200: " << bgsb_last_error() << std::endl;
     CV_Assert(rc == BGSB_OK);
     for (size_t k = 0; k < n; k++) {
-      plugins[k]->pre_frame = img_input.data;
+      plugins[k]->pre_valid = true;             // replaces whatever an earlier fan-out left unconsumed
       plugins[k]->pre_fg = fv[k] != 0;
       plugins[k]->pre_bg = bv[k] != 0;
     }

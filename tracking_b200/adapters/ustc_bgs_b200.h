@@ -71,6 +71,12 @@ public:
     BgsbBlobDetectorCC() : bd(0)
     {
         CV_Assert(bgsb_blobdetector_create(&bd, 0) == BGSB_OK);
+        // cvFindContours clears the mask's 1-px frame up to OpenCV 3.1 and keeps it afterwards
+#if defined(CV_MAJOR_VERSION) && (CV_MAJOR_VERSION > 3 || (CV_MAJOR_VERSION == 3 && CV_MINOR_VERSION >= 2))
+        bgsb_blobdetector_set_param(bd, "zeroBorder", 0);
+#else
+        bgsb_blobdetector_set_param(bd, "zeroBorder", 1);
+#endif
     }
     ~BgsbBlobDetectorCC() { bgsb_blobdetector_destroy(bd); }
     void Release() { delete this; }
@@ -91,7 +97,10 @@ public:
         int rc = bgsb_blobdetector_detect(bd, (const uint8_t *)pFGMask->imageData, pFGMask->width, pFGMask->height,
                                           (size_t)pFGMask->widthStep, old.empty() ? 0 : &old[0], (int)old.size(),
                                           nb, 1, &n_new, &result, 0, 0, 0);
-        CV_Assert(rc == BGSB_OK);
+        if (rc != BGSB_OK) {          // CvBlobDetectorCC has no failure path: report and return "no new blob"
+            std::cerr << "bgsb200: DetectNewBlob: " << bgsb_last_error() << std::endl;
+            return 0;
+        }
         if (result && n_new == 1 && pNewBlobList) {
             CvBlob B = cvBlob(nb[0].x, nb[0].y, nb[0].w, nb[0].h);
             pNewBlobList->AddBlob(&B);

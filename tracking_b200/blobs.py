@@ -71,7 +71,7 @@ class ConnectedComponents:
         mask = np.ascontiguousarray(mask, np.uint8)
         h, w = mask.shape
         labels = np.empty((h, w), np.int32) if want_labels else None
-        cap = h * w // 4 + 64
+        cap = ((w + 1) // 2) * ((h + 1) // 2) + 64          # the most 8-connected components an image can hold
         comps = (capi.Component * cap)()
         n = C.c_int(0)
         capi.check(capi.lib().bgsb_ccl_label(self._h, C.c_void_p(mask.ctypes.data), w, h, w, int(zero_border),

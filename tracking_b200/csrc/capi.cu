@@ -48,7 +48,12 @@ struct bgsb_ctx {
     // DPZivkovicAGMMBGS (defaults of its loadConfig, DPZivkovicAGMMBGS.cpp:97-100); its alpha default is set at create
     double dpz_threshold = 25.0;
     int gaussians = 3;
+    // ... which the reference hands to the model ONCE, on the first frame (DPZivkovicAGMMBGS.cpp:58-65): later changes
+    // of threshold / alpha / gaussians have no effect until the model is reset.  Latched copies used by the kernel:
+    double dpz_thr_l = 25.0, dpz_alpha_l = 0.001;
+    int dpz_K_l = 3;
     int abl_table = 1;         // ABL: 1 = lookup-table kernel, 0 = arithmetic kernel (A/B, identical results)
+    int abl_blend = 0, lut_blend = 0;   // ABL: 0 = OpenCV 4.x fp64 addWeighted, 1 = OpenCV 2.4 fp32 addWeighted (table kernels only)
     int mog2_variant = 0;      // see launch_mog2 (mog2.cu): 0 production, 1 straight restatement, 8/9 timing instruments
     // geometry / counters
     int w = 0, h = 0, npx = 0;
@@ -77,6 +82,11 @@ struct bgsb_ctx {
     cudaEvent_t ev_dn[2] = {};
     uint64_t seq = 0;
     bool inflight = false;
+    // the stream the model was last advanced on (see order_after_previous)
+    cudaStream_t last_stream = nullptr;
+    bool last_stream_set = false;
+    cudaEvent_t ev_order = nullptr;
+    int retain_input = 0;      // device path, FD / WMV / WMM: the caller's frames stay valid -> no history write-back
 };
 
 static bool gmm_state(int algo);
@@ -104,38 +114,59 @@ static int ensure_geometry(bgsb_ctx *c, int w, int h)
     BGSB_REQUIRE(w > 0 && h > 0, "empty frame");
     BGSB_REQUIRE((long long)w * h < (1LL << 30), "frame too large");
     BGSB_REQUIRE(!gmm_state(c->algo) || (long long)w * h <= (1LL << 27), "mixture-model frames are limited to 2^27 pixels");
-    free_buffers(c);
-    c->w = w; c->h = h; c->npx = w * h;
-    c->pstride = ((size_t)c->npx + MOG2_TILE - 1) / MOG2_TILE * MOG2_TILE;       // whole state tiles
+    free_buffers(c);                              // geometry fields are 0 from here until every allocation has succeeded
+    const int npx = w * h;
+    const size_t pstride = ((size_t)npx + MOG2_TILE - 1) / MOG2_TILE * MOG2_TILE;       // whole state tiles
     const size_t S = (size_t)c->nstreams;
+    cudaError_t e = cudaSuccess;
     if (gmm_state(c->algo)) {
-        size_t fb = S * MOG2_PLANES * c->pstride * sizeof(float);
-        BGSB_CUDA(cudaMalloc(&c->d_state, fb));
-        BGSB_CUDA(cudaMalloc(&c->d_nmodes, S * c->pstride));
-        BGSB_CUDA(cudaMemsetAsync(c->d_state, 0, fb, c->stream));
-        BGSB_CUDA(cudaMemsetAsync(c->d_nmodes, 0, S * c->pstride, c->stream));
-        BGSB_CUDA(cudaStreamSynchronize(c->stream));
+        const size_t fb = S * MOG2_PLANES * pstride * sizeof(float);
+        e = cudaMalloc(&c->d_state, fb);
+        if (e == cudaSuccess) e = cudaMalloc(&c->d_nmodes, S * pstride);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->d_state, 0, fb, c->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(c->d_nmodes, 0, S * pstride, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     } else {
         // ASBL: d_hist[0] = gray model, d_hist[1] = scratch (gray input + pre-median mask)
         int nh = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE || c->algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN ||
                   c->algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) ? 2 : 1;
-        for (int i = 0; i < nh; i++) BGSB_CUDA(cudaMalloc(&c->d_hist[i], S * c->npx * 3));
+        for (int i = 0; i < nh && e == cudaSuccess; i++) e = cudaMalloc(&c->d_hist[i], S * npx * 3);
     }
+    if (e != cudaSuccess) {                       // e.g. out of memory on a 2160p group: leave a context without geometry
+        set_error("ensure_geometry(%d x %d x %d streams): %s", w, h, c->nstreams, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        free_buffers(c);
+        return BGSB_ERR_CUDA;
+    }
+    c->w = w; c->h = h; c->npx = npx; c->pstride = pstride;
     return BGSB_OK;
+}
+
+// Staging buffers of the host paths; all-or-nothing like ensure_geometry.
+static int staging_fail(bgsb_ctx *c, cudaError_t e)
+{
+    set_error("host staging (%d x %d x %d streams): %s", c->w, c->h, c->nstreams, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    for (int i = 0; i < 3; i++) { cudaFree(c->d_ring[i]); c->d_ring[i] = nullptr; }
+    cudaFree(c->d_fg); c->d_fg = nullptr; cudaFree(c->d_bg); c->d_bg = nullptr;
+    cudaFree(c->d_fg2); c->d_fg2 = nullptr; cudaFree(c->d_bg2); c->d_bg2 = nullptr;
+    return BGSB_ERR_CUDA;
 }
 
 static int ensure_host_staging(bgsb_ctx *c)
 {
     const size_t S = (size_t)c->nstreams;
+    cudaError_t e = cudaSuccess;
     if (!c->d_ring[0]) {
         const bool two = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE || c->algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN);
         int nr = two ? 3 : (c->algo == BGSB_ALGO_FRAME_DIFFERENCE ? 2 : 1);
-        for (int i = 0; i < nr; i++) BGSB_CUDA(cudaMalloc(&c->d_ring[i], S * c->npx * 3));
+        for (int i = 0; i < nr && e == cudaSuccess; i++) e = cudaMalloc(&c->d_ring[i], S * c->npx * 3);
         c->ring_pos = 0;
     }
-    if (!c->d_fg) BGSB_CUDA(cudaMalloc(&c->d_fg, S * c->npx));
-    if (!c->d_bg && c->algo != BGSB_ALGO_FRAME_DIFFERENCE && c->algo != BGSB_ALGO_WEIGHTED_MOVING_VARIANCE)
-        BGSB_CUDA(cudaMalloc(&c->d_bg, S * c->npx * 3));
+    if (e == cudaSuccess && !c->d_fg) e = cudaMalloc(&c->d_fg, S * c->npx);
+    if (e == cudaSuccess && !c->d_bg && c->algo != BGSB_ALGO_FRAME_DIFFERENCE && c->algo != BGSB_ALGO_WEIGHTED_MOVING_VARIANCE)
+        e = cudaMalloc(&c->d_bg, S * c->npx * 3);
+    if (e != cudaSuccess) return staging_fail(c, e);
     return BGSB_OK;
 }
 
@@ -231,9 +262,10 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
             L.frame = d_frames + ((size_t)t * c->npx + p0) * 3; L.frame_stride = (size_t)T * c->npx * 3;
             L.fg = d_fg + (size_t)t * c->npx + p0; L.fg_stride = (size_t)T * c->npx;
             L.state = c->d_state + p0 * MOG2_PLANES; L.nmodes = c->d_nmodes + p0; L.pstride = c->pstride;
-            L.npx = pcount; L.K = c->gaussians;
+            if (c->nframes + t == 0 && p0 == 0) { c->dpz_thr_l = c->dpz_threshold; c->dpz_alpha_l = c->alpha; c->dpz_K_l = c->gaussians; }
+            L.npx = pcount; L.K = c->dpz_K_l;
             L.fresh = (c->nframes + t == 0);
-            L.low_thr = (float)c->dpz_threshold; L.alpha = (float)c->alpha;
+            L.low_thr = (float)c->dpz_thr_l; L.alpha = (float)c->dpz_alpha_l;
             int rc = launch_dpz(L, c->nstreams, stream);
             if (rc) return rc;
         }
@@ -266,7 +298,7 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
             // the end of the learning phase; stream-ordered before the kernel that reads it
             if (!c->d_abl_lut) BGSB_CUDA(cudaMalloc(&c->d_abl_lut, 65536));
             if (c->lut_alpha != L.alpha) {
-                int rcl = launch_abl_lut_build(c->d_abl_lut, L.alpha, stream);
+                int rcl = launch_abl_lut_build(c->d_abl_lut, L.alpha, 0, stream);
                 if (rcl) return rcl;
                 c->lut_alpha = L.alpha;
             }
@@ -294,10 +326,10 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
         L.alpha = c->alpha;
         if (c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING && c->abl_table) {
             if (!c->d_abl_lut) BGSB_CUDA(cudaMalloc(&c->d_abl_lut, 65536));
-            if (c->lut_alpha != c->alpha) {                 // stream-ordered before the kernel that reads it
-                int rcl = launch_abl_lut_build(c->d_abl_lut, c->alpha, stream);
+            if (c->lut_alpha != c->alpha || c->lut_blend != c->abl_blend) {     // stream-ordered before the kernel that reads it
+                int rcl = launch_abl_lut_build(c->d_abl_lut, c->alpha, c->abl_blend, stream);
                 if (rcl) return rcl;
-                c->lut_alpha = c->alpha;
+                c->lut_alpha = c->alpha; c->lut_blend = c->abl_blend;
             }
             L.abl_lut = c->d_abl_lut;
             L.abl_lut_mode = c->abl_table == 2 ? 1 : 0;
@@ -308,6 +340,26 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
         int rc = launch_simple(c->algo, L, c->nstreams, stream);
         if (rc) return rc;
     }
+    return BGSB_OK;
+}
+
+// The model (d_state, d_hist, the blend table) is advanced by kernels on ONE stream per call: the caller's for the
+// *_dev entry points, the context's own for the host-buffer ones.  When a call arrives on a different stream than the
+// previous one, it is ordered behind it (an event recorded now on the previous stream covers everything that call
+// enqueued there).  A stream handed to a *_dev call must therefore stay alive until the next call on this context;
+// if it was destroyed the library falls back to a device synchronisation.
+static int order_after_previous(bgsb_ctx *c, cudaStream_t next)
+{
+    if (c->last_stream_set && c->last_stream != next) {
+        if (!c->ev_order) BGSB_CUDA(cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming));
+        cudaError_t e = cudaEventRecord(c->ev_order, c->last_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(next, c->ev_order, 0);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            BGSB_CUDA(cudaDeviceSynchronize());
+        }
+    }
+    c->last_stream = next; c->last_stream_set = true;
     return BGSB_OK;
 }
 
@@ -334,6 +386,18 @@ static int run_frames(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_fg
 }
 
 namespace bgsb {
+int sm_count(int device)
+{
+    static std::atomic<int> cached[64];
+    if (device < 0 || device >= 64) return 148;
+    int v = cached[device].load(std::memory_order_relaxed);
+    if (v <= 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = 148;
+        cached[device].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 bool pdl_enabled()
 {
     static const bool on = [] { const char *e = getenv("BGSB_NO_PDL"); return !(e && e[0] == '1'); }();
@@ -431,6 +495,7 @@ void bgsb_destroy(bgsb_ctx *c)
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     for (int i = 0; i < 8; i++) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]); }
     for (int i = 0; i < 2; i++) if (c->ev_dn[i]) cudaEventDestroy(c->ev_dn[i]);
+    if (c->ev_order) cudaEventDestroy(c->ev_order);
     delete c;
 }
 
@@ -471,8 +536,22 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     else if (k == "shadowValue") c->shadow_value = (int)v;
     else if (k == "shadowThreshold") c->tau = (float)v;
     else if (k == "hostBands") { BGSB_REQUIRE(v >= 1 && v <= 8, "hostBands in [1,8]"); c->host_bands = (int)v; }
+    else if (k == "retainInput") c->retain_input = (v != 0);
+#ifdef BGSB_INSTRUMENT
     else if (k == "kernelVariant") { BGSB_REQUIRE(v == 0 || v == 1 || v == 8 || v == 9, "kernelVariant is 0 or 1 (8, 9: timing instruments)"); c->mog2_variant = (int)v; }
-    else if (k == "ablTable") { BGSB_REQUIRE(v == 0 || v == 1 || v == 2, "ablTable is 0, 1 or 2"); c->abl_table = (int)v; }
+#else
+    else if (k == "kernelVariant") { BGSB_REQUIRE(v == 0 || v == 1, "kernelVariant is 0 or 1"); c->mog2_variant = (int)v; }
+#endif
+    else if (k == "ablTable") {
+        BGSB_REQUIRE(v == 0 || v == 1 || v == 2, "ablTable is 0, 1 or 2");
+        BGSB_REQUIRE(v != 0 || c->abl_blend == 0, "the OpenCV 2.4 blend (ablBlend 1) exists in table form only");
+        c->abl_table = (int)v;
+    }
+    else if (k == "ablBlend") {
+        BGSB_REQUIRE(v == 0 || v == 1, "ablBlend is 0 (OpenCV 4.x, fp64) or 1 (OpenCV 2.4, fp32)");
+        BGSB_REQUIRE(v == 0 || c->abl_table != 0, "the OpenCV 2.4 blend (ablBlend 1) exists in table form only");
+        c->abl_blend = (int)v;
+    }
     else if (k == "showOutput" || k == "showForeground" || k == "showBackground") { /* GUI only */ }
     else { set_error("bgsb_set_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
     return BGSB_OK;
@@ -506,7 +585,9 @@ int bgsb_get_param(bgsb_ctx *c, const char *key, double *v)
     else if (k == "shadowThreshold") *v = c->tau;
     else if (k == "kernelVariant") *v = c->mog2_variant;
     else if (k == "hostBands") *v = c->host_bands;
+    else if (k == "retainInput") *v = c->retain_input;
     else if (k == "ablTable") *v = c->abl_table;
+    else if (k == "ablBlend") *v = c->abl_blend;
     else { set_error("bgsb_get_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
     return BGSB_OK;
 }
@@ -522,7 +603,7 @@ int bgsb_state_bytes(bgsb_ctx *c, size_t *bytes)
 {
     BGSB_REQUIRE(c && bytes, "null");
     if (c->algo == BGSB_ALGO_MOG2) *bytes = (size_t)c->npx * (MOG2_PLANES * 4 + 1);
-    else if (c->algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM) *bytes = (size_t)c->npx * (c->gaussians * 20 + 1);
+    else if (c->algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM) *bytes = (size_t)c->npx * ((c->nframes ? c->dpz_K_l : c->gaussians) * 20 + 1);
     else if (c->algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) *bytes = (size_t)c->npx;
     else if (history_images(c->algo) == 2) *bytes = (size_t)c->npx * 6;
     else *bytes = (size_t)c->npx * 3;
@@ -538,12 +619,30 @@ int bgsb_process_batch_dev(bgsb_ctx *c, const uint8_t *d_frames, int T, int w, i
     BGSB_CUDA(cudaSetDevice(c->device));
     int rc = ensure_geometry(c, w, h);
     if (rc) return rc;
+    rc = order_after_previous(c, (cudaStream_t)stream);
+    if (rc) return rc;
     int warm = warmup_frames(c->algo);
     int64_t first = std::max<int64_t>(0, warm - c->nframes);
     if (first_fg_valid) *first_fg_valid = (int)std::min<int64_t>(first, T);
     bool has_bg = writes_background(c->algo);
     // WMM writes its background only from the third frame on (WeightedMovingMeanBGS.cpp:40-51)
     if (bg_valid) *bg_valid = has_bg && d_bg && (first < T);
+    if (c->retain_input && ring_history(c->algo) && (T == 1 || c->nstreams == 1)) {
+        // "retainInput": the caller keeps the last one (FD) / two (WMV, WMM) frame buffers valid and unmodified, so
+        // the history IS those buffers -- as in the host path's upload ring -- and nothing is written back:
+        // FD moves its 7 algorithmic bytes per pixel, WMV its 10.
+        if (first < T) {
+            rc = launch_range(c, d_frames, T, d_fg, has_bg ? d_bg : nullptr, bg_last_only, false, (cudaStream_t)stream, 0, c->npx);
+            if (rc) return rc;
+        }
+        const size_t fb = (size_t)c->npx * 3;
+        const uint8_t *last = d_frames + (size_t)(T - 1) * fb;
+        const uint8_t *before = T >= 2 ? d_frames + (size_t)(T - 2) * fb : c->hist_ptr[0];
+        c->hist_ptr[1] = before; c->hist_ptr[0] = last;
+        c->have_hist = (int)std::min<int64_t>(history_images(c->algo), (int64_t)c->have_hist + T);
+        c->nframes += T;
+        return BGSB_OK;
+    }
     return run_frames(c, d_frames, T, d_fg, has_bg ? d_bg : nullptr, bg_last_only, true, (cudaStream_t)stream);
 }
 
@@ -569,6 +668,8 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
     rc = ensure_geometry(c, w, h);
     if (rc) return rc;
     rc = ensure_host_staging(c);
+    if (rc) return rc;
+    rc = order_after_previous(c, c->stream);
     if (rc) return rc;
     const size_t rows = (size_t)h * c->nstreams;
     const bool fdlike = ring_history(c->algo);
@@ -665,9 +766,15 @@ int bgsb_submit(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, ui
     if (rc) return rc;
     rc = ensure_pipe_streams(c);
     if (rc) return rc;
+    rc = order_after_previous(c, c->stream);
+    if (rc) return rc;
     const size_t S = (size_t)c->nstreams;
-    if (!c->d_fg2) BGSB_CUDA(cudaMalloc(&c->d_fg2, S * c->npx));
-    if (!c->d_bg2 && c->d_bg) BGSB_CUDA(cudaMalloc(&c->d_bg2, S * c->npx * 3));
+    {
+        cudaError_t e = cudaSuccess;
+        if (!c->d_fg2) e = cudaMalloc(&c->d_fg2, S * c->npx);
+        if (e == cudaSuccess && !c->d_bg2 && c->d_bg) e = cudaMalloc(&c->d_bg2, S * c->npx * 3);
+        if (e != cudaSuccess) { drain(c); return staging_fail(c, e); }
+    }
     const size_t rows = (size_t)h * c->nstreams;
     const bool fdlike = ring_history(c->algo);
     const int nring = history_images(c->algo) + 1;
@@ -741,6 +848,8 @@ int bgsb_process_fanout(bgsb_ctx *const *ctxs, int n, const uint8_t *bgr, int w,
         rc = ensure_host_staging(ctxs[k]);
         if (rc) return rc;
         rc = ensure_pipe_streams(ctxs[k]);
+        if (rc) return rc;
+        rc = order_after_previous(ctxs[k], ctxs[k]->stream);
         if (rc) return rc;
     }
     const size_t fbytes = (size_t)w * h * 3;

@@ -530,7 +530,8 @@ int bgsb_ccl_create_batch(bgsb_ccl **out, int device, int max_w, int max_h, int 
     c->img_px = (size_t)max_w * max_h;
     c->img_words = (size_t)((max_w + 31) / 32) * max_h;
     c->max_blocks = (int)((c->img_words + 255) / 256);
-    c->cap = (int)(c->img_px / 4 + 64);
+    // the most 8-connected components an image can hold: isolated pixels on every second row and column
+    c->cap = ((max_w + 1) / 2) * ((max_h + 1) / 2) + 64;
     const size_t N = (size_t)max_images;
     cudaError_t e = cudaSuccess;
     auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
@@ -577,8 +578,7 @@ int bgsb_ccl_label_batch_dev(bgsb_ccl *c, const uint8_t *d_masks, int w, int h, 
                              int32_t *d_labels, void *stream_)
 {
     BGSB_REQUIRE(c && d_masks, "null");
-    BGSB_REQUIRE(w > 0 && h > 0 && (size_t)w * h <= c->img_px && (size_t)((w + 31) / 32) * h <= c->img_words,
-                 "image larger than the labeller was created for");
+    BGSB_REQUIRE(w > 0 && h > 0 && w <= c->max_w && h <= c->max_h, "image larger than the labeller was created for");
     BGSB_REQUIRE(nimages >= 1 && nimages <= c->max_images, "more images than the labeller was created for");
     BGSB_CUDA(cudaSetDevice(c->device));
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -629,7 +629,7 @@ int bgsb_ccl_label_batch_dev(bgsb_ccl *c, const uint8_t *d_masks, int w, int h, 
     BGSB_LAUNCH_CHECK();
     {
         // at most cap components per image; the kernel exits early past the real count
-        const int maxc = std::min(c->cap, (int)(((size_t)w * h + 3) / 4 + 1));
+        const int maxc = std::min(c->cap, ((w + 1) / 2) * ((h + 1) / 2));
         dim3 rgrid(std::min((maxc + 255) / 256, 16), nimages);
         launch_pdl(ccl_resolve_external_kernel, dim3(rgrid), dim3(256), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_comp, c->d_ncomp,
                                                                c->cap, c->d_need_bg, w, wpr, ipx, iw);
@@ -724,7 +724,7 @@ int bgsb_ccl_label(bgsb_ccl *c, const uint8_t *mask, int w, int h, size_t stride
 {
     BGSB_REQUIRE(c && mask && n, "null");
     BGSB_REQUIRE(stride >= (size_t)w, "stride smaller than a row");
-    BGSB_REQUIRE(w > 0 && h > 0 && (size_t)w * h <= c->img_px, "image larger than the labeller was created for");
+    BGSB_REQUIRE(w > 0 && h > 0 && w <= c->max_w && h <= c->max_h, "image larger than the labeller was created for");
     BGSB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->own_stream;
     BGSB_CUDA(cudaMemcpy2DAsync(c->d_mask_own, w, mask, stride, w, h, cudaMemcpyHostToDevice, st));

@@ -10,7 +10,9 @@
 
 namespace bgsb {
 
-constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+// Number of SMs of `device` (148 on a B200: 2 dies x 74), queried once per device; persistent / cooperative grids are
+// sized from it.  capi.cu
+int sm_count(int device);
 
 // ---- error plumbing --------------------------------------------------------------------
 void set_error(const char *fmt, ...);
@@ -25,10 +27,16 @@ extern std::atomic<uint64_t> g_launches;
         }                                                                                    \
     } while (0)
 
+// launch_pdl() parks the status cudaLaunchKernelEx returned here; BGSB_LAUNCH_CHECK reads it first, so a failed launch is
+// reported by the call that made it even when the error is not sticky in the runtime's per-thread state.
+inline thread_local cudaError_t g_launch_status = cudaSuccess;
+
 #define BGSB_LAUNCH_CHECK()                                                                  \
     do {                                                                                     \
         bgsb::g_launches.fetch_add(1, std::memory_order_relaxed);                            \
-        cudaError_t _e = cudaGetLastError();                                                 \
+        cudaError_t _e = bgsb::g_launch_status;                                              \
+        bgsb::g_launch_status = cudaSuccess;                                                 \
+        if (_e == cudaSuccess) _e = cudaGetLastError(); else (void)cudaGetLastError();       \
         if (_e != cudaSuccess) {                                                             \
             bgsb::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
             return BGSB_ERR_CUDA;                                                            \
@@ -60,7 +68,8 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;          // BGSB_NO_PDL=1: plain stream order (A/B)
-    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);    // errors surface in BGSB_LAUNCH_CHECK
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    if (e != cudaSuccess && g_launch_status == cudaSuccess) g_launch_status = e;     // reported by BGSB_LAUNCH_CHECK
 }
 #endif
 

@@ -27,7 +27,8 @@ struct SimpleLaunch {
 };
 int launch_simple(int algo, const SimpleLaunch &L, int nstreams, cudaStream_t stream);
 // Fill the 64 KB ABL table for `alpha` with the arithmetic kernel's own blend (bit-exact by construction).
-int launch_abl_lut_build(uint8_t *d_lut, double alpha, cudaStream_t stream);
+// blend_variant 0: OpenCV 4.x double-precision addWeighted (pinned); 1: OpenCV 2.4 fp32 addWeighted (unpinned).
+int launch_abl_lut_build(uint8_t *d_lut, double alpha, int blend_variant, cudaStream_t stream);
 
 // ---- AdaptiveSelectiveBackgroundLearning (single-channel model; one frame per launch pair) --------
 struct AsblLaunch {

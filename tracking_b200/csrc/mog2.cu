@@ -149,7 +149,8 @@ int launch_mog2_fused(const Mog2Launch &L, int nstreams, cudaStream_t stream);
 
 // variant: 0 production (T == 1: two-phase kernel; T > 1: temporal-fusion kernel; csrc/mog2_t1.cu)
 //          1 straight restatement (this file) -- the reference point of profiles/r1_mog2_kernel_history.md
-//          8, 9 timing instruments with wrong results: T == 1 kernel without its generic phase / without arithmetic
+//          8, 9 (-DBGSB_INSTRUMENT builds only) timing instruments with wrong results: T == 1 kernel without its
+//          generic phase / without arithmetic
 int launch_mog2(const Mog2Launch &L, int nstreams, int variant, cudaStream_t stream)
 {
     if (variant == 0) return L.T == 1 ? launch_mog2_t1(L, nstreams, 0, stream) : launch_mog2_fused(L, nstreams, stream);
