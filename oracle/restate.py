@@ -178,6 +178,18 @@ class AdaptiveBackgroundLearning:
         return fg, self.bg.copy()
 
 
+def abl_blend_table_24(alpha):
+    """PARITY UNPINNED (no OpenCV 2.4 in this image).  New background byte of AdaptiveBackgroundLearning for every
+    (input byte x = row, background byte y = column) as OpenCV 2.4 computes `alpha*in_f + (1-alpha)*bg_f`
+    (AdaptiveBackgroundLearning.cpp:54): addWeighted on CV_32F in fp32 with the scalars cast to float (SURVEY
+    Appendix B), then convertTo(CV_8U, 255) = round-half-even + saturate (:56-58)."""
+    x = (np.arange(256, dtype=np.float32) * np.float32(1. / 255.))[:, None]
+    y = (np.arange(256, dtype=np.float32) * np.float32(1. / 255.))[None, :]
+    a, b = np.float32(alpha), np.float32(1. - alpha)
+    nb = (x * a).astype(np.float32) + (y * b).astype(np.float32)
+    return np.clip(np.rint(nb.astype(np.float32) * np.float32(255.)), 0, 255).astype(np.uint8)
+
+
 class AdaptiveSelectiveBackgroundLearning:
     """USTC_BGS type 7; defaults = loadConfig()'s (AdaptiveSelectiveBackgroundLearning.cpp:121-125)."""
 
