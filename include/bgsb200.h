@@ -235,6 +235,8 @@ BGSB_API int bgsb_ccl_components_of(bgsb_ccl *ccl, int image, bgsb_component *ou
 /* cvMoments(pFG[R], binary=0) for nrects rectangles of the mask last labelled:
  * out[6*i..] = m00 m10 m01 m20 m02 m11 (pixel-value weighted, ROI-relative, exact). */
 BGSB_API int bgsb_ccl_rect_moments(bgsb_ccl *ccl, const int32_t *rects_xywh, int nrects, uint64_t *out);
+/* Same for image `image` of the last batch. */
+BGSB_API int bgsb_ccl_rect_moments_of(bgsb_ccl *ccl, int image, const int32_t *rects_xywh, int nrects, uint64_t *out);
 /* Host-buffer convenience wrapper: label + fetch. */
 BGSB_API int bgsb_ccl_label(bgsb_ccl *ccl, const uint8_t *mask, int w, int h, size_t stride,
                             int zero_border, int32_t *labels, bgsb_component *out, int capacity, int *n);
@@ -264,6 +266,36 @@ BGSB_API int bgsb_blobdetector_detect_dev(bgsb_blobdetector *bd, const uint8_t *
                                           bgsb_blob *new_blobs, int new_cap, int *n_new, int *result,
                                           bgsb_blob *frame_blobs, int frame_cap, int *n_frame,
                                           void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * The foreground pipeline, device-resident, for a group of camera streams: what the reference's main loop does per
+ * frame (ustc_src/trackingMain.cpp:161-166 -> CvBlobTrackerAuto1::Process): USTC_BGS::Process = IBGS::process
+ * (ustc_src/ustc_bgs.cpp:87-113), the mask clean-up (erode / dilate chain, SURVEY 8a row aM; default OPEN 3x3), and
+ * steps 1-2 of CvBlobDetectorCC::DetectNewBlob (:626) -- BASELINE config 4.  The mask stays bit-packed between the
+ * stages; one launch sequence serves all streams of the group.
+ * ------------------------------------------------------------------------------------- */
+typedef struct bgsb_pipeline bgsb_pipeline;
+BGSB_API int bgsb_pipeline_create(bgsb_pipeline **out, int algo, int device, int nstreams);
+BGSB_API void bgsb_pipeline_destroy(bgsb_pipeline *p);
+/* The plugin context inside (owned by the pipeline): bgsb_set_param / bgsb_mog2_export_state ... on it. */
+BGSB_API bgsb_ctx *bgsb_pipeline_bgs(bgsb_pipeline *p);
+/* ops as in bgsb_morph_dev, at most 16 pairs; nops = 0: no clean-up stage. */
+BGSB_API int bgsb_pipeline_set_morph(bgsb_pipeline *p, const int *ops, int nops);
+/* "zeroBorder" (default 1, OpenCV 2.4 cvFindContours), "forceBackgroundPass"; any other key goes to the plugin. */
+BGSB_API int bgsb_pipeline_set_param(bgsb_pipeline *p, const char *key, double value);
+/* One frame per stream: d_frames [nstreams][h][w][3].  Optional outputs (NULL = not wanted):
+ *   d_mask   [nstreams][h][w]    the cleaned {0,255} mask (what CvFGDetector::GetMask hands to the tracker)
+ *   d_bg     [nstreams][h][w][3] the plugin's background image
+ *   d_labels [nstreams][h][w]    canonical labels of the 8-connected components (int32, 0 = background)
+ * *valid = 0 while the plugin has no mask yet (FD frame 0, WMV frames 0-1): nothing was labelled.
+ * Asynchronous on `stream`; the component tables stay on the device until fetched. */
+BGSB_API int bgsb_pipeline_process_dev(bgsb_pipeline *p, const uint8_t *d_frames, int w, int h, uint8_t *d_mask,
+                                       uint8_t *d_bg, int32_t *d_labels, int *valid, int *bg_valid, void *stream);
+/* Component table of stream `stream_index` for the last frame (synchronises the stream). */
+BGSB_API int bgsb_pipeline_components(bgsb_pipeline *p, int stream_index, bgsb_component *out, int capacity, int *n);
+/* cvMoments(pFGMask[R], 0) sums on that stream's cleaned mask, as bgsb_ccl_rect_moments. */
+BGSB_API int bgsb_pipeline_rect_moments(bgsb_pipeline *p, int stream_index, const int32_t *rects_xywh, int nrects,
+                                        uint64_t *out);
 
 /* ---------------------------------------------------------------------------------------
  * Synthetic video of SURVEY 8(d) generated on the device (bench / tests only):

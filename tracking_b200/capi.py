@@ -75,6 +75,7 @@ SIGNATURES = {
     "bgsb_ccl_label_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp]),
     "bgsb_ccl_components": (C.c_int, [vp, C.POINTER(Component), C.c_int, intp]),
     "bgsb_ccl_rect_moments": (C.c_int, [vp, i32p, C.c_int, C.POINTER(C.c_uint64)]),
+    "bgsb_ccl_rect_moments_of": (C.c_int, [vp, C.c_int, i32p, C.c_int, C.POINTER(C.c_uint64)]),
     "bgsb_ccl_label": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_size_t, C.c_int, vp, C.POINTER(Component),
                                  C.c_int, intp]),
     "bgsb_blobdetector_create": (C.c_int, [C.POINTER(vp), C.c_int]),
@@ -85,6 +86,14 @@ SIGNATURES = {
     "bgsb_blobdetector_detect_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(Blob), C.c_int,
                                                C.POINTER(Blob), C.c_int, intp, intp, C.POINTER(Blob), C.c_int,
                                                intp, vp]),
+    "bgsb_pipeline_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int]),
+    "bgsb_pipeline_destroy": (None, [vp]),
+    "bgsb_pipeline_bgs": (vp, [vp]),
+    "bgsb_pipeline_set_morph": (C.c_int, [vp, intp, C.c_int]),
+    "bgsb_pipeline_set_param": (C.c_int, [vp, C.c_char_p, C.c_double]),
+    "bgsb_pipeline_process_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, intp, intp, vp]),
+    "bgsb_pipeline_components": (C.c_int, [vp, C.c_int, C.POINTER(Component), C.c_int, intp]),
+    "bgsb_pipeline_rect_moments": (C.c_int, [vp, C.c_int, i32p, C.c_int, C.POINTER(C.c_uint64)]),
     "bgsb_synth_frames_dev": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, vp]),
 }
 

@@ -214,7 +214,8 @@ static bool writes_background(int algo)
 // Launch the kernel for pixels [p0, p0+pcount) of the frame(s); p0 must be a multiple of 64 (a MOG2 state tile).
 // A sub-range is only used for single-stream, single-frame calls (host-path chunk pipelining).
 static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_fg, uint8_t *d_bg,
-                        int bg_last_only, bool own_history, cudaStream_t stream, size_t p0, int pcount)
+                        int bg_last_only, bool own_history, cudaStream_t stream, size_t p0, int pcount,
+                        unsigned *d_bits = nullptr, int bit_thr = 0)
 {
     if (c->algo == BGSB_ALGO_MOG2) {
         BGSB_REQUIRE(T <= MOG2_TMAX, "temporal batch too long (max 32)");
@@ -226,8 +227,11 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
             Mog2Launch L;
             memset(&L, 0, sizeof(L));
             const size_t f0 = (size_t)i * c->npx;                  // first pixel of frame i in the batch buffers
-            L.frames = d_frames + (f0 + p0) * 3; L.fg = d_fg + f0 + p0;
+            L.frames = d_frames + (f0 + p0) * 3; L.fg = d_fg ? d_fg + f0 + p0 : nullptr;
             L.bg = nullptr;
+            if (d_bits) {                                  // whole single frames on the production kernel only (ctx_process_frame)
+                L.bits = d_bits; L.w = c->w; L.wpr = (c->w + 31) / 32; L.bits_stride = (size_t)L.wpr * c->h; L.bit_thr = bit_thr;
+            }
             if (d_bg) {
                 if (!per_frame) L.bg = d_bg + p0 * 3;
                 else if (!bg_last_only) L.bg = d_bg + (f0 + p0) * 3;
@@ -610,10 +614,21 @@ int bgsb_state_bytes(bgsb_ctx *c, size_t *bytes)
     return BGSB_OK;
 }
 
+static int process_batch_impl(bgsb_ctx *c, const uint8_t *d_frames, int T, int w, int h, uint8_t *d_fg,
+                              uint8_t *d_bg, int bg_last_only, int *first_fg_valid, int *bg_valid, void *stream,
+                              unsigned *d_bits, int bit_thr);
+
 int bgsb_process_batch_dev(bgsb_ctx *c, const uint8_t *d_frames, int T, int w, int h, uint8_t *d_fg,
                            uint8_t *d_bg, int bg_last_only, int *first_fg_valid, int *bg_valid, void *stream)
 {
     BGSB_REQUIRE(c && d_frames && d_fg, "null");
+    return process_batch_impl(c, d_frames, T, w, h, d_fg, d_bg, bg_last_only, first_fg_valid, bg_valid, stream, nullptr, 0);
+}
+
+static int process_batch_impl(bgsb_ctx *c, const uint8_t *d_frames, int T, int w, int h, uint8_t *d_fg,
+                              uint8_t *d_bg, int bg_last_only, int *first_fg_valid, int *bg_valid, void *stream,
+                              unsigned *d_bits, int bit_thr)
+{
     if (int drc = drain(c)) return drc;
     BGSB_REQUIRE(T >= 1, "T >= 1");
     BGSB_CUDA(cudaSetDevice(c->device));
@@ -643,7 +658,10 @@ int bgsb_process_batch_dev(bgsb_ctx *c, const uint8_t *d_frames, int T, int w, i
         c->nframes += T;
         return BGSB_OK;
     }
-    return run_frames(c, d_frames, T, d_fg, has_bg ? d_bg : nullptr, bg_last_only, true, (cudaStream_t)stream);
+    rc = launch_range(c, d_frames, T, d_fg, has_bg ? d_bg : nullptr, bg_last_only, true, (cudaStream_t)stream, 0, c->npx, d_bits, bit_thr);
+    if (rc) return rc;
+    advance(c, T, true);
+    return BGSB_OK;
 }
 
 int bgsb_process_dev(bgsb_ctx *c, const uint8_t *d_bgr, int w, int h, uint8_t *d_fg, uint8_t *d_bg,
@@ -969,3 +987,24 @@ int bgsb_synth_frames_dev(uint8_t *d_frames, int nstreams, int T, int w, int h, 
 }
 
 }  // extern "C"
+
+namespace bgsb {
+
+bool ctx_can_pack(const bgsb_ctx *c) { return c && c->algo == BGSB_ALGO_MOG2 && c->mog2_variant == 0; }
+int ctx_nstreams(const bgsb_ctx *c) { return c->nstreams; }
+int ctx_device(const bgsb_ctx *c) { return c->device; }
+
+int ctx_process_frame(bgsb_ctx *c, const uint8_t *d_frames, int w, int h, uint8_t *d_fg, uint8_t *d_bg, unsigned *d_bits,
+                      int bit_thr, int *packed, int *fg_valid, int *bg_valid, cudaStream_t stream)
+{
+    BGSB_REQUIRE(c && d_frames, "null");
+    const bool pack = d_bits && ctx_can_pack(c);
+    BGSB_REQUIRE(pack || d_fg, "this plugin needs a byte mask buffer");
+    if (packed) *packed = pack;
+    int first = 0;
+    int rc = process_batch_impl(c, d_frames, 1, w, h, d_fg, d_bg, 0, &first, bg_valid, (void *)stream, pack ? d_bits : nullptr, bit_thr);
+    if (fg_valid) *fg_valid = (rc == BGSB_OK && first == 0);
+    return rc;
+}
+
+}  // namespace bgsb

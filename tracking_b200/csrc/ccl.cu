@@ -7,30 +7,34 @@
 //     cvThreshold(pIB, pIB, 128, 255, CV_THRESH_BINARY); cvFindContours(pIB, ..., CV_RETR_EXTERNAL);
 //     CvRect r = ((CvContour*)cnt)->rect;   cvMoments(cvGetSubRect(pFGMask,&mat,r), &m, 0);
 //
-// Algorithm (all kernels one thread per 32-pixel word of the bit-packed mask; every launch covers a
-// whole batch of images, blockIdx.y = image):
-//   pack     bytes > 128 -> bits (optionally clearing the 1-px frame, OpenCV 2.4 behaviour)
-//   init     every horizontal run (within a word) is a union-find node named by its first pixel
-//   merge    unions found with bit tricks on (this row, row above): a run pair is linked exactly
-//            once (8-connectivity: vertical + the two diagonals that are not already implied);
-//            lock-free union by atomicMin with path halving, so a component's root is its
-//            minimum = raster-first pixel
-//   flatten  parent[node] = root; mark roots; count roots per 256-word block
-//   rank     scan of the block counts + in-block scan -> canonical label = 1 + rank of the root
-//   label    write labels, accumulate bbox/area per component with atomics
-//   nest     RETR_EXTERNAL drops components enclosed in a hole of another one.  That requires the
-//            enclosed component's bounding box to lie STRICTLY inside the other's, so one small
-//            kernel checks the boxes; only images where such a pair exists run the background pass:
-//   bg pass  the same init/merge/flatten on the 4-connected background; regions touching the frame
-//            are "outer"; the background pixel left of a component's first pixel lies in the region
-//            surrounding it, and the component is external iff that region is outer.
-//            (Typical masks have no such pair and skip it: the background is >98 % of the pixels.)
+// Four launches per batch of images (round 1 needed twelve), all one thread per 32-pixel word of the bit-packed
+// mask, blockIdx.y = image:
+//   1 pack/init  bytes > 128 -> bits (optionally clearing the 1-px frame, OpenCV 2.4 behaviour); every horizontal run
+//                inside a word becomes a union-find node named by its first pixel.  (The pipeline's morphology kernel
+//                produces the bits and the nodes itself: three launches.)
+//   2 merge      unions found with bit tricks on (this row, row above): a run pair is linked exactly once
+//                (8-connectivity: vertical + the two diagonals that are not already implied); lock-free union by
+//                atomicMin with path halving, so a component's root is its minimum = raster-first pixel.
+//   3 finish     roots are counted per 256-word chunk; a chunk's CTA waits for the counts of the chunks before it
+//                (CTAs take their chunk from a ticket counter, so a CTA only ever waits for CTAs that are already
+//                running), which makes canonical label = 1 + raster rank of the root known without a separate scan
+//                launch; the root's rank is published in its own forest slot (negative values), every other run
+//                chases its parent chain to it; bounding boxes / areas by atomics; optional label image.
+//   4 background one cooperative launch.  RETR_EXTERNAL drops components enclosed in a hole of another one, which
+//                requires the enclosed bounding box to lie STRICTLY inside the other's: all CTAs check the boxes, one
+//                grid-wide barrier, and unless some image has such a pair (typical masks have none: the background
+//                is > 98 % of the pixels) the launch ends there.  Otherwise the same init / merge / flatten runs on the
+//                4-connected background of the flagged images, regions touching the frame are "outer", and a
+//                component is external iff the background region left of its first pixel is outer.
 #include <limits.h>
 #include <algorithm>
 #include <vector>
+#include <cooperative_groups.h>
 
-#include "common.cuh"
+#include "ccl_internal.h"
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace bgsb {
 
@@ -82,19 +86,44 @@ __device__ __forceinline__ void unite(int *parent, int a, int b)
     }
 }
 
-// pack + foreground init in one pass: a word's run starts become their own union-find roots right away (the
-// init step only needs the word itself), and the per-block root counters / background-pass flag are cleared.
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// geometry + buffers of one labelling call (all per-image strides are the dense ones of this geometry)
+struct CclArgs {
+    const unsigned *bits;        // [nimages][h * wpr]
+    int *parent;                 // [nimages][w * h]
+    uint8_t *outer;              // [nimages][w * h]
+    CompRaw *comp;               // [nimages][cap]
+    unsigned *chunkstate;        // [nimages][nchunks]
+    int *ticket, *ncomp, *need_bg;
+    int *labels;                 // [nimages][w * h] or null
+    int w, h, wpr, nwords, nchunks, nimages, cap, zero_border, force_bg;
+    size_t img_px, img_words;
+};
+
+// the (border-cleared) word k of row y; 0 outside the image
+__device__ __forceinline__ unsigned ccl_word(const unsigned *bits, int y, int k, const CclArgs &A)
+{
+    if (k < 0 || k >= A.wpr || y < 0) return 0u;
+    return ccl_border(bits[y * A.wpr + k], y, k, A.w, A.h, A.wpr, A.zero_border);
+}
+
+// ---- launch 1 (byte masks): pack + node init -------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-ccl_pack_kernel(const uint8_t *__restrict__ mask, unsigned *__restrict__ bits, int *__restrict__ parent,
-                int *__restrict__ blockcount, int *__restrict__ need_bg, int nblocks, int w, int h, int wpr, int zero_border,
-                size_t img_px, size_t img_words)
+ccl_pack_kernel(const uint8_t *__restrict__ mask, unsigned *__restrict__ bits, int *__restrict__ parent, int w, int h, int wpr,
+                int zero_border, size_t img_px, size_t img_words)
 {
     pdl_entry();
     int wi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (threadIdx.x == 0) {
-        blockcount[blockIdx.y * (size_t)(nblocks + 1) + blockIdx.x] = 0;
-        if (blockIdx.x == 0) need_bg[blockIdx.y] = 0;
-    }
     if (wi >= h * wpr) return;
     mask += blockIdx.y * img_px; bits += blockIdx.y * img_words; parent += blockIdx.y * img_px;
     int y = wi / wpr, k = wi - y * wpr;
@@ -115,51 +144,25 @@ ccl_pack_kernel(const uint8_t *__restrict__ mask, unsigned *__restrict__ bits, i
     } else {
         for (int i = 0; i < nvalid; i++) word |= (p[i] > 128 ? 1u : 0u) << i;
     }
-    if (zero_border) {
-        if (y == 0 || y == h - 1) word = 0;
-        if (k == 0) word &= ~1u;
-        if (k == wpr - 1) word &= ~(1u << ((w - 1) & 31));
-    }
+    word = ccl_border(word, y, k, w, h, wpr, zero_border);
     bits[wi] = word;
-    const int base = y * w + k * 32;
-    unsigned s = word & ~(word << 1);                  // run starts inside the word
-    while (s) {
-        const int b = __ffs(s) - 1; s &= s - 1;
-        parent[base + b] = base + b;
-    }
+    ccl_init_word(parent, word, y * w + k * 32);
 }
 
-// BG = false: foreground runs;  BG = true: background runs (only for images flagged by the nest check)
-template <bool BG>
-__global__ void __launch_bounds__(BG ? 1024 : 256)
-ccl_init_kernel(const unsigned *__restrict__ bits, int *__restrict__ parent, uint8_t *__restrict__ outer,
-                int *__restrict__ blockcount, const int *__restrict__ need_bg, int w, int h, int wpr, size_t img_px,
-                size_t img_words, int nblocks)
+// ---- launch 1 (bit-packed masks whose producer did not create the nodes) -----------------------------------------
+__global__ void __launch_bounds__(256)
+ccl_init_kernel(const __grid_constant__ CclArgs A)
 {
     pdl_entry();
-    int wi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (BG) { if (!need_bg[blockIdx.y]) return; }
-    else if (threadIdx.x == 0) {
-        blockcount[blockIdx.y * (size_t)(nblocks + 1) + blockIdx.x] = 0;
-        if (blockIdx.x == 0) (const_cast<int *>(need_bg))[blockIdx.y] = 0;
-    }
-    if (wi >= h * wpr) return;
-    bits += blockIdx.y * img_words; parent += blockIdx.y * img_px; outer += blockIdx.y * img_px;
-    int y = wi / wpr, k = wi - y * wpr;
-    unsigned v = bits[wi];
-    if (BG) v = ~v & in_mask(k, w, wpr);
-    int base = y * w + k * 32;
-    unsigned s = v & ~(v << 1);
-    while (s) {
-        int b = __ffs(s) - 1; s &= s - 1;
-        parent[base + b] = base + b;
-        if (BG) outer[base + b] = 0;
-    }
+    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wi >= A.nwords) return;
+    const int y = wi / A.wpr, k = wi - y * A.wpr;
+    ccl_init_word(A.parent + blockIdx.y * A.img_px, ccl_word(A.bits + blockIdx.y * A.img_words, y, k, A), y * A.w + k * 32);
 }
 
 template <bool DIAG>
 __device__ __forceinline__ void merge_class(int *parent, unsigned v, unsigned vl, unsigned vr, unsigned u,
-                                            unsigned ul, unsigned ur, int base, int base_up, bool has_up, int k)
+                                            unsigned ul, unsigned ur, int base, int base_up, bool has_up)
 {
     // horizontal continuation across the word boundary
     if ((v & 1u) && (vl >> 31)) unite(parent, base, base - 32 + run_start(vl, 31));
@@ -185,198 +188,152 @@ __device__ __forceinline__ void merge_class(int *parent, unsigned v, unsigned vl
             unite(parent, base + run_start(v, x), other);
         }
     }
-    (void)k;
 }
 
+// one word of the merge step.  BG = false: foreground runs, 8-connected;  BG = true: background = complement inside
+// the image, 4-connected
 template <bool BG>
-__global__ void __launch_bounds__(BG ? 1024 : 256)
-ccl_merge_kernel(const unsigned *__restrict__ bits, int *parent, const int *__restrict__ need_bg, int w, int h, int wpr,
-                 size_t img_px, size_t img_words)
+__device__ __forceinline__ void merge_word(const CclArgs &A, const unsigned *bits, int *parent, int wi)
 {
-    pdl_entry();
-    int wi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (BG && !need_bg[blockIdx.y]) return;
-    if (wi >= h * wpr) return;
-    bits += blockIdx.y * img_words; parent += blockIdx.y * img_px;
-    int y = wi / wpr, k = wi - y * wpr;
-    unsigned v = bits[wi];
+    const int y = wi / A.wpr, k = wi - y * A.wpr;
+    const unsigned v = ccl_word(bits, y, k, A);
     if (!BG && v == 0) return;                     // no foreground in this word: nothing to link
-    unsigned vl = k > 0 ? bits[wi - 1] : 0u, vr = k + 1 < wpr ? bits[wi + 1] : 0u;
-    unsigned u = 0, ul = 0, ur = 0;
-    bool has_up = y > 0;
-    if (has_up) {
-        u = bits[wi - wpr];
-        ul = k > 0 ? bits[wi - wpr - 1] : 0u;
-        ur = k + 1 < wpr ? bits[wi - wpr + 1] : 0u;
-    }
-    int base = y * w + k * 32, base_up = base - w;
+    const unsigned vl = ccl_word(bits, y, k - 1, A), vr = ccl_word(bits, y, k + 1, A);
+    const bool has_up = y > 0;
+    const unsigned u = ccl_word(bits, y - 1, k, A), ul = ccl_word(bits, y - 1, k - 1, A), ur = ccl_word(bits, y - 1, k + 1, A);
+    const int base = y * A.w + k * 32, base_up = base - A.w;
     if (!BG) {
-        merge_class<true>(parent, v, vl, vr, u, ul, ur, base, base_up, has_up, k);          // 8-connected
+        merge_class<true>(parent, v, vl, vr, u, ul, ur, base, base_up, has_up);
     } else {
-        // background = complement inside the image, 4-connected
-        unsigned mk = in_mask(k, w, wpr), ml = in_mask(k - 1, w, wpr), mr = in_mask(k + 1, w, wpr);
+        const unsigned mk = in_mask(k, A.w, A.wpr), ml = in_mask(k - 1, A.w, A.wpr), mr = in_mask(k + 1, A.w, A.wpr);
         merge_class<false>(parent, ~v & mk, ~vl & ml, ~vr & mr, has_up ? (~u & mk) : 0u, has_up ? (~ul & ml) : 0u,
-                           has_up ? (~ur & mr) : 0u, base, base_up, has_up, k);
+                           has_up ? (~ur & mr) : 0u, base, base_up, has_up);
     }
 }
 
-template <bool BG>
-__global__ void __launch_bounds__(BG ? 1024 : 256)
-ccl_flatten_kernel(const unsigned *__restrict__ bits, int *parent, uint8_t *outer, unsigned *__restrict__ rootbits,
-                   int *__restrict__ blockcount, const int *__restrict__ need_bg, int w, int h, int wpr, size_t img_px,
-                   size_t img_words, int nblocks)
-{
-    pdl_entry();
-    int wi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (BG && !need_bg[blockIdx.y]) return;
-    if (wi >= h * wpr) return;
-    bits += blockIdx.y * img_words; parent += blockIdx.y * img_px; outer += blockIdx.y * img_px;
-    rootbits += blockIdx.y * img_words; blockcount += blockIdx.y * (size_t)(nblocks + 1);
-    int y = wi / wpr, k = wi - y * wpr;
-    unsigned v = bits[wi];
-    int base = y * w + k * 32;
-    if (!BG) {
-        unsigned roots = 0;
-        unsigned s = v & ~(v << 1);
-        while (s) {
-            int b = __ffs(s) - 1; s &= s - 1;
-            int r = find_root(parent, base + b);
-            parent[base + b] = r;
-            if (r == base + b) roots |= 1u << b;
-        }
-        rootbits[wi] = roots;
-        if (roots) atomicAdd(&blockcount[blockIdx.x], __popc(roots));     // roots per 256-word block, for the rank scan
-    } else {
-        // background runs: flatten, and flag regions that touch the image frame as "outer"
-        unsigned vb = ~v & in_mask(k, w, wpr);
-        const bool edge_row = (y == 0 || y == h - 1);
-        unsigned s = vb & ~(vb << 1);
-        while (s) {
-            int b = __ffs(s) - 1; s &= s - 1;
-            int r = find_root(parent, base + b);
-            parent[base + b] = r;
-            unsigned rest = ~(vb >> b);
-            int len = rest ? __ffs(rest) - 1 : 32 - b;
-            bool touches = edge_row || (k == 0 && b == 0) || (k * 32 + b + len - 1 == w - 1);
-            if (touches) outer[r] = 1;
-        }
-    }
-}
-
-struct CompRaw { int label, first_index, xmin, ymin, xmax, ymax, area, external; };
-
-// one CTA per image: exclusive scan of the per-block root counts (nblocks <= a few thousand)
-__global__ void __launch_bounds__(1024)
-ccl_blockscan_kernel(int *blockcount, int nblocks, int *ncomp)
-{
-    pdl_entry();
-    __shared__ int sums[1024];
-    int *bc = blockcount + blockIdx.x * (size_t)(nblocks + 1);
-    const int tid = threadIdx.x;
-    const int chunk = (nblocks + 1023) / 1024;
-    const int lo = min(nblocks, tid * chunk), hi = min(nblocks, lo + chunk);
-    int acc = 0;
-    for (int i = lo; i < hi; i++) acc += bc[i];
-    sums[tid] = acc;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {          // Hillis-Steele inclusive scan
-        int v = tid >= off ? sums[tid - off] : 0;
-        __syncthreads();
-        sums[tid] += v;
-        __syncthreads();
-    }
-    int run = sums[tid] - acc;
-    for (int i = lo; i < hi; i++) { int c = bc[i]; bc[i] = run; run += c; }
-    if (tid == 1023) { bc[nblocks] = sums[1023]; ncomp[blockIdx.x] = sums[1023]; }
-}
-
-// per 256-word block: exclusive rank of every word's roots, component table rows initialised
+// ---- launch 2: merge ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-ccl_rank_kernel(const unsigned *__restrict__ rootbits, int *__restrict__ wordrank, const int *__restrict__ blockcount,
-                CompRaw *comp, int cap, int w, int h, int wpr, size_t img_words, int nblocks)
+ccl_merge_kernel(const __grid_constant__ CclArgs A)
 {
     pdl_entry();
-    __shared__ int wsum[8];
-    rootbits += blockIdx.y * img_words; wordrank += blockIdx.y * img_words;
-    blockcount += blockIdx.y * (size_t)(nblocks + 1); comp += blockIdx.y * (size_t)cap;
     const int wi = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nwords = h * wpr;
-    unsigned r = wi < nwords ? rootbits[wi] : 0u;
-    int c = __popc(r);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (wi >= A.nwords) return;
+    merge_word<false>(A, A.bits + blockIdx.y * A.img_words, A.parent + blockIdx.y * A.img_px, wi);
+}
+
+// ---- launch 3: finish ----------------------------------------------------------------------------------------------
+// Chunk c = words [256c, 256c + 256) of one image in raster order.  ncomp[img] is written by the last chunk.
+template <bool LABELS>       // LABELS = false: component table only (no 32-register label row per thread)
+__global__ void __launch_bounds__(256)
+ccl_finish_kernel(const __grid_constant__ CclArgs A)
+{
+    pdl_entry();
+    __shared__ int s_chunk, s_prefix;
+    __shared__ int wsum[8];
+    const int img = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_chunk = atomicAdd(&A.ticket[img], 1);
+    __syncthreads();
+    const int chunk = s_chunk;
+    const unsigned *bits = A.bits + img * A.img_words;
+    int *parent = A.parent + img * A.img_px;
+    CompRaw *comp = A.comp + (size_t)img * A.cap;
+    unsigned *state = A.chunkstate + (size_t)img * A.nchunks;
+
+    const int wi = chunk * 256 + tid;
+    const bool valid = wi < A.nwords;
+    const int y = valid ? wi / A.wpr : 0, k = valid ? wi - y * A.wpr : 0;
+    const unsigned v = valid ? ccl_word(bits, y, k, A) : 0u;
+    const int base = y * A.w + k * 32;
+    const unsigned starts = v & ~(v << 1);
+
+    // which of this word's runs are roots (merge has completed: a root is a node that is its own parent)
+    unsigned roots = 0;
+    for (unsigned s = starts; s;) {
+        const int b = __ffs(s) - 1; s &= s - 1;
+        if (parent[base + b] == base + b) roots |= 1u << b;
+    }
+    const int c = __popc(roots);
     int incl = c;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += v;
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
     }
     if (lane == 31) wsum[wid] = incl;
     __syncthreads();
-    int base = blockcount[blockIdx.x];
-    for (int i = 0; i < wid; i++) base += wsum[i];
-    int run = base + incl - c;
-    if (wi >= nwords) return;
-    wordrank[wi] = run;
-    const int y = wi / wpr, k = wi - y * wpr;
-    while (r) {
-        int b = __ffs(r) - 1; r &= r - 1;
-        if (run < cap) {
+    int before = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const int t = wsum[i]; if (i < wid) before += t; total += t; }
+
+    // publish this chunk's root count, then add up the counts of all chunks before it (warp 0, 32 at a time)
+    if (wid == 0) {
+        if (lane == 0) st_release(reinterpret_cast<int *>(state + chunk), total + 1);
+        int sum = 0;
+        for (int j = lane; j < chunk; j += 32) {
+            int sv;
+            while ((sv = ld_acquire(reinterpret_cast<const int *>(state + j))) == 0) { }
+            sum += sv - 1;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        if (lane == 0) {
+            s_prefix = sum;
+            if (chunk == A.nchunks - 1) A.ncomp[img] = sum + total;
+        }
+    }
+    __syncthreads();
+    int run = s_prefix + before + incl - c;            // rank of this word's first root
+
+    // roots: table row, then the rank goes into the root's forest slot as ~rank (< 0) for the whole component to find
+    for (unsigned r = roots; r;) {
+        const int b = __ffs(r) - 1; r &= r - 1;
+        if (run < A.cap) {
             CompRaw cr;
-            cr.label = run + 1; cr.first_index = y * w + k * 32 + b;
-            cr.xmin = INT_MAX; cr.ymin = INT_MAX; cr.xmax = -1; cr.ymax = -1; cr.area = 0; cr.external = 0;
+            cr.label = run + 1; cr.first_index = base + b;
+            cr.xmin = INT_MAX; cr.ymin = INT_MAX; cr.xmax = -1; cr.ymax = -1; cr.area = 0;
+            cr.external = 1;                           // provisional; nested components are found by the background pass
             comp[run] = cr;
         }
+        st_release(parent + base + b, ~run);
         run++;
     }
-}
+    __syncthreads();
 
-template <bool LABELS>       // LABELS = false: component table only (no 32-register label row per thread)
-__global__ void __launch_bounds__(256)
-ccl_label_kernel(const unsigned *__restrict__ bits, const int *__restrict__ parent, const uint8_t *__restrict__ outer,
-                 const unsigned *__restrict__ rootbits, const int *__restrict__ wordrank, CompRaw *comp, int cap,
-                 int *__restrict__ labels, int w, int h, int wpr, size_t img_px, size_t img_words)
-{
-    pdl_entry();
-    int wi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (wi >= h * wpr) return;
-    bits += blockIdx.y * img_words; parent += blockIdx.y * img_px; outer += blockIdx.y * img_px;
-    rootbits += blockIdx.y * img_words; wordrank += blockIdx.y * img_words; comp += blockIdx.y * (size_t)cap;
-    if (LABELS) labels += blockIdx.y * img_px;
-    int y = wi / wpr, k = wi - y * wpr;
-    unsigned v = bits[wi];
-    int base = y * w + k * 32;
-    int nvalid = min(32, w - k * 32);
+    // every run: chase the chain to the root's published rank (a root that is still its own parent belongs to a chunk
+    // whose CTA has not got that far yet: it holds a smaller ticket, so it is running)
     int lab[LABELS ? 32 : 1];
     if (LABELS) {
 #pragma unroll
         for (int i = 0; i < 32; i++) lab[i] = 0;
     }
-    unsigned s = v & ~(v << 1);
-    while (s) {
-        int b = __ffs(s) - 1; s &= s - 1;
-        int p = base + b;
-        int r = parent[p];
-        int ry = r / w, rx = r - ry * w;
-        int rwi = ry * wpr + (rx >> 5);
-        int rank = wordrank[rwi] + __popc(rootbits[rwi] & ((rx & 31) ? (0xffffffffu >> (32 - (rx & 31))) : 0u));
-        unsigned rest = ~(v >> b);
-        int len = rest ? __ffs(rest) - 1 : 32 - b;
+    for (unsigned s = starts; s;) {
+        const int b = __ffs(s) - 1; s &= s - 1;
+        int cur = base + b;
+        int q = ld_acquire(parent + cur);
+        while (q >= 0) {
+            if (q != cur) cur = q;
+            q = ld_acquire(parent + cur);
+        }
+        const int rank = ~q;
+        const unsigned rest = ~(v >> b);
+        const int len = rest ? __ffs(rest) - 1 : 32 - b;
         if (LABELS) {
 #pragma unroll
             for (int i = 0; i < 32; i++)
                 if (i >= b && i < b + len) lab[i] = rank + 1;
         }
-        if (rank < cap) {
-            CompRaw *c = comp + rank;
-            int x0 = k * 32 + b;
-            atomicMin(&c->xmin, x0); atomicMax(&c->xmax, x0 + len - 1);
-            atomicMin(&c->ymin, y); atomicMax(&c->ymax, y);
-            atomicAdd(&c->area, len);
-            if (r == p) c->external = 1;           // provisional; nested components are found by the bg pass
+        if (rank < A.cap) {
+            CompRaw *cp = comp + rank;
+            const int x0 = k * 32 + b;
+            atomicMin(&cp->xmin, x0); atomicMax(&cp->xmax, x0 + len - 1);
+            atomicMin(&cp->ymin, y); atomicMax(&cp->ymax, y);
+            atomicAdd(&cp->area, len);
         }
     }
-    if (LABELS) {
-        int *o = labels + base;
+    if (LABELS && valid) {
+        int *o = A.labels + img * A.img_px + base;
+        const int nvalid = min(32, A.w - k * 32);
         if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
             for (int i = 0; i < 8; i++)
@@ -389,64 +346,124 @@ ccl_label_kernel(const unsigned *__restrict__ bits, const int *__restrict__ pare
     }
 }
 
-// Does any component's bounding box lie strictly inside another's?  (Necessary for a component to sit in a
-// hole of another one.)  grid = (16 tiles of 256 components, images); the j-loop runs over shared-memory tiles.
-// More than 4096 components: not worth checking, run the bg pass.  need_bg[] was zeroed by ccl_pack_kernel.
+// ---- launch 4: RETR_EXTERNAL (cooperative: grid-wide barriers between the phases) ---------------------------------------
 __global__ void __launch_bounds__(256)
-ccl_nest_kernel(const CompRaw *__restrict__ comp, const int *__restrict__ ncomp, int cap, int *__restrict__ need_bg)
+ccl_background_kernel(const __grid_constant__ CclArgs A)
 {
     pdl_entry();
+    cg::grid_group grid = cg::this_grid();
     __shared__ int4 box[256];
-    const int img = blockIdx.y;
-    const int n = ncomp[img];
-    if (n > 4096 || n > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) need_bg[img] = 1; return; }
-    if ((int)(blockIdx.x * 256) >= n) return;
-    const CompRaw *c = comp + (size_t)img * cap;
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-    if (i < n) { x0 = c[i].xmin; y0 = c[i].ymin; x1 = c[i].xmax; y1 = c[i].ymax; }
-    bool inside = false;
-    for (int t0 = 0; t0 < n; t0 += 256) {
-        const int j = t0 + threadIdx.x;
-        box[threadIdx.x] = j < n ? make_int4(c[j].xmin, c[j].ymin, c[j].xmax, c[j].ymax) : make_int4(1 << 30, 1 << 30, -1, -1);
-        __syncthreads();
-        if (i < n) {
+    const int tid = threadIdx.x;
+    const size_t gtid = (size_t)blockIdx.x * 256 + tid, gsize = (size_t)gridDim.x * 256;
+    // the finish kernel has completed: its look-back state goes back to zero for the next call
+    for (size_t i = gtid; i < (size_t)A.nimages * A.nchunks; i += gsize) A.chunkstate[i] = 0u;
+    for (size_t i = gtid; i < (size_t)A.nimages; i += gsize) A.ticket[i] = 0;
+
+    // phase 0: does any component's bounding box lie strictly inside another's?  (Necessary for a component to sit in a
+    // hole of another one.)  Work item = (image, tile of 256 components); more than 4096 components: not worth checking.
+    if (A.force_bg) {
+        for (size_t i = gtid; i < (size_t)A.nimages; i += gsize) A.need_bg[i] = 1;
+    } else {
+        for (int item = blockIdx.x; item < A.nimages * 16; item += gridDim.x) {
+            const int img = item >> 4, tile = item & 15;
+            const int n = A.ncomp[img];
+            if (n > 4096 || n > A.cap) { if (tile == 0 && tid == 0) A.need_bg[img] = 1; continue; }
+            if (tile * 256 >= n) continue;
+            const CompRaw *c = A.comp + (size_t)img * A.cap;
+            const int i = tile * 256 + tid;
+            int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+            if (i < n) { x0 = c[i].xmin; y0 = c[i].ymin; x1 = c[i].xmax; y1 = c[i].ymax; }
+            bool inside = false;
+            for (int t0 = 0; t0 < n; t0 += 256) {
+                const int j = t0 + tid;
+                box[tid] = j < n ? make_int4(c[j].xmin, c[j].ymin, c[j].xmax, c[j].ymax) : make_int4(1 << 30, 1 << 30, -1, -1);
+                __syncthreads();
+                if (i < n) {
 #pragma unroll 8
-            for (int q = 0; q < 256; q++) {
-                const int4 b = box[q];
-                inside |= (b.x < x0) & (b.y < y0) & (b.z > x1) & (b.w > y1);
+                    for (int q = 0; q < 256; q++) {
+                        const int4 b = box[q];
+                        inside |= (b.x < x0) & (b.y < y0) & (b.z > x1) & (b.w > y1);
+                    }
+                }
+                __syncthreads();
+            }
+            if (inside) A.need_bg[img] = 1;
+        }
+    }
+    grid.sync();
+    int any = 0;
+    for (int i = tid; i < A.nimages; i += 256) any |= A.need_bg[i];
+    if (!__syncthreads_or(any)) return;              // the same answer in every CTA: typical masks end here
+
+    // phase 1: background runs of the flagged images become nodes
+    for (int img = 0; img < A.nimages; img++) {
+        if (!A.need_bg[img]) continue;
+        const unsigned *bits = A.bits + img * A.img_words;
+        int *parent = A.parent + img * A.img_px;
+        uint8_t *outer = A.outer + img * A.img_px;
+        for (size_t wi = gtid; wi < (size_t)A.nwords; wi += gsize) {
+            const int y = (int)wi / A.wpr, k = (int)wi - y * A.wpr;
+            const unsigned vb = ~ccl_word(bits, y, k, A) & in_mask(k, A.w, A.wpr);
+            const int base = y * A.w + k * 32;
+            for (unsigned s = vb & ~(vb << 1); s;) {
+                const int b = __ffs(s) - 1; s &= s - 1;
+                parent[base + b] = base + b;
+                outer[base + b] = 0;
             }
         }
-        __syncthreads();
     }
-    if (inside) need_bg[img] = 1;
-}
-
-// After the bg pass: a component is external iff the background region left of its first pixel is outer.
-__global__ void __launch_bounds__(256)
-ccl_resolve_external_kernel(const unsigned *__restrict__ bits, const int *__restrict__ parent,
-                            const uint8_t *__restrict__ outer, CompRaw *comp, const int *__restrict__ ncomp, int cap,
-                            const int *__restrict__ need_bg, int w, int wpr, size_t img_px, size_t img_words)
-{
-    pdl_entry();
-    const int img = blockIdx.y;
-    if (!need_bg[img]) return;
-    const int n = min(ncomp[img], cap);
-    bits += img * img_words; parent += img * img_px; outer += img * img_px;
-    // the component count is only known on the device: a small grid strides over the table
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        CompRaw *c = comp + (size_t)img * cap + i;
-        const int r = c->first_index;
-        const int ry = r / w, rx = r - ry * w;
-        int ext = 1;
-        if (rx > 0) {
-            const int lk = (rx - 1) >> 5, lb = (rx - 1) & 31;
-            const unsigned lv = ~bits[ry * wpr + lk] & in_mask(lk, w, wpr);
-            const int node = ry * w + lk * 32 + run_start(lv, lb);
-            ext = outer[parent[node]];
+    grid.sync();
+    // phase 2: 4-connected merge
+    for (int img = 0; img < A.nimages; img++) {
+        if (!A.need_bg[img]) continue;
+        for (size_t wi = gtid; wi < (size_t)A.nwords; wi += gsize)
+            merge_word<true>(A, A.bits + img * A.img_words, A.parent + img * A.img_px, (int)wi);
+    }
+    grid.sync();
+    // phase 3: flatten; regions that touch the image frame are "outer"
+    for (int img = 0; img < A.nimages; img++) {
+        if (!A.need_bg[img]) continue;
+        const unsigned *bits = A.bits + img * A.img_words;
+        int *parent = A.parent + img * A.img_px;
+        uint8_t *outer = A.outer + img * A.img_px;
+        for (size_t wi = gtid; wi < (size_t)A.nwords; wi += gsize) {
+            const int y = (int)wi / A.wpr, k = (int)wi - y * A.wpr;
+            const unsigned vb = ~ccl_word(bits, y, k, A) & in_mask(k, A.w, A.wpr);
+            const int base = y * A.w + k * 32;
+            const bool edge_row = (y == 0 || y == A.h - 1);
+            for (unsigned s = vb & ~(vb << 1); s;) {
+                const int b = __ffs(s) - 1; s &= s - 1;
+                const int r = find_root(parent, base + b);
+                parent[base + b] = r;
+                const unsigned rest = ~(vb >> b);
+                const int len = rest ? __ffs(rest) - 1 : 32 - b;
+                if (edge_row || (k == 0 && b == 0) || (k * 32 + b + len - 1 == A.w - 1)) outer[r] = 1;
+            }
         }
-        c->external = ext;
     }
+    grid.sync();
+    // phase 4: a component is external iff the background region left of its first pixel is outer
+    for (int img = 0; img < A.nimages; img++) {
+        if (!A.need_bg[img]) continue;
+        const unsigned *bits = A.bits + img * A.img_words;
+        const int *parent = A.parent + img * A.img_px;
+        const uint8_t *outer = A.outer + img * A.img_px;
+        const int n = min(A.ncomp[img], A.cap);
+        for (size_t i = gtid; i < (size_t)n; i += gsize) {
+            CompRaw *c = A.comp + (size_t)img * A.cap + i;
+            const int r = c->first_index;
+            const int ry = r / A.w, rx = r - ry * A.w;
+            int ext = 1;
+            if (rx > 0) {
+                const int lk = (rx - 1) >> 5, lb = (rx - 1) & 31;
+                const unsigned lv = ~ccl_word(bits, ry, lk, A) & in_mask(lk, A.w, A.wpr);
+                ext = outer[parent[ry * A.w + lk * 32 + run_start(lv, lb)]];
+            }
+            c->external = ext;
+        }
+    }
+    grid.sync();
+    for (size_t i = gtid; i < (size_t)A.nimages; i += gsize) A.need_bg[i] = 0;       // all zero again between calls
 }
 
 // cvMoments(ROI, binary=0): pixel-value weighted raw moments, ROI-relative coordinates.
@@ -488,34 +505,110 @@ rect_moments_kernel(const uint8_t *__restrict__ mask, int w, int h, const int *_
     }
 }
 
+// The same sums from a bit-packed {0,255} mask (the pipeline keeps no byte mask): every set bit weighs 255.
+__global__ void __launch_bounds__(256)
+rect_moments_bits_kernel(const unsigned *__restrict__ bits, int w, int h, int wpr, const int *__restrict__ rects,
+                         unsigned long long *out)
+{
+    pdl_entry();
+    const int ri = blockIdx.x;
+    const int rx = rects[4 * ri], ry = rects[4 * ri + 1], rw = rects[4 * ri + 2], rh = rects[4 * ri + 3];
+    const int xa = max(rx, 0), xb = min(rx + rw, w);             // [xa, xb) inside the image
+    unsigned long long m[6] = {0, 0, 0, 0, 0, 0};
+    if (xa < xb) {
+        const int k0 = xa >> 5, k1 = (xb - 1) >> 5;
+        for (int yy = blockIdx.y; yy < rh; yy += gridDim.y) {
+            const int y = ry + yy;
+            if (y < 0 || y >= h) continue;
+            unsigned long long r0 = 0, r1 = 0, r2 = 0;
+            for (int k = k0 + (int)threadIdx.x; k <= k1; k += blockDim.x) {
+                unsigned v = bits[(size_t)y * wpr + k];
+                if (k == k0) v &= 0xffffffffu << (xa & 31);
+                if (k == k1 && (xb & 31)) v &= 0xffffffffu >> (32 - (xb & 31));
+                while (v) {
+                    const int b = __ffs(v) - 1; v &= v - 1;
+                    const unsigned long long xx = (unsigned long long)(k * 32 + b - rx);
+                    r0 += 255ull; r1 += 255ull * xx; r2 += 255ull * xx * xx;
+                }
+            }
+            m[0] += r0; m[1] += r1; m[2] += r0 * yy; m[3] += r2; m[4] += r0 * (unsigned long long)yy * yy; m[5] += r1 * yy;
+        }
+    }
+    __shared__ unsigned long long red[6][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        unsigned long long v = m[i];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) red[i][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        unsigned long long v = 0;
+        for (int i = 0; i < 8; i++) v += red[threadIdx.x][i];
+        if (v) atomicAdd(out + 6 * ri + threadIdx.x, v);
+    }
+}
+
+// launches 2-4 (and the node init when the producer of the words did not do it)
+int ccl_label_bits(bgsb_ccl *c, const unsigned *d_bits, bool parents_ready, int w, int h, int nimages, int zero_border,
+                   int32_t *d_labels, cudaStream_t stream)
+{
+    BGSB_REQUIRE(c && d_bits, "null");
+    BGSB_REQUIRE(w > 0 && h > 0 && w <= c->max_w && h <= c->max_h, "image larger than the labeller was created for");
+    BGSB_REQUIRE(nimages >= 1 && nimages <= c->max_images, "more images than the labeller was created for");
+    BGSB_CUDA(cudaSetDevice(c->device));
+    CclArgs A;
+    memset(&A, 0, sizeof(A));
+    A.bits = d_bits; A.parent = c->d_parent; A.outer = c->d_outer; A.comp = c->d_comp; A.chunkstate = c->d_chunkstate;
+    A.ticket = c->d_ticket; A.ncomp = c->d_ncomp; A.need_bg = c->d_need_bg; A.labels = d_labels;
+    A.w = w; A.h = h; A.wpr = (w + 31) / 32; A.nwords = A.wpr * h; A.nchunks = (A.nwords + 255) / 256;
+    A.nimages = nimages; A.cap = c->cap; A.zero_border = zero_border; A.force_bg = c->force_bg;
+    A.img_px = (size_t)w * h; A.img_words = (size_t)A.nwords;      // dense per-image strides for this geometry
+    if (c->dirty) {                                 // an earlier call failed between the launches
+        BGSB_CUDA(cudaMemsetAsync(c->d_chunkstate, 0, (size_t)c->max_images * c->max_chunks * sizeof(unsigned), stream));
+        BGSB_CUDA(cudaMemsetAsync(c->d_ticket, 0, (size_t)c->max_images * sizeof(int), stream));
+        BGSB_CUDA(cudaMemsetAsync(c->d_need_bg, 0, (size_t)c->max_images * sizeof(int), stream));
+    }
+    c->dirty = true;
+    const dim3 grid(A.nchunks, nimages), block(256);
+    if (!parents_ready) {
+        launch_pdl(ccl_init_kernel, grid, block, 0, stream, A);
+        BGSB_LAUNCH_CHECK();
+    }
+    launch_pdl(ccl_merge_kernel, grid, block, 0, stream, A);
+    BGSB_LAUNCH_CHECK();
+    if (d_labels) launch_pdl(ccl_finish_kernel<true>, grid, block, 0, stream, A);
+    else launch_pdl(ccl_finish_kernel<false>, grid, block, 0, stream, A);
+    BGSB_LAUNCH_CHECK();
+    {
+        // cooperative: every CTA must be resident at once; the grid strides over the work
+        if (c->coop_ctas <= 0) {
+            int per_sm = 0;
+            BGSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccl_background_kernel, 256, 0));
+            c->coop_ctas = std::max(1, per_sm) * sm_count(c->device);
+        }
+        const long long want = std::max<long long>((long long)nimages * 16, (long long)nimages * A.nchunks);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)std::min<long long>(c->coop_ctas, std::max<long long>(want, 1)));
+        cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, ccl_background_kernel, A);
+        if (e != cudaSuccess && g_launch_status == cudaSuccess) g_launch_status = e;
+        BGSB_LAUNCH_CHECK();
+    }
+    c->dirty = false;
+    c->w = w; c->h = h; c->nimages = nimages; c->last_stream = stream; c->labelled = true;
+    c->last_mask = nullptr; c->last_bits = d_bits;
+    return BGSB_OK;
+}
+
 }  // namespace bgsb
 
 using namespace bgsb;
-
-struct bgsb_ccl {
-    int device = 0, max_w = 0, max_h = 0, max_images = 1;
-    int w = 0, h = 0, nimages = 0;
-    size_t img_px = 0, img_words = 0;      // per-image strides of the work buffers
-    int max_blocks = 0;
-    unsigned *d_bits = nullptr, *d_rootbits = nullptr;
-    int *d_parent = nullptr, *d_wordrank = nullptr, *d_ncomp = nullptr, *d_blockcount = nullptr, *d_need_bg = nullptr;
-    int force_bg = 0;                       // 1: always run the background pass (A/B and tests)
-    uint8_t *d_outer = nullptr, *d_mask_own = nullptr;
-    int32_t *d_labels_own = nullptr;
-    CompRaw *d_comp = nullptr;
-    int cap = 0;
-    const uint8_t *last_mask = nullptr;
-    cudaStream_t last_stream = nullptr;
-    cudaStream_t own_stream = nullptr;
-    bool labelled = false;
-    // host round trips of the per-frame path: pinned staging (count + the first PIN_COMPS table rows, or moments) and
-    // device buffers for the rectangle queries that live as long as the context (no allocator calls per frame)
-    static constexpr int PIN_COMPS = 2048;
-    uint8_t *h_pin = nullptr;               // 64 + PIN_COMPS * sizeof(CompRaw) bytes
-    int *d_rects = nullptr;
-    unsigned long long *d_mom = nullptr;
-    int rect_cap = 0;
-};
 
 extern "C" {
 
@@ -529,22 +622,24 @@ int bgsb_ccl_create_batch(bgsb_ccl **out, int device, int max_w, int max_h, int 
     c->device = device; c->max_w = max_w; c->max_h = max_h; c->max_images = max_images;
     c->img_px = (size_t)max_w * max_h;
     c->img_words = (size_t)((max_w + 31) / 32) * max_h;
-    c->max_blocks = (int)((c->img_words + 255) / 256);
+    c->max_chunks = (int)((c->img_words + 255) / 256);
     // the most 8-connected components an image can hold: isolated pixels on every second row and column
     c->cap = ((max_w + 1) / 2) * ((max_h + 1) / 2) + 64;
     const size_t N = (size_t)max_images;
     cudaError_t e = cudaSuccess;
     auto A = [&](void **p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     A((void **)&c->d_bits, N * c->img_words * 4);
-    A((void **)&c->d_rootbits, N * c->img_words * 4);
-    A((void **)&c->d_wordrank, N * c->img_words * 4);
     A((void **)&c->d_parent, N * c->img_px * 4);
     A((void **)&c->d_outer, N * c->img_px);
     A((void **)&c->d_mask_own, c->img_px);
     A((void **)&c->d_comp, N * (size_t)c->cap * sizeof(CompRaw));
     A((void **)&c->d_ncomp, N * sizeof(int));
-    A((void **)&c->d_blockcount, N * (size_t)(c->max_blocks + 1) * sizeof(int));
+    A((void **)&c->d_chunkstate, N * (size_t)c->max_chunks * sizeof(unsigned));
+    A((void **)&c->d_ticket, N * sizeof(int));
     A((void **)&c->d_need_bg, N * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_chunkstate, 0, N * (size_t)c->max_chunks * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(c->d_ticket, 0, N * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_need_bg, 0, N * sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         set_error("bgsb_ccl_create: %s", cudaGetErrorString(e));
@@ -565,9 +660,9 @@ void bgsb_ccl_destroy(bgsb_ccl *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    cudaFree(c->d_bits); cudaFree(c->d_rootbits); cudaFree(c->d_wordrank); cudaFree(c->d_parent);
+    cudaFree(c->d_bits); cudaFree(c->d_parent);
     cudaFree(c->d_outer); cudaFree(c->d_mask_own); cudaFree(c->d_comp); cudaFree(c->d_ncomp);
-    cudaFree(c->d_blockcount); cudaFree(c->d_need_bg); cudaFree(c->d_labels_own);
+    cudaFree(c->d_chunkstate); cudaFree(c->d_ticket); cudaFree(c->d_need_bg); cudaFree(c->d_labels_own);
     cudaFree(c->d_rects); cudaFree(c->d_mom);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -583,59 +678,14 @@ int bgsb_ccl_label_batch_dev(bgsb_ccl *c, const uint8_t *d_masks, int w, int h, 
     BGSB_CUDA(cudaSetDevice(c->device));
     cudaStream_t stream = (cudaStream_t)stream_;
     const int wpr = (w + 31) / 32, nwords = wpr * h;
-    const int threads = 256, nblocks = (nwords + threads - 1) / threads;
-    const size_t ipx = (size_t)w * h, iw = (size_t)nwords;       // dense per-image strides for this geometry
-    dim3 grid(nblocks, nimages);
-    launch_pdl(ccl_pack_kernel, dim3(grid), dim3(threads), 0, stream, d_masks, c->d_bits, c->d_parent, c->d_blockcount, c->d_need_bg,
-               nblocks, w, h, wpr, zero_border, ipx, iw);
+    const dim3 grid((nwords + 255) / 256, nimages);
+    // launch 1: bytes -> bits with the frame already cleared, nodes created (the later launches then run with zero_border = 0)
+    launch_pdl(ccl_pack_kernel, grid, dim3(256), 0, stream, d_masks, c->d_bits, c->d_parent, w, h, wpr, zero_border,
+               (size_t)w * h, (size_t)nwords);
     BGSB_LAUNCH_CHECK();
-    launch_pdl(ccl_merge_kernel<false>, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_need_bg, w, h, wpr, ipx, iw);
-    BGSB_LAUNCH_CHECK();
-    launch_pdl(ccl_flatten_kernel<false>, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_rootbits,
-                                                           c->d_blockcount, c->d_need_bg, w, h, wpr, ipx, iw, nblocks);
-    BGSB_LAUNCH_CHECK();
-    launch_pdl(ccl_blockscan_kernel, dim3(nimages), dim3(1024), 0, stream, c->d_blockcount, nblocks, c->d_ncomp);
-    BGSB_LAUNCH_CHECK();
-    launch_pdl(ccl_rank_kernel, dim3(grid), dim3(threads), 0, stream, c->d_rootbits, c->d_wordrank, c->d_blockcount, c->d_comp, c->cap, w, h, wpr,
-                                                  iw, nblocks);
-    BGSB_LAUNCH_CHECK();
-    if (d_labels)
-        launch_pdl(ccl_label_kernel<true>, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_rootbits,
-                   c->d_wordrank, c->d_comp, c->cap, d_labels, w, h, wpr, ipx, iw);
-    else
-        launch_pdl(ccl_label_kernel<false>, dim3(grid), dim3(threads), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_rootbits,
-                   c->d_wordrank, c->d_comp, c->cap, d_labels, w, h, wpr, ipx, iw);
-    BGSB_LAUNCH_CHECK();
-    // RETR_EXTERNAL: background pass only for images where a bounding box lies strictly inside another
-    if (c->force_bg) {
-        std::vector<int> ones(nimages, 1);
-        BGSB_CUDA(cudaMemcpyAsync(c->d_need_bg, ones.data(), nimages * sizeof(int), cudaMemcpyHostToDevice, stream));
-        BGSB_CUDA(cudaStreamSynchronize(stream));
-    } else {
-        launch_pdl(ccl_nest_kernel, dim3(dim3(16, nimages)), dim3(256), 0, stream, c->d_comp, c->d_ncomp, c->cap, c->d_need_bg);
-        BGSB_LAUNCH_CHECK();
-    }
-    // The background pass exits at once for images that do not need it.  In a batch fat CTAs keep that exit cheap
-    // (4x fewer CTAs to retire); a single image keeps 256-thread CTAs so that a pass that IS taken fills the SMs.
-    const int bthreads = nimages >= 8 ? 1024 : 256;
-    const dim3 bgrid((nwords + bthreads - 1) / bthreads, nimages);
-    launch_pdl(ccl_init_kernel<true>, bgrid, dim3(bthreads), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_blockcount, c->d_need_bg,
-                                                       w, h, wpr, ipx, iw, nblocks);
-    BGSB_LAUNCH_CHECK();
-    launch_pdl(ccl_merge_kernel<true>, bgrid, dim3(bthreads), 0, stream, c->d_bits, c->d_parent, c->d_need_bg, w, h, wpr, ipx, iw);
-    BGSB_LAUNCH_CHECK();
-    launch_pdl(ccl_flatten_kernel<true>, bgrid, dim3(bthreads), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_rootbits,
-                                                          c->d_blockcount, c->d_need_bg, w, h, wpr, ipx, iw, nblocks);
-    BGSB_LAUNCH_CHECK();
-    {
-        // at most cap components per image; the kernel exits early past the real count
-        const int maxc = std::min(c->cap, ((w + 1) / 2) * ((h + 1) / 2));
-        dim3 rgrid(std::min((maxc + 255) / 256, 16), nimages);
-        launch_pdl(ccl_resolve_external_kernel, dim3(rgrid), dim3(256), 0, stream, c->d_bits, c->d_parent, c->d_outer, c->d_comp, c->d_ncomp,
-                                                               c->cap, c->d_need_bg, w, wpr, ipx, iw);
-        BGSB_LAUNCH_CHECK();
-    }
-    c->w = w; c->h = h; c->nimages = nimages; c->last_mask = d_masks; c->last_stream = stream; c->labelled = true;
+    int rc = ccl_label_bits(c, c->d_bits, true, w, h, nimages, 0, d_labels, stream);
+    if (rc) return rc;
+    c->last_mask = d_masks; c->last_bits = nullptr;
     return BGSB_OK;
 }
 
@@ -690,10 +740,11 @@ int bgsb_ccl_components(bgsb_ccl *c, bgsb_component *out, int capacity, int *n)
     return bgsb_ccl_components_of(c, 0, out, capacity, n);
 }
 
-int bgsb_ccl_rect_moments(bgsb_ccl *c, const int32_t *rects, int nrects, uint64_t *out)
+int bgsb_ccl_rect_moments_of(bgsb_ccl *c, int image, const int32_t *rects, int nrects, uint64_t *out)
 {
     BGSB_REQUIRE(c && out && (rects || nrects == 0), "null");
     if (!c->labelled) { set_error("bgsb_ccl_rect_moments: nothing labelled yet"); return BGSB_ERR_STATE; }
+    BGSB_REQUIRE(image >= 0 && image < c->nimages, "image index");
     if (nrects == 0) return BGSB_OK;
     BGSB_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->last_stream;
@@ -710,13 +761,25 @@ int bgsb_ccl_rect_moments(bgsb_ccl *c, const int32_t *rects, int nrects, uint64_
     BGSB_CUDA(cudaMemcpyAsync(c->d_rects, rects, (size_t)nrects * 16, cudaMemcpyHostToDevice, st));
     BGSB_CUDA(cudaMemsetAsync(c->d_mom, 0, (size_t)nrects * 48, st));
     dim3 grid(nrects, 16);
-    launch_pdl(rect_moments_kernel, dim3(grid), dim3(256), 0, st, c->last_mask, c->w, c->h, c->d_rects, c->d_mom);
+    if (c->last_mask)
+        launch_pdl(rect_moments_kernel, dim3(grid), dim3(256), 0, st, c->last_mask + (size_t)image * c->w * c->h, c->w, c->h,
+                   c->d_rects, c->d_mom);
+    else {
+        const int wpr = (c->w + 31) / 32;
+        launch_pdl(rect_moments_bits_kernel, dim3(grid), dim3(256), 0, st, c->last_bits + (size_t)image * wpr * c->h, c->w, c->h,
+                   wpr, c->d_rects, c->d_mom);
+    }
     BGSB_LAUNCH_CHECK();
     BGSB_CUDA(cudaMemcpyAsync(staged ? (void *)(c->h_pin + 64) : (void *)out, c->d_mom, (size_t)nrects * 48,
                               cudaMemcpyDeviceToHost, st));
     BGSB_CUDA(cudaStreamSynchronize(st));
     if (staged) memcpy(out, c->h_pin + 64, (size_t)nrects * 48);
     return BGSB_OK;
+}
+
+int bgsb_ccl_rect_moments(bgsb_ccl *c, const int32_t *rects, int nrects, uint64_t *out)
+{
+    return bgsb_ccl_rect_moments_of(c, 0, rects, nrects, out);
 }
 
 int bgsb_ccl_label(bgsb_ccl *c, const uint8_t *mask, int w, int h, size_t stride, int zero_border, int32_t *labels,

@@ -68,6 +68,12 @@ struct Mog2Launch {
     float *state;            // [S][pstride/64 tiles][25][64]  (mog2_tile_off)
     uint8_t *nmodes;         // [S][pstride]
     size_t pstride;          // pixels per stream rounded up to whole tiles (64)
+    // T == 1 production kernel only: the mask as bit-packed rows [S][h][wpr] (bit i of word k = pixel 32k+i), nullable.
+    // The words must be zero on entry; the kernel sets the bits of the pixels whose mask byte is > bit_thr.  With `bits`
+    // the byte mask `fg` may be null.
+    unsigned *bits;
+    size_t bits_stride;      // words per stream
+    int w, wpr, bit_thr;
     int npx, T;
     int bg_last_only;
     int fresh;               // 1: state is uninitialised -> treat nmodes as 0 (first frame after create/reset)
@@ -82,6 +88,18 @@ struct Mog2Launch {
     float prune[MOG2_TMAX];
 };
 int launch_mog2(const Mog2Launch &L, int nstreams, int variant, cudaStream_t stream);
+
+}  // namespace bgsb
+struct bgsb_ctx;
+namespace bgsb {
+// One frame per stream of the context's group, device buffers (what bgsb_process_dev does), for the pipeline: a MOG2
+// context on its production kernel can emit the mask bit-packed into d_bits (zeroed by the caller; see Mog2Launch) and
+// then needs no byte mask (d_fg may be null); every other context needs d_fg and leaves d_bits alone (*packed = 0).
+int ctx_process_frame(bgsb_ctx *c, const uint8_t *d_frames, int w, int h, uint8_t *d_fg, uint8_t *d_bg, unsigned *d_bits,
+                      int bit_thr, int *packed, int *fg_valid, int *bg_valid, cudaStream_t stream);
+bool ctx_can_pack(const bgsb_ctx *c);
+int ctx_nstreams(const bgsb_ctx *c);
+int ctx_device(const bgsb_ctx *c);
 
 // ---- DPZivkovicAGMMBGS (the reference's own adaptive GMM; state in the MOG2 tile layout, K <= 5) ----
 struct DpzLaunch {
@@ -99,6 +117,16 @@ int launch_dpz(const DpzLaunch &L, int nstreams, cudaStream_t stream);
 // ---- morphology -------------------------------------------------------------------------------
 int launch_morph_chain(const uint8_t *d_in, uint8_t *d_out, int w, int h, int nimages, const int *ops, int nops,
                        cudaStream_t stream);
+// Any mix of byte and bit-packed masks ([nimages][h][(w+31)/32] words, bit i of word k = pixel 32k+i).
+struct MorphIO {
+    const uint8_t *in_bytes;     // exactly one of in_bytes / in_bits
+    const unsigned *in_bits;
+    uint8_t *out_bytes;          // either or both outputs
+    unsigned *out_bits;
+    int *parent;                 // with out_bits: the labeller's forest [nimages][w*h]; the output runs become its nodes
+    int zero_border;             // ... after clearing the 1-px frame (nodes only; the stored words keep it)
+};
+int launch_morph_chain_io(const MorphIO &io, int w, int h, int nimages, const int *ops, int nops, cudaStream_t stream);
 
 // ---- synthetic video ----------------------------------------------------------------------------
 int launch_synth(uint8_t *d_frames, int nstreams, int T, int w, int h, int t0, uint32_t seed0,

@@ -13,7 +13,7 @@
 // is 3 shifted ANDs/ORs per word and per row), and unpacks the interior back to bytes.  HBM
 // traffic is one byte read and one byte written per pixel for the whole chain.
 #include <string.h>
-#include "common.cuh"
+#include "ccl_internal.h"
 #include "kernels.h"
 
 namespace bgsb {
@@ -65,14 +65,23 @@ __device__ __forceinline__ unsigned unpack4(unsigned nib)
 
 // Thread (tx, ty) = (tid & 63, tid >> 6) owns shared-memory column tx and rows ty, ty+4, ...: the column's
 // in-image masks are computed once, and no index is divided.
+// IN_BITS: the input is already bit-packed ([nimages][h][wpr] words, e.g. the MOG2 kernel's packed mask) -- the tile
+// load is one word per thread and row instead of 32 bytes.  Outputs (either or both): {0,255} bytes, and / or
+// bit-packed words; with `parent` the words' runs also become the labeller's union-find nodes (ccl_internal.h), which
+// saves the labeller's own first launch.
+template <bool IN_BITS>
 __global__ void __launch_bounds__(256)
-morph_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, int h, int wpr, MorphChain chain, int R)
+morph_kernel(const MorphIO io, int w, int h, int wpr, MorphChain chain, int R)
 {
     pdl_entry();
     __shared__ unsigned buf[2][MORPH_ROWS][MORPH_SW];
     const int img = blockIdx.z;
-    const size_t npx = (size_t)w * h;
-    in += img * npx; out += img * npx;
+    const size_t npx = (size_t)w * h, nwords = (size_t)wpr * h;
+    const uint8_t *in = IN_BITS ? nullptr : io.in_bytes + img * npx;
+    const unsigned *inb = IN_BITS ? io.in_bits + img * nwords : nullptr;
+    uint8_t *out = io.out_bytes ? io.out_bytes + img * npx : nullptr;
+    unsigned *outb = io.out_bits ? io.out_bits + img * nwords : nullptr;
+    int *parent = (io.parent && outb) ? io.parent + img * npx : nullptr;
     const int k0 = blockIdx.x * MORPH_TW - 1;          // word index of smem column 0 (halo)
     const int y0 = blockIdx.y * MORPH_TH - R;          // image row of smem row 0 (halo)
     const int rows = MORPH_TH + 2 * R;
@@ -88,23 +97,26 @@ morph_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, i
         return (1u << (w & 31)) - 1u;
     };
     const unsigned cm = colmask(k), cl = colmask(k - 1), cr = colmask(k + 1);
-    const bool vec = cm == 0xffffffffu && ((reinterpret_cast<uintptr_t>(in) | (size_t)w) & 15) == 0;   // 32 whole, aligned bytes
+    const bool vec = !IN_BITS && cm == 0xffffffffu && ((reinterpret_cast<uintptr_t>(in) | (size_t)w) & 15) == 0;   // 32 whole, aligned bytes
 
-    // ---- pack: bytes -> bits (bit i of word k = pixel 32k+i is set) ----
+    // ---- load: bytes -> bits (bit i of word k = pixel 32k+i is set), or the packed words as they are ----
     if (col_used) {
         for (int r = ty; r < rows; r += 4) {
             const int y = y0 + r;
             unsigned word = 0;
             if (y >= 0 && y < h && cm) {
-                const uint8_t *p = in + (size_t)y * w + (size_t)k * 32;
-                if (vec) {
-                    const uint4 *q = reinterpret_cast<const uint4 *>(p);
-                    const uint4 a = __ldg(q), b = __ldg(q + 1);
-                    const unsigned ws[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                    word = pack32(ws);
-                } else {
-                    const int nvalid = min(32, w - k * 32);
-                    for (int i = 0; i < nvalid; i++) word |= (p[i] ? 1u : 0u) << i;
+                if (IN_BITS) word = inb[(size_t)y * wpr + k] & cm;
+                else {
+                    const uint8_t *p = in + (size_t)y * w + (size_t)k * 32;
+                    if (vec) {
+                        const uint4 *q = reinterpret_cast<const uint4 *>(p);
+                        const uint4 a = __ldg(q), b = __ldg(q + 1);
+                        const unsigned ws[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                        word = pack32(ws);
+                    } else {
+                        const int nvalid = min(32, w - k * 32);
+                        for (int i = 0; i < nvalid; i++) word |= (p[i] ? 1u : 0u) << i;
+                    }
                 }
             }
             buf[0][r][c] = word;
@@ -153,42 +165,36 @@ morph_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int w, i
         }
     }
 
-    // ---- unpack the interior: bits -> {0,255} bytes ----
+    // ---- store the interior: packed words (+ labeller nodes) and / or {0,255} bytes ----
     if (c >= 1 && c < tw - 1) {
         for (int r = ty; r < MORPH_TH; r += 4) {
             const int y = blockIdx.y * MORPH_TH + r;
             if (y >= h) break;
             const unsigned word = buf[cur][r + R][c];
-            uint8_t *p = out + (size_t)y * w + (size_t)k * 32;
-            if (cm == 0xffffffffu && ((reinterpret_cast<uintptr_t>(out) | (size_t)w) & 15) == 0) {
-                uint4 *q = reinterpret_cast<uint4 *>(p);
-                q[0] = make_uint4(unpack4(word & 0xfu), unpack4((word >> 4) & 0xfu), unpack4((word >> 8) & 0xfu),
-                                  unpack4((word >> 12) & 0xfu));
-                q[1] = make_uint4(unpack4((word >> 16) & 0xfu), unpack4((word >> 20) & 0xfu), unpack4((word >> 24) & 0xfu),
-                                  unpack4(word >> 28));
-            } else {
-                const int nvalid = min(32, w - k * 32);
-                for (int i = 0; i < nvalid; i++) p[i] = ((word >> i) & 1u) ? 255 : 0;
+            if (outb) {
+                outb[(size_t)y * wpr + k] = word;
+                if (parent) ccl_init_word(parent, ccl_border(word, y, k, w, h, wpr, io.zero_border), y * w + k * 32);
+            }
+            if (out) {
+                uint8_t *p = out + (size_t)y * w + (size_t)k * 32;
+                if (cm == 0xffffffffu && ((reinterpret_cast<uintptr_t>(out) | (size_t)w) & 15) == 0) {
+                    uint4 *q = reinterpret_cast<uint4 *>(p);
+                    q[0] = make_uint4(unpack4(word & 0xfu), unpack4((word >> 4) & 0xfu), unpack4((word >> 8) & 0xfu),
+                                      unpack4((word >> 12) & 0xfu));
+                    q[1] = make_uint4(unpack4((word >> 16) & 0xfu), unpack4((word >> 20) & 0xfu), unpack4((word >> 24) & 0xfu),
+                                      unpack4(word >> 28));
+                } else {
+                    const int nvalid = min(32, w - k * 32);
+                    for (int i = 0; i < nvalid; i++) p[i] = ((word >> i) & 1u) ? 255 : 0;
+                }
             }
         }
     }
 }
 
-// plain byte copy with "non-zero -> 255"?  No: an empty chain is a no-op COPY (iterations = 0,
-// SURVEY A.5), values pass through unchanged.
-static int copy_mask(const uint8_t *in, uint8_t *out, size_t bytes, cudaStream_t stream)
+static int parse_chain(const int *ops, int nops, int (*items)[2], int &ni, int &total)
 {
-    if (in != out) BGSB_CUDA(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
-    return BGSB_OK;
-}
-
-int launch_morph_chain(const uint8_t *d_in, uint8_t *d_out, int w, int h, int nimages, const int *ops, int nops,
-                       cudaStream_t stream)
-{
-    // expand into passes of at most MORPH_RMAX total iterations per launch
-    struct Item { int op, iters; };
-    Item items[64];
-    int ni = 0, total = 0;
+    ni = 0; total = 0;
     for (int i = 0; i < nops; i++) {
         int op = ops[2 * i], it = ops[2 * i + 1];
         if (op != BGSB_MORPH_ERODE && op != BGSB_MORPH_DILATE) { set_error("morph: bad op %d", op); return BGSB_ERR_ARG; }
@@ -196,47 +202,82 @@ int launch_morph_chain(const uint8_t *d_in, uint8_t *d_out, int w, int h, int ni
         while (it > 0) {
             int take = it < MORPH_RMAX ? it : MORPH_RMAX;
             if (ni >= 64) { set_error("morph: chain too long"); return BGSB_ERR_ARG; }
-            items[ni++] = {op, take};
+            items[ni][0] = op; items[ni][1] = take; ni++;
             it -= take; total += take;
         }
     }
-    const size_t bytes = (size_t)w * h * nimages;
-    if (total == 0) return copy_mask(d_in, d_out, bytes, stream);
+    return BGSB_OK;
+}
 
+// The chain on any mix of byte / bit-packed inputs and outputs.  Passes of at most MORPH_RMAX total iterations share a
+// launch; between launches the mask stays bit-packed (1/8 of the byte traffic).  An empty chain still converts
+// (bytes != 0 -> set bits -> {0,255} bytes).
+int launch_morph_chain_io(const MorphIO &io_, int w, int h, int nimages, const int *ops, int nops, cudaStream_t stream)
+{
+    if ((io_.in_bytes == nullptr) == (io_.in_bits == nullptr)) { set_error("morph: exactly one input form"); return BGSB_ERR_ARG; }
+    if (!io_.out_bytes && !io_.out_bits) { set_error("morph: no output"); return BGSB_ERR_ARG; }
+    int items[64][2], ni = 0, total = 0;
+    int rc = parse_chain(ops, nops, items, ni, total);
+    if (rc) return rc;
     // group items into launches
-    int nlaunch = 0, lstart[64], lend[64];
+    int nlaunch = 0, lstart[65], lend[65];
     for (int i = 0; i < ni;) {
         int r = 0, j = i;
-        while (j < ni && r + items[j].iters <= MORPH_RMAX && j - i < 16) { r += items[j].iters; j++; }
+        while (j < ni && r + items[j][1] <= MORPH_RMAX && j - i < 16) { r += items[j][1]; j++; }
         lstart[nlaunch] = i; lend[nlaunch] = j; nlaunch++;
         i = j;
     }
-    // ping-pong through temporaries when more than one launch is needed or in == out
-    uint8_t *tmp[2] = {nullptr, nullptr};
-    const bool inplace = (d_in == d_out);
-    const int ntmp = (nlaunch > 2) ? 2 : ((nlaunch > 1 || inplace) ? 1 : 0);
-    for (int i = 0; i < ntmp; i++) BGSB_CUDA(cudaMallocAsync(&tmp[i], bytes, stream));
-
+    if (nlaunch == 0) { lstart[0] = lend[0] = 0; nlaunch = 1; }          // pure conversion
+    // a CTA reads a halo that another CTA may already have overwritten: in-place runs go through a packed temporary
+    const bool inplace = (io_.in_bytes && io_.in_bytes == io_.out_bytes) || (io_.in_bits && io_.in_bits == io_.out_bits);
+    if (inplace && nlaunch == 1 && lend[0] > lstart[0]) { lstart[1] = lend[1] = ni; nlaunch = 2; }
     const int wpr = (w + 31) / 32;
-    dim3 grid((wpr + MORPH_TW - 1) / MORPH_TW, (h + MORPH_TH - 1) / MORPH_TH, nimages);
-    const uint8_t *src = d_in;
+    const size_t tbytes = (size_t)wpr * h * nimages * sizeof(unsigned);
+    unsigned *tmp[2] = {nullptr, nullptr};
+    const int ntmp = nlaunch > 2 ? 2 : (nlaunch > 1 ? 1 : 0);
+    for (int i = 0; i < ntmp; i++) BGSB_CUDA(cudaMallocAsync(&tmp[i], tbytes, stream));
+    const dim3 grid((wpr + MORPH_TW - 1) / MORPH_TW, (h + MORPH_TH - 1) / MORPH_TH, nimages);
+    const unsigned *src_bits = nullptr;
     for (int l = 0; l < nlaunch; l++) {
-        const bool last = (l == nlaunch - 1);
-        uint8_t *dst = (last && src != d_out) ? d_out : ((src == tmp[0]) ? tmp[1] : tmp[0]);
+        const bool first = (l == 0), last = (l == nlaunch - 1);
+        MorphIO io;
+        memset(&io, 0, sizeof(io));
+        if (first) { io.in_bytes = io_.in_bytes; io.in_bits = io_.in_bits; }
+        else io.in_bits = src_bits;
+        if (last) { io.out_bytes = io_.out_bytes; io.out_bits = io_.out_bits; io.parent = io_.parent; io.zero_border = io_.zero_border; }
+        else io.out_bits = (src_bits == tmp[0]) ? tmp[1] : tmp[0];
         MorphChain ch;
         ch.n = 0;
         int R = 0;
         for (int i = lstart[l]; i < lend[l]; i++) {
-            ch.op[ch.n] = (signed char)items[i].op; ch.iters[ch.n] = (signed char)items[i].iters; ch.n++;
-            R += items[i].iters;
+            ch.op[ch.n] = (signed char)items[i][0]; ch.iters[ch.n] = (signed char)items[i][1]; ch.n++;
+            R += items[i][1];
         }
-        launch_pdl(morph_kernel, dim3(grid), dim3(256), 0, stream, src, dst, w, h, wpr, ch, R);
+        if (io.in_bits) launch_pdl(morph_kernel<true>, dim3(grid), dim3(256), 0, stream, io, w, h, wpr, ch, R);
+        else launch_pdl(morph_kernel<false>, dim3(grid), dim3(256), 0, stream, io, w, h, wpr, ch, R);
         BGSB_LAUNCH_CHECK();
-        src = dst;
+        src_bits = io.out_bits;
     }
-    if (src != d_out) BGSB_CUDA(cudaMemcpyAsync(d_out, src, bytes, cudaMemcpyDeviceToDevice, stream));
     for (int i = 0; i < ntmp; i++) BGSB_CUDA(cudaFreeAsync(tmp[i], stream));
     return BGSB_OK;
+}
+
+// byte masks in and out (bgsb_morph_dev).  An empty chain is a no-op COPY (iterations = 0): values pass
+// through unchanged.
+int launch_morph_chain(const uint8_t *d_in, uint8_t *d_out, int w, int h, int nimages, const int *ops, int nops,
+                       cudaStream_t stream)
+{
+    int items[64][2], ni = 0, total = 0;
+    int rc = parse_chain(ops, nops, items, ni, total);
+    if (rc) return rc;
+    if (total == 0) {
+        if (d_in != d_out) BGSB_CUDA(cudaMemcpyAsync(d_out, d_in, (size_t)w * h * nimages, cudaMemcpyDeviceToDevice, stream));
+        return BGSB_OK;
+    }
+    MorphIO io;
+    memset(&io, 0, sizeof(io));
+    io.in_bytes = d_in; io.out_bytes = d_out;
+    return launch_morph_chain_io(io, w, h, nimages, ops, nops, stream);
 }
 
 }  // namespace bgsb
