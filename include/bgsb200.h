@@ -293,9 +293,42 @@ BGSB_API int bgsb_pipeline_process_dev(bgsb_pipeline *p, const uint8_t *d_frames
                                        uint8_t *d_bg, int32_t *d_labels, int *valid, int *bg_valid, void *stream);
 /* Component table of stream `stream_index` for the last frame (synchronises the stream). */
 BGSB_API int bgsb_pipeline_components(bgsb_pipeline *p, int stream_index, bgsb_component *out, int capacity, int *n);
+/* The tables of ALL streams for the last frame into one dense device buffer (one download for the whole group):
+ * d_out is int32 [nstreams][(rows_per_stream + 1) * 8]: per stream 8 ints of header {component count, 0 x 7} followed
+ * by the first rows_per_stream components (raster order) as bgsb_component rows.  Asynchronous on `stream`, which
+ * must be the stream the frame was processed on. */
+BGSB_API int bgsb_pipeline_tables_dev(bgsb_pipeline *p, int32_t *d_out, int rows_per_stream, void *stream);
 /* cvMoments(pFGMask[R], 0) sums on that stream's cleaned mask, as bgsb_ccl_rect_moments. */
 BGSB_API int bgsb_pipeline_rect_moments(bgsb_pipeline *p, int stream_index, const int32_t *rects_xywh, int nrects,
                                         uint64_t *out);
+
+/* ---------------------------------------------------------------------------------------
+ * Stream pool: N camera streams of one geometry over the GPUs of this process (BASELINE configs 4 / 5).
+ * The reference's main loop (ustc_src/trackingMain.cpp:161-166; FrameProcessor.cpp:176-195 for the plugin family) serves
+ * one camera; the pool runs that loop for many: stream s lives on devices[s % ndevices], each GPU has one host worker
+ * thread, one bgsb_pipeline over its streams, and `ring` slots of page-locked frame / mask / table buffers on three CUDA
+ * streams, so that slot k+1 uploads while slot k computes and slot k-1 downloads.  Streams never exchange data.
+ *   capture side : write frame t of stream s into bgsb_pool_frame_buffer(pool, s, t % ring)   (h*w*3 bytes, dense BGR)
+ *   bgsb_pool_submit(pool, slot, want_masks) : every stream's frame of that slot is ready; returns at once
+ *   bgsb_pool_wait(pool, slot, &valid)       : that slot's results are on the host; valid = 0 while the plugin warms up
+ *   bgsb_pool_mask / bgsb_pool_components    : the cleaned {0,255} mask (if asked for) and the component table
+ *                                              (first 256 components in raster order) of one stream
+ * A slot may be refilled and resubmitted once it has been waited for.  One thread drives submit / wait.
+ * ------------------------------------------------------------------------------------- */
+typedef struct bgsb_pool bgsb_pool;
+BGSB_API int bgsb_pool_create(bgsb_pool **out, int algo, int nstreams, const int *devices, int ndevices, int w, int h,
+                              int ring);
+BGSB_API void bgsb_pool_destroy(bgsb_pool *pool);
+/* As bgsb_pipeline_set_param / bgsb_pipeline_set_morph, applied to every GPU's pipeline; call before the first submit. */
+BGSB_API int bgsb_pool_set_param(bgsb_pool *pool, const char *key, double value);
+BGSB_API int bgsb_pool_set_morph(bgsb_pool *pool, const int *ops, int nops);
+BGSB_API int bgsb_pool_device_of(bgsb_pool *pool, int stream, int *device);
+BGSB_API int bgsb_pool_info(bgsb_pool *pool, int *ngroups, int *ring, int *table_rows);
+BGSB_API uint8_t *bgsb_pool_frame_buffer(bgsb_pool *pool, int stream, int slot);
+BGSB_API int bgsb_pool_submit(bgsb_pool *pool, int slot, int want_masks);
+BGSB_API int bgsb_pool_wait(bgsb_pool *pool, int slot, int *valid);
+BGSB_API const uint8_t *bgsb_pool_mask(bgsb_pool *pool, int stream, int slot);
+BGSB_API int bgsb_pool_components(bgsb_pool *pool, int stream, int slot, bgsb_component *out, int capacity, int *n);
 
 /* ---------------------------------------------------------------------------------------
  * Synthetic video of SURVEY 8(d) generated on the device (bench / tests only):

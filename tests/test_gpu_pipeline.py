@@ -156,7 +156,7 @@ def test_pipeline_config4_shape_8x1080p(oracle):
             before = tb.kernel_launch_count()
             pipe.process_dev(d[t].data_ptr(), w, h, d_mask.data_ptr() if full else None, None,
                              d_lab.data_ptr() if full else None)
-            assert tb.kernel_launch_count() - before == 5         # plugin, morphology, merge, finish, background
+            assert tb.kernel_launch_count() - before == 6         # plugin, morphology, merge, roots, label, background
             exp = list(ex.map(lambda s: expect(s, t), range(S)))
             torch.cuda.synchronize()
             mask, lab = d_mask.cpu().numpy(), d_lab.cpu().numpy()

@@ -93,7 +93,19 @@ SIGNATURES = {
     "bgsb_pipeline_set_param": (C.c_int, [vp, C.c_char_p, C.c_double]),
     "bgsb_pipeline_process_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, intp, intp, vp]),
     "bgsb_pipeline_components": (C.c_int, [vp, C.c_int, C.POINTER(Component), C.c_int, intp]),
+    "bgsb_pipeline_tables_dev": (C.c_int, [vp, vp, C.c_int, vp]),
     "bgsb_pipeline_rect_moments": (C.c_int, [vp, C.c_int, i32p, C.c_int, C.POINTER(C.c_uint64)]),
+    "bgsb_pool_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, intp, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "bgsb_pool_destroy": (None, [vp]),
+    "bgsb_pool_set_param": (C.c_int, [vp, C.c_char_p, C.c_double]),
+    "bgsb_pool_set_morph": (C.c_int, [vp, intp, C.c_int]),
+    "bgsb_pool_device_of": (C.c_int, [vp, C.c_int, intp]),
+    "bgsb_pool_info": (C.c_int, [vp, intp, intp, intp]),
+    "bgsb_pool_frame_buffer": (vp, [vp, C.c_int, C.c_int]),
+    "bgsb_pool_submit": (C.c_int, [vp, C.c_int, C.c_int]),
+    "bgsb_pool_wait": (C.c_int, [vp, C.c_int, intp]),
+    "bgsb_pool_mask": (vp, [vp, C.c_int, C.c_int]),
+    "bgsb_pool_components": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(Component), C.c_int, intp]),
     "bgsb_synth_frames_dev": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, vp]),
 }
 

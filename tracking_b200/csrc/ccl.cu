@@ -7,26 +7,27 @@
 //     cvThreshold(pIB, pIB, 128, 255, CV_THRESH_BINARY); cvFindContours(pIB, ..., CV_RETR_EXTERNAL);
 //     CvRect r = ((CvContour*)cnt)->rect;   cvMoments(cvGetSubRect(pFGMask,&mat,r), &m, 0);
 //
-// Four launches per batch of images (round 1 needed twelve), all one thread per 32-pixel word of the bit-packed
-// mask, blockIdx.y = image:
+// Five launches per batch of images (round 1 needed twelve), all one thread per 32-pixel word of the bit-packed
+// mask, blockIdx.y = image; no CTA ever waits for another one:
 //   1 pack/init  bytes > 128 -> bits (optionally clearing the 1-px frame, OpenCV 2.4 behaviour); every horizontal run
 //                inside a word becomes a union-find node named by its first pixel.  (The pipeline's morphology kernel
-//                produces the bits and the nodes itself: three launches.)
+//                produces the bits and the nodes itself: four launches.)
 //   2 merge      unions found with bit tricks on (this row, row above): a run pair is linked exactly once
 //                (8-connectivity: vertical + the two diagonals that are not already implied); lock-free union by
 //                atomicMin with path halving, so a component's root is its minimum = raster-first pixel.
-//   3 finish     roots are counted per 256-word chunk; a chunk's CTA waits for the counts of the chunks before it
-//                (CTAs take their chunk from a ticket counter, so a CTA only ever waits for CTAs that are already
-//                running), which makes canonical label = 1 + raster rank of the root known without a separate scan
-//                launch; the root's rank is published in its own forest slot (negative values), every other run
-//                chases its parent chain to it; bounding boxes / areas by atomics; optional label image.
-//   4 background one cooperative launch.  RETR_EXTERNAL drops components enclosed in a hole of another one, which
-//                requires the enclosed bounding box to lie STRICTLY inside the other's: all CTAs check the boxes, one
-//                grid-wide barrier, and unless some image has such a pair (typical masks have none: the background
-//                is > 98 % of the pixels) the launch ends there.  Otherwise the same init / merge / flatten runs on the
+//   3 roots      every run is pointed straight at its root; a root gets its rank among the roots of its 256-word chunk
+//                (kept in its own forest slot as a negative value); the last CTA of an image to finish scans the
+//                per-chunk root counts, which makes canonical label = 1 + raster rank of the root a two-load lookup.
+//   4 label      labels, bounding boxes / areas by atomics into table rows that need no initialisation (zeroed rows,
+//                maxima only); optional label image; the last CTA of an image checks whether any bounding box lies
+//                STRICTLY inside another one -- necessary for a component to sit in a hole of another component.
+//   5 background one cooperative launch that ends at once unless some image was flagged (typical masks have no such
+//                pair: the background is > 98 % of the pixels).  Otherwise the same init / merge / flatten runs on the
 //                4-connected background of the flagged images, regions touching the frame are "outer", and a
-//                component is external iff the background region left of its first pixel is outer.
+//                component is external (RETR_EXTERNAL keeps it) iff the background region left of its first pixel is
+//                outer.
 #include <limits.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 #include <cooperative_groups.h>
@@ -86,25 +87,15 @@ __device__ __forceinline__ void unite(int *parent, int a, int b)
     }
 }
 
-__device__ __forceinline__ int ld_acquire(const int *p)
-{
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(int *p, int v)
-{
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-
 // geometry + buffers of one labelling call (all per-image strides are the dense ones of this geometry)
 struct CclArgs {
     const unsigned *bits;        // [nimages][h * wpr]
     int *parent;                 // [nimages][w * h]
     uint8_t *outer;              // [nimages][w * h]
     CompRaw *comp;               // [nimages][cap]
-    unsigned *chunkstate;        // [nimages][nchunks]
-    int *ticket, *ncomp, *need_bg;
+    int *chunkcount, *chunkprefix;   // [nimages][nchunks]: roots per 256-word chunk, and their exclusive prefix
+    int *done_a, *done_b;        // per image: CTAs of the roots / label kernel that have finished (zero between calls)
+    int *ncomp, *need_bg;
     int *labels;                 // [nimages][w * h] or null
     int w, h, wpr, nwords, nchunks, nimages, cap, zero_border, force_bg;
     size_t img_px, img_words;
@@ -211,139 +202,245 @@ __device__ __forceinline__ void merge_word(const CclArgs &A, const unsigned *bit
     }
 }
 
+// Launches 2-4 exist in two shapes: one word per thread (a single image: 254 CTAs at 1080p fill the SMs), and WPT = 4
+// words per thread with the loads of the four words in flight together (batches: 16 k CTAs of one word per thread run
+// in 14 waves whose CTAs mostly hold empty words and still pay the full launch / arrive latency; a quarter of the
+// CTAs does the same work in a quarter of the waves).  A chunk = the 256 * WPT words of one CTA, in raster order:
+// word (chunk, j, tid) = chunk * 256 * WPT + j * 256 + tid.
+
 // ---- launch 2: merge ------------------------------------------------------------------------------------------------
+template <int WPT>
 __global__ void __launch_bounds__(256)
 ccl_merge_kernel(const __grid_constant__ CclArgs A)
 {
     pdl_entry();
-    const int wi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (wi >= A.nwords) return;
-    merge_word<false>(A, A.bits + blockIdx.y * A.img_words, A.parent + blockIdx.y * A.img_px, wi);
+    {   // the table rows the previous call filled go back to zero (the label kernel accumulates into zeroed rows)
+        const int nprev = min(A.ncomp[blockIdx.y], A.cap);
+        int4 *rows = reinterpret_cast<int4 *>(A.comp + (size_t)blockIdx.y * A.cap);
+        for (int i = blockIdx.x * 256 + threadIdx.x; i < 2 * nprev; i += gridDim.x * 256) rows[i] = make_int4(0, 0, 0, 0);
+    }
+    const unsigned *bits = A.bits + blockIdx.y * A.img_words;
+    int *parent = A.parent + blockIdx.y * A.img_px;
+#pragma unroll
+    for (int j = 0; j < WPT; j++) {
+        const int wi = (blockIdx.x * WPT + j) * 256 + threadIdx.x;
+        if (wi < A.nwords) merge_word<false>(A, bits, parent, wi);
+    }
 }
 
-// ---- launch 3: finish ----------------------------------------------------------------------------------------------
-// Chunk c = words [256c, 256c + 256) of one image in raster order.  ncomp[img] is written by the last chunk.
-template <bool LABELS>       // LABELS = false: component table only (no 32-register label row per thread)
+// ---- launch 3: roots ---------------------------------------------------------------------------------------------------
+// Every run finds its root (merge has completed: a root is a node that is its own parent) and points straight at it; a
+// root gets its rank AMONG THE ROOTS OF ITS CHUNK, stored in its own forest slot as ~rank (< 0); the chunk's root count
+// goes to chunkcount[].  The last CTA of an image to finish turns the counts into exclusive prefixes (chunkprefix[]) and
+// the component count -- no CTA ever waits for another.
+template <int WPT>
 __global__ void __launch_bounds__(256)
-ccl_finish_kernel(const __grid_constant__ CclArgs A)
+ccl_roots_kernel(const __grid_constant__ CclArgs A)
 {
     pdl_entry();
-    __shared__ int s_chunk, s_prefix;
     __shared__ int wsum[8];
-    const int img = blockIdx.y;
+    __shared__ int s_last, s_carry;
+    const int img = blockIdx.y, chunk = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) s_chunk = atomicAdd(&A.ticket[img], 1);
-    __syncthreads();
-    const int chunk = s_chunk;
     const unsigned *bits = A.bits + img * A.img_words;
     int *parent = A.parent + img * A.img_px;
+    unsigned v[WPT], roots[WPT];
+    int base[WPT];
+#pragma unroll
+    for (int j = 0; j < WPT; j++) {
+        const int wi = (chunk * WPT + j) * 256 + tid;
+        const bool valid = wi < A.nwords;
+        const int y = valid ? wi / A.wpr : 0, k = valid ? wi - y * A.wpr : 0;
+        v[j] = valid ? ccl_word(bits, y, k, A) : 0u;
+        base[j] = y * A.w + k * 32;
+    }
+#pragma unroll
+    for (int j = 0; j < WPT; j++) {
+        roots[j] = 0;
+        for (unsigned s = v[j] & ~(v[j] << 1); s;) {
+            const int b = __ffs(s) - 1; s &= s - 1;
+            const int p = base[j] + b;
+            int cur = p, q = parent[cur];
+            while (q != cur && q >= 0) { cur = q; q = parent[cur]; }     // q < 0: that root already carries its rank
+            if (cur == p) roots[j] |= 1u << b;
+            else parent[p] = cur;
+        }
+    }
+    int carry = 0;                                   // roots of this chunk in the word groups before j
+#pragma unroll
+    for (int j = 0; j < WPT; j++) {
+        const int c = __popc(roots[j]);
+        int incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (j) __syncthreads();                      // wsum of the previous group has been read
+        if (lane == 31) wsum[wid] = incl;
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const int t = wsum[i]; if (i < wid) before += t; total += t; }
+        int run = carry + before + incl - c;
+        for (unsigned r = roots[j]; r;) {
+            const int b = __ffs(r) - 1; r &= r - 1;
+            parent[base[j] + b] = ~run;
+            run++;
+        }
+        carry += total;
+    }
+    int *count = A.chunkcount + (size_t)img * A.nchunks;
+    if (tid == 0) count[chunk] = carry;
+    // the last CTA of the image: exclusive scan of the chunk counts
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) { s_last = (atomicAdd(&A.done_a[img], 1) == A.nchunks - 1); s_carry = 0; }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    int *prefix = A.chunkprefix + (size_t)img * A.nchunks;
+    for (int c0 = 0; c0 < A.nchunks; c0 += 256) {
+        const int j = c0 + tid;
+        const int cnt = j < A.nchunks ? __ldcg(count + j) : 0;
+        int inc2 = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc2, off);
+            if (lane >= off) inc2 += t;
+        }
+        __syncthreads();                               // wsum / s_carry of the previous round have been read
+        if (lane == 31) wsum[wid] = inc2;
+        __syncthreads();
+        int bef = s_carry, tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const int t = wsum[i]; if (i < wid) bef += t; tot += t; }
+        if (j < A.nchunks) prefix[j] = bef + inc2 - cnt;
+        __syncthreads();
+        if (tid == 0) s_carry += tot;
+    }
+    __syncthreads();
+    if (tid == 0) A.ncomp[img] = s_carry;
+}
+
+// ---- launch 4: label -------------------------------------------------------------------------------------------------
+// canonical label = 1 + (roots in the chunks before the root's chunk) + (the root's rank inside its chunk).  The table
+// rows are zero on entry and are only ever touched by atomics (and by the root's own thread for the fields nobody else
+// writes), so no row has to be initialised before another CTA may use it: maxima as they are, minima as CCL_BIG - value.
+constexpr int CCL_BIG = 1 << 30;
+
+template <bool LABELS, int WPT>       // LABELS = false: component table only (no 32-register label row per thread)
+__global__ void __launch_bounds__(256)
+ccl_label_kernel(const __grid_constant__ CclArgs A)
+{
+    pdl_entry();
+    __shared__ int4 s_box[256];
+    __shared__ int s_last;
+    const int img = blockIdx.y, chunk = blockIdx.x;
+    const int tid = threadIdx.x;
+    const unsigned *bits = A.bits + img * A.img_words;
+    const int *parent = A.parent + img * A.img_px;
+    const int *prefix = A.chunkprefix + (size_t)img * A.nchunks;
     CompRaw *comp = A.comp + (size_t)img * A.cap;
-    unsigned *state = A.chunkstate + (size_t)img * A.nchunks;
-
-    const int wi = chunk * 256 + tid;
-    const bool valid = wi < A.nwords;
-    const int y = valid ? wi / A.wpr : 0, k = valid ? wi - y * A.wpr : 0;
-    const unsigned v = valid ? ccl_word(bits, y, k, A) : 0u;
-    const int base = y * A.w + k * 32;
-    const unsigned starts = v & ~(v << 1);
-
-    // which of this word's runs are roots (merge has completed: a root is a node that is its own parent)
-    unsigned roots = 0;
-    for (unsigned s = starts; s;) {
-        const int b = __ffs(s) - 1; s &= s - 1;
-        if (parent[base + b] == base + b) roots |= 1u << b;
-    }
-    const int c = __popc(roots);
-    int incl = c;
+    constexpr int CSHIFT = WPT == 1 ? 8 : 10;          // log2(words per chunk)
+    static_assert(WPT == 1 || WPT == 4, "chunk sizes 256 / 1024 words");
+    unsigned v[WPT];
+    int yy[WPT], kk[WPT];
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += t;
+    for (int j = 0; j < WPT; j++) {
+        const int wi = (chunk * WPT + j) * 256 + tid;
+        const bool valid = wi < A.nwords;
+        yy[j] = valid ? wi / A.wpr : -1; kk[j] = valid ? wi - yy[j] * A.wpr : 0;
+        v[j] = valid ? ccl_word(bits, yy[j], kk[j], A) : 0u;
     }
-    if (lane == 31) wsum[wid] = incl;
-    __syncthreads();
-    int before = 0, total = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) { const int t = wsum[i]; if (i < wid) before += t; total += t; }
-
-    // publish this chunk's root count, then add up the counts of all chunks before it (warp 0, 32 at a time)
-    if (wid == 0) {
-        if (lane == 0) st_release(reinterpret_cast<int *>(state + chunk), total + 1);
-        int sum = 0;
-        for (int j = lane; j < chunk; j += 32) {
-            int sv;
-            while ((sv = ld_acquire(reinterpret_cast<const int *>(state + j))) == 0) { }
-            sum += sv - 1;
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
-        if (lane == 0) {
-            s_prefix = sum;
-            if (chunk == A.nchunks - 1) A.ncomp[img] = sum + total;
-        }
-    }
-    __syncthreads();
-    int run = s_prefix + before + incl - c;            // rank of this word's first root
-
-    // roots: table row, then the rank goes into the root's forest slot as ~rank (< 0) for the whole component to find
-    for (unsigned r = roots; r;) {
-        const int b = __ffs(r) - 1; r &= r - 1;
-        if (run < A.cap) {
-            CompRaw cr;
-            cr.label = run + 1; cr.first_index = base + b;
-            cr.xmin = INT_MAX; cr.ymin = INT_MAX; cr.xmax = -1; cr.ymax = -1; cr.area = 0;
-            cr.external = 1;                           // provisional; nested components are found by the background pass
-            comp[run] = cr;
-        }
-        st_release(parent + base + b, ~run);
-        run++;
-    }
-    __syncthreads();
-
-    // every run: chase the chain to the root's published rank (a root that is still its own parent belongs to a chunk
-    // whose CTA has not got that far yet: it holds a smaller ticket, so it is running)
-    int lab[LABELS ? 32 : 1];
-    if (LABELS) {
-#pragma unroll
-        for (int i = 0; i < 32; i++) lab[i] = 0;
-    }
-    for (unsigned s = starts; s;) {
-        const int b = __ffs(s) - 1; s &= s - 1;
-        int cur = base + b;
-        int q = ld_acquire(parent + cur);
-        while (q >= 0) {
-            if (q != cur) cur = q;
-            q = ld_acquire(parent + cur);
-        }
-        const int rank = ~q;
-        const unsigned rest = ~(v >> b);
-        const int len = rest ? __ffs(rest) - 1 : 32 - b;
+    for (int j = 0; j < WPT; j++) {
+        const int y = yy[j], k = kk[j];
+        const int base = y * A.w + k * 32;
+        int lab[LABELS ? 32 : 1];
         if (LABELS) {
 #pragma unroll
-            for (int i = 0; i < 32; i++)
-                if (i >= b && i < b + len) lab[i] = rank + 1;
+            for (int i = 0; i < 32; i++) lab[i] = 0;
         }
-        if (rank < A.cap) {
-            CompRaw *cp = comp + rank;
-            const int x0 = k * 32 + b;
-            atomicMin(&cp->xmin, x0); atomicMax(&cp->xmax, x0 + len - 1);
-            atomicMin(&cp->ymin, y); atomicMax(&cp->ymax, y);
-            atomicAdd(&cp->area, len);
+        for (unsigned s = v[j] & ~(v[j] << 1); s;) {
+            const int b = __ffs(s) - 1; s &= s - 1;
+            const int p = base + b;
+            const int q = parent[p];
+            const int root = q < 0 ? p : q;
+            const int local = ~(q < 0 ? q : parent[root]);
+            const int ry = root / A.w, rx = root - ry * A.w;
+            const int rank = prefix[(ry * A.wpr + (rx >> 5)) >> CSHIFT] + local;
+            const unsigned rest = ~(v[j] >> b);
+            const int len = rest ? __ffs(rest) - 1 : 32 - b;
+            if (LABELS) {
+#pragma unroll
+                for (int i = 0; i < 32; i++)
+                    if (i >= b && i < b + len) lab[i] = rank + 1;
+            }
+            if (rank < A.cap) {
+                CompRaw *cp = comp + rank;
+                const int x0 = k * 32 + b;
+                if (q < 0) { cp->label = rank + 1; cp->first_index = p; cp->external = 1; }   // provisional; see the background pass
+                atomicMax(&cp->xmin, CCL_BIG - x0); atomicMax(&cp->xmax, x0 + len - 1);
+                atomicMax(&cp->ymin, CCL_BIG - y); atomicMax(&cp->ymax, y);
+                atomicAdd(&cp->area, len);
+            }
+        }
+        if (LABELS && y >= 0) {
+            int *o = A.labels + img * A.img_px + base;
+            const int nvalid = min(32, A.w - k * 32);
+            if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                for (int i = 0; i < 8; i++)
+                    reinterpret_cast<int4 *>(o)[i] = make_int4(lab[4 * i], lab[4 * i + 1], lab[4 * i + 2], lab[4 * i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; i++)
+                    if (i < nvalid) o[i] = lab[i];
+            }
         }
     }
-    if (LABELS && valid) {
-        int *o = A.labels + img * A.img_px + base;
-        const int nvalid = min(32, A.w - k * 32);
-        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+
+    // ---- the last CTA of the image to get here decides whether the image needs the background pass: does any
+    // component's bounding box lie strictly inside another's?  (Necessary for a component to sit in a hole of another
+    // one.)  More than 1024 components: not worth checking in one CTA, take the pass.
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&A.done_b[img], 1) == A.nchunks - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int n = __ldcg(A.ncomp + img);
+    int need = 0;
+    if (A.force_bg || n > 1024 || n > A.cap) need = (n > 0) || A.force_bg;
+    else {
+        int4 mine[4];
 #pragma unroll
-            for (int i = 0; i < 8; i++)
-                reinterpret_cast<int4 *>(o)[i] = make_int4(lab[4 * i], lab[4 * i + 1], lab[4 * i + 2], lab[4 * i + 3]);
-        } else {
+        for (int u = 0; u < 4; u++) {
+            const int i = u * 256 + tid;
+            mine[u] = make_int4(0, 0, 0, 0);
+            if (i < n) mine[u] = make_int4(CCL_BIG - __ldcg(&comp[i].xmin), CCL_BIG - __ldcg(&comp[i].ymin), __ldcg(&comp[i].xmax), __ldcg(&comp[i].ymax));
+        }
 #pragma unroll
-            for (int i = 0; i < 32; i++)
-                if (i < nvalid) o[i] = lab[i];
+        for (int tt = 0; tt < 4; tt++) {
+            if (tt * 256 < n) {                        // uniform over the CTA
+                s_box[tid] = (tt * 256 + tid < n) ? mine[tt] : make_int4(1 << 30, 1 << 30, -1, -1);
+                __syncthreads();
+                const int m = min(256, n - tt * 256);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (u * 256 + tid < n) {
+                        for (int q2 = 0; q2 < m; q2++) {
+                            const int4 bx = s_box[q2];
+                            need |= (bx.x < mine[u].x) & (bx.y < mine[u].y) & (bx.z > mine[u].z) & (bx.w > mine[u].w);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
+    if (need) A.need_bg[img] = 1;
 }
 
 // ---- launch 4: RETR_EXTERNAL (cooperative: grid-wide barriers between the phases) ---------------------------------------
@@ -352,45 +449,12 @@ ccl_background_kernel(const __grid_constant__ CclArgs A)
 {
     pdl_entry();
     cg::grid_group grid = cg::this_grid();
-    __shared__ int4 box[256];
     const int tid = threadIdx.x;
     const size_t gtid = (size_t)blockIdx.x * 256 + tid, gsize = (size_t)gridDim.x * 256;
-    // the finish kernel has completed: its look-back state goes back to zero for the next call
-    for (size_t i = gtid; i < (size_t)A.nimages * A.nchunks; i += gsize) A.chunkstate[i] = 0u;
-    for (size_t i = gtid; i < (size_t)A.nimages; i += gsize) A.ticket[i] = 0;
+    // the roots / label kernels have completed: their arrival counters go back to zero for the next call
+    for (size_t i = gtid; i < (size_t)A.nimages; i += gsize) { A.done_a[i] = 0; A.done_b[i] = 0; }
 
-    // phase 0: does any component's bounding box lie strictly inside another's?  (Necessary for a component to sit in a
-    // hole of another one.)  Work item = (image, tile of 256 components); more than 4096 components: not worth checking.
-    if (A.force_bg) {
-        for (size_t i = gtid; i < (size_t)A.nimages; i += gsize) A.need_bg[i] = 1;
-    } else {
-        for (int item = blockIdx.x; item < A.nimages * 16; item += gridDim.x) {
-            const int img = item >> 4, tile = item & 15;
-            const int n = A.ncomp[img];
-            if (n > 4096 || n > A.cap) { if (tile == 0 && tid == 0) A.need_bg[img] = 1; continue; }
-            if (tile * 256 >= n) continue;
-            const CompRaw *c = A.comp + (size_t)img * A.cap;
-            const int i = tile * 256 + tid;
-            int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-            if (i < n) { x0 = c[i].xmin; y0 = c[i].ymin; x1 = c[i].xmax; y1 = c[i].ymax; }
-            bool inside = false;
-            for (int t0 = 0; t0 < n; t0 += 256) {
-                const int j = t0 + tid;
-                box[tid] = j < n ? make_int4(c[j].xmin, c[j].ymin, c[j].xmax, c[j].ymax) : make_int4(1 << 30, 1 << 30, -1, -1);
-                __syncthreads();
-                if (i < n) {
-#pragma unroll 8
-                    for (int q = 0; q < 256; q++) {
-                        const int4 b = box[q];
-                        inside |= (b.x < x0) & (b.y < y0) & (b.z > x1) & (b.w > y1);
-                    }
-                }
-                __syncthreads();
-            }
-            if (inside) A.need_bg[img] = 1;
-        }
-    }
-    grid.sync();
+    // the label kernel's last CTA per image has flagged the images where a bounding box lies strictly inside another
     int any = 0;
     for (int i = tid; i < A.nimages; i += 256) any |= A.need_bg[i];
     if (!__syncthreads_or(any)) return;              // the same answer in every CTA: typical masks end here
@@ -550,6 +614,37 @@ rect_moments_bits_kernel(const unsigned *__restrict__ bits, int w, int h, int wp
     }
 }
 
+// The component tables of all images of the last call, decoded, in one dense buffer: per image 8 ints of header
+// (count, 7 x 0) followed by `rows` bgsb_component rows (x, y, w, h form); one download then serves a whole stream group.
+__global__ void __launch_bounds__(256)
+ccl_gather_kernel(const CompRaw *__restrict__ comp, const int *__restrict__ ncomp, int cap, int rows, int *__restrict__ out)
+{
+    pdl_entry();
+    const int img = blockIdx.x;
+    const int n = ncomp[img];
+    int *o = out + (size_t)img * (rows + 1) * 8;
+    if (threadIdx.x < 8) o[threadIdx.x] = threadIdx.x == 0 ? n : 0;
+    const int m = min(min(n, rows), cap);
+    const CompRaw *c = comp + (size_t)img * cap;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const CompRaw r = c[i];
+        const int x = CCL_BIG - r.xmin, y = CCL_BIG - r.ymin;
+        int4 *d = reinterpret_cast<int4 *>(o + (size_t)(i + 1) * 8);
+        d[0] = make_int4(r.label, r.first_index, x, y);
+        d[1] = make_int4(r.xmax - x + 1, r.ymax - y + 1, r.area, r.external);
+    }
+}
+
+int ccl_gather_tables(bgsb_ccl *c, int32_t *d_out, int rows, cudaStream_t stream)
+{
+    BGSB_REQUIRE(c && d_out && rows >= 0, "bad args");
+    if (!c->labelled) { set_error("ccl_gather_tables: nothing labelled yet"); return BGSB_ERR_STATE; }
+    launch_pdl(ccl_gather_kernel, dim3(c->nimages), dim3(256), 0, stream, (const CompRaw *)c->d_comp, (const int *)c->d_ncomp, c->cap,
+               rows, (int *)d_out);
+    BGSB_LAUNCH_CHECK();
+    return BGSB_OK;
+}
+
 // launches 2-4 (and the node init when the producer of the words did not do it)
 int ccl_label_bits(bgsb_ccl *c, const unsigned *d_bits, bool parents_ready, int w, int h, int nimages, int zero_border,
                    int32_t *d_labels, cudaStream_t stream)
@@ -560,27 +655,52 @@ int ccl_label_bits(bgsb_ccl *c, const unsigned *d_bits, bool parents_ready, int 
     BGSB_CUDA(cudaSetDevice(c->device));
     CclArgs A;
     memset(&A, 0, sizeof(A));
-    A.bits = d_bits; A.parent = c->d_parent; A.outer = c->d_outer; A.comp = c->d_comp; A.chunkstate = c->d_chunkstate;
-    A.ticket = c->d_ticket; A.ncomp = c->d_ncomp; A.need_bg = c->d_need_bg; A.labels = d_labels;
+    A.bits = d_bits; A.parent = c->d_parent; A.outer = c->d_outer; A.comp = c->d_comp;
+    A.chunkcount = c->d_chunkcount; A.chunkprefix = c->d_chunkprefix; A.done_a = c->d_done; A.done_b = c->d_done + c->max_images;
+    A.ncomp = c->d_ncomp; A.need_bg = c->d_need_bg; A.labels = d_labels;
     A.w = w; A.h = h; A.wpr = (w + 31) / 32; A.nwords = A.wpr * h; A.nchunks = (A.nwords + 255) / 256;
     A.nimages = nimages; A.cap = c->cap; A.zero_border = zero_border; A.force_bg = c->force_bg;
+
     A.img_px = (size_t)w * h; A.img_words = (size_t)A.nwords;      // dense per-image strides for this geometry
     if (c->dirty) {                                 // an earlier call failed between the launches
-        BGSB_CUDA(cudaMemsetAsync(c->d_chunkstate, 0, (size_t)c->max_images * c->max_chunks * sizeof(unsigned), stream));
-        BGSB_CUDA(cudaMemsetAsync(c->d_ticket, 0, (size_t)c->max_images * sizeof(int), stream));
+        BGSB_CUDA(cudaMemsetAsync(c->d_done, 0, 2 * (size_t)c->max_images * sizeof(int), stream));
         BGSB_CUDA(cudaMemsetAsync(c->d_need_bg, 0, (size_t)c->max_images * sizeof(int), stream));
     }
+    if (nimages < c->table_images) {
+        // fewer images than the previous call: the rows of the images that now sit out are cleared here (the merge kernel
+        // clears those of the images it works on)
+        const size_t first = (size_t)nimages, cnt = (size_t)(c->table_images - nimages);
+        BGSB_CUDA(cudaMemsetAsync(c->d_comp + first * c->cap, 0, cnt * c->cap * sizeof(CompRaw), stream));
+        BGSB_CUDA(cudaMemsetAsync(c->d_ncomp + first, 0, cnt * sizeof(int), stream));
+    }
+    c->table_images = nimages;
     c->dirty = true;
-    const dim3 grid(A.nchunks, nimages), block(256);
+    const dim3 block(256);
     if (!parents_ready) {
-        launch_pdl(ccl_init_kernel, grid, block, 0, stream, A);
+        launch_pdl(ccl_init_kernel, dim3((A.nwords + 255) / 256, nimages), block, 0, stream, A);
         BGSB_LAUNCH_CHECK();
     }
-    launch_pdl(ccl_merge_kernel, grid, block, 0, stream, A);
-    BGSB_LAUNCH_CHECK();
-    if (d_labels) launch_pdl(ccl_finish_kernel<true>, grid, block, 0, stream, A);
-    else launch_pdl(ccl_finish_kernel<false>, grid, block, 0, stream, A);
-    BGSB_LAUNCH_CHECK();
+    // batches too big for one wave of one-word-per-thread CTAs (8 per SM) take the four-words-per-thread kernels
+    const bool wide = (long long)nimages * ((A.nwords + 255) / 256) > 8LL * sm_count(c->device);
+    A.nchunks = wide ? (A.nwords + 1023) / 1024 : (A.nwords + 255) / 256;
+    const dim3 grid(A.nchunks, nimages);
+    if (wide) {
+        launch_pdl(ccl_merge_kernel<4>, grid, block, 0, stream, A);
+        BGSB_LAUNCH_CHECK();
+        launch_pdl(ccl_roots_kernel<4>, grid, block, 0, stream, A);
+        BGSB_LAUNCH_CHECK();
+        if (d_labels) launch_pdl(ccl_label_kernel<true, 4>, grid, block, 0, stream, A);
+        else launch_pdl(ccl_label_kernel<false, 4>, grid, block, 0, stream, A);
+        BGSB_LAUNCH_CHECK();
+    } else {
+        launch_pdl(ccl_merge_kernel<1>, grid, block, 0, stream, A);
+        BGSB_LAUNCH_CHECK();
+        launch_pdl(ccl_roots_kernel<1>, grid, block, 0, stream, A);
+        BGSB_LAUNCH_CHECK();
+        if (d_labels) launch_pdl(ccl_label_kernel<true, 1>, grid, block, 0, stream, A);
+        else launch_pdl(ccl_label_kernel<false, 1>, grid, block, 0, stream, A);
+        BGSB_LAUNCH_CHECK();
+    }
     {
         // cooperative: every CTA must be resident at once; the grid strides over the work
         if (c->coop_ctas <= 0) {
@@ -588,7 +708,7 @@ int ccl_label_bits(bgsb_ccl *c, const unsigned *d_bits, bool parents_ready, int 
             BGSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccl_background_kernel, 256, 0));
             c->coop_ctas = std::max(1, per_sm) * sm_count(c->device);
         }
-        const long long want = std::max<long long>((long long)nimages * 16, (long long)nimages * A.nchunks);
+        const long long want = (long long)nimages * ((A.nwords + 255) / 256);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)std::min<long long>(c->coop_ctas, std::max<long long>(want, 1)));
         cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
@@ -634,11 +754,13 @@ int bgsb_ccl_create_batch(bgsb_ccl **out, int device, int max_w, int max_h, int 
     A((void **)&c->d_mask_own, c->img_px);
     A((void **)&c->d_comp, N * (size_t)c->cap * sizeof(CompRaw));
     A((void **)&c->d_ncomp, N * sizeof(int));
-    A((void **)&c->d_chunkstate, N * (size_t)c->max_chunks * sizeof(unsigned));
-    A((void **)&c->d_ticket, N * sizeof(int));
+    A((void **)&c->d_chunkcount, N * (size_t)c->max_chunks * sizeof(int));
+    A((void **)&c->d_chunkprefix, N * (size_t)c->max_chunks * sizeof(int));
+    A((void **)&c->d_done, 2 * N * sizeof(int));
     A((void **)&c->d_need_bg, N * sizeof(int));
-    if (e == cudaSuccess) e = cudaMemset(c->d_chunkstate, 0, N * (size_t)c->max_chunks * sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaMemset(c->d_ticket, 0, N * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_done, 0, 2 * N * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_ncomp, 0, N * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_comp, 0, N * (size_t)c->cap * sizeof(CompRaw));
     if (e == cudaSuccess) e = cudaMemset(c->d_need_bg, 0, N * sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -662,7 +784,7 @@ void bgsb_ccl_destroy(bgsb_ccl *c)
     cudaDeviceSynchronize();
     cudaFree(c->d_bits); cudaFree(c->d_parent);
     cudaFree(c->d_outer); cudaFree(c->d_mask_own); cudaFree(c->d_comp); cudaFree(c->d_ncomp);
-    cudaFree(c->d_chunkstate); cudaFree(c->d_ticket); cudaFree(c->d_need_bg); cudaFree(c->d_labels_own);
+    cudaFree(c->d_chunkcount); cudaFree(c->d_chunkprefix); cudaFree(c->d_done); cudaFree(c->d_need_bg); cudaFree(c->d_labels_own);
     cudaFree(c->d_rects); cudaFree(c->d_mom);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -728,7 +850,9 @@ int bgsb_ccl_components_of(bgsb_ccl *c, int image, bgsb_component *out, int capa
     if (cnt > want)
         BGSB_CUDA(cudaMemcpy(out + want, c->d_comp + (size_t)image * c->cap + want, (size_t)(cnt - want) * sizeof(CompRaw),
                              cudaMemcpyDeviceToHost));
-    for (int i = 0; i < cnt; i++) {       // (xmin,ymin,xmax,ymax) -> (x,y,w,h)
+    for (int i = 0; i < cnt; i++) {       // device rows hold (BIG - xmin, BIG - ymin, xmax, ymax) -> (x, y, w, h)
+        out[i].x = CCL_BIG - out[i].x;
+        out[i].y = CCL_BIG - out[i].y;
         out[i].w = out[i].w - out[i].x + 1;
         out[i].h = out[i].h - out[i].y + 1;
     }

@@ -13,15 +13,17 @@ struct bgsb_ccl {
     int max_chunks = 0;                    // 256-word chunks per image at the largest geometry
     unsigned *d_bits = nullptr;            // bit-packed masks of the byte entry points (border already cleared)
     int *d_parent = nullptr;               // union-find forest, one slot per pixel, only run starts are used
-    unsigned *d_chunkstate = nullptr;      // per image and chunk: root count + 1 (0 = not published yet); all zero between calls
-    int *d_ticket = nullptr, *d_ncomp = nullptr, *d_need_bg = nullptr;
+    int *d_chunkcount = nullptr, *d_chunkprefix = nullptr;   // per image and 256-word chunk: roots, exclusive prefix
+    int *d_done = nullptr;                 // [2][max_images] arrival counters of the roots / label kernels (zero between calls)
+    int *d_ncomp = nullptr, *d_need_bg = nullptr;
+    int table_images = 0;                  // images whose table rows the previous call may have filled
     int force_bg = 0;                      // 1: always run the background pass (A/B and tests)
     uint8_t *d_outer = nullptr, *d_mask_own = nullptr;
     int32_t *d_labels_own = nullptr;
     bgsb::CompRaw *d_comp = nullptr;
     int cap = 0;
     int coop_ctas = 0;                     // co-resident CTAs of the cooperative background kernel on this device
-    bool dirty = false;                    // a call failed half-way: the look-back state is cleared before the next one
+    bool dirty = false;                    // a call failed half-way: the arrival counters are cleared before the next one
     // what the moments are taken from: the byte masks of the last call, or its bit-packed masks (pipeline)
     const uint8_t *last_mask = nullptr;
     const unsigned *last_bits = nullptr;
@@ -45,6 +47,10 @@ namespace bgsb {
 // (ccl_init_word); otherwise an init launch does it.
 int ccl_label_bits(bgsb_ccl *c, const unsigned *d_bits, bool parents_ready, int w, int h, int nimages, int zero_border,
                    int32_t *d_labels, cudaStream_t stream);
+
+// [nimages][(rows + 1) * 8] ints: per image {count, 0 x 7} then `rows` decoded bgsb_component rows (the first `rows`
+// components in raster order); asynchronous on `stream`, which must be the stream of the labelling call.
+int ccl_gather_tables(bgsb_ccl *c, int32_t *d_out, int rows, cudaStream_t stream);
 
 #ifdef __CUDACC__
 // the word as the labeller sees it: the 1-px image frame cleared when zero_border is set (OpenCV <= 3.1 cvFindContours)

@@ -182,6 +182,14 @@ int bgsb_pipeline_components(bgsb_pipeline *p, int stream_index, bgsb_component 
     return bgsb_ccl_components_of(p->ccl, stream_index, out, capacity, n);
 }
 
+int bgsb_pipeline_tables_dev(bgsb_pipeline *p, int32_t *d_out, int rows_per_stream, void *stream)
+{
+    BGSB_REQUIRE(p && d_out && rows_per_stream >= 0, "bad args");
+    if (!p->labelled) { set_error("bgsb_pipeline_tables_dev: no frame has produced a mask yet"); return BGSB_ERR_STATE; }
+    BGSB_CUDA(cudaSetDevice(p->device));
+    return ccl_gather_tables(p->ccl, d_out, rows_per_stream, (cudaStream_t)stream);
+}
+
 int bgsb_pipeline_rect_moments(bgsb_pipeline *p, int stream_index, const int32_t *rects, int nrects, uint64_t *out)
 {
     BGSB_REQUIRE(p && out, "null");
