@@ -73,6 +73,11 @@ BGSB_API int bgsb_device_count(int *count);
  * fill sequentially and for the GPU to read, slow for the CPU to read back: use it for INPUT frames only). */
 BGSB_API int bgsb_host_alloc(void **ptr, size_t bytes, int write_combined);
 BGSB_API void bgsb_host_free(void *ptr);
+/* Diagnostic: what the PCIe link of `device` sustains from this process -- seconds per iteration for a page-locked
+ * upload of bytes_up alone, a download of bytes_down alone, and both at once on two streams (no kernels).  The host-
+ * buffer entry points (bgsb_process, bgsb_submit, bgsb_pool_*) cannot be faster than max(up, down) per frame. */
+BGSB_API int bgsb_copy_probe(int device, size_t bytes_up, size_t bytes_down, int iters, double *sec_up, double *sec_down,
+                             double *sec_both);
 /* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
 BGSB_API uint64_t bgsb_kernel_launch_count(void);
 
@@ -336,6 +341,10 @@ BGSB_API int bgsb_pool_components(bgsb_pool *pool, int stream, int slot, bgsb_co
  * ------------------------------------------------------------------------------------- */
 BGSB_API int bgsb_synth_frames_dev(uint8_t *d_frames, int nstreams, int T, int w, int h,
                                    int t0, uint32_t seed0, void *stream);
+/* Mode-churn video: every pixel shows one of five well-separated colours, redrawn every second frame -- the stream
+ * on which all K = 5 mixture modes of every pixel stay live (the dense 209 B/px case of SURVEY 8d).  Same layout. */
+BGSB_API int bgsb_synth_churn_frames_dev(uint8_t *d_frames, int nstreams, int T, int w, int h,
+                                         int t0, uint32_t seed0, void *stream);
 
 #ifdef __cplusplus
 }

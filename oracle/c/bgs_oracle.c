@@ -624,3 +624,21 @@ ORC_API void orc_synth_frame(int w, int h, int t, uint32_t seed, uint8_t *bgr)
                 for (int c = 0; c < 3; c++) bgr[((size_t)y * w + x) * 3 + c] = col[c];
     }
 }
+
+/* Mode-churn video (tracking_b200/csrc/synth.cu: synth_churn_kernel): five colours per pixel, redrawn every 2nd frame. */
+ORC_API void orc_synth_churn_frame(int w, int h, int t, uint32_t seed, uint8_t *bgr)
+{
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            uint32_t hi = ((uint32_t)x * 73856093U) ^ ((uint32_t)y * 19349663U) ^ ((uint32_t)(t >> 1) * 83492791U) ^ (seed * 2246822519U);
+            int i = (int)(mix32(hi) % 5U);
+            int col[3] = { 20 + 50 * i, 230 - 45 * i, (90 + 110 * i) & 255 };
+            for (int c = 0; c < 3; c++) {
+                uint32_t hsh = ((uint32_t)x * 73856093U) ^ ((uint32_t)y * 19349663U) ^
+                               ((uint32_t)t * 83492791U) ^ ((uint32_t)c * 2654435761U) ^ seed;
+                int v = col[c] + (int)(mix32(hsh) % 5U) - 2;
+                if (v < 0) v = 0; if (v > 255) v = 255;
+                bgr[((size_t)y * w + x) * 3 + c] = (uint8_t)v;
+            }
+        }
+}

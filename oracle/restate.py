@@ -68,6 +68,7 @@ def lib():
         L.orc_rect_moments.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.POINTER(C.c_uint64)]
         L.orc_synth_frame.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, u8p]
+        L.orc_synth_churn_frame.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, u8p]
         _lib = L
     return _lib
 
@@ -375,4 +376,10 @@ def rect_moments(img, rect):
 def synth_frame(w, h, t, seed):
     out = np.empty((h, w, 3), np.uint8)
     lib().orc_synth_frame(w, h, t, seed & 0xFFFFFFFF, _u8(out))
+    return out
+
+
+def synth_churn_frame(w, h, t, seed):
+    out = np.empty((h, w, 3), np.uint8)
+    lib().orc_synth_churn_frame(w, h, t, seed & 0xFFFFFFFF, _u8(out))
     return out

@@ -45,6 +45,8 @@ SIGNATURES = {
     "bgsb_version": (C.c_char_p, []),
     "bgsb_device_count": (C.c_int, [intp]),
     "bgsb_kernel_launch_count": (C.c_uint64, []),
+    "bgsb_copy_probe": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_double)]),
     "bgsb_host_alloc": (C.c_int, [C.POINTER(vp), C.c_size_t, C.c_int]),
     "bgsb_host_free": (None, [vp]),
     "bgsb_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int]),
@@ -107,6 +109,7 @@ SIGNATURES = {
     "bgsb_pool_mask": (vp, [vp, C.c_int, C.c_int]),
     "bgsb_pool_components": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(Component), C.c_int, intp]),
     "bgsb_synth_frames_dev": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, vp]),
+    "bgsb_synth_churn_frames_dev": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, vp]),
 }
 
 _lib = None

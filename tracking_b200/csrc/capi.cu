@@ -9,6 +9,7 @@
 #include <string.h>
 #include <algorithm>
 
+#include <chrono>
 #include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
@@ -984,6 +985,54 @@ int bgsb_synth_frames_dev(uint8_t *d_frames, int nstreams, int T, int w, int h, 
 {
     BGSB_REQUIRE(d_frames && nstreams >= 1 && T >= 1, "bad args");
     return launch_synth(d_frames, nstreams, T, w, h, t0, seed0, (cudaStream_t)stream);
+}
+
+// PCIe ceiling of one GPU as this process sees it: page-locked host buffers, two copy streams, no kernels.
+int bgsb_copy_probe(int device, size_t bytes_up, size_t bytes_down, int iters, double *sec_up, double *sec_down, double *sec_both)
+{
+    BGSB_REQUIRE(bytes_up > 0 && bytes_down > 0 && iters >= 1 && sec_up && sec_down && sec_both, "bad args");
+    BGSB_CUDA(cudaSetDevice(device));
+    void *h_up = nullptr, *h_dn = nullptr, *d_up = nullptr, *d_dn = nullptr;
+    cudaStream_t s1 = nullptr, s2 = nullptr;
+    cudaError_t e = cudaHostAlloc(&h_up, bytes_up, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(&h_dn, bytes_down, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&d_up, bytes_up);
+    if (e == cudaSuccess) e = cudaMalloc(&d_dn, bytes_down);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) { memset(h_up, 1, bytes_up); memset(h_dn, 0, bytes_down); }
+    auto run = [&](bool up, bool down) -> double {
+        for (int w = 0; w < 3 && e == cudaSuccess; w++) {
+            if (up) e = cudaMemcpyAsync(d_up, h_up, bytes_up, cudaMemcpyHostToDevice, s1);
+            if (down && e == cudaSuccess) e = cudaMemcpyAsync(h_dn, d_dn, bytes_down, cudaMemcpyDeviceToHost, s2);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s1);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s2);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int i = 0; i < iters && e == cudaSuccess; i++) {
+            if (up) e = cudaMemcpyAsync(d_up, h_up, bytes_up, cudaMemcpyHostToDevice, s1);
+            if (down && e == cudaSuccess) e = cudaMemcpyAsync(h_dn, d_dn, bytes_down, cudaMemcpyDeviceToHost, s2);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s1);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s2);
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / iters;
+    };
+    if (e == cudaSuccess) *sec_up = run(true, false);
+    if (e == cudaSuccess) *sec_down = run(false, true);
+    if (e == cudaSuccess) *sec_both = run(true, true);
+    if (s1) cudaStreamDestroy(s1);
+    if (s2) cudaStreamDestroy(s2);
+    cudaFree(d_up); cudaFree(d_dn);
+    if (h_up) cudaFreeHost(h_up);
+    if (h_dn) cudaFreeHost(h_dn);
+    if (e != cudaSuccess) { set_error("bgsb_copy_probe: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return BGSB_ERR_CUDA; }
+    return BGSB_OK;
+}
+
+int bgsb_synth_churn_frames_dev(uint8_t *d_frames, int nstreams, int T, int w, int h, int t0, uint32_t seed0, void *stream)
+{
+    BGSB_REQUIRE(d_frames && nstreams >= 1 && T >= 1, "bad args");
+    return launch_synth_churn(d_frames, nstreams, T, w, h, t0, seed0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -131,5 +131,6 @@ int launch_morph_chain_io(const MorphIO &io, int w, int h, int nimages, const in
 // ---- synthetic video ----------------------------------------------------------------------------
 int launch_synth(uint8_t *d_frames, int nstreams, int T, int w, int h, int t0, uint32_t seed0,
                  cudaStream_t stream);
+int launch_synth_churn(uint8_t *d_frames, int nstreams, int T, int w, int h, int t0, uint32_t seed0, cudaStream_t stream);
 
 }  // namespace bgsb

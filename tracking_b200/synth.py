@@ -49,3 +49,24 @@ def frames_dev(d_ptr, nstreams, T, w, h, t0=0, seed0=SEED0, stream=0):
     """Fill a device buffer [nstreams][T][h][w][3] with synthetic frames (K-GEN)."""
     capi.check(capi.lib().bgsb_synth_frames_dev(C.c_void_p(d_ptr), nstreams, T, w, h, t0, seed0 & 0xFFFFFFFF,
                                                 C.c_void_p(stream)))
+
+
+def churn_frame(w, h, t, seed=SEED0):
+    """One frame of the mode-churn video (numpy twin of synth_churn_kernel): five well-separated colours per pixel,
+    redrawn every second frame, noise in [-2, 2] -- keeps all K = 5 mixture modes of every pixel live."""
+    x = np.arange(w, dtype=np.int64)[None, :, None]
+    y = np.arange(h, dtype=np.int64)[:, None, None]
+    c = np.arange(3, dtype=np.int64)[None, None, :]
+    with np.errstate(over="ignore"):
+        xy = (x.astype(np.uint32) * np.uint32(73856093)) ^ (y.astype(np.uint32) * np.uint32(19349663))
+        hi = xy ^ np.uint32(((t >> 1) * 83492791) & 0xFFFFFFFF) ^ np.uint32(((seed & 0xFFFFFFFF) * 2246822519) & 0xFFFFFFFF)
+        i = (_mix32(hi) % np.uint32(5)).astype(np.int64)                       # (h, w, 1)
+        hsh = xy ^ np.uint32((t * 83492791) & 0xFFFFFFFF) ^ (c.astype(np.uint32) * np.uint32(2654435761)) ^ np.uint32(seed & 0xFFFFFFFF)
+        N = (_mix32(hsh) % np.uint32(5)).astype(np.int64) - 2
+    col = np.concatenate([20 + 50 * i, 230 - 45 * i, (90 + 110 * i) & 255], axis=2)
+    return np.clip(col + N, 0, 255).astype(np.uint8)
+
+
+def churn_frames_dev(d_ptr, nstreams, T, w, h, t0=0, seed0=SEED0, stream=0):
+    capi.check(capi.lib().bgsb_synth_churn_frames_dev(C.c_void_p(d_ptr), nstreams, T, w, h, t0, seed0 & 0xFFFFFFFF,
+                                                      C.c_void_p(stream)))
