@@ -293,15 +293,20 @@ BGSB_API int bgsb_pipeline_set_param(bgsb_pipeline *p, const char *key, double v
  *   d_bg     [nstreams][h][w][3] the plugin's background image
  *   d_labels [nstreams][h][w]    canonical labels of the 8-connected components (int32, 0 = background)
  * *valid = 0 while the plugin has no mask yet (FD frame 0, WMV frames 0-1): nothing was labelled.
- * Asynchronous on `stream`; the component tables stay on the device until fetched. */
+ * Asynchronous.  The plugin kernel runs on `stream`; clean-up and labelling run on a stream of the pipeline behind
+ * it, so that they overlap whatever the caller enqueues next on `stream` (normally the next frame's plugin kernel).
+ * `stream` is made to wait for them only when d_mask or d_labels were given; otherwise the component tables (which
+ * stay on the device until fetched) are ordered by the fetching calls below or by bgsb_pipeline_join_dev. */
 BGSB_API int bgsb_pipeline_process_dev(bgsb_pipeline *p, const uint8_t *d_frames, int w, int h, uint8_t *d_mask,
                                        uint8_t *d_bg, int32_t *d_labels, int *valid, int *bg_valid, void *stream);
-/* Component table of stream `stream_index` for the last frame (synchronises the stream). */
+/* Make `stream` wait for everything the pipeline has enqueued so far (e.g. before an event that ends a timed region). */
+BGSB_API int bgsb_pipeline_join_dev(bgsb_pipeline *p, void *stream);
+/* Component table of stream `stream_index` for the last frame (synchronises with the labelling). */
 BGSB_API int bgsb_pipeline_components(bgsb_pipeline *p, int stream_index, bgsb_component *out, int capacity, int *n);
 /* The tables of ALL streams for the last frame into one dense device buffer (one download for the whole group):
  * d_out is int32 [nstreams][(rows_per_stream + 1) * 8]: per stream 8 ints of header {component count, 0 x 7} followed
- * by the first rows_per_stream components (raster order) as bgsb_component rows.  Asynchronous on `stream`, which
- * must be the stream the frame was processed on. */
+ * by the first rows_per_stream components (raster order) as bgsb_component rows.  Asynchronous: `stream` (any stream of
+ * the device, e.g. the one a download is enqueued on next) waits for the buffer to be complete. */
 BGSB_API int bgsb_pipeline_tables_dev(bgsb_pipeline *p, int32_t *d_out, int rows_per_stream, void *stream);
 /* cvMoments(pFGMask[R], 0) sums on that stream's cleaned mask, as bgsb_ccl_rect_moments. */
 BGSB_API int bgsb_pipeline_rect_moments(bgsb_pipeline *p, int stream_index, const int32_t *rects_xywh, int nrects,

@@ -8,12 +8,13 @@ import tracking_b200 as tb
 from tracking_b200 import blobs, synth
 from tracking_b200.pipeline import ForegroundPipeline
 
-def timed(fn, iters, warm=3):
+def timed(fn, iters, warm=3, join=None):
     for _ in range(warm): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters): fn()
+    if join: join()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters * 1e3     # us
 
@@ -28,7 +29,7 @@ k = [0]
 def step():
     pipe.process_dev(frames[k[0] % NT].data_ptr(), w, h, None, None, None, stream=st); k[0] += 1
 for _ in range(4 * NT): step()
-t_pipe = timed(step, 48, warm=0)
+t_pipe = timed(step, 48, warm=0, join=lambda: pipe.join_dev(st))
 pipe.close()
 pipe = ForegroundPipeline(5, nstreams=S)
 d_mask = torch.empty((S, h, w), dtype=torch.uint8, device="cuda")
@@ -36,7 +37,7 @@ k = [0]
 def step_m():
     pipe.process_dev(frames[k[0] % NT].data_ptr(), w, h, d_mask.data_ptr(), None, None, stream=st); k[0] += 1
 for _ in range(4 * NT): step_m()
-t_pipe_m = timed(step_m, 48, warm=0)
+t_pipe_m = timed(step_m, 48, warm=0, join=lambda: pipe.join_dev(st))
 print(json.dumps(dict(probe="pipeline packed", streams=S, us_per_step=t_pipe, mpixel_s=S*w*h/t_pipe, us_with_byte_mask=t_pipe_m,
                       components_stream0=len(pipe.components(0)))), flush=True)
 # byte chain (round-1 form)

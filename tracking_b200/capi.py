@@ -94,6 +94,7 @@ SIGNATURES = {
     "bgsb_pipeline_set_morph": (C.c_int, [vp, intp, C.c_int]),
     "bgsb_pipeline_set_param": (C.c_int, [vp, C.c_char_p, C.c_double]),
     "bgsb_pipeline_process_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp, intp, intp, vp]),
+    "bgsb_pipeline_join_dev": (C.c_int, [vp, vp]),
     "bgsb_pipeline_components": (C.c_int, [vp, C.c_int, C.POINTER(Component), C.c_int, intp]),
     "bgsb_pipeline_tables_dev": (C.c_int, [vp, vp, C.c_int, vp]),
     "bgsb_pipeline_rect_moments": (C.c_int, [vp, C.c_int, i32p, C.c_int, C.POINTER(C.c_uint64)]),

@@ -706,7 +706,8 @@ int ccl_label_bits(bgsb_ccl *c, const unsigned *d_bits, bool parents_ready, int 
         if (c->coop_ctas <= 0) {
             int per_sm = 0;
             BGSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccl_background_kernel, 256, 0));
-            c->coop_ctas = std::max(1, per_sm) * sm_count(c->device);
+            // at most two CTAs per SM: the launch has to become resident as a whole, possibly beside another stream's kernel
+            c->coop_ctas = std::min(2, std::max(1, per_sm)) * sm_count(c->device);
         }
         const long long want = (long long)nimages * ((A.nwords + 255) / 256);
         cudaLaunchConfig_t cfg = {};

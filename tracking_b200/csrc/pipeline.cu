@@ -31,15 +31,25 @@ struct bgsb_pipeline {
     int zero_border = 1;              // OpenCV 2.4 cvFindContours (the version the reference builds against)
     int force_bg = 0;
     int w = 0, h = 0;
-    unsigned *d_raw = nullptr, *d_clean = nullptr;      // [S][h][wpr] packed masks: plugin output, after the chain
-    uint8_t *d_fg = nullptr;                            // [S][h][w] byte mask of plugins that cannot emit bits
+    unsigned *d_raw[2] = {nullptr, nullptr};            // [S][h][wpr] packed plugin masks, alternating between frames
+    unsigned *d_clean = nullptr;                        // ... after the chain
+    uint8_t *d_fg[2] = {nullptr, nullptr};              // [S][h][w] byte masks of plugins that cannot emit bits
     bool labelled = false;
+    // Clean-up + labelling of frame t run on the pipeline's own high-priority stream, so that they overlap the plugin
+    // kernel of frame t+1 (their launches are latency-bound and leave the SMs almost empty): the caller's stream only
+    // waits for them when it has to (device outputs requested, or bgsb_pipeline_join_dev).
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_plugin = nullptr, ev_chain[2] = {nullptr, nullptr}, ev_out = nullptr;
+    bool chain_used[2] = {false, false};
+    uint64_t nframe = 0;
+    int last_slot = -1;                                 // slot of the last frame whose chain was enqueued, -1: none
 };
 
 static void pipeline_free(bgsb_pipeline *p)
 {
-    cudaFree(p->d_raw); cudaFree(p->d_clean); cudaFree(p->d_fg);
-    p->d_raw = p->d_clean = nullptr; p->d_fg = nullptr;
+    for (int i = 0; i < 2; i++) { cudaFree(p->d_raw[i]); cudaFree(p->d_fg[i]); p->d_raw[i] = nullptr; p->d_fg[i] = nullptr; }
+    cudaFree(p->d_clean); p->d_clean = nullptr;
+    p->chain_used[0] = p->chain_used[1] = false; p->last_slot = -1;
     if (p->ccl) { bgsb_ccl_destroy(p->ccl); p->ccl = nullptr; }
     p->w = p->h = 0; p->labelled = false;
 }
@@ -49,8 +59,21 @@ static int pipeline_geometry(bgsb_pipeline *p, int w, int h)
     if (p->w == w && p->h == h) return BGSB_OK;
     pipeline_free(p);
     const size_t S = (size_t)p->nstreams, words = (size_t)((w + 31) / 32) * h;
-    cudaError_t e = cudaMalloc(&p->d_raw, S * words * 4);
+    if (p->side) cudaStreamSynchronize(p->side);
+    cudaError_t e = cudaMalloc(&p->d_raw[0], S * words * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_raw[1], S * words * 4);
     if (e == cudaSuccess) e = cudaMalloc(&p->d_clean, S * words * 4);
+    if (e == cudaSuccess) e = cudaMemset(p->d_raw[0], 0, S * words * 4);
+    if (e == cudaSuccess) e = cudaMemset(p->d_raw[1], 0, S * words * 4);
+    if (e == cudaSuccess && !p->side) {
+        int lo = 0, hi = 0;
+        e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_plugin, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_chain[0], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_chain[1], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         set_error("bgsb_pipeline(%d x %d x %d streams): %s", w, h, p->nstreams, cudaGetErrorString(e));
         (void)cudaGetLastError();
@@ -85,6 +108,10 @@ void bgsb_pipeline_destroy(bgsb_pipeline *p)
     cudaSetDevice(p->device);
     cudaDeviceSynchronize();
     pipeline_free(p);
+    if (p->side) cudaStreamDestroy(p->side);
+    if (p->ev_plugin) cudaEventDestroy(p->ev_plugin);
+    for (int i = 0; i < 2; i++) if (p->ev_chain[i]) cudaEventDestroy(p->ev_chain[i]);
+    if (p->ev_out) cudaEventDestroy(p->ev_out);
     bgsb_destroy(p->bgs);
     delete p;
 }
@@ -133,45 +160,66 @@ int bgsb_pipeline_process_dev(bgsb_pipeline *p, const uint8_t *d_frames, int w, 
     double thr_on = 1.;
     (void)bgsb_get_param(p->bgs, "enableThreshold", &thr_on);
     const bool pack = ctx_can_pack(p->bgs) && (p->total_iters > 0 || thr_on != 0.);
-    if (!pack && !p->d_fg) BGSB_CUDA(cudaMalloc(&p->d_fg, (size_t)S * w * h));
+    const int slot = (int)(p->nframe & 1);
+    if (!pack && !p->d_fg[slot]) BGSB_CUDA(cudaMalloc(&p->d_fg[slot], (size_t)S * w * h));
+    // this slot's plugin mask was last read by the chain of the frame before the previous one
+    if (p->chain_used[slot]) BGSB_CUDA(cudaStreamWaitEvent(stream, p->ev_chain[slot], 0));
     int packed = 0, fv = 0, bv = 0;
     if (pack) {
         // the plugin kernel ORs its foreground bits into zeroed rows; a pixel counts when its mask byte would be non-zero
         // (what the morphology reads) or, without a chain, > 128 (what cvThreshold(128) in DetectNewBlob keeps)
-        BGSB_CUDA(cudaMemsetAsync(p->d_raw, 0, S * words * 4, stream));
-        rc = ctx_process_frame(p->bgs, d_frames, w, h, nullptr, d_bg, p->d_raw, p->total_iters > 0 ? 0 : 128, &packed, &fv, &bv, stream);
+        // (the rows are zero: cleared at allocation and, after every use, behind the chain that read them)
+        rc = ctx_process_frame(p->bgs, d_frames, w, h, nullptr, d_bg, p->d_raw[slot], p->total_iters > 0 ? 0 : 128, &packed, &fv, &bv, stream);
     } else {
-        rc = ctx_process_frame(p->bgs, d_frames, w, h, p->d_fg, d_bg, nullptr, 0, &packed, &fv, &bv, stream);
+        rc = ctx_process_frame(p->bgs, d_frames, w, h, p->d_fg[slot], d_bg, nullptr, 0, &packed, &fv, &bv, stream);
     }
     if (rc) return rc;
     if (bg_valid) *bg_valid = bv;
     if (!fv) return BGSB_OK;                       // FD frame 0 / WMV frames 0-1: no mask yet (reference early returns)
+    p->nframe++;
+    // ---- clean-up + labelling on the side stream ----
+    cudaStream_t cs = p->side;
+    BGSB_CUDA(cudaEventRecord(p->ev_plugin, stream));
+    BGSB_CUDA(cudaStreamWaitEvent(cs, p->ev_plugin, 0));
     MorphIO io;
     memset(&io, 0, sizeof(io));
     io.parent = p->ccl->d_parent; io.zero_border = p->zero_border;
     io.out_bytes = d_mask;
     if (packed) {
-        if (p->total_iters > 0 || d_mask) {
-            io.in_bits = p->d_raw; io.out_bits = p->d_clean;
-            rc = launch_morph_chain_io(io, w, h, S, p->ops, p->nops, stream);
-            if (rc) return rc;
-            rc = ccl_label_bits(p->ccl, p->d_clean, true, w, h, S, p->zero_border, d_labels, stream);
-        } else {
-            rc = ccl_label_bits(p->ccl, p->d_raw, false, w, h, S, p->zero_border, d_labels, stream);
-        }
-    } else if (p->total_iters > 0) {
-        io.in_bytes = p->d_fg; io.out_bits = p->d_clean;
-        rc = launch_morph_chain_io(io, w, h, S, p->ops, p->nops, stream);
+        // (an empty chain still goes through the kernel: it copies the rows to d_clean -- the plugin's rows are cleared
+        // below for their next use -- and creates the labeller's nodes)
+        io.in_bits = p->d_raw[slot]; io.out_bits = p->d_clean;
+        rc = launch_morph_chain_io(io, w, h, S, p->ops, p->nops, cs);
         if (rc) return rc;
-        rc = ccl_label_bits(p->ccl, p->d_clean, true, w, h, S, p->zero_border, d_labels, stream);
+        rc = ccl_label_bits(p->ccl, p->d_clean, true, w, h, S, p->zero_border, d_labels, cs);
+    } else if (p->total_iters > 0) {
+        io.in_bytes = p->d_fg[slot]; io.out_bits = p->d_clean;
+        rc = launch_morph_chain_io(io, w, h, S, p->ops, p->nops, cs);
+        if (rc) return rc;
+        rc = ccl_label_bits(p->ccl, p->d_clean, true, w, h, S, p->zero_border, d_labels, cs);
     } else {
         // no chain on a byte mask: the labeller's own pack step applies DetectNewBlob's threshold (> 128)
-        if (d_mask) BGSB_CUDA(cudaMemcpyAsync(d_mask, p->d_fg, (size_t)S * w * h, cudaMemcpyDeviceToDevice, stream));
-        rc = bgsb_ccl_label_batch_dev(p->ccl, p->d_fg, w, h, S, p->zero_border, d_labels, stream);
+        if (d_mask) BGSB_CUDA(cudaMemcpyAsync(d_mask, p->d_fg[slot], (size_t)S * w * h, cudaMemcpyDeviceToDevice, cs));
+        rc = bgsb_ccl_label_batch_dev(p->ccl, p->d_fg[slot], w, h, S, p->zero_border, d_labels, cs);
     }
     if (rc) return rc;
+    if (packed) BGSB_CUDA(cudaMemsetAsync(p->d_raw[slot], 0, S * words * 4, cs));    // ready for the plugin two frames on
+    BGSB_CUDA(cudaEventRecord(p->ev_chain[slot], cs));
+    p->chain_used[slot] = true;
+    p->last_slot = slot;
+    // device outputs the caller may consume on its stream: that stream waits for them now; table-only frames leave the
+    // chain running beside whatever the caller enqueues next (the next frame's plugin kernel)
+    if (d_mask || d_labels) BGSB_CUDA(cudaStreamWaitEvent(stream, p->ev_chain[slot], 0));
     p->labelled = true;
     if (valid) *valid = 1;
+    return BGSB_OK;
+}
+
+int bgsb_pipeline_join_dev(bgsb_pipeline *p, void *stream)
+{
+    BGSB_REQUIRE(p, "null");
+    BGSB_CUDA(cudaSetDevice(p->device));
+    if (p->last_slot >= 0) BGSB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, p->ev_chain[p->last_slot], 0));
     return BGSB_OK;
 }
 
@@ -187,7 +235,11 @@ int bgsb_pipeline_tables_dev(bgsb_pipeline *p, int32_t *d_out, int rows_per_stre
     BGSB_REQUIRE(p && d_out && rows_per_stream >= 0, "bad args");
     if (!p->labelled) { set_error("bgsb_pipeline_tables_dev: no frame has produced a mask yet"); return BGSB_ERR_STATE; }
     BGSB_CUDA(cudaSetDevice(p->device));
-    return ccl_gather_tables(p->ccl, d_out, rows_per_stream, (cudaStream_t)stream);
+    int rc = ccl_gather_tables(p->ccl, d_out, rows_per_stream, p->side);       // behind the labelling, on its stream
+    if (rc) return rc;
+    BGSB_CUDA(cudaEventRecord(p->ev_out, p->side));
+    BGSB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, p->ev_out, 0));
+    return BGSB_OK;
 }
 
 int bgsb_pipeline_rect_moments(bgsb_pipeline *p, int stream_index, const int32_t *rects, int nrects, uint64_t *out)

@@ -100,12 +100,15 @@ static void worker_main(bgsb_pool *P, GpuGroup *G)
             rc = bgsb_pipeline_process_dev(G->pipe, G->d_in[k], P->w, P->h, j.want_masks ? G->d_mask[k] : nullptr, nullptr, nullptr,
                                            &valid, &bgv, G->s_k);
             if (rc) { err = bgsb_last_error(); break; }
-            if (valid) {
-                rc = bgsb_pipeline_tables_dev(G->pipe, G->d_tab[k], P->table_rows, G->s_k);
-                if (rc) { err = bgsb_last_error(); break; }
-            }
             if (fail(cudaEventRecord(G->ev_k[k], G->s_k), "record")) break;
             if (fail(cudaStreamWaitEvent(G->s_d2h, G->ev_k[k], 0), "wait(kernels)")) break;
+            if (valid) {
+                // clean-up and labelling run on the pipeline's own stream beside the NEXT frame set's plugin kernel; only
+                // the download stream waits for them (masks and tables), the kernel stream goes straight on
+                rc = bgsb_pipeline_join_dev(G->pipe, G->s_d2h);
+                if (!rc) rc = bgsb_pipeline_tables_dev(G->pipe, G->d_tab[k], P->table_rows, G->s_d2h);
+                if (rc) { err = bgsb_last_error(); break; }
+            }
             if (valid) {
                 if (j.want_masks && fail(cudaMemcpyAsync(G->h_mask[k], G->d_mask[k], S * P->mask_bytes, cudaMemcpyDeviceToHost, G->s_d2h), "download masks")) break;
                 if (fail(cudaMemcpyAsync(G->h_tab[k], G->d_tab[k], S * P->tab_ints * sizeof(int32_t), cudaMemcpyDeviceToHost, G->s_d2h), "download tables")) break;

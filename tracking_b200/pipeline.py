@@ -60,6 +60,10 @@ class ForegroundPipeline:
         self._shape = (w, h)
         return bool(v.value), bool(bv.value)
 
+    def join_dev(self, stream=0):
+        """`stream` waits for all clean-up / labelling work enqueued so far (they run on the pipeline's own stream)."""
+        capi.check(capi.lib().bgsb_pipeline_join_dev(self._h, C.c_void_p(stream)))
+
     def components(self, stream_index=0):
         n = C.c_int(0)
         capi.check(capi.lib().bgsb_pipeline_components(self._h, stream_index, None, 0, C.byref(n)))
