@@ -64,3 +64,14 @@ def test_adapters_compile_against_stub_opencv():
                            "-I", os.path.join(ROOT, "tracking_b200", "adapters", "stub_opencv"),
                            "-I", os.path.join(ROOT, "tracking_b200", "adapters"),
                            "-I", os.path.join(ROOT, "include"), test_cpp])
+
+
+def test_dropin_test_program_links_against_the_library(tmp_path):
+    """adapters/dropin_test.cpp (run under -m gpu by tests/test_gpu_cpp_dropin.py) compiles against the functional
+    OpenCV stand-in, for both OpenCV generations it can claim, and links against libbgsb200.so."""
+    ad = os.path.join(ROOT, "tracking_b200", "adapters")
+    for major in (2, 4):
+        subprocess.check_call(["g++", "-std=c++11", "-O0", "-Wall", "-Wextra", "-DBGSB_STUB_CV_MAJOR=%d" % major,
+                               "-I", os.path.join(ad, "stub_opencv"), "-I", ad, "-I", os.path.join(ROOT, "include"),
+                               os.path.join(ad, "dropin_test.cpp"), "-L", os.path.join(ROOT, "tracking_b200"), "-lbgsb200",
+                               "-Wl,-rpath," + os.path.join(ROOT, "tracking_b200"), "-o", str(tmp_path / ("dropin%d" % major))])

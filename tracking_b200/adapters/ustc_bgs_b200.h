@@ -111,6 +111,75 @@ public:
 
 inline CvBlobDetector *cvCreateBlobDetectorCC_B200() { return new BgsbBlobDetectorCC; }
 
+// Tracker-side use of the same mask.  The tracker modules the reference lists at
+// ustc_src/trackingMain.cpp:70-78 and runs per frame at :166 (pTracker->Process(pImg, pFG)) look at the foreground
+// mask again: CvBlobTrackerCC / CCMSPF re-run cvFindContours(RETR_EXTERNAL) on it to get the blobs' contour
+// rectangles, and CvBlobTrackerAuto1's blob deleter sums the mask under each tracked blob (cvSum of the ROI).  Both
+// are answered here from ONE labelling of the mask on the GPU -- the component table and exact integer ROI sums --
+// so the mask is not walked again on the CPU.
+class BgsbTrackerFeed
+{
+    bgsb_ccl *ccl;
+    int cw, ch;
+    std::vector<bgsb_component> comps;
+    std::vector<CvRect> rects;
+
+public:
+    BgsbTrackerFeed() : ccl(0), cw(0), ch(0) {}
+    ~BgsbTrackerFeed() { if (ccl) bgsb_ccl_destroy(ccl); }
+
+    // once per frame, with the mask CvFGDetector::GetMask() returned
+    void Update(IplImage *pFGMask)
+    {
+        CV_Assert(pFGMask && pFGMask->nChannels == 1 && pFGMask->depth == IPL_DEPTH_8U);
+        const int w = pFGMask->width, h = pFGMask->height;
+        if (!ccl || w > cw || h > ch) {
+            if (ccl) bgsb_ccl_destroy(ccl);
+            ccl = 0;
+            CV_Assert(bgsb_ccl_create(&ccl, 0, w, h) == BGSB_OK);
+            cw = w; ch = h;
+        }
+        // cvFindContours clears the mask's 1-px frame up to OpenCV 3.1 and keeps it afterwards
+#if defined(CV_MAJOR_VERSION) && (CV_MAJOR_VERSION > 3 || (CV_MAJOR_VERSION == 3 && CV_MINOR_VERSION >= 2))
+        const int zero_border = 0;
+#else
+        const int zero_border = 1;
+#endif
+        comps.resize((size_t)((w + 1) / 2) * ((h + 1) / 2) + 1);
+        int n = 0;
+        int rc = bgsb_ccl_label(ccl, (const uint8_t *)pFGMask->imageData, w, h, (size_t)pFGMask->widthStep, zero_border, 0,
+                                &comps[0], (int)comps.size(), &n);
+        if (rc != BGSB_OK) std::cerr << "bgsb200: " << bgsb_last_error() << std::endl;
+        CV_Assert(rc == BGSB_OK);
+        comps.resize(n);
+        rects.clear();
+        // cvFindContours(RETR_EXTERNAL) lists the outer contours in reverse raster order of their first pixels
+        for (int i = n - 1; i >= 0; i--)
+            if (comps[i].external) rects.push_back(cvRect(comps[i].x, comps[i].y, comps[i].w, comps[i].h));
+    }
+    // the external contours of the mask: count, and ((CvContour*)cnt)->rect of the i-th one in cvFindContours order
+    int GetContourNum() const { return (int)rects.size(); }
+    CvRect GetContourRect(int i) const { return rects[i]; }
+    // cvSum(mask(ROI)).val[0] for each rectangle (clipped to the mask), exact
+    void SumROIs(const CvRect *rois, int n, double *sums)
+    {
+        if (n <= 0) return;
+        std::vector<int32_t> flat((size_t)n * 4);
+        for (int i = 0; i < n; i++) {
+            int x0 = rois[i].x < 0 ? 0 : rois[i].x, y0 = rois[i].y < 0 ? 0 : rois[i].y;
+            int x1 = rois[i].x + rois[i].width, y1 = rois[i].y + rois[i].height;
+            if (x1 > cw) x1 = cw;
+            if (y1 > ch) y1 = ch;
+            flat[4 * i] = x0; flat[4 * i + 1] = y0;
+            flat[4 * i + 2] = x1 > x0 ? x1 - x0 : 0; flat[4 * i + 3] = y1 > y0 ? y1 - y0 : 0;
+        }
+        std::vector<uint64_t> mom((size_t)n * 6);
+        CV_Assert(bgsb_ccl_rect_moments(ccl, &flat[0], n, &mom[0]) == BGSB_OK);
+        for (int i = 0; i < n; i++) sums[i] = (double)mom[6 * (size_t)i];
+    }
+    double SumROI(CvRect roi) { double s = 0; SumROIs(&roi, 1, &s); return s; }
+};
+
 // cvErode / cvDilate(mask, mask, NULL, n) on an 8-bit single-channel IplImage, on the GPU.
 inline void bgsbMorph(IplImage *mask, int op /* BGSB_MORPH_ERODE | BGSB_MORPH_DILATE */, int iterations)
 {
