@@ -45,14 +45,14 @@ def out(**kw):
     print(json.dumps(kw), flush=True)
 
 
-def simple_streams(algo_cls, name, bpp, S=16, w=1920, h=1080, NT=6, iters=40):
+def simple_streams(algo_cls, name, bpp, S=16, w=1920, h=1080, NT=6, iters=40, retain=False):
     st = torch.cuda.current_stream().cuda_stream
     frames = torch.empty((NT, S, h, w, 3), dtype=torch.uint8, device="cuda")
     for t in range(NT):        # layout per time step: [S][1][h][w][3]
         synth.frames_dev(frames[t].data_ptr(), S, 1, w, h, t0=t, stream=st)
     fg = torch.empty((S, h, w), dtype=torch.uint8, device="cuda")
     bg = torch.empty((S, h, w, 3), dtype=torch.uint8, device="cuda")
-    p = algo_cls(nstreams=S)
+    p = algo_cls(nstreams=S, **({"retainInput": 1} if retain else {}))
     k = [0]
 
     def step():
@@ -60,7 +60,7 @@ def simple_streams(algo_cls, name, bpp, S=16, w=1920, h=1080, NT=6, iters=40):
         k[0] += 1
     dt = timed(step, iters, warm=4)
     px = S * w * h
-    out(config={"FD": "fd", "ABL": "3", "WMV": "3"}.get(name, "sibling"), algo=name, streams=S, resolution=[w, h], ms_per_step=dt * 1e3,
+    out(config={"FD": "fd", "ABL": "3", "WMV": "3"}.get(name.split()[0], "sibling"), algo=name, streams=S, resolution=[w, h], ms_per_step=dt * 1e3,
         mpixel_s=px / dt / 1e6, algorithmic_bytes_per_px=bpp, achieved_gbs=px * bpp / dt / 1e9,
         frac_of_measured_peak=px * bpp / dt / 1e9 / PEAK)
     p.close()
@@ -93,47 +93,39 @@ def mog2_batches(S, w, h, Ts, label, NF=48, iters=2):
         del fg, bg, wins
 
 
-def pipeline(S=64, w=1920, h=1080, NT=24, iters=24):
+def pipeline(S=64, w=1920, h=1080, NT=24, iters=48):
+    """Config 4 through the pipeline object (packed mask between the stages); stage split: tools/pipeline_probe.py."""
+    from tracking_b200.pipeline import ForegroundPipeline
     st = torch.cuda.current_stream().cuda_stream
     frames = torch.empty((NT, S, h, w, 3), dtype=torch.uint8, device="cuda")
     for t in range(NT):
         synth.frames_dev(frames[t].data_ptr(), S, 1, w, h, t0=t, stream=st)
-    fg = torch.empty((S, h, w), dtype=torch.uint8, device="cuda")
-    clean = torch.empty((S, h, w), dtype=torch.uint8, device="cuda")
-    p = tb.MixtureOfGaussianV2BGS(nstreams=S)
-    cc = blobs.ConnectedComponents(w, h, max_images=S)
+    pipe = ForegroundPipeline(5, nstreams=S)
     k = [0]
-    parts = {"mog2": 0.0, "morph": 0.0, "cc": 0.0}
 
-    def step(measure=False):
-        f = frames[k[0] % NT]
+    def step():
+        pipe.process_dev(frames[k[0] % NT].data_ptr(), w, h, None, None, None, stream=st)
         k[0] += 1
-        p.process_dev(f.data_ptr(), w, h, fg.data_ptr(), None, stream=st)
-        blobs.morph_dev(fg.data_ptr(), w, h, S, [("erode", 1), ("dilate", 1)], clean.data_ptr(), stream=st)
-        cc.label_batch_dev(clean.data_ptr(), w, h, S, True, None, stream=st)
-    for _ in range(2 * NT):     # let the models settle on the moving scene
+    for _ in range(3 * NT):     # let the models settle on the moving scene
         step()
-    dt = timed(step, iters, warm=0)
-    ncomp = len(cc.components(0))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    pipe.join_dev(st)
+    e1.record()
+    torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) / iters * 1e-3
+    ncomp = len(pipe.components(0))
+    nm = pipe.export_mog2_state(0)[1]
+    live = 5 + 40 * float(nm.mean()) + 0.5
     px = S * w * h
-    out(config="4", algo="MOG2+OPEN+CC", streams=S, resolution=[w, h], ms_per_step=dt * 1e3, mpixel_s=px / dt / 1e6,
-        components_stream0=ncomp, dense_model_bytes_per_px=218, dense_equiv_gbs=px * 218 / dt / 1e9)
-    # stage split (MOG2 keeps walking the video so that its share of generic-path pixels is the steady-state one)
-    def mog_only():
-        f = frames[k[0] % NT]
-        k[0] += 1
-        p.process_dev(f.data_ptr(), w, h, fg.data_ptr(), None, stream=st)
-    t_m = timed(mog_only, iters, warm=0)
-    t_o = timed(lambda: blobs.morph_dev(fg.data_ptr(), w, h, S, [("erode", 1), ("dilate", 1)], clean.data_ptr(), stream=st), iters, warm=1)
-    t_c = timed(lambda: cc.label_batch_dev(clean.data_ptr(), w, h, S, True, None, stream=st), iters, warm=1)
-    nm = p.export_state(0)[1]
-    live = 9 + 40 * float(nm.mean())
-    out(config="4-split", mog2_ms=t_m * 1e3, morph_ms=t_o * 1e3, cc_ms=t_c * 1e3, components_stream0=len(cc.components(0)),
-        mean_live_modes=float(nm.mean()), mog2_live_gbs=px * live / t_m / 1e9, mog2_frac_of_peak=px * live / t_m / 1e9 / PEAK,
-        morph_gbs=px * 2 / t_o / 1e9, cc_gbs_no_label_image=px * 1 / t_c / 1e9,
-        pipeline_live_bytes_per_px=live + 4 + 1, pipeline_frac_of_peak=px * (live + 5) / dt / 1e9 / PEAK)
-    cc.close()
-    p.close()
+    out(config="4", algo="MOG2+OPEN+CC (bgsb_pipeline, packed mask)", streams=S, resolution=[w, h], ms_per_step=dt * 1e3,
+        mpixel_s=px / dt / 1e6, components_stream0=ncomp, mean_live_modes=float(nm.mean()), live_bytes_per_px=live,
+        live_gbs=px * live / dt / 1e9, frac_of_peak_live=px * live / dt / 1e9 / PEAK, dense_model_bytes_per_px=218,
+        dense_equiv_gbs=px * 218 / dt / 1e9)
+    pipe.close()
 
 
 def config1(clip):
@@ -228,6 +220,9 @@ def main():
     z = np.load(os.path.join(ROOT, "tests", "golden", "clips.npz"))
     config1(z["video_clip"])
     pcie_probe()
+    simple_streams(tb.FrameDifferenceBGS, "FD retainInput (SURVEY 8d bytes: 7 B/px)", 7, retain=True)
+    simple_streams(tb.WeightedMovingVarianceBGS, "WMV retainInput (SURVEY 8d bytes: 10 B/px)", 10, retain=True)
+    simple_streams(tb.WeightedMovingMeanBGS, "WMM retainInput (9 in + 1 mask + 3 bg)", 13, retain=True)
     simple_streams(tb.FrameDifferenceBGS, "FD", 7 + 3)        # device path also writes the 3 B/px history
     simple_streams(tb.AdaptiveBackgroundLearning, "ABL", 10)
     simple_streams(tb.WeightedMovingVarianceBGS, "WMV", 10 + 6)  # device path writes both history images

@@ -459,50 +459,52 @@ ccl_background_kernel(const __grid_constant__ CclArgs A)
     for (int i = tid; i < A.nimages; i += 256) any |= A.need_bg[i];
     if (!__syncthreads_or(any)) return;              // the same answer in every CTA: typical masks end here
 
+    // The phases stride over (image, word) pairs of ALL images at once: the background of an image is essentially one
+    // huge component, whose unions contend on one root -- latency, not throughput -- so flagged images must progress
+    // side by side, not one after the other.
+    const size_t nitems = (size_t)A.nimages * A.nwords;
     // phase 1: background runs of the flagged images become nodes
-    for (int img = 0; img < A.nimages; img++) {
+    for (size_t it = gtid; it < nitems; it += gsize) {
+        const int img = (int)(it / A.nwords), wi = (int)(it - (size_t)img * A.nwords);
         if (!A.need_bg[img]) continue;
         const unsigned *bits = A.bits + img * A.img_words;
         int *parent = A.parent + img * A.img_px;
         uint8_t *outer = A.outer + img * A.img_px;
-        for (size_t wi = gtid; wi < (size_t)A.nwords; wi += gsize) {
-            const int y = (int)wi / A.wpr, k = (int)wi - y * A.wpr;
-            const unsigned vb = ~ccl_word(bits, y, k, A) & in_mask(k, A.w, A.wpr);
-            const int base = y * A.w + k * 32;
-            for (unsigned s = vb & ~(vb << 1); s;) {
-                const int b = __ffs(s) - 1; s &= s - 1;
-                parent[base + b] = base + b;
-                outer[base + b] = 0;
-            }
+        const int y = wi / A.wpr, k = wi - y * A.wpr;
+        const unsigned vb = ~ccl_word(bits, y, k, A) & in_mask(k, A.w, A.wpr);
+        const int base = y * A.w + k * 32;
+        for (unsigned s = vb & ~(vb << 1); s;) {
+            const int b = __ffs(s) - 1; s &= s - 1;
+            parent[base + b] = base + b;
+            outer[base + b] = 0;
         }
     }
     grid.sync();
     // phase 2: 4-connected merge
-    for (int img = 0; img < A.nimages; img++) {
+    for (size_t it = gtid; it < nitems; it += gsize) {
+        const int img = (int)(it / A.nwords), wi = (int)(it - (size_t)img * A.nwords);
         if (!A.need_bg[img]) continue;
-        for (size_t wi = gtid; wi < (size_t)A.nwords; wi += gsize)
-            merge_word<true>(A, A.bits + img * A.img_words, A.parent + img * A.img_px, (int)wi);
+        merge_word<true>(A, A.bits + img * A.img_words, A.parent + img * A.img_px, wi);
     }
     grid.sync();
     // phase 3: flatten; regions that touch the image frame are "outer"
-    for (int img = 0; img < A.nimages; img++) {
+    for (size_t it = gtid; it < nitems; it += gsize) {
+        const int img = (int)(it / A.nwords), wi = (int)(it - (size_t)img * A.nwords);
         if (!A.need_bg[img]) continue;
         const unsigned *bits = A.bits + img * A.img_words;
         int *parent = A.parent + img * A.img_px;
         uint8_t *outer = A.outer + img * A.img_px;
-        for (size_t wi = gtid; wi < (size_t)A.nwords; wi += gsize) {
-            const int y = (int)wi / A.wpr, k = (int)wi - y * A.wpr;
-            const unsigned vb = ~ccl_word(bits, y, k, A) & in_mask(k, A.w, A.wpr);
-            const int base = y * A.w + k * 32;
-            const bool edge_row = (y == 0 || y == A.h - 1);
-            for (unsigned s = vb & ~(vb << 1); s;) {
-                const int b = __ffs(s) - 1; s &= s - 1;
-                const int r = find_root(parent, base + b);
-                parent[base + b] = r;
-                const unsigned rest = ~(vb >> b);
-                const int len = rest ? __ffs(rest) - 1 : 32 - b;
-                if (edge_row || (k == 0 && b == 0) || (k * 32 + b + len - 1 == A.w - 1)) outer[r] = 1;
-            }
+        const int y = wi / A.wpr, k = wi - y * A.wpr;
+        const unsigned vb = ~ccl_word(bits, y, k, A) & in_mask(k, A.w, A.wpr);
+        const int base = y * A.w + k * 32;
+        const bool edge_row = (y == 0 || y == A.h - 1);
+        for (unsigned s = vb & ~(vb << 1); s;) {
+            const int b = __ffs(s) - 1; s &= s - 1;
+            const int r = find_root(parent, base + b);
+            parent[base + b] = r;
+            const unsigned rest = ~(vb >> b);
+            const int len = rest ? __ffs(rest) - 1 : 32 - b;
+            if (edge_row || (k == 0 && b == 0) || (k * 32 + b + len - 1 == A.w - 1)) outer[r] = 1;
         }
     }
     grid.sync();
@@ -706,8 +708,8 @@ int ccl_label_bits(bgsb_ccl *c, const unsigned *d_bits, bool parents_ready, int 
         if (c->coop_ctas <= 0) {
             int per_sm = 0;
             BGSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccl_background_kernel, 256, 0));
-            // at most two CTAs per SM: the launch has to become resident as a whole, possibly beside another stream's kernel
-            c->coop_ctas = std::min(2, std::max(1, per_sm)) * sm_count(c->device);
+            // at most four CTAs per SM: the launch has to become resident as a whole, possibly beside another stream's kernel
+            c->coop_ctas = std::min(4, std::max(1, per_sm)) * sm_count(c->device);
         }
         const long long want = (long long)nimages * ((A.nwords + 255) / 256);
         cudaLaunchConfig_t cfg = {};
