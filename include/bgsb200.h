@@ -119,6 +119,7 @@ BGSB_API int bgsb_reset(bgsb_ctx *ctx);
  * against cv2 4.13, default), 1 = as OpenCV 2.4 does (fp32 arithmetic, scalars cast to float; SURVEY Appendix B --
  * "parity unpinned": no OpenCV 2.4 in the build image), table kernels only;
  * "hostBands" (default 2, 1..8): row bands of the upload / kernel / download pipeline inside bgsb_process;
+ * "trace" (default 0): per-stage timing of bgsb_process, see bgsb_trace_last;
  * "retainInput" (default 0; FrameDifference, WeightedMovingVariance, WeightedMovingMean on the *_dev entry points):
  * 1 = the caller promises that the device frame given to a call stays valid and unmodified until the next call (FD)
  * / the next two calls (WMV, WMM) have completed, so the previous-frame history is read from those buffers and never
@@ -181,6 +182,20 @@ BGSB_API int bgsb_process_dev(bgsb_ctx *ctx, const uint8_t *d_bgr, int w, int h,
 BGSB_API int bgsb_process_batch_dev(bgsb_ctx *ctx, const uint8_t *d_frames, int T, int w, int h,
                                     uint8_t *d_fg, uint8_t *d_bg, int bg_last_only,
                                     int *first_fg_valid, int *bg_valid, void *stream);
+
+/* Tracing (FrameProcessor::tic / toc, FrameProcessor.cpp:484-494, which times one plugin's process() call on the host and
+ * keeps working unchanged around the drop-in): with the context parameter "trace" = 1, or BGSB_TRACE=1 in the
+ * environment, every bgsb_process call is also timed per stage on the device (CUDA events around the uploads, the
+ * kernels and the downloads; with row bands the stages overlap, so they need not add up to the wall time).
+ * BGSB_TRACE=1 prints toc's line "<Plugin>\ttime(sec):<s>" plus the stage split on stderr.  Every entry point that
+ * enqueues work is wrapped in an NVTX range named after the plugin (visible in Nsight Systems). */
+typedef struct bgsb_trace {
+    int64_t frame;          /* index of the traced frame */
+    double wall_ms;         /* host wall time of the call */
+    double upload_ms, kernel_ms, download_ms;
+    int bands;              /* row bands of the call's upload / kernel / download pipeline */
+} bgsb_trace;
+BGSB_API int bgsb_trace_last(bgsb_ctx *ctx, bgsb_trace *out);
 
 /* Number of frames this context has consumed since create/reset. */
 BGSB_API int bgsb_frame_count(bgsb_ctx *ctx, int64_t *nframes);

@@ -828,3 +828,38 @@ def test_max_size_2160p_parity(oracle):
         e, _ = ofd.process(frames[t])
         if e is not None:
             assert np.array_equal(d_fg[t].cpu().numpy(), e), t
+
+
+def test_trace_stage_times_and_toc_line(tmp_path):
+    """Tracing (FrameProcessor::tic / toc equivalent, per stage): the "trace" parameter fills bgsb_trace_last;
+    BGSB_TRACE=1 prints toc's line with the stage split on stderr."""
+    import os
+    import subprocess
+    import sys
+    import tracking_b200 as tb
+    from tracking_b200 import synth
+    f = [synth.frame(1920, 1080, t) for t in range(3)]
+    p = tb.MixtureOfGaussianV2BGS()
+    with pytest.raises(tb.BgsbError):
+        p.trace_last()                                   # nothing traced yet
+    p.set("trace", 1)
+    for x in f:
+        p.process(x)
+    t = p.trace_last()
+    assert t["frame"] == 2 and t["bands"] == 2
+    assert t["upload_ms"] > 0.02 and t["download_ms"] > 0.02 and t["kernel_ms"] > 0.005
+    assert t["wall_ms"] >= max(t["upload_ms"], t["download_ms"]) * 0.9
+    p.close()
+    small = tb.FrameDifferenceBGS(trace=1)
+    small.process(np.zeros((40, 50, 3), np.uint8))       # warm-up frame: uploaded, no kernel output
+    small.process(np.zeros((40, 50, 3), np.uint8))
+    assert small.trace_last()["bands"] == 1
+    small.close()
+    code = ("import numpy as np, tracking_b200 as tb\n"
+            "p = tb.AdaptiveBackgroundLearning()\n"
+            "for _ in range(2): p.process(np.zeros((64, 64, 3), np.uint8))\n")
+    env = dict(os.environ, BGSB_TRACE="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1500:]
+    lines = [l for l in r.stderr.splitlines() if l.startswith("AdaptiveBackgroundLearning\ttime(sec):")]
+    assert len(lines) == 2 and "upload" in lines[0] and "download" in lines[0]

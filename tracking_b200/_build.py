@@ -64,7 +64,7 @@ def build(force=False, verbose=False, instrument=False):
         f.write(log)
     if verbose:
         sys.stderr.write(log)
-    cmd = [NVCC, "-shared", "-o", LIB, *[r[0] for r in results], "-Xcompiler", "-fPIC", "-cudart", "static", "-lpthread"]
+    cmd = [NVCC, "-shared", "-o", LIB, *[r[0] for r in results], "-Xcompiler", "-fPIC", "-cudart", "static", "-lpthread", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -136,6 +136,13 @@ class _Plugin:
                                                      C.byref(first), C.byref(bv), C.c_void_p(stream)))
         return first.value, bool(bv.value)
 
+    def trace_last(self):
+        """Stage times of the last traced process() call (set("trace", 1) first): dict of ms."""
+        t = capi.Trace()
+        capi.check(capi.lib().bgsb_trace_last(self._h, C.byref(t)))
+        return dict(frame=t.frame, wall_ms=t.wall_ms, upload_ms=t.upload_ms, kernel_ms=t.kernel_ms,
+                    download_ms=t.download_ms, bands=t.bands)
+
     def state_bytes(self):
         n = C.c_size_t()
         capi.check(capi.lib().bgsb_state_bytes(self._h, C.byref(n)))

@@ -29,6 +29,11 @@ class Component(C.Structure):
                 ("w", C.c_int32), ("h", C.c_int32), ("area", C.c_int32), ("external", C.c_int32)]
 
 
+class Trace(C.Structure):
+    _fields_ = [("frame", C.c_int64), ("wall_ms", C.c_double), ("upload_ms", C.c_double), ("kernel_ms", C.c_double),
+                ("download_ms", C.c_double), ("bands", C.c_int)]
+
+
 class Blob(C.Structure):
     _fields_ = [("x", C.c_float), ("y", C.c_float), ("w", C.c_float), ("h", C.c_float), ("id", C.c_int32)]
 
@@ -62,6 +67,7 @@ SIGNATURES = {
                                       C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(C.c_size_t), intp, intp]),
     "bgsb_process_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, intp, intp, vp]),
     "bgsb_process_batch_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, intp, intp, vp]),
+    "bgsb_trace_last": (C.c_int, [vp, C.POINTER(Trace)]),
     "bgsb_frame_count": (C.c_int, [vp, C.POINTER(C.c_int64)]),
     "bgsb_state_bytes": (C.c_int, [vp, C.POINTER(C.c_size_t)]),
     "bgsb_mog2_export_state": (C.c_int, [vp, C.c_int, f32p, u8p]),

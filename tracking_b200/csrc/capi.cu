@@ -11,6 +11,7 @@
 
 #include <chrono>
 #include <cstdlib>
+#include <nvtx3/nvToolsExt.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -88,7 +89,31 @@ struct bgsb_ctx {
     bool last_stream_set = false;
     cudaEvent_t ev_order = nullptr;
     int retain_input = 0;      // device path, FD / WMV / WMM: the caller's frames stay valid -> no history write-back
+    // per-call stage timing of the host path (FrameProcessor::tic / toc, FrameProcessor.cpp:484-494, per stage)
+    int trace = 0;
+    cudaEvent_t ev_t[6] = {};  // upload begin / end, kernels begin / end, download begin / end
+    bgsb_trace last_trace = {};
 };
+
+static const char *algo_name(int algo)
+{
+    switch (algo) {
+    case BGSB_ALGO_FRAME_DIFFERENCE: return "FrameDifferenceBGS";
+    case BGSB_ALGO_STATIC_FRAME_DIFFERENCE: return "StaticFrameDifferenceBGS";
+    case BGSB_ALGO_WEIGHTED_MOVING_MEAN: return "WeightedMovingMeanBGS";
+    case BGSB_ALGO_WEIGHTED_MOVING_VARIANCE: return "WeightedMovingVarianceBGS";
+    case BGSB_ALGO_MOG2: return "MixtureOfGaussianV2BGS";
+    case BGSB_ALGO_ADAPTIVE_BG_LEARNING: return "AdaptiveBackgroundLearning";
+    case BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING: return "AdaptiveSelectiveBackgroundLearning";
+    case BGSB_ALGO_DP_ZIVKOVIC_AGMM: return "DPZivkovicAGMMBGS";
+    }
+    return "?";
+}
+static bool trace_env()
+{
+    static const bool on = [] { const char *e = getenv("BGSB_TRACE"); return e && e[0] && e[0] != '0'; }();
+    return on;
+}
 
 static bool gmm_state(int algo);
 static void free_buffers(bgsb_ctx *c)
@@ -501,6 +526,7 @@ void bgsb_destroy(bgsb_ctx *c)
     for (int i = 0; i < 8; i++) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]); }
     for (int i = 0; i < 2; i++) if (c->ev_dn[i]) cudaEventDestroy(c->ev_dn[i]);
     if (c->ev_order) cudaEventDestroy(c->ev_order);
+    for (int i = 0; i < 6; i++) if (c->ev_t[i]) cudaEventDestroy(c->ev_t[i]);
     delete c;
 }
 
@@ -542,6 +568,7 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     else if (k == "shadowThreshold") c->tau = (float)v;
     else if (k == "hostBands") { BGSB_REQUIRE(v >= 1 && v <= 8, "hostBands in [1,8]"); c->host_bands = (int)v; }
     else if (k == "retainInput") c->retain_input = (v != 0);
+    else if (k == "trace") c->trace = (v != 0);
 #ifdef BGSB_INSTRUMENT
     else if (k == "kernelVariant") { BGSB_REQUIRE(v == 0 || v == 1 || v == 8 || v == 9, "kernelVariant is 0 or 1 (8, 9: timing instruments)"); c->mog2_variant = (int)v; }
 #else
@@ -591,9 +618,18 @@ int bgsb_get_param(bgsb_ctx *c, const char *key, double *v)
     else if (k == "kernelVariant") *v = c->mog2_variant;
     else if (k == "hostBands") *v = c->host_bands;
     else if (k == "retainInput") *v = c->retain_input;
+    else if (k == "trace") *v = c->trace;
     else if (k == "ablTable") *v = c->abl_table;
     else if (k == "ablBlend") *v = c->abl_blend;
     else { set_error("bgsb_get_param: unknown key '%s'", key); return BGSB_ERR_ARG; }
+    return BGSB_OK;
+}
+
+int bgsb_trace_last(bgsb_ctx *c, bgsb_trace *out)
+{
+    BGSB_REQUIRE(c && out, "null");
+    if (!c->ev_t[0]) { set_error("bgsb_trace_last: no traced bgsb_process call yet (set the \"trace\" parameter or BGSB_TRACE=1)"); return BGSB_ERR_STATE; }
+    *out = c->last_trace;
     return BGSB_OK;
 }
 
@@ -715,36 +751,66 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
         rc = ensure_pipe_streams(c);
         if (rc) return rc;
     }
+    // stage timing (parameter "trace" or BGSB_TRACE=1): events around the uploads, the kernels and the downloads
+    const bool tracing = c->trace || trace_env();
+    const auto t_wall0 = std::chrono::steady_clock::now();
+    nvtxRangePushA(algo_name(c->algo));
+    struct NvtxPop { ~NvtxPop() { nvtxRangePop(); } } nvtx_pop;
+    if (tracing && !c->ev_t[0]) for (int i = 0; i < 6; i++) BGSB_CUDA(cudaEventCreate(&c->ev_t[i]));
+    auto mark = [&](int i, cudaStream_t st) { if (tracing) cudaEventRecord(c->ev_t[i], st); };
     if (nchunks == 1) {
+        mark(0, c->stream);
         BGSB_CUDA(copy_rows(d_in, (size_t)w * 3, bgr, stride, (size_t)w * 3, rows, cudaMemcpyHostToDevice, c->stream));
+        mark(1, c->stream); mark(2, c->stream);
         if (out_fg) {
             rc = launch_range(c, d_in, 1, c->d_fg, want_bg ? c->d_bg : nullptr, 0, own_hist, c->stream, 0, c->npx);
             if (rc) return rc;
+            mark(3, c->stream); mark(4, c->stream);
             BGSB_CUDA(copy_rows(fg, fg_stride, c->d_fg, (size_t)w, (size_t)w, rows, cudaMemcpyDeviceToHost, c->stream));
             if (want_bg)
                 BGSB_CUDA(copy_rows(bg, bg_stride, c->d_bg, bgw, bgw, rows, cudaMemcpyDeviceToHost, c->stream));
-        }
+        } else { mark(3, c->stream); mark(4, c->stream); }
+        mark(5, c->stream);
         BGSB_CUDA(cudaStreamSynchronize(c->stream));
     } else {
         for (int i = 0; i < nchunks; i++) {
             const int r0 = i * band, nr = std::min(band, h - r0);
             const size_t p0 = (size_t)r0 * w;
+            if (i == 0) mark(0, c->s_h2d);
             BGSB_CUDA(copy_rows(d_in + p0 * 3, (size_t)w * 3, bgr + (size_t)r0 * stride, stride, (size_t)w * 3, nr,
                                         cudaMemcpyHostToDevice, c->s_h2d));
             BGSB_CUDA(cudaEventRecord(c->ev_up[i], c->s_h2d));
+            if (i == nchunks - 1) mark(1, c->s_h2d);
             BGSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up[i], 0));
+            if (i == 0) mark(2, c->stream);
             rc = launch_range(c, d_in, 1, c->d_fg, want_bg ? c->d_bg : nullptr, 0, own_hist, c->stream, p0, nr * w);
             if (rc) return rc;
             BGSB_CUDA(cudaEventRecord(c->ev_k[i], c->stream));
+            if (i == nchunks - 1) mark(3, c->stream);
             BGSB_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_k[i], 0));
+            if (i == 0) mark(4, c->s_d2h);
             BGSB_CUDA(copy_rows(fg + (size_t)r0 * fg_stride, fg_stride, c->d_fg + p0, (size_t)w, (size_t)w, nr,
                                         cudaMemcpyDeviceToHost, c->s_d2h));
             if (want_bg)
                 BGSB_CUDA(copy_rows(bg + (size_t)r0 * bg_stride, bg_stride, c->d_bg + p0 * 3, bgw, bgw, nr,
                                             cudaMemcpyDeviceToHost, c->s_d2h));
         }
+        mark(5, c->s_d2h);
         BGSB_CUDA(cudaStreamSynchronize(c->s_d2h));
         BGSB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (tracing) {
+        bgsb_trace &T = c->last_trace;
+        float up = 0.f, kn = 0.f, dn = 0.f;
+        cudaEventElapsedTime(&up, c->ev_t[0], c->ev_t[1]);
+        cudaEventElapsedTime(&kn, c->ev_t[2], c->ev_t[3]);
+        cudaEventElapsedTime(&dn, c->ev_t[4], c->ev_t[5]);
+        (void)cudaGetLastError();
+        T.frame = c->nframes; T.upload_ms = up; T.kernel_ms = kn; T.download_ms = dn; T.bands = nchunks;
+        T.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wall0).count();
+        if (trace_env())        // the line FrameProcessor::toc prints (FrameProcessor.cpp:490-494), plus the stage split
+            fprintf(stderr, "%s\ttime(sec):%.6f\tupload %.6f kernels %.6f download %.6f (%d band%s, stages overlap)\n", algo_name(c->algo),
+                    T.wall_ms * 1e-3, up * 1e-3, kn * 1e-3, dn * 1e-3, nchunks, nchunks > 1 ? "s" : "");
     }
     if (out_fg) advance(c, 1, own_hist);
     else c->nframes += 1;

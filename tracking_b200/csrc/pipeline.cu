@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "ccl_internal.h"
 #include "kernels.h"
 
@@ -150,6 +152,8 @@ int bgsb_pipeline_process_dev(bgsb_pipeline *p, const uint8_t *d_frames, int w, 
     BGSB_CUDA(cudaSetDevice(p->device));
     cudaStream_t stream = (cudaStream_t)stream_;
     if (valid) *valid = 0;
+    nvtxRangePushA("bgsb_pipeline: plugin + clean-up + labelling");
+    struct NvtxPop { ~NvtxPop() { nvtxRangePop(); } } nvtx_pop;
     int rc = pipeline_geometry(p, w, h);
     if (rc) return rc;
     p->ccl->force_bg = p->force_bg;
