@@ -301,7 +301,9 @@ BGSB_API void bgsb_pipeline_destroy(bgsb_pipeline *p);
 BGSB_API bgsb_ctx *bgsb_pipeline_bgs(bgsb_pipeline *p);
 /* ops as in bgsb_morph_dev, at most 16 pairs; nops = 0: no clean-up stage. */
 BGSB_API int bgsb_pipeline_set_morph(bgsb_pipeline *p, const int *ops, int nops);
-/* "zeroBorder" (default 1, OpenCV 2.4 cvFindContours), "forceBackgroundPass"; any other key goes to the plugin. */
+/* "zeroBorder" (default 1, OpenCV 2.4 cvFindContours), "forceBackgroundPass", "chainCtas" (> 0: the labeller's
+ * background pass as four plain launches of at most that many CTAs instead of one cooperative launch; default 0);
+ * any other key goes to the plugin. */
 BGSB_API int bgsb_pipeline_set_param(bgsb_pipeline *p, const char *key, double value);
 /* One frame per stream: d_frames [nstreams][h][w][3].  Optional outputs (NULL = not wanted):
  *   d_mask   [nstreams][h][w]    the cleaned {0,255} mask (what CvFGDetector::GetMask hands to the tracker)

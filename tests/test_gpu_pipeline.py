@@ -97,6 +97,47 @@ def test_pipeline_ragged_widths_packed_mask(oracle, shape, zb):
         pipe.close()
 
 
+@pytest.mark.parametrize("chain_ctas", [0, 200])
+def test_pipeline_background_pass_forms(oracle, chain_ctas):
+    """RETR_EXTERNAL's background pass inside the pipeline, forced on every frame: as one cooperative launch (default)
+    and as four plain launches ("chainCtas"); external flags and tables against the oracle on 3 streams."""
+    import torch
+    from tracking_b200.pipeline import ForegroundPipeline
+    S, n = 3, 8
+    h, w = 120, 200
+    yy, xx = np.mgrid[0:h, 0:w]
+
+    def scene(s, t):
+        """rings with islands, blinking: FrameDifference sees ring + island, the island sits in the ring's hole"""
+        img = np.zeros((h, w, 3), np.uint8)
+        if t % 2 == 0:
+            return img                                   # every other frame is empty: the difference is the whole drawing
+        for cy, cx, r in ((40 + t % 5, 50 + 2 * s, 30), (70, 140 - t % 7, 38 + s)):
+            d = (yy - cy) ** 2 + (xx - cx) ** 2
+            img[(d < r * r) & (d >= (r - 6) ** 2)] = 220
+            img[d < 25] = 180
+        return img
+
+    chain = (("dilate", 1),)
+    pipe = ForegroundPipeline(0, nstreams=S, morph=chain, forceBackgroundPass=1, chainCtas=chain_ctas)
+    os_ = [oracle.FrameDifferenceBGS() for _ in range(S)]
+    seen_nested = False
+    for t in range(n):
+        frames = np.stack([scene(s, t) for s in range(S)])
+        d_in = torch.from_numpy(frames).cuda()
+        valid, _ = pipe.process_dev(d_in.data_ptr(), w, h)
+        for s in range(S):
+            ofg, _ = os_[s].process(frames[s])
+            assert valid == (ofg is not None)
+            if ofg is None:
+                continue
+            exp = oracle_chain(oracle, ofg, chain, True)
+            seen_nested |= bool((exp[4] == 0).any())
+            check_stream(pipe, s, None, None, exp, oracle)
+    assert seen_nested            # some component really sits in a hole of another one on these masks
+    pipe.close()
+
+
 def test_pipeline_raw_mask_without_threshold_and_chain(oracle, clips):
     """enableThreshold = 0 (raw {0,127,255}) and no chain: DetectNewBlob's own threshold (> 128) decides what is
     labelled, and the moments weigh the raw mask values (shadow pixels = 127)."""

@@ -39,7 +39,7 @@ def step_m():
 for _ in range(4 * NT): step_m()
 t_pipe_m = timed(step_m, 48, warm=0, join=lambda: pipe.join_dev(st))
 print(json.dumps(dict(probe="pipeline packed", streams=S, us_per_step=t_pipe, mpixel_s=S*w*h/t_pipe, us_with_byte_mask=t_pipe_m,
-                      components_stream0=len(pipe.components(0)))), flush=True)
+                      components_stream0=(len(pipe.components(0)) if not os.environ.get('BGSB_PIPE_DBG') == '1' else -1))), flush=True)
 # byte chain (round-1 form)
 p = tb.MixtureOfGaussianV2BGS(nstreams=S); cc = blobs.ConnectedComponents(w, h, max_images=S)
 fg = torch.empty((S, h, w), dtype=torch.uint8, device="cuda"); clean = torch.empty_like(fg)

@@ -221,10 +221,12 @@ ccl_merge_kernel(const __grid_constant__ CclArgs A)
     }
     const unsigned *bits = A.bits + blockIdx.y * A.img_words;
     int *parent = A.parent + blockIdx.y * A.img_px;
+    for (int chunk = blockIdx.x; chunk < A.nchunks; chunk += gridDim.x) {
 #pragma unroll
-    for (int j = 0; j < WPT; j++) {
-        const int wi = (blockIdx.x * WPT + j) * 256 + threadIdx.x;
-        if (wi < A.nwords) merge_word<false>(A, bits, parent, wi);
+        for (int j = 0; j < WPT; j++) {
+            const int wi = (chunk * WPT + j) * 256 + threadIdx.x;
+            if (wi < A.nwords) merge_word<false>(A, bits, parent, wi);
+        }
     }
 }
 
@@ -240,10 +242,13 @@ ccl_roots_kernel(const __grid_constant__ CclArgs A)
     pdl_entry();
     __shared__ int wsum[8];
     __shared__ int s_last, s_carry;
-    const int img = blockIdx.y, chunk = blockIdx.x;
+    const int img = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned *bits = A.bits + img * A.img_words;
     int *parent = A.parent + img * A.img_px;
+    int *count = A.chunkcount + (size_t)img * A.nchunks;
+    // one chunk per CTA, or (capped grids: the pipeline beside the plugin kernel) the CTA's share of the image's chunks
+    for (int chunk = blockIdx.x; chunk < A.nchunks; chunk += gridDim.x) {
     unsigned v[WPT], roots[WPT];
     int base[WPT];
 #pragma unroll
@@ -253,6 +258,15 @@ ccl_roots_kernel(const __grid_constant__ CclArgs A)
         const int y = valid ? wi / A.wpr : 0, k = valid ? wi - y * A.wpr : 0;
         v[j] = valid ? ccl_word(bits, y, k, A) : 0u;
         base[j] = y * A.w + k * 32;
+    }
+    {   // most chunks of a typical mask hold no foreground at all: nothing to rank
+        unsigned any = 0;
+#pragma unroll
+        for (int j = 0; j < WPT; j++) any |= v[j];
+        if (!__syncthreads_or(any != 0u)) {
+            if (tid == 0) count[chunk] = 0;
+            continue;
+        }
     }
 #pragma unroll
     for (int j = 0; j < WPT; j++) {
@@ -290,12 +304,13 @@ ccl_roots_kernel(const __grid_constant__ CclArgs A)
         }
         carry += total;
     }
-    int *count = A.chunkcount + (size_t)img * A.nchunks;
     if (tid == 0) count[chunk] = carry;
-    // the last CTA of the image: exclusive scan of the chunk counts
-    __threadfence();
+    __syncthreads();                                   // wsum is reused by the CTA's next chunk
+    }
+    // the last CTA of the image: exclusive scan of the chunk counts.  (One fence by the arriving thread is enough: the
+    // barrier orders the CTA's writes before it, and fences are cumulative.)
     __syncthreads();
-    if (tid == 0) { s_last = (atomicAdd(&A.done_a[img], 1) == A.nchunks - 1); s_carry = 0; }
+    if (tid == 0) { __threadfence(); s_last = (atomicAdd(&A.done_a[img], 1) == (int)gridDim.x - 1); s_carry = 0; }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
@@ -336,7 +351,7 @@ ccl_label_kernel(const __grid_constant__ CclArgs A)
     pdl_entry();
     __shared__ int4 s_box[256];
     __shared__ int s_last;
-    const int img = blockIdx.y, chunk = blockIdx.x;
+    const int img = blockIdx.y;
     const int tid = threadIdx.x;
     const unsigned *bits = A.bits + img * A.img_words;
     const int *parent = A.parent + img * A.img_px;
@@ -344,6 +359,7 @@ ccl_label_kernel(const __grid_constant__ CclArgs A)
     CompRaw *comp = A.comp + (size_t)img * A.cap;
     constexpr int CSHIFT = WPT == 1 ? 8 : 10;          // log2(words per chunk)
     static_assert(WPT == 1 || WPT == 4, "chunk sizes 256 / 1024 words");
+    for (int chunk = blockIdx.x; chunk < A.nchunks; chunk += gridDim.x) {
     unsigned v[WPT];
     int yy[WPT], kk[WPT];
 #pragma unroll
@@ -401,12 +417,12 @@ ccl_label_kernel(const __grid_constant__ CclArgs A)
         }
     }
 
+    }
     // ---- the last CTA of the image to get here decides whether the image needs the background pass: does any
     // component's bounding box lie strictly inside another's?  (Necessary for a component to sit in a hole of another
     // one.)  More than 1024 components: not worth checking in one CTA, take the pass.
-    __threadfence();
     __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&A.done_b[img], 1) == A.nchunks - 1);
+    if (tid == 0) { __threadfence(); s_last = (atomicAdd(&A.done_b[img], 1) == (int)gridDim.x - 1); }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
@@ -440,10 +456,67 @@ ccl_label_kernel(const __grid_constant__ CclArgs A)
             }
         }
     }
-    if (need) A.need_bg[img] = 1;
+    need = __syncthreads_or(need);
+    if (tid == 0) {
+        A.need_bg[img] = need ? 1 : 0;               // every image of the call gets its answer (no stale flags)
+        A.done_a[img] = 0; A.done_b[img] = 0;        // both kernels' CTAs have all arrived: zero again for the next call
+    }
 }
 
-// ---- launch 4: RETR_EXTERNAL (cooperative: grid-wide barriers between the phases) ---------------------------------------
+// ---- launch 5: RETR_EXTERNAL ------------------------------------------------------------------------------------------
+// the background pass, one word / one component at a time
+__device__ __forceinline__ void bg_init_word(const CclArgs &A, int img, int wi)
+{
+    const unsigned *bits = A.bits + img * A.img_words;
+    int *parent = A.parent + img * A.img_px;
+    uint8_t *outer = A.outer + img * A.img_px;
+    const int y = wi / A.wpr, k = wi - y * A.wpr;
+    const unsigned vb = ~ccl_word(bits, y, k, A) & in_mask(k, A.w, A.wpr);
+    const int base = y * A.w + k * 32;
+    for (unsigned s = vb & ~(vb << 1); s;) {
+        const int b = __ffs(s) - 1; s &= s - 1;
+        parent[base + b] = base + b;
+        outer[base + b] = 0;
+    }
+}
+// flatten; regions that touch the image frame are "outer"
+__device__ __forceinline__ void bg_flatten_word(const CclArgs &A, int img, int wi)
+{
+    const unsigned *bits = A.bits + img * A.img_words;
+    int *parent = A.parent + img * A.img_px;
+    uint8_t *outer = A.outer + img * A.img_px;
+    const int y = wi / A.wpr, k = wi - y * A.wpr;
+    const unsigned vb = ~ccl_word(bits, y, k, A) & in_mask(k, A.w, A.wpr);
+    const int base = y * A.w + k * 32;
+    const bool edge_row = (y == 0 || y == A.h - 1);
+    for (unsigned s = vb & ~(vb << 1); s;) {
+        const int b = __ffs(s) - 1; s &= s - 1;
+        const int r = find_root(parent, base + b);
+        parent[base + b] = r;
+        const unsigned rest = ~(vb >> b);
+        const int len = rest ? __ffs(rest) - 1 : 32 - b;
+        if (edge_row || (k == 0 && b == 0) || (k * 32 + b + len - 1 == A.w - 1)) outer[r] = 1;
+    }
+}
+// a component is external iff the background region left of its first pixel is outer
+__device__ __forceinline__ void bg_resolve_comp(const CclArgs &A, int img, int i)
+{
+    const unsigned *bits = A.bits + img * A.img_words;
+    const int *parent = A.parent + img * A.img_px;
+    const uint8_t *outer = A.outer + img * A.img_px;
+    CompRaw *c = A.comp + (size_t)img * A.cap + i;
+    const int r = c->first_index;
+    const int ry = r / A.w, rx = r - ry * A.w;
+    int ext = 1;
+    if (rx > 0) {
+        const int lk = (rx - 1) >> 5, lb = (rx - 1) & 31;
+        const unsigned lv = ~ccl_word(bits, ry, lk, A) & in_mask(lk, A.w, A.wpr);
+        ext = outer[parent[ry * A.w + lk * 32 + run_start(lv, lb)]];
+    }
+    c->external = ext;
+}
+
+// One cooperative launch (grid-wide barriers between the phases): the form for a labeller that has the GPU to itself.
 __global__ void __launch_bounds__(256)
 ccl_background_kernel(const __grid_constant__ CclArgs A)
 {
@@ -451,9 +524,6 @@ ccl_background_kernel(const __grid_constant__ CclArgs A)
     cg::grid_group grid = cg::this_grid();
     const int tid = threadIdx.x;
     const size_t gtid = (size_t)blockIdx.x * 256 + tid, gsize = (size_t)gridDim.x * 256;
-    // the roots / label kernels have completed: their arrival counters go back to zero for the next call
-    for (size_t i = gtid; i < (size_t)A.nimages; i += gsize) { A.done_a[i] = 0; A.done_b[i] = 0; }
-
     // the label kernel's last CTA per image has flagged the images where a bounding box lies strictly inside another
     int any = 0;
     for (int i = tid; i < A.nimages; i += 256) any |= A.need_bg[i];
@@ -463,73 +533,46 @@ ccl_background_kernel(const __grid_constant__ CclArgs A)
     // huge component, whose unions contend on one root -- latency, not throughput -- so flagged images must progress
     // side by side, not one after the other.
     const size_t nitems = (size_t)A.nimages * A.nwords;
-    // phase 1: background runs of the flagged images become nodes
     for (size_t it = gtid; it < nitems; it += gsize) {
         const int img = (int)(it / A.nwords), wi = (int)(it - (size_t)img * A.nwords);
-        if (!A.need_bg[img]) continue;
-        const unsigned *bits = A.bits + img * A.img_words;
-        int *parent = A.parent + img * A.img_px;
-        uint8_t *outer = A.outer + img * A.img_px;
-        const int y = wi / A.wpr, k = wi - y * A.wpr;
-        const unsigned vb = ~ccl_word(bits, y, k, A) & in_mask(k, A.w, A.wpr);
-        const int base = y * A.w + k * 32;
-        for (unsigned s = vb & ~(vb << 1); s;) {
-            const int b = __ffs(s) - 1; s &= s - 1;
-            parent[base + b] = base + b;
-            outer[base + b] = 0;
-        }
+        if (A.need_bg[img]) bg_init_word(A, img, wi);
     }
     grid.sync();
-    // phase 2: 4-connected merge
     for (size_t it = gtid; it < nitems; it += gsize) {
         const int img = (int)(it / A.nwords), wi = (int)(it - (size_t)img * A.nwords);
-        if (!A.need_bg[img]) continue;
-        merge_word<true>(A, A.bits + img * A.img_words, A.parent + img * A.img_px, wi);
+        if (A.need_bg[img]) merge_word<true>(A, A.bits + img * A.img_words, A.parent + img * A.img_px, wi);
     }
     grid.sync();
-    // phase 3: flatten; regions that touch the image frame are "outer"
     for (size_t it = gtid; it < nitems; it += gsize) {
         const int img = (int)(it / A.nwords), wi = (int)(it - (size_t)img * A.nwords);
-        if (!A.need_bg[img]) continue;
-        const unsigned *bits = A.bits + img * A.img_words;
-        int *parent = A.parent + img * A.img_px;
-        uint8_t *outer = A.outer + img * A.img_px;
-        const int y = wi / A.wpr, k = wi - y * A.wpr;
-        const unsigned vb = ~ccl_word(bits, y, k, A) & in_mask(k, A.w, A.wpr);
-        const int base = y * A.w + k * 32;
-        const bool edge_row = (y == 0 || y == A.h - 1);
-        for (unsigned s = vb & ~(vb << 1); s;) {
-            const int b = __ffs(s) - 1; s &= s - 1;
-            const int r = find_root(parent, base + b);
-            parent[base + b] = r;
-            const unsigned rest = ~(vb >> b);
-            const int len = rest ? __ffs(rest) - 1 : 32 - b;
-            if (edge_row || (k == 0 && b == 0) || (k * 32 + b + len - 1 == A.w - 1)) outer[r] = 1;
-        }
+        if (A.need_bg[img]) bg_flatten_word(A, img, wi);
     }
     grid.sync();
-    // phase 4: a component is external iff the background region left of its first pixel is outer
     for (int img = 0; img < A.nimages; img++) {
         if (!A.need_bg[img]) continue;
-        const unsigned *bits = A.bits + img * A.img_words;
-        const int *parent = A.parent + img * A.img_px;
-        const uint8_t *outer = A.outer + img * A.img_px;
         const int n = min(A.ncomp[img], A.cap);
-        for (size_t i = gtid; i < (size_t)n; i += gsize) {
-            CompRaw *c = A.comp + (size_t)img * A.cap + i;
-            const int r = c->first_index;
-            const int ry = r / A.w, rx = r - ry * A.w;
-            int ext = 1;
-            if (rx > 0) {
-                const int lk = (rx - 1) >> 5, lb = (rx - 1) & 31;
-                const unsigned lv = ~ccl_word(bits, ry, lk, A) & in_mask(lk, A.w, A.wpr);
-                ext = outer[parent[ry * A.w + lk * 32 + run_start(lv, lb)]];
-            }
-            c->external = ext;
-        }
+        for (size_t i = gtid; i < (size_t)n; i += gsize) bg_resolve_comp(A, img, (int)i);
     }
-    grid.sync();
-    for (size_t i = gtid; i < (size_t)A.nimages; i += gsize) A.need_bg[i] = 0;       // all zero again between calls
+}
+
+// The same pass as four plain launches (PHASE 0 init, 1 merge, 2 flatten, 3 resolve), grid (X, images), whose CTAs leave at
+// once for images that were not flagged: the form for the pipeline, where the labeller runs BESIDE the next frame
+// set's plugin kernel -- a cooperative grid would have to wait until that kernel has drained to become resident as a
+// whole, and the plugin kernel after it would wait for the labeller.
+template <int PHASE>
+__global__ void __launch_bounds__(256)
+ccl_background_phase_kernel(const __grid_constant__ CclArgs A)
+{
+    pdl_entry();
+    const int img = blockIdx.y;
+    if (!A.need_bg[img]) return;
+    const int limit = PHASE == 3 ? min(A.ncomp[img], A.cap) : A.nwords;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < limit; i += gridDim.x * 256) {
+        if (PHASE == 0) bg_init_word(A, img, i);
+        else if (PHASE == 1) merge_word<true>(A, A.bits + img * A.img_words, A.parent + img * A.img_px, i);
+        else if (PHASE == 2) bg_flatten_word(A, img, i);
+        else bg_resolve_comp(A, img, i);
+    }
 }
 
 // cvMoments(ROI, binary=0): pixel-value weighted raw moments, ROI-relative coordinates.
@@ -682,33 +725,44 @@ int ccl_label_bits(bgsb_ccl *c, const unsigned *d_bits, bool parents_ready, int 
         launch_pdl(ccl_init_kernel, dim3((A.nwords + 255) / 256, nimages), block, 0, stream, A);
         BGSB_LAUNCH_CHECK();
     }
-    // batches too big for one wave of one-word-per-thread CTAs (8 per SM) take the four-words-per-thread kernels
-    const bool wide = (long long)nimages * ((A.nwords + 255) / 256) > 8LL * sm_count(c->device);
-    A.nchunks = wide ? (A.nwords + 1023) / 1024 : (A.nwords + 255) / 256;
+    // Words per thread: 1 for a single image (254 CTAs at 1080p fill the SMs), 4 for batches too big for one wave of
+    // one-word CTAs.  (16 words per thread was measured and removed: a sixteenth of the CTAs, but the per-word work of a
+    // thread is serial -- 64 masks 166 -> 284 us, 8 masks 44 -> 117 us.)
+    const long long n256 = (long long)nimages * ((A.nwords + 255) / 256);
+    const int wpt = n256 > 8LL * sm_count(c->device) ? 4 : 1;
+    A.nchunks = (A.nwords + 256 * wpt - 1) / (256 * wpt);
+    // (the kernels loop over chunks, so capped grids work; measured, capping them beside the plugin kernel only makes
+    // the chain longer: tools/chain_ctas_probe.py)
     const dim3 grid(A.nchunks, nimages);
-    if (wide) {
-        launch_pdl(ccl_merge_kernel<4>, grid, block, 0, stream, A);
+#define BGSB_CCL_LAUNCH(W)                                                                                      \
+    do {                                                                                                        \
+        launch_pdl(ccl_merge_kernel<W>, grid, block, 0, stream, A);                                             \
+        BGSB_LAUNCH_CHECK();                                                                                    \
+        launch_pdl(ccl_roots_kernel<W>, grid, block, 0, stream, A);                                             \
+        BGSB_LAUNCH_CHECK();                                                                                    \
+        if (d_labels) launch_pdl(ccl_label_kernel<true, W>, grid, block, 0, stream, A);                         \
+        else launch_pdl(ccl_label_kernel<false, W>, grid, block, 0, stream, A);                                 \
+        BGSB_LAUNCH_CHECK();                                                                                    \
+    } while (0)
+    if (wpt == 4) BGSB_CCL_LAUNCH(4);
+    else BGSB_CCL_LAUNCH(1);
+#undef BGSB_CCL_LAUNCH
+    if (c->max_ctas > 0) {
+        // beside another kernel (pipeline): four plain launches that leave at once for images that were not flagged
+        const dim3 bgrid(std::max(1, std::min((A.nwords + 255) / 256, c->max_ctas / nimages)), nimages);
+        launch_pdl(ccl_background_phase_kernel<0>, bgrid, block, 0, stream, A);
         BGSB_LAUNCH_CHECK();
-        launch_pdl(ccl_roots_kernel<4>, grid, block, 0, stream, A);
+        launch_pdl(ccl_background_phase_kernel<1>, bgrid, block, 0, stream, A);
         BGSB_LAUNCH_CHECK();
-        if (d_labels) launch_pdl(ccl_label_kernel<true, 4>, grid, block, 0, stream, A);
-        else launch_pdl(ccl_label_kernel<false, 4>, grid, block, 0, stream, A);
+        launch_pdl(ccl_background_phase_kernel<2>, bgrid, block, 0, stream, A);
+        BGSB_LAUNCH_CHECK();
+        launch_pdl(ccl_background_phase_kernel<3>, bgrid, block, 0, stream, A);
         BGSB_LAUNCH_CHECK();
     } else {
-        launch_pdl(ccl_merge_kernel<1>, grid, block, 0, stream, A);
-        BGSB_LAUNCH_CHECK();
-        launch_pdl(ccl_roots_kernel<1>, grid, block, 0, stream, A);
-        BGSB_LAUNCH_CHECK();
-        if (d_labels) launch_pdl(ccl_label_kernel<true, 1>, grid, block, 0, stream, A);
-        else launch_pdl(ccl_label_kernel<false, 1>, grid, block, 0, stream, A);
-        BGSB_LAUNCH_CHECK();
-    }
-    {
         // cooperative: every CTA must be resident at once; the grid strides over the work
         if (c->coop_ctas <= 0) {
             int per_sm = 0;
             BGSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ccl_background_kernel, 256, 0));
-            // at most four CTAs per SM: the launch has to become resident as a whole, possibly beside another stream's kernel
             c->coop_ctas = std::min(4, std::max(1, per_sm)) * sm_count(c->device);
         }
         const long long want = (long long)nimages * ((A.nwords + 255) / 256);

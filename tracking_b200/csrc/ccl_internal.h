@@ -23,6 +23,8 @@ struct bgsb_ccl {
     bgsb::CompRaw *d_comp = nullptr;
     int cap = 0;
     int coop_ctas = 0;                     // co-resident CTAs of the cooperative background kernel on this device
+    int max_ctas = 0;                      // > 0: the labeller runs BESIDE another kernel (pipeline): background pass as plain
+                                           // launches of at most this many CTAs instead of one cooperative launch
     bool dirty = false;                    // a call failed half-way: the arrival counters are cleared before the next one
     // what the moments are taken from: the byte masks of the last call, or its bit-packed masks (pipeline)
     const uint8_t *last_mask = nullptr;

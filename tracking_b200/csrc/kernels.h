@@ -125,6 +125,7 @@ struct MorphIO {
     unsigned *out_bits;
     int *parent;                 // with out_bits: the labeller's forest [nimages][w*h]; the output runs become its nodes
     int zero_border;             // ... after clearing the 1-px frame (nodes only; the stored words keep it)
+    int max_ctas;                // > 0: cap on the grid (CTAs loop over the tiles); 0: one CTA per tile
 };
 int launch_morph_chain_io(const MorphIO &io, int w, int h, int nimages, const int *ops, int nops, cudaStream_t stream);
 

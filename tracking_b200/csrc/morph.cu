@@ -13,16 +13,16 @@
 // is 3 shifted ANDs/ORs per word and per row), and unpacks the interior back to bytes.  HBM
 // traffic is one byte read and one byte written per pixel for the whole chain.
 #include <string.h>
+#include <algorithm>
 #include "ccl_internal.h"
 #include "kernels.h"
 
 namespace bgsb {
 
-constexpr int MORPH_TH = 16;        // interior rows per tile
 constexpr int MORPH_TW = 62;        // interior words per tile (+2 halo words = 64)
 constexpr int MORPH_RMAX = 8;       // max total iterations fused in one launch
-constexpr int MORPH_ROWS = MORPH_TH + 2 * MORPH_RMAX;
 constexpr int MORPH_SW = MORPH_TW + 2;
+// interior rows per tile: a template parameter of the kernel, 16 in production
 
 struct MorphChain {
     int n;
@@ -69,24 +69,29 @@ __device__ __forceinline__ unsigned unpack4(unsigned nib)
 // load is one word per thread and row instead of 32 bytes.  Outputs (either or both): {0,255} bytes, and / or
 // bit-packed words; with `parent` the words' runs also become the labeller's union-find nodes (ccl_internal.h), which
 // saves the labeller's own first launch.
-template <bool IN_BITS>
+template <bool IN_BITS, int MORPH_TH>
 __global__ void __launch_bounds__(256)
-morph_kernel(const MorphIO io, int w, int h, int wpr, MorphChain chain, int R)
+morph_kernel(const MorphIO io, int w, int h, int wpr, MorphChain chain, int R, int ntx, int nty, int ntiles)
 {
     pdl_entry();
+    constexpr int MORPH_ROWS = MORPH_TH + 2 * MORPH_RMAX;
     __shared__ unsigned buf[2][MORPH_ROWS][MORPH_SW];
-    const int img = blockIdx.z;
+    // a CTA takes tiles tile = blockIdx.x, blockIdx.x + gridDim.x, ... of all images (normally one tile per CTA; the
+    // pipeline caps the grid so that the kernel runs beside the plugin kernel without evicting its CTAs)
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tbx = tile % ntx, tby = (tile / ntx) % nty;
+    const int img = tile / (ntx * nty);
     const size_t npx = (size_t)w * h, nwords = (size_t)wpr * h;
     const uint8_t *in = IN_BITS ? nullptr : io.in_bytes + img * npx;
     const unsigned *inb = IN_BITS ? io.in_bits + img * nwords : nullptr;
     uint8_t *out = io.out_bytes ? io.out_bytes + img * npx : nullptr;
     unsigned *outb = io.out_bits ? io.out_bits + img * nwords : nullptr;
     int *parent = (io.parent && outb) ? io.parent + img * npx : nullptr;
-    const int k0 = blockIdx.x * MORPH_TW - 1;          // word index of smem column 0 (halo)
-    const int y0 = blockIdx.y * MORPH_TH - R;          // image row of smem row 0 (halo)
+    const int k0 = tbx * MORPH_TW - 1;                 // word index of smem column 0 (halo)
+    const int y0 = tby * MORPH_TH - R;                 // image row of smem row 0 (halo)
     const int rows = MORPH_TH + 2 * R;
     const int rblock = (rows + 3) >> 2;                 // consecutive rows per thread in the passes (4 row groups)
-    const int tw = min(MORPH_TW, wpr - blockIdx.x * MORPH_TW) + 2;   // smem columns in use
+    const int tw = min(MORPH_TW, wpr - tbx * MORPH_TW) + 2;   // smem columns in use
     const int c = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const int k = k0 + c;
     const bool col_used = c < tw;
@@ -168,7 +173,7 @@ morph_kernel(const MorphIO io, int w, int h, int wpr, MorphChain chain, int R)
     // ---- store the interior: packed words (+ labeller nodes) and / or {0,255} bytes ----
     if (c >= 1 && c < tw - 1) {
         for (int r = ty; r < MORPH_TH; r += 4) {
-            const int y = blockIdx.y * MORPH_TH + r;
+            const int y = tby * MORPH_TH + r;
             if (y >= h) break;
             const unsigned word = buf[cur][r + R][c];
             if (outb) {
@@ -189,6 +194,8 @@ morph_kernel(const MorphIO io, int w, int h, int wpr, MorphChain chain, int R)
                 }
             }
         }
+    }
+    __syncthreads();                                   // the tile buffers are reused by the CTA's next tile
     }
 }
 
@@ -236,7 +243,12 @@ int launch_morph_chain_io(const MorphIO &io_, int w, int h, int nimages, const i
     unsigned *tmp[2] = {nullptr, nullptr};
     const int ntmp = nlaunch > 2 ? 2 : (nlaunch > 1 ? 1 : 0);
     for (int i = 0; i < ntmp; i++) BGSB_CUDA(cudaMallocAsync(&tmp[i], tbytes, stream));
-    const dim3 grid((wpr + MORPH_TW - 1) / MORPH_TW, (h + MORPH_TH - 1) / MORPH_TH, nimages);
+    const int TH = 16;      // (64-row tiles for batches were measured and dropped: OPEN on 8 masks 12.7 -> 26.3 us)
+    const int ntx = (wpr + MORPH_TW - 1) / MORPH_TW, nty = (h + TH - 1) / TH;
+    const long long ntiles_ll = (long long)ntx * nty * nimages;
+    if (ntiles_ll > 0x7fffffffLL) { set_error("morph: too many tiles"); return BGSB_ERR_ARG; }
+    const int ntiles = (int)ntiles_ll;
+    const dim3 grid((unsigned)(io_.max_ctas > 0 ? std::min(ntiles, io_.max_ctas) : ntiles));
     const unsigned *src_bits = nullptr;
     for (int l = 0; l < nlaunch; l++) {
         const bool first = (l == 0), last = (l == nlaunch - 1);
@@ -253,8 +265,8 @@ int launch_morph_chain_io(const MorphIO &io_, int w, int h, int nimages, const i
             ch.op[ch.n] = (signed char)items[i][0]; ch.iters[ch.n] = (signed char)items[i][1]; ch.n++;
             R += items[i][1];
         }
-        if (io.in_bits) launch_pdl(morph_kernel<true>, dim3(grid), dim3(256), 0, stream, io, w, h, wpr, ch, R);
-        else launch_pdl(morph_kernel<false>, dim3(grid), dim3(256), 0, stream, io, w, h, wpr, ch, R);
+        if (io.in_bits) launch_pdl(morph_kernel<true, 16>, dim3(grid), dim3(256), 0, stream, io, w, h, wpr, ch, R, ntx, nty, ntiles);
+        else launch_pdl(morph_kernel<false, 16>, dim3(grid), dim3(256), 0, stream, io, w, h, wpr, ch, R, ntx, nty, ntiles);
         BGSB_LAUNCH_CHECK();
         src_bits = io.out_bits;
     }
