@@ -863,3 +863,38 @@ def test_trace_stage_times_and_toc_line(tmp_path):
     assert r.returncode == 0, r.stderr[-1500:]
     lines = [l for l in r.stderr.splitlines() if l.startswith("AdaptiveBackgroundLearning\ttime(sec):")]
     assert len(lines) == 2 and "upload" in lines[0] and "download" in lines[0]
+
+
+def test_churn_generator_matches_numpy_twin_and_keeps_modes_live(oracle):
+    import torch
+    import tracking_b200 as tb
+    from tracking_b200 import synth
+    S, T, h, w = 2, 3, 97, 131
+    d = torch.zeros((S, T, h, w, 3), dtype=torch.uint8, device="cuda")
+    synth.churn_frames_dev(d.data_ptr(), S, T, w, h, t0=5, seed0=synth.SEED0)
+    torch.cuda.synchronize()
+    got = d.cpu().numpy()
+    for s in range(S):
+        for t in range(T):
+            assert np.array_equal(got[s, t], synth.churn_frame(w, h, 5 + t, synth.SEED0 + s))
+    # MOG2 on the churn stream: the dense case (most pixels at 5 modes), masks / background / state against the oracle
+    p, o = tb.MixtureOfGaussianV2BGS(), oracle.MixtureOfGaussianV2BGS()
+    for t in range(40):
+        f = synth.churn_frame(w, h, t)
+        fg, bg = p.process(f)
+        ofg, obg = o.process(f)
+        assert np.array_equal(fg, ofg) and np.array_equal(bg, obg), t
+    _, nm = p.export_state()
+    assert np.array_equal(nm, o.nmodes) and (nm == 5).mean() > 0.6
+    p.close()
+
+
+def test_copy_probe_reports_plausible_pcie_rates():
+    import ctypes as C
+    from tracking_b200 import capi
+    up, dn, both = C.c_double(0), C.c_double(0), C.c_double(0)
+    capi.check(capi.lib().bgsb_copy_probe(0, 6 << 20, 8 << 20, 20, C.byref(up), C.byref(dn), C.byref(both)))
+    for t in (up.value, dn.value, both.value):
+        assert 1e-5 < t < 1e-2                       # 6-8 MB at somewhere between 1 and 800 GB/s
+    assert both.value >= max(up.value, dn.value) * 0.8
+    assert capi.lib().bgsb_copy_probe(0, 0, 1, 1, C.byref(up), C.byref(dn), C.byref(both)) == capi.ERR_ARG
