@@ -350,6 +350,7 @@ ccl_label_kernel(const __grid_constant__ CclArgs A)
 {
     pdl_entry();
     __shared__ int4 s_box[256];
+    __shared__ int4 s_stage[LABELS ? 8 * 256 : 1];     // per warp: 32 label rows of 128 bytes on their way to global memory
     __shared__ int s_last;
     const int img = blockIdx.y;
     const int tid = threadIdx.x;
@@ -402,17 +403,45 @@ ccl_label_kernel(const __grid_constant__ CclArgs A)
                 atomicAdd(&cp->area, len);
             }
         }
-        if (LABELS && y >= 0) {
+        if (LABELS) {
+            // The 32 words of a warp are consecutive in raster order: when the width is a multiple of 32 their label rows
+            // are ONE contiguous 4 KB piece of the label image.  A thread's own row is 128 bytes, so thread-wise stores
+            // touch 32 different lines per instruction; instead the warp stages its rows in shared memory (swizzled:
+            // conflict-free both ways) and every store instruction writes 512 contiguous bytes.
             int *o = A.labels + img * A.img_px + base;
-            const int nvalid = min(32, A.w - k * 32);
-            if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+            const int lane = tid & 31, warp = tid >> 5;
+            const int wi0 = (chunk * WPT + j) * 256 + warp * 32;                   // the warp's first word
+            const bool whole = (A.w & 31) == 0 && wi0 + 32 <= A.nwords;
+            int *o0 = A.labels + img * A.img_px + (size_t)wi0 * 32;                  // valid when `whole` (w == 32 * wpr)
+            if (whole && (reinterpret_cast<uintptr_t>(o0) & 15) == 0) {
+                int4 *dst = reinterpret_cast<int4 *>(o0);
+                if (__ballot_sync(0xffffffffu, v[j] != 0u) == 0u) {
 #pragma unroll
-                for (int i = 0; i < 8; i++)
-                    reinterpret_cast<int4 *>(o)[i] = make_int4(lab[4 * i], lab[4 * i + 1], lab[4 * i + 2], lab[4 * i + 3]);
-            } else {
+                    for (int q = 0; q < 8; q++) dst[q * 32 + lane] = make_int4(0, 0, 0, 0);
+                } else {
+                    int4 *stage = s_stage + warp * 256;
 #pragma unroll
-                for (int i = 0; i < 32; i++)
-                    if (i < nvalid) o[i] = lab[i];
+                    for (int i = 0; i < 8; i++)
+                        stage[lane * 8 + (i ^ (lane & 7))] = make_int4(lab[4 * i], lab[4 * i + 1], lab[4 * i + 2], lab[4 * i + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int idx = q * 32 + lane, sw = idx >> 3, part = idx & 7;
+                        dst[idx] = stage[sw * 8 + (part ^ (sw & 7))];
+                    }
+                    __syncwarp();
+                }
+            } else if (y >= 0) {
+                const int nvalid = min(32, A.w - k * 32);
+                if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+                        reinterpret_cast<int4 *>(o)[i] = make_int4(lab[4 * i], lab[4 * i + 1], lab[4 * i + 2], lab[4 * i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        if (i < nvalid) o[i] = lab[i];
+                }
             }
         }
     }
