@@ -898,3 +898,18 @@ def test_copy_probe_reports_plausible_pcie_rates():
         assert 1e-5 < t < 1e-2                       # 6-8 MB at somewhere between 1 and 800 GB/s
     assert both.value >= max(up.value, dn.value) * 0.8
     assert capi.lib().bgsb_copy_probe(0, 0, 1, 1, C.byref(up), C.byref(dn), C.byref(both)) == capi.ERR_ARG
+
+
+def test_gray_variant_24_golden_hashes(clips):
+    """`grayVariant` 1 (OpenCV 2.4 BGR2GRAY constants, what the C++ adapters select in a 2.4 build) against hashes of a
+    pure-numpy restatement committed in tests/golden/golden_gray24.json (tests/golden/make_golden_gray24.py)."""
+    import json
+    import os
+    import tracking_b200 as tb
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_gray24.json")))
+    for name, clip in clips.items():
+        for aid, key in ((0, "FrameDifferenceBGS:grayVariant=1"), (1, "StaticFrameDifferenceBGS:grayVariant=1")):
+            p = tb.ALGOS[aid](grayVariant=1)
+            fgs, _ = run_host(p, list(clip))
+            assert sha(fgs) == gold[name][key], (name, key)
+            p.close()

@@ -117,3 +117,20 @@ def test_stream_pool_sharding_rule_matches_shard_streams():
         ng = min(n, g)
         for r in range(ng):
             assert streams.shard_streams(n, ng, r) == list(range(r, n, ng))
+
+
+def test_gray24_golden_matches_the_oracle_variant(oracle, clips):
+    """tests/golden/golden_gray24.json (pure-numpy restatement of FD / StaticFD with the OpenCV 2.4 gray constants) ==
+    the C oracle's gray_variant = 1, so the GPU test that checks `grayVariant` 1 against the oracle is anchored to an
+    independent statement of the formula."""
+    import hashlib
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_gray24.json")))
+    for name, clip in clips.items():
+        for aid, key in ((0, "FrameDifferenceBGS:grayVariant=1"), (1, "StaticFrameDifferenceBGS:grayVariant=1")):
+            o = oracle.ALGOS[aid](gray_variant=1)
+            h = hashlib.sha256()
+            for f in clip:
+                fg, _ = o.process(f)
+                if fg is not None:
+                    h.update(np.ascontiguousarray(fg).tobytes())
+            assert h.hexdigest() == gold[name][key], (name, key)
