@@ -40,9 +40,29 @@ def sfd_masks(clip, thr=15):
     return [((gray24(np.abs(f.astype(np.int16) - clip[0].astype(np.int16)).astype(np.uint8)) > thr) * 255).astype(np.uint8) for f in clip]
 
 
+def tie_frames():
+    """Two frames whose difference image holds every colour (b, g, r < 48) on which the 2.4 and the 4.x constants put the
+    gray value on different sides of the plugins' threshold 15 -- the only inputs where `grayVariant` is observable."""
+    b, g, r = np.meshgrid(np.arange(48), np.arange(48), np.arange(48), indexing="ij")
+    g24 = (1868 * b + 9617 * g + 4899 * r + 8192) >> 14
+    g4x = (3735 * b + 19235 * g + 9798 * r + 16384) >> 15
+    sel = (g24 > 15) != (g4x > 15)
+    cols = np.stack([b[sel], g[sel], r[sel]], -1).astype(np.uint8)
+    n = len(cols)
+    w = 64
+    h = (n + w - 1) // w
+    cur = np.zeros((h * w, 3), np.uint8)
+    cur[:n] = cols
+    return np.stack([np.zeros((h, w, 3), np.uint8), cur.reshape(h, w, 3)]), n
+
+
 def main():
     z = np.load(os.path.join(HERE, "clips.npz"))
     out = {}
+    ties, n = tie_frames()
+    m24, m4x = fd_masks(ties)[0], fd_masks_4x(ties)[0]
+    assert n > 0 and int((m24 != m4x).sum()) == n
+    out["gray_ties"] = {"colours": n, "FrameDifferenceBGS:grayVariant=1": sha([m24]), "FrameDifferenceBGS:grayVariant=0": sha([m4x])}
     for name in z.files:
         clip = z[name]
         out[name] = {"FrameDifferenceBGS:grayVariant=1": sha(fd_masks(clip)),

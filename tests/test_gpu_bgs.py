@@ -906,7 +906,18 @@ def test_gray_variant_24_golden_hashes(clips):
     import json
     import os
     import tracking_b200 as tb
-    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_gray24.json")))
+    import sys
+    gdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = json.load(open(os.path.join(gdir, "golden_gray24.json")))
+    sys.path.insert(0, gdir)
+    import make_golden_gray24 as mk
+    ties, n = mk.tie_frames()                    # every colour on which the two generations of constants disagree at threshold 15
+    assert n == gold["gray_ties"]["colours"]
+    for variant in (0, 1):
+        p = tb.FrameDifferenceBGS(grayVariant=variant)
+        fgs, _ = run_host(p, list(ties))
+        assert sha(fgs) == gold["gray_ties"]["FrameDifferenceBGS:grayVariant=%d" % variant]
+        p.close()
     for name, clip in clips.items():
         for aid, key in ((0, "FrameDifferenceBGS:grayVariant=1"), (1, "StaticFrameDifferenceBGS:grayVariant=1")):
             p = tb.ALGOS[aid](grayVariant=1)

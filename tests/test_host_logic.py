@@ -125,6 +125,15 @@ def test_gray24_golden_matches_the_oracle_variant(oracle, clips):
     independent statement of the formula."""
     import hashlib
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_gray24.json")))
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_gray24 as mk
+    ties, n = mk.tie_frames()
+    assert n == gold["gray_ties"]["colours"] and n > 100
+    for variant in (0, 1):
+        o = oracle.FrameDifferenceBGS(gray_variant=variant)
+        o.process(ties[0])
+        fg, _ = o.process(ties[1])
+        assert hashlib.sha256(fg.tobytes()).hexdigest() == gold["gray_ties"]["FrameDifferenceBGS:grayVariant=%d" % variant]
     for name, clip in clips.items():
         for aid, key in ((0, "FrameDifferenceBGS:grayVariant=1"), (1, "StaticFrameDifferenceBGS:grayVariant=1")):
             o = oracle.ALGOS[aid](gray_variant=1)
