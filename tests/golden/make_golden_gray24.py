@@ -41,9 +41,10 @@ def sfd_masks(clip, thr=15):
 
 
 def tie_frames():
-    """Two frames whose difference image holds every colour (b, g, r < 48) on which the 2.4 and the 4.x constants put the
-    gray value on different sides of the plugins' threshold 15 -- the only inputs where `grayVariant` is observable."""
-    b, g, r = np.meshgrid(np.arange(48), np.arange(48), np.arange(48), indexing="ij")
+    """Two frames whose difference image holds every colour (b < 144, g < 32, r < 56: all colours whose gray value can be
+    15 or 16) on which the 2.4 and the 4.x constants put the gray value on different sides of the plugins' threshold 15 --
+    the only inputs where `grayVariant` is observable."""
+    b, g, r = np.meshgrid(np.arange(144), np.arange(32), np.arange(56), indexing="ij")
     g24 = (1868 * b + 9617 * g + 4899 * r + 8192) >> 14
     g4x = (3735 * b + 19235 * g + 9798 * r + 16384) >> 15
     sel = (g24 > 15) != (g4x > 15)
