@@ -1060,7 +1060,9 @@ int bgsb_copy_probe(int device, size_t bytes_up, size_t bytes_down, int iters, d
     BGSB_CUDA(cudaSetDevice(device));
     void *h_up = nullptr, *h_dn = nullptr, *d_up = nullptr, *d_dn = nullptr;
     cudaStream_t s1 = nullptr, s2 = nullptr;
-    cudaError_t e = cudaHostAlloc(&h_up, bytes_up, cudaHostAllocDefault);
+    // BGSB_PROBE_WC=1: the upload buffer as write-combined memory (what bgsb_host_alloc(.., 1) hands out for input frames)
+    static const bool wc = [] { const char *e = getenv("BGSB_PROBE_WC"); return e && e[0] == '1'; }();
+    cudaError_t e = cudaHostAlloc(&h_up, bytes_up, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc(&h_dn, bytes_down, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc(&d_up, bytes_up);
     if (e == cudaSuccess) e = cudaMalloc(&d_dn, bytes_down);
