@@ -120,6 +120,9 @@ BGSB_API int bgsb_reset(bgsb_ctx *ctx);
  * "parity unpinned": no OpenCV 2.4 in the build image), table kernels only;
  * "hostBands" (default 2, 1..8): row bands of the upload / kernel / download pipeline inside bgsb_process;
  * "trace" (default 0): per-stage timing of bgsb_process, see bgsb_trace_last;
+ * "quietGroups" (WeightedMovingVariance, default 1): with the threshold on, a 16-pixel group whose bytes moved by at most
+ * R over the three frames gets its all-zero mask without the arithmetic; R is derived from the threshold by running all
+ * 2^24 byte triples through the kernel's own routine once per weight set (identical results; 0 = always compute);
  * "retainInput" (default 0; FrameDifference, WeightedMovingVariance, WeightedMovingMean on the *_dev entry points):
  * 1 = the caller promises that the device frame given to a call stays valid and unmodified until the next call (FD)
  * / the next two calls (WMV, WMM) have completed, so the previous-frame history is read from those buffers and never

@@ -274,7 +274,8 @@ def test_retain_input_no_history_writeback(oracle, clips, aid):
                 if obg is not None:
                     assert bv and np.array_equal(bg[s], obg), (aid, S, s, t)
         warm = 1 if aid == 0 else 2
-        assert tb.kernel_launch_count() - before == n - warm      # warm-up frames are only remembered, not launched
+        extra = 1 if aid == 3 else 0          # WMV builds its quiet-group bound table once per context (one launch)
+        assert tb.kernel_launch_count() - before == n - warm + extra      # warm-up frames are only remembered, not launched
         assert p.frame_count == n
         p.close()
     # a single-stream batch with retainInput: history = the tail of the previous batch

@@ -89,6 +89,11 @@ struct bgsb_ctx {
     bool last_stream_set = false;
     cudaEvent_t ev_order = nullptr;
     int retain_input = 0;      // device path, FD / WMV / WMM: the caller's frames stay valid -> no history write-back
+    // WMV quiet-group shortcut: wmv_bound[ew][r] = largest standard-deviation byte over all triples of range r for the
+    // weight set ew (computed once per weight set on the device, launch_wmv_bound_table); wmv_quiet 0 switches it off
+    int wmv_quiet = 1;
+    int wmv_bound_valid[2] = {0, 0};
+    unsigned char wmv_bound[2][256] = {};
     // per-call stage timing of the host path (FrameProcessor::tic / toc, FrameProcessor.cpp:484-494, per stage)
     int trace = 0;
     cudaEvent_t ev_t[6] = {};  // upload begin / end, kernels begin / end, download begin / end
@@ -367,6 +372,26 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
         L.abl_update = (c->limit == -1);   // the limit>0 branch never fires: counter stays 0 (.cpp:52,60-61)
         if (c->enable_weight) { L.w0 = 0.5; L.w1 = 0.3; L.w2 = 0.2; }      // WeightedMovingVarianceBGS.cpp:67-68
         else { L.w0 = 0.3; L.w1 = 0.3; L.w2 = 0.3; }                          // :70
+        L.quiet_range = -1;
+        if (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE && c->wmv_quiet && c->enable_thr && c->thr >= 0) {
+            const int ew = c->enable_weight ? 1 : 0;
+            if (!c->wmv_bound_valid[ew]) {          // once per weight set: 2^24 triples through the kernel's own routine
+                unsigned *d_tab = nullptr, h_tab[256];
+                BGSB_CUDA(cudaMalloc(&d_tab, sizeof(h_tab)));
+                int rct = launch_wmv_bound_table(d_tab, L.w0, L.w1, L.w2, stream);
+                cudaError_t e = rct ? cudaErrorUnknown : cudaMemcpyAsync(h_tab, d_tab, sizeof(h_tab), cudaMemcpyDeviceToHost, stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+                cudaFree(d_tab);
+                if (rct) return rct;
+                BGSB_CUDA(e);
+                for (int r = 0; r < 256; r++) c->wmv_bound[ew][r] = (unsigned char)std::min(255u, h_tab[r]);
+                c->wmv_bound_valid[ew] = 1;
+            }
+            // the largest range R such that every triple of range <= R stays at or below the threshold
+            int R = -1;
+            while (R + 1 < 256 && (int)c->wmv_bound[ew][R + 1] <= c->thr) R++;
+            L.quiet_range = R;
+        }
         int rc = launch_simple(c->algo, L, c->nstreams, stream);
         if (rc) return rc;
     }
@@ -568,6 +593,7 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     else if (k == "shadowThreshold") c->tau = (float)v;
     else if (k == "hostBands") { BGSB_REQUIRE(v >= 1 && v <= 8, "hostBands in [1,8]"); c->host_bands = (int)v; }
     else if (k == "retainInput") c->retain_input = (v != 0);
+    else if (k == "quietGroups") c->wmv_quiet = (v != 0);
     else if (k == "trace") c->trace = (v != 0);
 #ifdef BGSB_INSTRUMENT
     else if (k == "kernelVariant") { BGSB_REQUIRE(v == 0 || v == 1 || v == 8 || v == 9, "kernelVariant is 0 or 1 (8, 9: timing instruments)"); c->mog2_variant = (int)v; }
@@ -618,6 +644,7 @@ int bgsb_get_param(bgsb_ctx *c, const char *key, double *v)
     else if (k == "kernelVariant") *v = c->mog2_variant;
     else if (k == "hostBands") *v = c->host_bands;
     else if (k == "retainInput") *v = c->retain_input;
+    else if (k == "quietGroups") *v = c->wmv_quiet;
     else if (k == "trace") *v = c->trace;
     else if (k == "ablTable") *v = c->abl_table;
     else if (k == "ablBlend") *v = c->abl_blend;

@@ -23,9 +23,14 @@ struct SimpleLaunch {
     const uint8_t *abl_lut;  // ABL: 64 KB table of the blend for this alpha (abl_lut_index), null = arithmetic kernel
     int abl_lut_mode;        // ABL table kernels: 0 = warp-coalesced where the alignment allows, 1 = per-thread groups
     double w0, w1, w2;       // WMV weights (0.5,0.3,0.2 | 0.3,0.3,0.3)
+    int quiet_range;         // WMV, thresholded output: a 16-pixel group whose 48 bytes each moved by at most this much over the
+                             // three frames has an all-zero mask (launch_wmv_bound_table proves it); -1 = no shortcut
     float one;               // 1.0f at run time: keeps ptxas from contracting packed mul + add (mog2_fastmath.cuh)
 };
 int launch_simple(int algo, const SimpleLaunch &L, int nstreams, cudaStream_t stream);
+// WMV: d_table[r] (256 unsigned, zeroed by the callee) = the largest re-quantised standard deviation byte over ALL byte
+// triples (b0, b1, b2) with max - min == r, computed with the kernel's own per-channel routine for these weights.
+int launch_wmv_bound_table(unsigned *d_table, double w0, double w1, double w2, cudaStream_t stream);
 // Fill the 64 KB ABL table for `alpha` with the arithmetic kernel's own blend (bit-exact by construction).
 // blend_variant 0: OpenCV 4.x double-precision addWeighted (pinned); 1: OpenCV 2.4 fp32 addWeighted (unpinned).
 int launch_abl_lut_build(uint8_t *d_lut, double alpha, int blend_variant, cudaStream_t stream);
