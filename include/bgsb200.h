@@ -123,6 +123,9 @@ BGSB_API int bgsb_reset(bgsb_ctx *ctx);
  * "quietGroups" (WeightedMovingVariance, default 1): with the threshold on, a 16-pixel group whose bytes moved by at most
  * R over the three frames gets its all-zero mask without the arithmetic; R is derived from the threshold by running all
  * 2^24 byte triples through the kernel's own routine once per weight set (identical results; 0 = always compute);
+ * AdaptiveBackgroundLearning's table kernel uses the same switch: 16 model bytes that all lie within the table's quiet
+ * radius of the input (largest D with blend(x, y) == y for |x - y| <= D, read off the finished table on the device:
+ * 9 at alpha 0.05) are kept without the 16 lookups;
  * "retainInput" (default 0; FrameDifference, WeightedMovingVariance, WeightedMovingMean on the *_dev entry points):
  * 1 = the caller promises that the device frame given to a call stays valid and unmodified until the next call (FD)
  * / the next two calls (WMV, WMM) have completed, so the previous-frame history is read from those buffers and never

@@ -320,3 +320,23 @@ def test_abl_opencv24_fp32_blend_variant_all_byte_pairs(oracle):
     assert 0 < ndiff < 65536 * 0.1
     with pytest.raises(tb.BgsbError):
         tb.AdaptiveBackgroundLearning(ablTable=0, ablBlend=1)
+
+
+@pytest.mark.parametrize("alpha", [0.05, 0.0, 1.0, 0.4, 0.004])
+def test_abl_quiet_radius_shortcut_matches_plain_lookups(oracle, clips, alpha):
+    """ABL's warp-coalesced table kernel skips the lookups of words whose bytes all lie within the table's quiet radius
+    (read off the table on the device): same masks and models as with "quietGroups" 0 and as the oracle, on a noisy
+    clip tiled to a multiple of 512 pixels (so the coalesced kernel runs), alpha from 0 (radius 255) to 1 (radius 0)."""
+    import tracking_b200 as tb
+    clip = clips["video_clip"]
+    frames = [np.ascontiguousarray(np.tile(f, (2, 2, 1))[:128, :256]) for f in clip[:12]]
+    assert frames[0].shape[0] * frames[0].shape[1] % 512 == 0
+    a, b = tb.AdaptiveBackgroundLearning(alpha=alpha), tb.AdaptiveBackgroundLearning(alpha=alpha, quietGroups=0)
+    o = oracle.AdaptiveBackgroundLearning(alpha=alpha)
+    for i, f in enumerate(frames):
+        fa, ba = a.process(f)
+        fb, bb = b.process(f)
+        fo, bo = o.process(f)
+        assert np.array_equal(fa, fb) and np.array_equal(ba, bb), i
+        assert np.array_equal(fa, fo) and np.array_equal(ba, bo), i
+    a.close(); b.close()

@@ -331,7 +331,7 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
             L.thr = c->thr; L.gray_variant = c->gray_variant;
             // the blend of two bytes as a 64 KB table (ABL's, simple_bgs.cu): rebuilt when alpha changes, i.e. once at
             // the end of the learning phase; stream-ordered before the kernel that reads it
-            if (!c->d_abl_lut) BGSB_CUDA(cudaMalloc(&c->d_abl_lut, 65536));
+            if (!c->d_abl_lut) BGSB_CUDA(cudaMalloc(&c->d_abl_lut, ABL_LUT_BYTES));
             if (c->lut_alpha != L.alpha) {
                 int rcl = launch_abl_lut_build(c->d_abl_lut, L.alpha, 0, stream);
                 if (rcl) return rcl;
@@ -360,7 +360,7 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
         L.enable_thr = c->enable_thr; L.thr = c->thr; L.gray_variant = c->gray_variant;
         L.alpha = c->alpha;
         if (c->algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING && c->abl_table) {
-            if (!c->d_abl_lut) BGSB_CUDA(cudaMalloc(&c->d_abl_lut, 65536));
+            if (!c->d_abl_lut) BGSB_CUDA(cudaMalloc(&c->d_abl_lut, ABL_LUT_BYTES));
             if (c->lut_alpha != c->alpha || c->lut_blend != c->abl_blend) {     // stream-ordered before the kernel that reads it
                 int rcl = launch_abl_lut_build(c->d_abl_lut, c->alpha, c->abl_blend, stream);
                 if (rcl) return rcl;
@@ -368,6 +368,7 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
             }
             L.abl_lut = c->d_abl_lut;
             L.abl_lut_mode = c->abl_table == 2 ? 1 : 0;
+            L.abl_quiet = c->wmv_quiet;
         }
         L.abl_update = (c->limit == -1);   // the limit>0 branch never fires: counter stays 0 (.cpp:52,60-61)
         if (c->enable_weight) { L.w0 = 0.5; L.w1 = 0.3; L.w2 = 0.2; }      // WeightedMovingVarianceBGS.cpp:67-68

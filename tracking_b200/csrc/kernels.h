@@ -22,6 +22,7 @@ struct SimpleLaunch {
     int abl_update;          // ABL: limit == -1 (AdaptiveBackgroundLearning.cpp:52); 0 freezes the model
     const uint8_t *abl_lut;  // ABL: 64 KB table of the blend for this alpha (abl_lut_index), null = arithmetic kernel
     int abl_lut_mode;        // ABL table kernels: 0 = warp-coalesced where the alignment allows, 1 = per-thread groups
+    int abl_quiet;           // ABL, warp-coalesced kernel: use the table's quiet radius (stored behind the table) to skip lookups
     double w0, w1, w2;       // WMV weights (0.5,0.3,0.2 | 0.3,0.3,0.3)
     int quiet_range;         // WMV, thresholded output: a 16-pixel group whose 48 bytes each moved by at most this much over the
                              // three frames has an all-zero mask (launch_wmv_bound_table proves it); -1 = no shortcut
@@ -33,6 +34,8 @@ int launch_simple(int algo, const SimpleLaunch &L, int nstreams, cudaStream_t st
 int launch_wmv_bound_table(unsigned *d_table, double w0, double w1, double w2, cudaStream_t stream);
 // Fill the 64 KB ABL table for `alpha` with the arithmetic kernel's own blend (bit-exact by construction).
 // blend_variant 0: OpenCV 4.x double-precision addWeighted (pinned); 1: OpenCV 2.4 fp32 addWeighted (unpinned).
+// the 64 KB byte-pair table plus the int that holds its quiet radius (abl_lut_radius_kernel)
+#define ABL_LUT_BYTES (65536 + 256)
 int launch_abl_lut_build(uint8_t *d_lut, double alpha, int blend_variant, cudaStream_t stream);
 
 // ---- AdaptiveSelectiveBackgroundLearning (single-channel model; one frame per launch pair) --------
