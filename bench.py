@@ -172,11 +172,11 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    # bounded sample of a 1024-frame step: 8 frames per step keeps `--steps 20 --warmup 5` within ~1 minute
-    sample = 8
+    # bounded sample of a 1024-frame step: 32 frames per step keeps `--steps 20 --warmup 5` at about 15-20 s of CPU work
+    sample = 32
     warm_frames = max(50, args.warmup * sample)
     val, dt, threads = cpu_reference_run(args.steps, warm_frames, sample, cores)
-    v1, dt1, _ = cpu_reference_run(1, 50, 8, 1, nuniq=64)
+    v1, dt1, _ = cpu_reference_run(1, 50, 96, 1)
     import cv2
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -189,7 +189,7 @@ def run_reference(args):
                                        "C++ not buildable here: needs OpenCV 2.4 headers), %d host cores"
                                        % (sample, FRAMES_PER_STEP, args.steps, warm_frames, NFRAMES_RESIDENT, cv2.__version__, cores),
                              "one_thread": {"value": v1, "unit": UNIT, "cores": 1,
-                                            "sample": "8 frames after 50 warm-up frames, cv2.setNumThreads(1), %.1f s" % dt1}},
+                                            "sample": "96 frames after 50 warm-up frames, cv2.setNumThreads(1), %.1f s" % dt1}},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(json.dumps(line))
@@ -693,12 +693,14 @@ def run_ours(args):
     cpu = None
     if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        v, cdt, threads = cpu_reference_run(4, 50, 8, cores, nuniq=64)
-        v1, cdt1, _ = cpu_reference_run(1, 50, 8, 1, nuniq=64)
+        # about 10 s of wall clock on all host cores, about 4 s on one
+        v, cdt, threads = cpu_reference_run(16, 50, 24, cores)
+        v1, cdt1, _ = cpu_reference_run(1, 50, 96, 1)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "32 frames (4 steps x 8) of the same synthetic 1080p stream after 50 warm-up frames; OpenCV "
-                         "call-for-call replay of MixtureOfGaussianV2BGS::process on %d host cores, %.1f s" % (cores, cdt),
-               "one_thread": {"value": v1, "unit": UNIT, "cores": 1, "sample": "8 frames after 50 warm-up frames, %.1f s" % cdt1}}
+               "sample": "384 frames (16 steps x 24) of the same synthetic 1080p stream (same ring of %d unique frames) after "
+                         "50 warm-up frames; OpenCV call-for-call replay of MixtureOfGaussianV2BGS::process on %d host "
+                         "cores, %.1f s" % (NFRAMES_RESIDENT, cores, cdt),
+               "one_thread": {"value": v1, "unit": UNIT, "cores": 1, "sample": "96 frames after 50 warm-up frames, %.1f s" % cdt1}}
 
     if ctx.rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": K, "warmup": Wm,
