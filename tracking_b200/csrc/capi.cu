@@ -1087,37 +1087,46 @@ int bgsb_copy_probe(int device, size_t bytes_up, size_t bytes_down, int iters, d
     BGSB_REQUIRE(bytes_up > 0 && bytes_down > 0 && iters >= 1 && sec_up && sec_down && sec_both, "bad args");
     BGSB_CUDA(cudaSetDevice(device));
     void *h_up = nullptr, *h_dn = nullptr, *d_up = nullptr, *d_dn = nullptr;
-    cudaStream_t s1 = nullptr, s2 = nullptr;
     // BGSB_PROBE_WC=1: the upload buffer as write-combined memory (what bgsb_host_alloc(.., 1) hands out for input frames)
     static const bool wc = [] { const char *e = getenv("BGSB_PROBE_WC"); return e && e[0] == '1'; }();
+    // BGSB_PROBE_SPLIT=k (1..4): each transfer as k pieces on k streams (k copy engines per direction)
+    static const int nsplit = [] { const char *e = getenv("BGSB_PROBE_SPLIT"); int k = e ? atoi(e) : 1; return k < 1 ? 1 : (k > 4 ? 4 : k); }();
+    cudaStream_t su[4] = {nullptr, nullptr, nullptr, nullptr}, sd[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaError_t e = cudaHostAlloc(&h_up, bytes_up, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaHostAlloc(&h_dn, bytes_down, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaMalloc(&d_up, bytes_up);
     if (e == cudaSuccess) e = cudaMalloc(&d_dn, bytes_down);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+    for (int i = 0; i < nsplit && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&su[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sd[i], cudaStreamNonBlocking);
+    }
     if (e == cudaSuccess) { memset(h_up, 1, bytes_up); memset(h_dn, 0, bytes_down); }
+    auto piece = [&](size_t bytes, int i, size_t *off) { const size_t per = (bytes / nsplit) & ~(size_t)255; *off = per * i; return i == nsplit - 1 ? bytes - per * i : per; };
+    auto issue = [&](bool up, bool down) {
+        for (int i = 0; i < nsplit && e == cudaSuccess; i++) {
+            size_t off = 0, n = 0;
+            if (up) { n = piece(bytes_up, i, &off); e = cudaMemcpyAsync((char *)d_up + off, (char *)h_up + off, n, cudaMemcpyHostToDevice, su[i]); }
+            if (down && e == cudaSuccess) { n = piece(bytes_down, i, &off); e = cudaMemcpyAsync((char *)h_dn + off, (char *)d_dn + off, n, cudaMemcpyDeviceToHost, sd[i]); }
+        }
+    };
+    auto sync_all = [&]() {
+        for (int i = 0; i < nsplit; i++) {
+            if (e == cudaSuccess) e = cudaStreamSynchronize(su[i]);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(sd[i]);
+        }
+    };
     auto run = [&](bool up, bool down) -> double {
-        for (int w = 0; w < 3 && e == cudaSuccess; w++) {
-            if (up) e = cudaMemcpyAsync(d_up, h_up, bytes_up, cudaMemcpyHostToDevice, s1);
-            if (down && e == cudaSuccess) e = cudaMemcpyAsync(h_dn, d_dn, bytes_down, cudaMemcpyDeviceToHost, s2);
-        }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s1);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s2);
+        for (int w = 0; w < 3; w++) issue(up, down);
+        sync_all();
         const auto t0 = std::chrono::steady_clock::now();
-        for (int i = 0; i < iters && e == cudaSuccess; i++) {
-            if (up) e = cudaMemcpyAsync(d_up, h_up, bytes_up, cudaMemcpyHostToDevice, s1);
-            if (down && e == cudaSuccess) e = cudaMemcpyAsync(h_dn, d_dn, bytes_down, cudaMemcpyDeviceToHost, s2);
-        }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s1);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s2);
+        for (int i = 0; i < iters; i++) issue(up, down);
+        sync_all();
         return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / iters;
     };
     if (e == cudaSuccess) *sec_up = run(true, false);
     if (e == cudaSuccess) *sec_down = run(false, true);
     if (e == cudaSuccess) *sec_both = run(true, true);
-    if (s1) cudaStreamDestroy(s1);
-    if (s2) cudaStreamDestroy(s2);
+    for (int i = 0; i < 4; i++) { if (su[i]) cudaStreamDestroy(su[i]); if (sd[i]) cudaStreamDestroy(sd[i]); }
     cudaFree(d_up); cudaFree(d_dn);
     if (h_up) cudaFreeHost(h_up);
     if (h_dn) cudaFreeHost(h_dn);
