@@ -38,3 +38,16 @@ for bands in (1, 2, 3, 4, 6, 8):
         t0 = time.perf_counter(); run(256); dt = (time.perf_counter() - t0) / 256
         print("bands", bands, "bg" if want_bg else "no-bg", "us/frame %.1f  Gpx/s %.2f" % (dt * 1e6, W * H / dt / 1e9), flush=True)
         p.close()
+# stage split of the synchronous call (parameter "trace"): event spans of the uploads, kernels, downloads + wall clock
+for bands in (1, 2, 3, 4):
+    p = tb.MixtureOfGaussianV2BGS(hostBands=bands, trace=1)
+    fv, bv = C.c_int(0), C.c_int(0)
+    acc = {}
+    for i in range(96):
+        L.bgsb_process(p._h, C.c_void_p(h_in[i % NF].data_ptr()), W, H, W * 3, C.c_void_p(h_fg.data_ptr()), W,
+                       C.c_void_p(h_bg.data_ptr()), W * 3, C.byref(fv), C.byref(bv))
+        if i >= 32:
+            for k, v in p.trace_last().items():
+                acc[k] = acc.get(k, 0.0) + v / 64
+    print("trace bands", bands, {k: round(v * 1e3, 1) for k, v in acc.items() if k.endswith("_ms")}, "(us)", flush=True)
+    p.close()
