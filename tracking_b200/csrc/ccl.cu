@@ -39,6 +39,8 @@ namespace cg = cooperative_groups;
 
 namespace bgsb {
 
+constexpr int CCL_TW = 4;                 // width in words of the label kernel's 2-D tiles
+
 __device__ __forceinline__ unsigned in_mask(int k, int w, int wpr)
 {
     if (k < 0 || k >= wpr) return 0u;
@@ -338,123 +340,16 @@ ccl_roots_kernel(const __grid_constant__ CclArgs A)
     if (tid == 0) A.ncomp[img] = s_carry;
 }
 
-// ---- launch 4: label -------------------------------------------------------------------------------------------------
 // canonical label = 1 + (roots in the chunks before the root's chunk) + (the root's rank inside its chunk).  The table
 // rows are zero on entry and are only ever touched by atomics (and by the root's own thread for the fields nobody else
 // writes), so no row has to be initialised before another CTA may use it: maxima as they are, minima as CCL_BIG - value.
 constexpr int CCL_BIG = 1 << 30;
 
-template <bool LABELS, int WPT>       // LABELS = false: component table only (no 32-register label row per thread)
-__global__ void __launch_bounds__(256)
-ccl_label_kernel(const __grid_constant__ CclArgs A)
+// The last CTA of an image decides whether the image needs the background pass: does any component's bounding box lie
+// strictly inside another's?  (Necessary for a component to sit in a hole of another one.)  More than 1024 components:
+// not worth checking in one CTA, take the pass.
+__device__ __forceinline__ void ccl_nest_check(const CclArgs &A, int img, const CompRaw *comp, int4 *s_box, int tid)
 {
-    pdl_entry();
-    __shared__ int4 s_box[256];
-    __shared__ int4 s_stage[LABELS ? 8 * 256 : 1];     // per warp: 32 label rows of 128 bytes on their way to global memory
-    __shared__ int s_last;
-    const int img = blockIdx.y;
-    const int tid = threadIdx.x;
-    const unsigned *bits = A.bits + img * A.img_words;
-    const int *parent = A.parent + img * A.img_px;
-    const int *prefix = A.chunkprefix + (size_t)img * A.nchunks;
-    CompRaw *comp = A.comp + (size_t)img * A.cap;
-    constexpr int CSHIFT = WPT == 1 ? 8 : 10;          // log2(words per chunk)
-    static_assert(WPT == 1 || WPT == 4, "chunk sizes 256 / 1024 words");
-    for (int chunk = blockIdx.x; chunk < A.nchunks; chunk += gridDim.x) {
-    unsigned v[WPT];
-    int yy[WPT], kk[WPT];
-#pragma unroll
-    for (int j = 0; j < WPT; j++) {
-        const int wi = (chunk * WPT + j) * 256 + tid;
-        const bool valid = wi < A.nwords;
-        yy[j] = valid ? wi / A.wpr : -1; kk[j] = valid ? wi - yy[j] * A.wpr : 0;
-        v[j] = valid ? ccl_word(bits, yy[j], kk[j], A) : 0u;
-    }
-#pragma unroll
-    for (int j = 0; j < WPT; j++) {
-        const int y = yy[j], k = kk[j];
-        const int base = y * A.w + k * 32;
-        int lab[LABELS ? 32 : 1];
-        if (LABELS) {
-#pragma unroll
-            for (int i = 0; i < 32; i++) lab[i] = 0;
-        }
-        for (unsigned s = v[j] & ~(v[j] << 1); s;) {
-            const int b = __ffs(s) - 1; s &= s - 1;
-            const int p = base + b;
-            const int q = parent[p];
-            const int root = q < 0 ? p : q;
-            const int local = ~(q < 0 ? q : parent[root]);
-            const int ry = root / A.w, rx = root - ry * A.w;
-            const int rank = prefix[(ry * A.wpr + (rx >> 5)) >> CSHIFT] + local;
-            const unsigned rest = ~(v[j] >> b);
-            const int len = rest ? __ffs(rest) - 1 : 32 - b;
-            if (LABELS) {
-#pragma unroll
-                for (int i = 0; i < 32; i++)
-                    if (i >= b && i < b + len) lab[i] = rank + 1;
-            }
-            if (rank < A.cap) {
-                CompRaw *cp = comp + rank;
-                const int x0 = k * 32 + b;
-                if (q < 0) { cp->label = rank + 1; cp->first_index = p; cp->external = 1; }   // provisional; see the background pass
-                atomicMax(&cp->xmin, CCL_BIG - x0); atomicMax(&cp->xmax, x0 + len - 1);
-                atomicMax(&cp->ymin, CCL_BIG - y); atomicMax(&cp->ymax, y);
-                atomicAdd(&cp->area, len);
-            }
-        }
-        if (LABELS) {
-            // The 32 words of a warp are consecutive in raster order: when the width is a multiple of 32 their label rows
-            // are ONE contiguous 4 KB piece of the label image.  A thread's own row is 128 bytes, so thread-wise stores
-            // touch 32 different lines per instruction; instead the warp stages its rows in shared memory (swizzled:
-            // conflict-free both ways) and every store instruction writes 512 contiguous bytes.
-            int *o = A.labels + img * A.img_px + base;
-            const int lane = tid & 31, warp = tid >> 5;
-            const int wi0 = (chunk * WPT + j) * 256 + warp * 32;                   // the warp's first word
-            const bool whole = (A.w & 31) == 0 && wi0 + 32 <= A.nwords;
-            int *o0 = A.labels + img * A.img_px + (size_t)wi0 * 32;                  // valid when `whole` (w == 32 * wpr)
-            if (whole && (reinterpret_cast<uintptr_t>(o0) & 15) == 0) {
-                int4 *dst = reinterpret_cast<int4 *>(o0);
-                if (__ballot_sync(0xffffffffu, v[j] != 0u) == 0u) {
-#pragma unroll
-                    for (int q = 0; q < 8; q++) dst[q * 32 + lane] = make_int4(0, 0, 0, 0);
-                } else {
-                    int4 *stage = s_stage + warp * 256;
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        stage[lane * 8 + (i ^ (lane & 7))] = make_int4(lab[4 * i], lab[4 * i + 1], lab[4 * i + 2], lab[4 * i + 3]);
-                    __syncwarp();
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const int idx = q * 32 + lane, sw = idx >> 3, part = idx & 7;
-                        dst[idx] = stage[sw * 8 + (part ^ (sw & 7))];
-                    }
-                    __syncwarp();
-                }
-            } else if (y >= 0) {
-                const int nvalid = min(32, A.w - k * 32);
-                if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++)
-                        reinterpret_cast<int4 *>(o)[i] = make_int4(lab[4 * i], lab[4 * i + 1], lab[4 * i + 2], lab[4 * i + 3]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; i++)
-                        if (i < nvalid) o[i] = lab[i];
-                }
-            }
-        }
-    }
-
-    }
-    // ---- the last CTA of the image to get here decides whether the image needs the background pass: does any
-    // component's bounding box lie strictly inside another's?  (Necessary for a component to sit in a hole of another
-    // one.)  More than 1024 components: not worth checking in one CTA, take the pass.
-    __syncthreads();
-    if (tid == 0) { __threadfence(); s_last = (atomicAdd(&A.done_b[img], 1) == (int)gridDim.x - 1); }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
     const int n = __ldcg(A.ncomp + img);
     int need = 0;
     if (A.force_bg || n > 1024 || n > A.cap) need = (n > 0) || A.force_bg;
@@ -490,6 +385,206 @@ ccl_label_kernel(const __grid_constant__ CclArgs A)
         A.need_bg[img] = need ? 1 : 0;               // every image of the call gets its answer (no stale flags)
         A.done_a[img] = 0; A.done_b[img] = 0;        // both kernels' CTAs have all arrived: zero again for the next call
     }
+}
+
+// ---- launch 4: label ------------------------------------------------------------------------------------------------
+// A CTA owns a 2-D tile of 4 words x 64 * WPT rows, so that a component's statistics leave the CTA ONCE: a blob of the
+// size the tracker cares about lies in a handful of such tiles (a raster chunk of 256 words is 4 rows of a 1080p mask).
+// The runs of the tile accumulate bounding box and area in a small shared-memory table keyed by the root; one thread
+// per occupied slot looks the component's rank up and issues the five global atomics; with LABELS the runs then read
+// the rank back from the table.  (The first round-2 kernel worked on raster chunks and sent five atomics PER RUN to the
+// component's row -- 1600 same-sector atomics for a 100 x 80 blob: 15 us on a single 1080p mask; this form: one mask
+// 35 -> 29 us, 64 masks 200 -> 154 us.)  Tiles of noise (many runs per word, more components than slots) and runs that
+// find no slot take the per-run path.
+constexpr int CCL_NS = 128;               // slots of the per-CTA table
+constexpr int CCL_PROBES = 8;
+
+template <int WPT>
+__device__ __forceinline__ int ccl_rank_of_root(const CclArgs &A, const int *parent, const int *prefix, int root, int local)
+{
+    constexpr int CSHIFT = WPT == 1 ? 8 : 10;
+    const int ry = root / A.w, rx = root - ry * A.w;
+    return prefix[(ry * A.wpr + (rx >> 5)) >> CSHIFT] + local;
+}
+
+template <bool LABELS, int WPT>
+__global__ void __launch_bounds__(256)
+ccl_label_tile_kernel(const __grid_constant__ CclArgs A)
+{
+    pdl_entry();
+    __shared__ int4 s_box[256];
+    __shared__ int4 s_stage[LABELS ? 8 * 256 : 1];
+    __shared__ int s_key[CCL_NS], s_val[CCL_NS][5], s_rank[CCL_NS];
+    __shared__ int s_last;
+    static_assert(WPT == 1 || WPT == 4, "chunk sizes 256 / 1024 words");
+    const int img = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned *bits = A.bits + img * A.img_words;
+    const int *parent = A.parent + img * A.img_px;
+    const int *prefix = A.chunkprefix + (size_t)img * A.nchunks;
+    CompRaw *comp = A.comp + (size_t)img * A.cap;
+    constexpr int TH = 64 * WPT;
+    const int ntx = (A.wpr + CCL_TW - 1) / CCL_TW, nty = (A.h + TH - 1) / TH, ntiles = ntx * nty;
+    const int col = tid & 3, row = tid >> 2;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int ty = tile / ntx, tx = tile - ty * ntx;
+        const int k = tx * CCL_TW + col;
+        for (int i = tid; i < CCL_NS; i += 256) {
+            s_key[i] = -1; s_val[i][0] = 0; s_val[i][1] = 0; s_val[i][2] = 0; s_val[i][3] = 0; s_val[i][4] = 0;
+        }
+        unsigned v[WPT];
+        int yy[WPT];
+        unsigned any = 0;
+#pragma unroll
+        for (int j = 0; j < WPT; j++) {
+            const int y = ty * TH + j * 64 + row;
+            const bool valid = k < A.wpr && y < A.h;
+            yy[j] = valid ? y : -1;
+            v[j] = valid ? ccl_word(bits, y, k, A) : 0u;
+            any |= v[j];
+        }
+        const bool work = __syncthreads_or(any != 0u);           // also: the table is initialised
+        // a tile of noise (many runs per word) holds more components than the table has slots: per-run path at once
+        bool dense = false;
+        if (work) {
+            int heavy = 0;
+#pragma unroll
+            for (int j = 0; j < WPT; j++) heavy |= __popc(v[j] & ~(v[j] << 1)) >= 3;
+            dense = __syncthreads_count(heavy) > 32;
+        }
+        const int probes = dense ? 0 : CCL_PROBES;
+        if (work) {
+            // phase 1: every run adds itself to its root's slot
+#pragma unroll
+            for (int j = 0; j < WPT; j++) {
+                const int y = yy[j];
+                const int base = y * A.w + k * 32;
+                for (unsigned s = v[j] & ~(v[j] << 1); s;) {
+                    const int b = __ffs(s) - 1; s &= s - 1;
+                    const int p = base + b;
+                    const int q = parent[p];
+                    const int root = q < 0 ? p : q;
+                    const unsigned rest = ~(v[j] >> b);
+                    const int len = rest ? __ffs(rest) - 1 : 32 - b;
+                    const int x0 = k * 32 + b;
+                    if (q < 0) {                                    // the root's own thread: fields nobody else writes
+                        const int rank = ccl_rank_of_root<WPT>(A, parent, prefix, p, ~q);
+                        if (rank < A.cap) { CompRaw *cp = comp + rank; cp->label = rank + 1; cp->first_index = p; cp->external = 1; }
+                    }
+                    unsigned hsh = ((unsigned)root * 2654435761u) >> 25;      // 7 bits
+                    bool placed = false;
+#pragma unroll 1
+                    for (int t = 0; t < probes && !placed; t++) {
+                        const int old = atomicCAS(&s_key[hsh], -1, root);
+                        if (old == -1 || old == root) {
+                            atomicMax(&s_val[hsh][0], CCL_BIG - x0); atomicMax(&s_val[hsh][1], x0 + len - 1);
+                            atomicMax(&s_val[hsh][2], CCL_BIG - y); atomicMax(&s_val[hsh][3], y);
+                            atomicAdd(&s_val[hsh][4], len);
+                            placed = true;
+                        } else hsh = (hsh + 1) & (CCL_NS - 1);
+                    }
+                    if (!placed) {                                  // crowded tile: this run goes to the row itself
+                        const int rank = ccl_rank_of_root<WPT>(A, parent, prefix, root, ~(q < 0 ? q : parent[root]));
+                        if (rank < A.cap) {
+                            CompRaw *cp = comp + rank;
+                            atomicMax(&cp->xmin, CCL_BIG - x0); atomicMax(&cp->xmax, x0 + len - 1);
+                            atomicMax(&cp->ymin, CCL_BIG - y); atomicMax(&cp->ymax, y);
+                            atomicAdd(&cp->area, len);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // phase 2: one thread per occupied slot: rank of the component, its statistics to the table row
+            if (tid < CCL_NS && s_key[tid] >= 0) {
+                const int root = s_key[tid];
+                const int rank = ccl_rank_of_root<WPT>(A, parent, prefix, root, ~parent[root]);
+                s_rank[tid] = rank;
+                if (rank < A.cap) {
+                    CompRaw *cp = comp + rank;
+                    atomicMax(&cp->xmin, s_val[tid][0]); atomicMax(&cp->xmax, s_val[tid][1]);
+                    atomicMax(&cp->ymin, s_val[tid][2]); atomicMax(&cp->ymax, s_val[tid][3]);
+                    atomicAdd(&cp->area, s_val[tid][4]);
+                }
+            }
+        }
+        if (LABELS) {
+            if (work) __syncthreads();                              // s_rank is complete
+#pragma unroll
+            for (int j = 0; j < WPT; j++) {
+                const int y = yy[j];
+                const int base = y * A.w + k * 32;
+                int lab[32];
+#pragma unroll
+                for (int i = 0; i < 32; i++) lab[i] = 0;
+                for (unsigned s = v[j] & ~(v[j] << 1); s;) {
+                    const int b = __ffs(s) - 1; s &= s - 1;
+                    const int p = base + b;
+                    const int q = parent[p];
+                    const int root = q < 0 ? p : q;
+                    unsigned hsh = ((unsigned)root * 2654435761u) >> 25;
+                    int rank = -1;
+#pragma unroll 1
+                    for (int t = 0; t < probes && rank < 0; t++) {
+                        const int key = s_key[hsh];
+                        if (key == root) rank = s_rank[hsh];
+                        else if (key == -1) break;
+                        else hsh = (hsh + 1) & (CCL_NS - 1);
+                    }
+                    if (rank < 0) rank = ccl_rank_of_root<WPT>(A, parent, prefix, root, ~(q < 0 ? q : parent[root]));
+                    const unsigned rest = ~(v[j] >> b);
+                    const int len = rest ? __ffs(rest) - 1 : 32 - b;
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        if (i >= b && i < b + len) lab[i] = rank + 1;
+                }
+                // the warp's 32 words are 8 rows x 4 words: per row 512 contiguous bytes of the label image
+                int *limg = A.labels + img * A.img_px;
+                const int y0 = ty * TH + j * 64 + warp * 8;          // the warp's first row
+                const bool whole = (A.w & 31) == 0 && tx * CCL_TW + CCL_TW <= A.wpr &&
+                                   (reinterpret_cast<uintptr_t>(limg + (size_t)y0 * A.w + tx * CCL_TW * 32) & 15) == 0;
+                if (whole) {
+                    const bool empty = __ballot_sync(0xffffffffu, v[j] != 0u) == 0u;
+                    int4 *stage = s_stage + warp * 256;
+                    if (!empty) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            stage[lane * 8 + (i ^ (lane & 7))] = make_int4(lab[4 * i], lab[4 * i + 1], lab[4 * i + 2], lab[4 * i + 3]);
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        if (y0 + q < A.h) {
+                            const int sw = q * 4 + (lane >> 3), part = lane & 7;       // source thread of the warp, its int4
+                            int4 *dst = reinterpret_cast<int4 *>(limg + (size_t)(y0 + q) * A.w + tx * CCL_TW * 32) + lane;
+                            *dst = empty ? make_int4(0, 0, 0, 0) : stage[sw * 8 + (part ^ (sw & 7))];
+                        }
+                    }
+                    __syncwarp();
+                } else if (y >= 0) {
+                    int *o = limg + base;
+                    const int nvalid = min(32, A.w - k * 32);
+                    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            reinterpret_cast<int4 *>(o)[i] = make_int4(lab[4 * i], lab[4 * i + 1], lab[4 * i + 2], lab[4 * i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i++)
+                            if (i < nvalid) o[i] = lab[i];
+                    }
+                }
+            }
+        }
+        __syncthreads();                                            // the table is reused by the CTA's next tile
+    }
+    // ---- the last CTA of the image: does the image need the background pass?
+    __syncthreads();
+    if (tid == 0) { __threadfence(); s_last = (atomicAdd(&A.done_b[img], 1) == (int)gridDim.x - 1); }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    ccl_nest_check(A, img, comp, s_box, tid);
 }
 
 // ---- launch 5: RETR_EXTERNAL ------------------------------------------------------------------------------------------
@@ -769,8 +864,9 @@ int ccl_label_bits(bgsb_ccl *c, const unsigned *d_bits, bool parents_ready, int 
         BGSB_LAUNCH_CHECK();                                                                                    \
         launch_pdl(ccl_roots_kernel<W>, grid, block, 0, stream, A);                                             \
         BGSB_LAUNCH_CHECK();                                                                                    \
-        if (d_labels) launch_pdl(ccl_label_kernel<true, W>, grid, block, 0, stream, A);                         \
-        else launch_pdl(ccl_label_kernel<false, W>, grid, block, 0, stream, A);                                 \
+        const dim3 tgrid(((A.wpr + CCL_TW - 1) / CCL_TW) * ((A.h + 64 * W - 1) / (64 * W)), nimages);           \
+        if (d_labels) launch_pdl(ccl_label_tile_kernel<true, W>, tgrid, block, 0, stream, A);                   \
+        else launch_pdl(ccl_label_tile_kernel<false, W>, tgrid, block, 0, stream, A);                           \
         BGSB_LAUNCH_CHECK();                                                                                    \
     } while (0)
     if (wpt == 4) BGSB_CCL_LAUNCH(4);
