@@ -239,3 +239,48 @@ def test_pipeline_on_device_mog2_open_cc(oracle, clips):
         on, olab, ost, oext = oracle.ccl8(om, True)
         assert np.array_equal(d_open.cpu().numpy(), om)
         assert len(comps) == on and np.array_equal(d_lab.cpu().numpy(), olab)
+
+
+@pytest.mark.parametrize("shape", [(70, 128), (65, 160), (130, 96), (257, 416), (64, 2080), (300, 1920)])
+def test_ccl_label_tiles_word_aligned_widths(oracle, shape):
+    """Widths that are multiples of 32 take the label kernel's staged 512-byte row stores where a tile column is whole and
+    the per-thread stores where it is not (wpr % 4 != 0), tile rows past the image bottom, single image and a batch big
+    enough for the four-words-per-thread form; blobs larger than a tile, specks, and a noise image (per-run path)."""
+    import torch
+    from tracking_b200 import blobs
+    h, w = shape
+    rng = np.random.default_rng(h * 7 + w)
+    yy, xx = np.mgrid[0:h, 0:w]
+    blobby = np.zeros((h, w), np.uint8)
+    for _ in range(5):
+        cy, cx, r = rng.integers(0, h), rng.integers(0, w), rng.integers(5, 90)
+        blobby[((yy - cy) ** 2 + ((xx - cx) // 2) ** 2) < r * r] = 255
+    blobby[rng.random((h, w)) < 0.003] = 255
+    noise = (rng.random((h, w)) < 0.35).astype(np.uint8) * 255
+    cc1 = blobs.ConnectedComponents(w, h)
+    for m in (blobby, noise):
+        for zb in (False, True):
+            n, lab, comps = cc1.label(m, zero_border=zb)
+            on, olab, ost, oext = oracle.ccl8(m, zb)
+            assert n == on and np.array_equal(lab, olab), (shape, zb)
+            assert [(c["x"], c["y"], c["w"], c["h"], c["area"]) for c in comps] == \
+                [(int(s[0]), int(s[1]), int(s[2] - s[0] + 1), int(s[3] - s[1] + 1), int(s[4])) for s in ost]
+    cc1.close()
+    S = max(2, 2400 // max(1, ((w + 31) // 32 * h + 255) // 256))            # enough 256-word chunks for the batch form
+    S = min(S, 48)
+    ms = np.stack([np.roll(blobby if s % 3 else noise, 5 * s, axis=1) for s in range(S)])
+    d = torch.from_numpy(ms).cuda()
+    lab = torch.full((S, h, w), -7, dtype=torch.int32, device="cuda")
+    ccS = blobs.ConnectedComponents(w, h, max_images=S)
+    for with_labels in (True, False):
+        ccS.label_batch_dev(d.data_ptr(), w, h, S, False, lab.data_ptr() if with_labels else None)
+        torch.cuda.synchronize()
+        for i in (0, 1, S // 2, S - 1):
+            on, olab, ost, oext = oracle.ccl8(ms[i], False)
+            comps = ccS.components(i)
+            assert len(comps) == on
+            assert [c["area"] for c in comps] == [int(s[4]) for s in ost]
+            assert [c["external"] for c in comps] == [int(e) for e in oext]
+            if with_labels:
+                assert np.array_equal(lab[i].cpu().numpy(), olab), (shape, i)
+    ccS.close()
