@@ -92,6 +92,20 @@ __device__ __forceinline__ unsigned gray_bgr(unsigned b, unsigned g, unsigned r)
     return (1868u * b + 9617u * g + 4899u * r + 8192u) >> 14;
 }
 
+// The same value from a pixel's three bytes packed B | G << 8 | R << 16 (the fourth byte is ignored): the 15- / 14-bit
+// coefficients split into two bytes each, so the weighted sum is two 4-way byte dot products (IDP.4A) and a shift-add
+// instead of three extractions and three multiply-adds -- the same integers, the same result.
+template <int VARIANT>
+__device__ __forceinline__ unsigned gray_px(unsigned px)
+{
+    if (VARIANT == 0) {                 // 3735 = 14 * 256 + 151, 19235 = 75 * 256 + 35, 9798 = 38 * 256 + 70
+        const unsigned lo = __dp4a(px, 0x00462397u, 16384u), hi = __dp4a(px, 0x00264b0eu, 0u);
+        return ((hi << 8) + lo) >> 15;
+    }
+    const unsigned lo = __dp4a(px, 0x0023914cu, 8192u), hi = __dp4a(px, 0x00132507u, 0u);      // 1868, 9617, 4899
+    return ((hi << 8) + lo) >> 14;
+}
+
 // cv::threshold(..., THRESH_BINARY): strict '>' ; thr < 0 encodes enableThreshold == false
 // only where the caller says so (see kernels).
 __device__ __forceinline__ unsigned thr_u8(unsigned v, int enable, int thr)
