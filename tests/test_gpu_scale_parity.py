@@ -340,3 +340,52 @@ def test_abl_quiet_radius_shortcut_matches_plain_lookups(oracle, clips, alpha):
         assert np.array_equal(fa, fb) and np.array_equal(ba, bb), i
         assert np.array_equal(fa, fo) and np.array_equal(ba, bo), i
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("shape", [(64, 512), (48, 32), (96, 1024)])
+@pytest.mark.parametrize("retain", [0, 1])
+def test_wmv_bulk_copy_kernel_tiles(oracle, shape, retain):
+    """Frames of whole 512-pixel tiles with the threshold on take WMV's bulk-copy kernel (persistent warps, cp.async.bulk
+    prefetch; own history written back by bulk stores) once the two history frames exist: one stream and a group of three,
+    caller-retained and library-owned history, both weightings, a threshold change mid-stream, noisy moving content so
+    that quiet and busy groups mix.  (Ragged sizes -- the clips of the other tests -- take the per-thread kernel.)"""
+    import torch
+    import tracking_b200 as tb
+    h, w = shape
+    assert (h * w) % 512 == 0
+    rng = np.random.default_rng(h + w + retain)
+    n = 9
+
+    def video(seed):
+        r = np.random.default_rng(seed)
+        base = r.integers(30, 200, (h, w, 3)).astype(np.int16)
+        out = []
+        for t in range(n):
+            f = base + r.integers(-5, 6, (h, w, 3))
+            x0 = (7 * t + seed) % max(1, w - 8)
+            f[h // 4:h // 2, x0:x0 + 8] = r.integers(0, 256, 3)
+            out.append(np.clip(f, 0, 255).astype(np.uint8))
+        return out
+
+    for S in (1, 3):
+        for ew in (1, 0):
+            vids = [video(10 * S + s + ew) for s in range(S)]
+            host = np.stack([np.stack([vids[s][t] for s in range(S)]) for t in range(n)])          # n,S,h,w,3
+            d_all = torch.from_numpy(host).cuda()
+            p = tb.WeightedMovingVarianceBGS(nstreams=S, enableWeight=ew, **({"retainInput": 1} if retain else {}))
+            os_ = [oracle.WeightedMovingVarianceBGS(enableWeight=bool(ew)) for _ in range(S)]
+            d_fg = torch.full((S, h, w), 9, dtype=torch.uint8, device="cuda")
+            for t in range(n):
+                if t == 6:
+                    p.set("threshold", 4)
+                    for o in os_:
+                        o.threshold = 4
+                fv, _ = p.process_dev(d_all[t].data_ptr(), w, h, d_fg.data_ptr(), None)
+                fg = d_fg.cpu().numpy()
+                for s in range(S):
+                    ofg, _ = os_[s].process(vids[s][t])
+                    assert fv == (ofg is not None)
+                    if ofg is not None:
+                        assert np.array_equal(fg[s], ofg), (shape, retain, S, ew, s, t)
+                        assert 0 < int((ofg > 0).sum()) < ofg.size or t < 3
+            p.close()
