@@ -114,6 +114,7 @@ BGSB_API int bgsb_reset(bgsb_ctx *ctx);
  * A/B measurements).  (8, 9 = timing instruments with WRONG results exist only in a library built with
  * -DBGSB_INSTRUMENT for tools/floor_probe.py; the shipped library rejects them);
  * "ablTable" (AdaptiveBackgroundLearning): 1 = lookup-table kernels (default), 2 = only the per-thread table kernel,
+ * 3 = as 1, with the bulk-copy kernel whenever the geometry allows (by default only for groups of ~3.6 Mpx and more),
  * 0 = arithmetic kernel -- identical results;
  * "ablBlend" (AdaptiveBackgroundLearning): 0 = cv::addWeighted as OpenCV 4.x computes it (double precision; pinned
  * against cv2 4.13, default), 1 = as OpenCV 2.4 does (fp32 arithmetic, scalars cast to float; SURVEY Appendix B --

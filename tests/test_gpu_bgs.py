@@ -156,7 +156,7 @@ def test_mog2_auto_learning_rate_and_params(oracle):
         assert np.array_equal(fg, ofg) and np.array_equal(bg, obg), i
 
 
-@pytest.mark.parametrize("table", [1, 2, 0])
+@pytest.mark.parametrize("table", [1, 2, 0, 3])
 def test_abl_exhaustive_byte_pairs(oracle, table):
     """Every (input, background) byte pair, lookup-table kernel and arithmetic kernel; alpha changes mid-stream
     (the table is rebuilt)."""

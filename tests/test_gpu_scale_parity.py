@@ -389,3 +389,53 @@ def test_wmv_bulk_copy_kernel_tiles(oracle, shape, retain):
                         assert np.array_equal(fg[s], ofg), (shape, retain, S, ew, s, t)
                         assert 0 < int((ofg > 0).sum()) < ofg.size or t < 3
             p.close()
+
+
+@pytest.mark.parametrize("shape", [(64, 512), (48, 32), (96, 1024)])
+@pytest.mark.parametrize("alpha", [0.05, 1.0, 0.0, 0.3])
+def test_abl_bulk_copy_kernel_tiles(oracle, shape, alpha):
+    """ABL's bulk-copy kernel ("ablTable" 3 forces it on frames this small; by default it takes groups of at least ~3.6
+    Mpx): persistent warps, input and model tiles by cp.async.bulk, changed model pieces written back into the ring and
+    stored by bulk copies.  One stream and a group of three, with and without a background image, raw and thresholded
+    output, a threshold change mid-stream; alpha 0 (nothing ever changes), 1 (model = input) and in between.  The model
+    is checked through the following frames and, at the end, by a call that asks for the background image."""
+    import torch
+    import tracking_b200 as tb
+    h, w = shape
+    assert (h * w) % 512 == 0
+    n = 8
+
+    def video(seed):
+        r = np.random.default_rng(seed)
+        base = r.integers(30, 200, (h, w, 3)).astype(np.int16)
+        out = []
+        for t in range(n):
+            f = base + r.integers(-7, 8, (h, w, 3))
+            x0 = (7 * t + seed) % max(1, w - 8)
+            f[h // 4:h // 2, x0:x0 + 8] = r.integers(0, 256, 3)
+            out.append(np.clip(f, 0, 255).astype(np.uint8))
+        return out
+
+    for S in (1, 3):
+        for thr_on, want_bg in ((1, 1), (1, 0), (0, 1)):
+            vids = [video(100 * S + 10 * thr_on + s + want_bg) for s in range(S)]
+            host = np.stack([np.stack([vids[s][t] for s in range(S)]) for t in range(n)])          # n,S,h,w,3
+            d_all = torch.from_numpy(host).cuda()
+            p = tb.AdaptiveBackgroundLearning(nstreams=S, alpha=alpha, ablTable=3, enableThreshold=thr_on)
+            os_ = [oracle.AdaptiveBackgroundLearning(alpha=alpha, enableThreshold=bool(thr_on)) for _ in range(S)]
+            d_fg = torch.full((S, h, w), 9, dtype=torch.uint8, device="cuda")
+            d_bg = torch.full((S, h, w, 3), 9, dtype=torch.uint8, device="cuda")
+            for t in range(n):
+                if t == 5:
+                    p.set("threshold", 3)
+                    for o in os_:
+                        o.threshold = 3
+                ask = want_bg or t == n - 1
+                p.process_dev(d_all[t].data_ptr(), w, h, d_fg.data_ptr(), d_bg.data_ptr() if ask else None)
+                fg, bg = d_fg.cpu().numpy(), d_bg.cpu().numpy()
+                for s in range(S):
+                    ofg, obg = os_[s].process(vids[s][t])
+                    assert np.array_equal(fg[s], ofg), (shape, alpha, S, thr_on, want_bg, s, t)
+                    if ask:
+                        assert np.array_equal(bg[s], obg), (shape, alpha, S, thr_on, want_bg, s, t)
+            p.close()

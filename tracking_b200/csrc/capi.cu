@@ -367,7 +367,7 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
                 c->lut_alpha = c->alpha; c->lut_blend = c->abl_blend;
             }
             L.abl_lut = c->d_abl_lut;
-            L.abl_lut_mode = c->abl_table == 2 ? 1 : 0;
+            L.abl_lut_mode = c->abl_table == 2 ? 1 : (c->abl_table == 3 ? 2 : 0);
             L.abl_quiet = c->wmv_quiet;
         }
         L.abl_update = (c->limit == -1);   // the limit>0 branch never fires: counter stays 0 (.cpp:52,60-61)
@@ -602,7 +602,7 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     else if (k == "kernelVariant") { BGSB_REQUIRE(v == 0 || v == 1, "kernelVariant is 0 or 1"); c->mog2_variant = (int)v; }
 #endif
     else if (k == "ablTable") {
-        BGSB_REQUIRE(v == 0 || v == 1 || v == 2, "ablTable is 0, 1 or 2");
+        BGSB_REQUIRE(v == 0 || v == 1 || v == 2 || v == 3, "ablTable is 0, 1, 2 or 3");
         BGSB_REQUIRE(v != 0 || c->abl_blend == 0, "the OpenCV 2.4 blend (ablBlend 1) exists in table form only");
         c->abl_table = (int)v;
     }
