@@ -439,3 +439,35 @@ def test_abl_bulk_copy_kernel_tiles(oracle, shape, alpha):
                     if ask:
                         assert np.array_equal(bg[s], obg), (shape, alpha, S, thr_on, want_bg, s, t)
             p.close()
+
+
+def test_abl_and_wmv_bulk_kernels_at_bench_geometry(oracle):
+    """The geometry tools/bench_configs.py times (1080p stream groups on the K-GEN video): with default parameters a
+    group of 3 x 1080p streams is routed to abl_bulk_kernel (>= ~3.6 Mpx per launch) and wmv_bulk_kernel; 30 frames over a
+    10-frame ring -- long enough for the rectangles' trails to sit at the blend table's quiet radius -- against
+    independent oracles per stream: masks every frame, background images every frame (ABL)."""
+    import torch
+    import tracking_b200 as tb
+    S, w, h, nres, n = 3, 1920, 1080, 10, 30
+    d, host = synth_resident(S, nres, w, h)
+    d_in = torch.empty((S, h, w, 3), dtype=torch.uint8, device="cuda")
+    d_fg = torch.zeros((S, h, w), dtype=torch.uint8, device="cuda")
+    d_bg = torch.zeros((S, h, w, 3), dtype=torch.uint8, device="cuda")
+    for name in ("AdaptiveBackgroundLearning", "WeightedMovingVarianceBGS"):
+        p = getattr(tb, name)(nstreams=S)
+        os_ = [getattr(oracle, name)() for _ in range(S)]
+        with ThreadPoolExecutor(max_workers=S) as ex:
+            for t in range(n):
+                d_in.copy_(d[:, t % nres])
+                fv, bv = p.process_dev(d_in.data_ptr(), w, h, d_fg.data_ptr(), d_bg.data_ptr())
+                res = list(ex.map(lambda s: os_[s].process(host[s, t % nres]), range(S)))
+                fg = d_fg.cpu().numpy()
+                bg = d_bg.cpu().numpy() if bv else None
+                for s in range(S):
+                    ofg, obg = res[s]
+                    assert fv == (ofg is not None), (name, t)
+                    if ofg is not None:
+                        assert np.array_equal(fg[s], ofg), (name, s, t)
+                    if bv:
+                        assert np.array_equal(bg[s], obg), (name, s, t)
+        p.close()
