@@ -591,6 +591,43 @@ def _asbl_frames(h, w, n, seed):
 
 
 @pytest.mark.parametrize("kw", [{}, {"learningFrames": 3}, {"learningFrames": -1, "alphaDetection": 0.3, "threshold": 10},
+                                {"learningFrames": 5, "alphaLearn": 0.5, "threshold": 40},
+                                {"learningFrames": 2, "threshold": 150}, {"learningFrames": 2, "alphaDetection": 0.0, "threshold": 0}])
+def test_asbl_quad_kernel_geometries(oracle, kw):
+    """asbl_fused16_kernel (frame width a multiple of 16): tiles cut by the right / bottom image border (400 px = 100
+    words: the last tile holds 4; 70 and 33 rows), a single quad, a one-row image, an exact tile grid; thresholds on both
+    sides of 127 (the word-wise and the byte-wise compare), alpha 0 (quiet radius 255: no lookups at all); host path,
+    then the device path on the same model, then a three-stream group."""
+    import torch
+    import tracking_b200 as tb
+    for (h, w) in ((70, 400), (33, 16), (1, 48), (64, 256), (40, 144)):
+        frames = _asbl_frames(h, w, 10, 5)
+        p, o = tb.AdaptiveSelectiveBackgroundLearning(**kw), oracle.AdaptiveSelectiveBackgroundLearning(**kw)
+        for i, f in enumerate(frames[:6]):
+            fa, ba = p.process(f)
+            fb, bb = o.process(f)
+            assert np.array_equal(fa, fb) and np.array_equal(ba, bb), (h, w, i)
+        d_fg = torch.zeros((h, w), dtype=torch.uint8, device="cuda")
+        d_bg = torch.zeros((h, w), dtype=torch.uint8, device="cuda")
+        for i, f in enumerate(frames[6:]):
+            d_in = torch.from_numpy(f).cuda()
+            p.process_dev(d_in.data_ptr(), w, h, d_fg.data_ptr(), d_bg.data_ptr())
+            fb, bb = o.process(f)
+            assert np.array_equal(d_fg.cpu().numpy(), fb) and np.array_equal(d_bg.cpu().numpy(), bb), (h, w, i)
+        p.close()
+    h, w = 48, 160
+    vids = [_asbl_frames(h, w, 6, 20 + s) for s in range(3)]
+    g = tb.AdaptiveSelectiveBackgroundLearning(nstreams=3, **kw)
+    os_ = [oracle.AdaptiveSelectiveBackgroundLearning(**kw) for _ in range(3)]
+    for i in range(6):
+        fg, bg = g.process(np.stack([v[i] for v in vids]))
+        for s in range(3):
+            fb, bb = os_[s].process(vids[s][i])
+            assert np.array_equal(fg[s], fb) and np.array_equal(bg[s], bb), (s, i)
+    g.close()
+
+
+@pytest.mark.parametrize("kw", [{}, {"learningFrames": 3}, {"learningFrames": -1, "alphaDetection": 0.3, "threshold": 10},
                                 {"learningFrames": 5, "alphaLearn": 0.5, "threshold": 40}])
 def test_asbl_sibling_plugin(oracle, kw):
     """AdaptiveSelectiveBackgroundLearning (USTC_BGS type 7): gray model, 3x3 median with replicated border, learning
