@@ -277,6 +277,80 @@ ORC_API void orc_dpz_apply(const uint8_t *in, int npx, int K, double threshold, 
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* DPAdaptiveMedianBGS / DPMeanBGS / DPWrenGABGS (USTC_BGS types 9, 12, 13): the simple per-pixel models of */
+/* the DP package.  Every wrapper (package_bgs/dp/DPAdaptiveMedianBGS.cpp:28-82, DPMeanBGS.cpp:28-84,         */
+/* DPWrenGABGS.cpp:28-84) initialises the model from the first frame, then per frame: Subtract -> the HIGH-     */
+/* threshold mask is the output (high = 2 * threshold in the parameter class's own type), the low mask is      */
+/* cleared, Update() on every pixel.  img_bgmodel is never written.  Pinned against a build of the reference's */
+/* own sources (oracle/_ref/libdp_ref.so, `make ref`; tests/golden/golden_dp.json).                            */
+/* `first`: no model yet (InitModel from this frame).  frame_num: the wrapper's frameNumber (0 on the first).  */
+/* ------------------------------------------------------------------------------------ */
+/* AdaptiveMedianBGS.cpp:53-140; thresholds are `unsigned char` members (AdaptiveMedianBGS.h:49-50).            */
+ORC_API void orc_dp_median(const uint8_t *in, int npx, int first, int frame_num, int threshold, int sampling_rate,
+                           uint8_t *median, uint8_t *fg)
+{
+    const unsigned char low = (unsigned char)threshold;                      /* DPAdaptiveMedianBGS.cpp:56 */
+    const unsigned char high = (unsigned char)(2 * low);                     /* :57 */
+    if (first) memcpy(median, in, (size_t)npx * 3);                          /* InitModel :53-63 */
+    for (int i = 0; i < npx; i++) {                                          /* SubtractPixel :92-111 */
+        int d0 = abs(in[3 * i] - median[3 * i]), d1 = abs(in[3 * i + 1] - median[3 * i + 1]), d2 = abs(in[3 * i + 2] - median[3 * i + 2]);
+        fg[i] = (d0 <= high && d1 <= high && d2 <= high) ? 0 : 255;
+    }
+    if (frame_num % sampling_rate == 1) {                                    /* Update :65-90, mask cleared: every pixel */
+        for (int i = 0; i < npx * 3; i++) {
+            if (in[i] > median[i]) median[i]++;
+            else if (in[i] < median[i]) median[i]--;
+        }
+    }
+}
+
+/* MeanBGS.cpp:32-131; thresholds are `unsigned int` members, alpha is a float member (MeanBGS.h:47-62).        */
+ORC_API void orc_dp_mean(const uint8_t *in, int npx, int first, int threshold, double alpha_d, float *mean, uint8_t *fg)
+{
+    const unsigned int low = (unsigned int)threshold;                        /* DPMeanBGS.cpp:56 */
+    const unsigned int high = 2 * low;                                       /* :57 */
+    const float alpha = (float)alpha_d;                                      /* :59 */
+    if (first) for (int i = 0; i < npx * 3; i++) mean[i] = (float)in[i];     /* InitModel :40-52 */
+    for (int i = 0; i < npx; i++) {                                          /* SubtractPixel :77-99 */
+        float dist = 0;
+        for (int ch = 0; ch < 3; ch++) dist += (in[3 * i + ch] - mean[3 * i + ch]) * (in[3 * i + ch] - mean[3 * i + ch]);
+        fg[i] = dist > high ? 255 : 0;
+    }
+    for (int i = 0; i < npx * 3; i++)                                        /* Update :54-75 */
+        mean[i] = alpha * mean[i] + (1.0f - alpha) * in[i];
+}
+
+/* WrenGA.cpp:47-173; thresholds and alpha are float members (WrenGA.h:48-62); one variance per pixel (var[0]). */
+/* state[4 * i + {0, 1, 2}] = mu, state[4 * i + 3] = var[0].                                                    */
+ORC_API void orc_dp_wren(const uint8_t *in, int npx, int first, double threshold, double alpha_d, float *state, uint8_t *fg)
+{
+    const float low = (float)threshold;                                      /* DPWrenGABGS.cpp:56 */
+    const float high = 2 * low;                                              /* :57 */
+    const float alpha = (float)alpha_d;                                      /* :58 */
+    const float variance = 36.0f;                                            /* WrenGA.cpp:51 */
+    (void)low;
+    if (first)                                                               /* InitModel :67-85 */
+        for (int i = 0; i < npx; i++) {
+            for (int ch = 0; ch < 3; ch++) state[4 * i + ch] = in[3 * i + ch];
+            state[4 * i + 3] = variance;
+        }
+    for (int i = 0; i < npx; i++) {
+        float *g = state + 4 * (size_t)i;
+        float dist = 0;                                                      /* SubtractPixel :121-147 */
+        for (int ch = 0; ch < 3; ch++) { float delta = g[ch] - in[3 * i + ch]; dist += delta * delta; }
+        fg[i] = dist > high * g[3] ? 255 : 0;
+    }
+    for (int i = 0; i < npx; i++) {                                          /* Update :87-119 */
+        float *g = state + 4 * (size_t)i;
+        float dR = g[0] - in[3 * i], dG = g[1] - in[3 * i + 1], dB = g[2] - in[3 * i + 2];
+        float dist = (dR * dR + dG * dG + dB * dB);
+        g[0] -= alpha * (dR); g[1] -= alpha * (dG); g[2] -= alpha * (dB);
+        float sigmanew = g[3] + alpha * (dist - g[3]);
+        g[3] = sigmanew < 4 ? 4 : sigmanew > 5 * variance ? 5 * variance : sigmanew;
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* WeightedMovingVariance (package_bgs/WeightedMovingVarianceBGS.cpp:53-106,126-138)       */
 /* ------------------------------------------------------------------------------------ */
 ORC_API void orc_wmv(const uint8_t *cur, const uint8_t *p1, const uint8_t *p2, int npx,

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE.  Minimal stand-in for <opencv2/opencv.hpp>, written for this repository, so that the
 // reference's own DP background-subtraction sources (package_bgs/dp/{ZivkovicAGMM,Image}.cpp) compile from
 // where they lie under /root/reference without OpenCV: those files use OpenCV only as an image CONTAINER
-// (IplImage, cvCreateImage, cvReleaseImage, cvZero, cvSize) -- every arithmetic operation of the algorithm is
+// (IplImage, cvCreateImage, cvReleaseImage, cvZero, cvSet, cvSize) -- every arithmetic operation of the algorithm is
 // the reference's own C++.  Nothing here computes anything.
 #pragma once
 #include <cassert>      // the real header pulls these in; Image.h relies on it
@@ -36,3 +36,16 @@ static inline void cvReleaseImage(IplImage **img)
     if (img && *img) { std::free((*img)->imageData); std::free(*img); *img = 0; }
 }
 static inline void cvZero(IplImage *img) { std::memset(img->imageData, 0, img->imageSize); }
+
+// AdaptiveMedianBGS::Initalize fills its model image with a constant before InitModel overwrites it
+struct CvScalar { double val[4]; };
+#define CV_RGB(r, g, b) cvScalarRGB((b), (g), (r))
+static inline CvScalar cvScalarRGB(double v0, double v1, double v2) { CvScalar s; s.val[0] = v0; s.val[1] = v1; s.val[2] = v2; s.val[3] = 0; return s; }
+static inline void cvSet(IplImage *img, CvScalar v)
+{
+    assert(img->depth == IPL_DEPTH_8U);
+    for (int y = 0; y < img->height; y++)
+        for (int x = 0; x < img->width; x++)
+            for (int c = 0; c < img->nChannels; c++)
+                ((unsigned char *)(img->imageData + (size_t)y * img->widthStep))[x * img->nChannels + c] = (unsigned char)v.val[c];
+}

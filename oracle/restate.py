@@ -56,6 +56,9 @@ def lib():
         L.orc_abl.argtypes = [u8p, u8p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, u8p]
         L.orc_asbl.argtypes = [u8p, u8p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, u8p, u8p]
         L.orc_dpz_apply.argtypes = [u8p, C.c_int, C.c_int, C.c_double, C.c_double, f32p, u8p, u8p]
+        L.orc_dp_median.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, u8p]
+        L.orc_dp_mean.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_double, f32p, u8p]
+        L.orc_dp_wren.argtypes = [u8p, C.c_int, C.c_int, C.c_double, C.c_double, f32p, u8p]
         L.orc_wmv.argtypes = [u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
         L.orc_mog2_default_params.argtypes = [C.POINTER(Mog2Params)]
         L.orc_mog2_learning_rate.argtypes = [C.c_double, C.c_int, C.c_int]
@@ -269,6 +272,104 @@ class ReferenceDPZivkovic:
             self.p = None
 
 
+class DPAdaptiveMedianBGS:
+    """USTC_BGS type 9 (package_bgs/dp/DPAdaptiveMedianBGS.cpp); defaults of its loadConfig (:101-104).  Never writes
+    img_bgmodel.  `learningFrames` has no effect: the wrapper clears the low mask before Update (:69-70)."""
+
+    def __init__(self, threshold=40, samplingRate=7, learningFrames=30):
+        self.threshold, self.samplingRate, self.learningFrames = threshold, samplingRate, learningFrames
+        self.median = None
+        self.frame = 0
+
+    def process(self, img):
+        if img is None or img.size == 0:
+            return None, None
+        img = _dense(img)
+        h, w = img.shape[:2]
+        first = self.median is None
+        if first:                                            # parameters are handed over once (:56-59)
+            self.median = np.zeros((h, w, 3), np.uint8)
+            self._thr, self._rate = int(self.threshold), int(self.samplingRate)
+        fg = np.empty((h, w), np.uint8)
+        lib().orc_dp_median(_u8(img), h * w, int(first), self.frame, self._thr, self._rate, _u8(self.median), _u8(fg))
+        self.frame += 1
+        return fg, None
+
+
+class DPMeanBGS:
+    """USTC_BGS type 12 (package_bgs/dp/DPMeanBGS.cpp); defaults of its loadConfig (:103-106)."""
+
+    def __init__(self, threshold=2700, alpha=float(np.float32(1e-6)), learningFrames=30):
+        self.threshold, self.alpha, self.learningFrames = threshold, alpha, learningFrames
+        self.mean = None
+
+    def process(self, img):
+        if img is None or img.size == 0:
+            return None, None
+        img = _dense(img)
+        h, w = img.shape[:2]
+        first = self.mean is None
+        if first:
+            self.mean = np.zeros((h, w, 3), np.float32)
+            self._thr, self._alpha = int(self.threshold), float(self.alpha)
+        fg = np.empty((h, w), np.uint8)
+        lib().orc_dp_mean(_u8(img), h * w, int(first), self._thr, self._alpha, self.mean.ctypes.data_as(C.POINTER(C.c_float)), _u8(fg))
+        return fg, None
+
+
+class DPWrenGABGS:
+    """USTC_BGS type 13 (package_bgs/dp/DPWrenGABGS.cpp); defaults of its loadConfig (:103-106)."""
+
+    def __init__(self, threshold=12.25, alpha=float(np.float32(0.005)), learningFrames=30):
+        self.threshold, self.alpha, self.learningFrames = threshold, alpha, learningFrames
+        self.state = None
+
+    def process(self, img):
+        if img is None or img.size == 0:
+            return None, None
+        img = _dense(img)
+        h, w = img.shape[:2]
+        first = self.state is None
+        if first:
+            self.state = np.zeros((h, w, 4), np.float32)     # mu[3], var[0]
+            self._thr, self._alpha = float(self.threshold), float(self.alpha)
+        fg = np.empty((h, w), np.uint8)
+        lib().orc_dp_wren(_u8(img), h * w, int(first), self._thr, self._alpha, self.state.ctypes.data_as(C.POINTER(C.c_float)), _u8(fg))
+        return fg, None
+
+
+class ReferenceDPSimple:
+    """The reference's own AdaptiveMedianBGS / MeanBGS / WrenGA classes ("median" / "mean" / "wren"), compiled from
+    /root/reference by `make -C oracle ref` (oracle/_ref/libdp_ref.so) and driven as their DP*BGS::process wrappers do.
+    Raises FileNotFoundError when that build is absent."""
+
+    def __init__(self, kind, w, h, *params):
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libdp_ref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.L = C.CDLL(path)
+        pre = {"median": "dpmed", "mean": "dpmean", "wren": "dpwren"}[kind]
+        sig = {"median": [C.c_int, C.c_int, C.c_int], "mean": [C.c_int, C.c_double, C.c_int], "wren": [C.c_double, C.c_double, C.c_int]}[kind]
+        self._create, self._process, self._destroy = (getattr(self.L, pre + "_ref_" + n) for n in ("create", "process", "destroy"))
+        self._create.restype = C.c_void_p
+        self._create.argtypes = [C.c_int, C.c_int] + sig
+        self._process.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]
+        self._destroy.argtypes = [C.c_void_p]
+        self.w, self.h = w, h
+        self.p = self._create(w, h, *params)
+
+    def process(self, img):
+        img = _dense(img)
+        fg = np.empty((self.h, self.w), np.uint8)
+        self._process(self.p, _u8(img), _u8(fg))
+        return fg, None
+
+    def close(self):
+        if self.p:
+            self._destroy(self.p)
+            self.p = None
+
+
 class WeightedMovingVarianceBGS:
     def __init__(self, enableWeight=True, enableThreshold=True, threshold=15, gray_variant=0):
         self.enableWeight, self.enableThreshold, self.threshold = enableWeight, enableThreshold, threshold
@@ -340,7 +441,7 @@ class MixtureOfGaussianV2BGS:
 ALGOS = {0: FrameDifferenceBGS, 1: StaticFrameDifferenceBGS, 2: WeightedMovingMeanBGS,
          3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS,
          6: AdaptiveBackgroundLearning, 7: AdaptiveSelectiveBackgroundLearning,
-         11: DPZivkovicAGMMBGS}                  # ids of ustc_src/ustc_bgs.cpp:8-21
+         9: DPAdaptiveMedianBGS, 11: DPZivkovicAGMMBGS, 12: DPMeanBGS, 13: DPWrenGABGS}   # ids of ustc_src/ustc_bgs.cpp:8-25
 
 
 def morph(mask, op, iterations=1):

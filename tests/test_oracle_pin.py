@@ -182,6 +182,69 @@ def test_dpzivkovic_restatement_matches_reference_build_live(oracle, kw):
     ref.close()
 
 
+def _dp_simple_cases():
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("mgd", os.path.join(os.path.dirname(__file__), "golden", "make_golden_dp.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("plugin", ["DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS"])
+def test_dp_simple_restatements_match_reference_golden(oracle, clips, plugin):
+    """orc_dp_median / orc_dp_mean / orc_dp_wren vs the masks a build of the reference's OWN AdaptiveMedianBGS / MeanBGS /
+    WrenGA sources produced (tests/golden/golden_dp.json, written by make_golden_dp.py from oracle/_ref/libdp_ref.so):
+    both clips and the stress sequence, four parameter sets each (incl. a median threshold whose doubled value wraps in
+    the reference's unsigned char member)."""
+    import hashlib
+    import json
+    import os
+    from conftest import stress_sequence
+    m = _dp_simple_cases()
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_dp.json")))["plugins"][plugin]
+    seqs = {"video_clip": list(clips["video_clip"]), "png_clip": list(clips["png_clip"]),
+            "stress_120x40x52": stress_sequence(120, 40, 52)}
+    for kw in m.PLUGINS[plugin][2]:
+        for name, frames in seqs.items():
+            o = getattr(oracle, plugin)(**kw)
+            hs = hashlib.sha256()
+            fgsum = 0
+            for f in frames:
+                fg, bg = o.process(f)
+                assert bg is None
+                hs.update(fg.tobytes())
+                fgsum += int((fg != 0).sum())
+            want = g[name]["params"][json.dumps(kw, sort_keys=True)]
+            assert fgsum == want["foreground_pixels"] and hs.hexdigest() == want["masks_sha256"], (name, kw)
+            assert 0 < fgsum < len(frames) * frames[0].shape[0] * frames[0].shape[1]
+
+
+@pytest.mark.parametrize("plugin", ["DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS"])
+def test_dp_simple_restatements_match_reference_build_live(oracle, plugin):
+    """The same, frame by frame against the compiled reference itself, on a sequence the golden file does not hold.
+    Skipped where oracle/_ref/libdp_ref.so has not been built (`make -C oracle ref` needs /root/reference)."""
+    m = _dp_simple_cases()
+    kind, order, sets = m.PLUGINS[plugin]
+    rng = np.random.default_rng(11)
+    base = rng.integers(0, 256, (57, 83, 3), dtype=np.uint8)
+    frames = []
+    for t in range(50):
+        f = np.clip(base.astype(np.int16) + rng.integers(-8, 9, base.shape), 0, 255).astype(np.uint8)
+        f[5 + t // 2:25 + t // 2, 10 + t:40 + t] = rng.integers(0, 256, 3)
+        frames.append(f)
+    for kw in sets:
+        full = dict(m.DEFAULTS[plugin], **kw)
+        try:
+            ref = oracle.ReferenceDPSimple(kind, 83, 57, *[full[k] for k in order])
+        except (FileNotFoundError, AttributeError):
+            pytest.skip("oracle/_ref/libdp_ref.so not built (or built before these plugins were added)")
+        o = getattr(oracle, plugin)(**kw)
+        for i, f in enumerate(frames):
+            assert np.array_equal(o.process(f)[0], ref.process(f)[0]), (kw, i)
+        ref.close()
+
+
 def test_morph_and_ccl_against_opencv(oracle):
     from oracle import cv2_chain
     rng = np.random.default_rng(3)
