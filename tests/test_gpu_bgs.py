@@ -496,7 +496,7 @@ def test_submit_wait_pipeline_matches_oracle(oracle, pinned):
     alloc = tb.pinned_empty if pinned else (lambda shape: np.empty(shape, np.uint8))
     names = ["FrameDifferenceBGS", "StaticFrameDifferenceBGS", "WeightedMovingMeanBGS", "WeightedMovingVarianceBGS",
              "MixtureOfGaussianV2BGS", "AdaptiveBackgroundLearning", "AdaptiveSelectiveBackgroundLearning",
-             "DPZivkovicAGMMBGS"]
+             "DPZivkovicAGMMBGS", "DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS"]
     for nm in names:
         p, o = getattr(tb, nm)(), getattr(oracle, nm)()
         bgshape = (h, w, 3) if p.BG_CHANNELS == 3 else (h, w)
@@ -540,7 +540,7 @@ def test_tiny_and_ragged_frames_all_plugins(oracle, shape):
     frames[3] = 255 - frames[3]
     for nm in ["FrameDifferenceBGS", "StaticFrameDifferenceBGS", "WeightedMovingMeanBGS", "WeightedMovingVarianceBGS",
                "MixtureOfGaussianV2BGS", "AdaptiveBackgroundLearning", "AdaptiveSelectiveBackgroundLearning",
-               "DPZivkovicAGMMBGS"]:
+               "DPZivkovicAGMMBGS", "DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS"]:
         p, q, o = getattr(tb, nm)(), getattr(tb, nm)(), getattr(oracle, nm)()
         bgshape = (h, w, 3) if q.BG_CHANNELS == 3 else (h, w)
         outs = []
@@ -730,6 +730,100 @@ def test_dpzivkovic_sibling_plugin(oracle, clips, kw):
     g.close()
 
 
+DP_SIMPLE_CASES = [("DPAdaptiveMedianBGS", {}), ("DPAdaptiveMedianBGS", {"threshold": 10, "samplingRate": 2}),
+                   ("DPAdaptiveMedianBGS", {"threshold": 200, "samplingRate": 3}), ("DPAdaptiveMedianBGS", {"threshold": 25, "samplingRate": 1}),
+                   ("DPMeanBGS", {}), ("DPMeanBGS", {"threshold": 300, "alpha": 0.9}), ("DPMeanBGS", {"threshold": 50, "alpha": 0.999}),
+                   ("DPWrenGABGS", {}), ("DPWrenGABGS", {"threshold": 3.0, "alpha": 0.2}), ("DPWrenGABGS", {"threshold": 0.5, "alpha": 0.9})]
+
+
+@pytest.mark.parametrize("name,kw", DP_SIMPLE_CASES)
+def test_dp_simple_sibling_plugins(oracle, clips, name, kw):
+    """DPAdaptiveMedianBGS / DPMeanBGS / DPWrenGABGS (USTC_BGS types 9, 12, 13): bit-exact masks against the restatements
+    that are pinned to a build of the reference's own sources (tests/test_oracle_pin.py, golden_dp.json).  The reference
+    clip and the stress sequence through the host path (the clip is large enough... the stress frames are ragged: 40 x 52),
+    then the device path on the same model, a two-stream group, a temporal batch, parameters latched on the first frame,
+    and reset."""
+    import torch
+    import tracking_b200 as tb
+    from conftest import stress_sequence
+    cls, ocls = getattr(tb, name), getattr(oracle, name)
+    for frames in (list(clips["video_clip"][:40]), stress_sequence(60, 40, 52)):
+        h, w = frames[0].shape[:2]
+        p, o = cls(**kw), ocls(**kw)
+        half = len(frames) // 2
+        for i, f in enumerate(frames[:half]):
+            fa, ba = p.process(f)
+            fb, bb = o.process(f)
+            assert ba is None and bb is None
+            assert np.array_equal(fa, fb), (name, kw, i)
+        # a parameter changed after the first frame has no effect until reset (the wrappers hand them over once)
+        p.set("threshold", 1)
+        d_fg = torch.zeros((h, w), dtype=torch.uint8, device="cuda")
+        for i, f in enumerate(frames[half:]):
+            d_in = torch.from_numpy(np.ascontiguousarray(f)).cuda()
+            fv, bv = p.process_dev(d_in.data_ptr(), w, h, d_fg.data_ptr(), None)
+            fb, _ = o.process(f)
+            assert fv and not bv
+            assert np.array_equal(d_fg.cpu().numpy(), fb), (name, kw, half + i)
+        p.reset()
+        for k, v in kw.items():
+            p.set(k, v)
+        if "threshold" not in kw:
+            p.set("threshold", ocls().threshold)
+        o2 = ocls(**kw)
+        for i, f in enumerate(frames[:4]):
+            assert np.array_equal(p.process(f)[0], o2.process(f)[0]), (name, kw, "after reset", i)
+        p.close()
+    # two streams advanced by one launch; then a temporal batch of four frames per stream
+    fa_, fb_ = list(clips["video_clip"][:12]), list(clips["video_clip"][20:32])
+    h, w = fa_[0].shape[:2]
+    g = cls(nstreams=2, **kw)
+    oa, ob = ocls(**kw), ocls(**kw)
+    for i in range(8):
+        fg, bg = g.process(np.stack([fa_[i], fb_[i]]))
+        assert np.array_equal(fg[0], oa.process(fa_[i])[0]) and np.array_equal(fg[1], ob.process(fb_[i])[0]), (name, kw, i)
+    batch = np.stack([np.stack(fa_[8:12]), np.stack(fb_[8:12])])                 # [S][T][h][w][3]
+    d_b = torch.from_numpy(batch).cuda()
+    d_fg = torch.zeros((2, 4, h, w), dtype=torch.uint8, device="cuda")
+    g.process_batch_dev(d_b.data_ptr(), 4, w, h, d_fg.data_ptr(), None)
+    out = d_fg.cpu().numpy()
+    for t in range(4):
+        assert np.array_equal(out[0, t], oa.process(fa_[8 + t])[0]) and np.array_equal(out[1, t], ob.process(fb_[8 + t])[0]), (name, kw, t)
+    g.close()
+
+
+def test_dp_simple_plugins_at_1080p(oracle):
+    """The three DP models on a 1080p K-GEN stream through the banded host path (row-band sub-launches) and on a
+    two-stream device group: 12 frames against the restatements."""
+    import torch
+    import tracking_b200 as tb
+    from tracking_b200 import synth
+    w, h, n = 1920, 1080, 12
+    d = torch.empty((2, n, h, w, 3), dtype=torch.uint8, device="cuda")
+    synth.frames_dev(d.data_ptr(), 2, n, w, h)
+    torch.cuda.synchronize()
+    host = d.cpu().numpy()
+    for name in ("DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS"):
+        kw = {"DPAdaptiveMedianBGS": {"threshold": 8, "samplingRate": 2}, "DPMeanBGS": {"threshold": 60, "alpha": 0.9},
+              "DPWrenGABGS": {"threshold": 2.0, "alpha": 0.05}}[name]
+        p, g = getattr(tb, name)(**kw), getattr(tb, name)(nstreams=2, **kw)
+        os_ = [getattr(oracle, name)(**kw) for _ in range(2)]
+        d_in = torch.empty((2, h, w, 3), dtype=torch.uint8, device="cuda")
+        d_fg = torch.zeros((2, h, w), dtype=torch.uint8, device="cuda")
+        total = 0
+        for t in range(n):
+            ref = [os_[s].process(host[s, t])[0] for s in range(2)]
+            fa, _ = p.process(host[0, t])
+            assert np.array_equal(fa, ref[0]), (name, t)
+            d_in.copy_(d[:, t])
+            g.process_dev(d_in.data_ptr(), w, h, d_fg.data_ptr(), None)
+            out = d_fg.cpu().numpy()
+            assert np.array_equal(out[0], ref[0]) and np.array_equal(out[1], ref[1]), (name, t)
+            total += int((ref[0] != 0).sum())
+        assert 0 < total < n * w * h
+        p.close(); g.close()
+
+
 def test_second_device_in_one_process(oracle, clips):
     """Contexts on two devices of one process (per-device function attributes, stream and buffer ownership).
     Skipped on single-GPU boxes."""
@@ -738,7 +832,7 @@ def test_second_device_in_one_process(oracle, clips):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     frames = _asbl_frames(600, 700, 4, 11)
-    for aid in (6, 5, 3, 0, 7, 11):
+    for aid in (6, 5, 3, 0, 7, 11, 9, 12, 13):
         p0, p1 = tb.ALGOS[aid](device=0), tb.ALGOS[aid](device=1)
         o = oracle.ALGOS[aid]()
         for f in frames:

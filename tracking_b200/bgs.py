@@ -187,6 +187,24 @@ class DPZivkovicAGMMBGS(_Plugin):
     ALGO = capi.ALGO_DP_ZIVKOVIC_AGMM
 
 
+class DPAdaptiveMedianBGS(_Plugin):
+    """package_bgs/dp/DPAdaptiveMedianBGS.cpp (USTC_BGS type 9): McFarlane & Schofield's adaptive median; keys threshold,
+    samplingRate, learningFrames (:88-104).  Never writes img_bgmodel."""
+    ALGO = capi.ALGO_DP_ADAPTIVE_MEDIAN
+
+
+class DPMeanBGS(_Plugin):
+    """package_bgs/dp/DPMeanBGS.cpp (USTC_BGS type 12): temporal mean; keys threshold, alpha, learningFrames (:86-106).
+    Never writes img_bgmodel."""
+    ALGO = capi.ALGO_DP_MEAN
+
+
+class DPWrenGABGS(_Plugin):
+    """package_bgs/dp/DPWrenGABGS.cpp (USTC_BGS type 13): Wren's single Gaussian per pixel; keys threshold, alpha,
+    learningFrames (:86-106).  Never writes img_bgmodel."""
+    ALGO = capi.ALGO_DP_WREN_GA
+
+
 class MixtureOfGaussianV2BGS(_Plugin):
     """package_bgs/MixtureOfGaussianV2BGS.cpp; keys alpha, enableThreshold, threshold (:92-95)."""
     ALGO = capi.ALGO_MOG2
@@ -257,7 +275,8 @@ def process_fanout(plugins, img_input, want_bg=True):
 # integer ids of the USTC_BGS factory (ustc_src/ustc_bgs.cpp:8-14)
 ALGOS = {0: FrameDifferenceBGS, 1: StaticFrameDifferenceBGS, 2: WeightedMovingMeanBGS,
          3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS, 6: AdaptiveBackgroundLearning,
-         7: AdaptiveSelectiveBackgroundLearning, 11: DPZivkovicAGMMBGS}
+         7: AdaptiveSelectiveBackgroundLearning, 9: DPAdaptiveMedianBGS, 11: DPZivkovicAGMMBGS, 12: DPMeanBGS,
+         13: DPWrenGABGS}
 
 
 class USTC_BGS:
@@ -265,7 +284,7 @@ class USTC_BGS:
 
     def __init__(self, type, device=0):
         if type not in ALGOS:                   # CV_Assert(type>=0 && type<=37), .cpp:6
-            raise ValueError("USTC_BGS type %r is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL, 11 DPZivkovicAGMM)" % type)
+            raise ValueError("USTC_BGS type %r is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL, 9 DPAdaptiveMedian, 11 DPZivkovicAGMM, 12 DPMean, 13 DPWrenGA)" % type)
         self.bgs = ALGOS[type](device=device)
         self.frameNum = 0
         self.img_mask = None

@@ -15,6 +15,7 @@ ALGO_FRAME_DIFFERENCE, ALGO_WEIGHTED_MOVING_VARIANCE, ALGO_MOG2, ALGO_ADAPTIVE_B
 ALGO_STATIC_FRAME_DIFFERENCE, ALGO_WEIGHTED_MOVING_MEAN = 1, 2        # sibling plugins
 ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING = 7
 ALGO_DP_ZIVKOVIC_AGMM = 11
+ALGO_DP_ADAPTIVE_MEDIAN, ALGO_DP_MEAN, ALGO_DP_WREN_GA = 9, 12, 13     # the DP package's simple per-pixel models
 MORPH_ERODE, MORPH_DILATE = 0, 1
 
 

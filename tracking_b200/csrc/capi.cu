@@ -54,6 +54,9 @@ struct bgsb_ctx {
     // of threshold / alpha / gaussians have no effect until the model is reset.  Latched copies used by the kernel:
     double dpz_thr_l = 25.0, dpz_alpha_l = 0.001;
     int dpz_K_l = 3;
+    // DPAdaptiveMedianBGS / DPMeanBGS / DPWrenGABGS: "threshold" (kept in dpz_threshold), "alpha", "samplingRate",
+    // "learningFrames"; handed to the model once, on the first frame, like DPZivkovic's (latched in dpz_thr_l / dpz_alpha_l)
+    int sampling_rate = 7, sampling_rate_l = 7;
     int abl_table = 1;         // ABL: 1 = lookup-table kernel, 0 = arithmetic kernel (A/B, identical results)
     int abl_blend = 0, lut_blend = 0;   // ABL: 0 = OpenCV 4.x fp64 addWeighted, 1 = OpenCV 2.4 fp32 addWeighted (table kernels only)
     int mog2_variant = 0;      // see launch_mog2 (mog2.cu): 0 production, 1 straight restatement, 8/9 timing instruments
@@ -111,6 +114,9 @@ static const char *algo_name(int algo)
     case BGSB_ALGO_ADAPTIVE_BG_LEARNING: return "AdaptiveBackgroundLearning";
     case BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING: return "AdaptiveSelectiveBackgroundLearning";
     case BGSB_ALGO_DP_ZIVKOVIC_AGMM: return "DPZivkovicAGMMBGS";
+    case BGSB_ALGO_DP_ADAPTIVE_MEDIAN: return "DPAdaptiveMedianBGS";
+    case BGSB_ALGO_DP_MEAN: return "DPMeanBGS";
+    case BGSB_ALGO_DP_WREN_GA: return "DPWrenGABGS";
     }
     return "?";
 }
@@ -121,6 +127,7 @@ static bool trace_env()
 }
 
 static bool gmm_state(int algo);
+static int dp_float_planes(int algo);
 static void free_buffers(bgsb_ctx *c)
 {
     cudaFree(c->d_state); c->d_state = nullptr;
@@ -157,6 +164,8 @@ static int ensure_geometry(bgsb_ctx *c, int w, int h)
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_state, 0, fb, c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_nmodes, 0, S * pstride, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    } else if (dp_float_planes(c->algo)) {
+        e = cudaMalloc(&c->d_state, S * dp_float_planes(c->algo) * pstride * sizeof(float));      // written in full by the first frame
     } else {
         // ASBL: d_hist[0] = gray model, d_hist[1] = scratch (gray input + pre-median mask)
         int nh = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE || c->algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN ||
@@ -220,7 +229,7 @@ static int warmup_frames(int algo)
 static int history_images(int algo)
 {
     if (algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN) return 2;
-    return gmm_state(algo) ? 0 : 1;
+    return (gmm_state(algo) || dp_float_planes(algo)) ? 0 : 1;
 }
 // FD / WMV / WMM: the history is the previous input frame(s) -> on the host path it lives in the upload ring
 static bool ring_history(int algo)
@@ -230,6 +239,8 @@ static bool ring_history(int algo)
 }
 // per-pixel mixture state in the MOG2 tile layout (d_state / d_nmodes)
 static bool gmm_state(int algo) { return algo == BGSB_ALGO_MOG2 || algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM; }
+// fp32 planes per pixel of the DP package's float models (d_state, [S][planes][pstride]): MeanBGS 3 means, WrenGA 3 means + variance
+static int dp_float_planes(int algo) { return algo == BGSB_ALGO_DP_MEAN ? 3 : (algo == BGSB_ALGO_DP_WREN_GA ? 4 : 0); }
 // channels of img_bgmodel: ASBL's model is the gray image (AdaptiveSelectiveBackgroundLearning.cpp:103)
 static int bg_channels(int algo) { return algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING ? 1 : 3; }
 // the mask depends on neighbouring pixels (3x3 median): no row-band sub-launches
@@ -302,6 +313,35 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
             L.fresh = (c->nframes + t == 0);
             L.low_thr = (float)c->dpz_thr_l; L.alpha = (float)c->dpz_alpha_l;
             int rc = launch_dpz(L, c->nstreams, stream);
+            if (rc) return rc;
+        }
+    } else if (c->algo == BGSB_ALGO_DP_ADAPTIVE_MEDIAN || c->algo == BGSB_ALGO_DP_MEAN || c->algo == BGSB_ALGO_DP_WREN_GA) {
+        for (int t = 0; t < T; t++) {
+            DpsLaunch L;
+            memset(&L, 0, sizeof(L));
+            const int64_t frame_num = c->nframes + t;                      // the wrappers' frameNumber
+            if (frame_num == 0 && p0 == 0) { c->dpz_thr_l = c->dpz_threshold; c->dpz_alpha_l = c->alpha; c->sampling_rate_l = c->sampling_rate; }
+            L.kind = c->algo == BGSB_ALGO_DP_ADAPTIVE_MEDIAN ? DPS_MEDIAN : (c->algo == BGSB_ALGO_DP_MEAN ? DPS_MEAN : DPS_WREN);
+            L.frame = d_frames + ((size_t)t * c->npx + p0) * 3; L.frame_stride = (size_t)T * c->npx * 3;
+            L.fg = d_fg + (size_t)t * c->npx + p0; L.fg_stride = (size_t)T * c->npx;
+            L.pstride = c->pstride;
+            if (L.kind == DPS_MEDIAN) { L.median = c->d_hist[0] + p0 * 3; L.median_stride = (size_t)c->npx * 3; }
+            else L.state = c->d_state + p0;
+            L.npx = pcount; L.fresh = frame_num == 0;
+            if (L.kind == DPS_MEDIAN) {
+                // thresholds are unsigned char members: high = (uchar)(2 * (uchar)threshold) (AdaptiveMedianBGS.h:49-50)
+                const unsigned char low = (unsigned char)(int)c->dpz_thr_l;
+                L.high_u = (unsigned char)(2 * low);
+                L.update = (frame_num % c->sampling_rate_l) == 1;          // AdaptiveMedianBGS.cpp:67
+            } else if (L.kind == DPS_MEAN) {
+                const unsigned low = (unsigned)(int)c->dpz_thr_l;          // unsigned int members (MeanBGS.h:47-48)
+                L.high_f = (float)(2u * low);
+            } else {
+                const float low = (float)c->dpz_thr_l;                     // float members (WrenGA.h:48-49)
+                L.high_f = 2 * low;
+            }
+            L.alpha = (float)c->dpz_alpha_l; L.one_minus_alpha = 1.0f - L.alpha;
+            int rc = launch_dp_simple(L, c->nstreams, stream);
             if (rc) return rc;
         }
     } else if (c->algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) {
@@ -519,14 +559,21 @@ int bgsb_create_group(bgsb_ctx **out, int algo, int device, int nstreams)
     BGSB_REQUIRE(algo == BGSB_ALGO_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE ||
                  algo == BGSB_ALGO_MOG2 || algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING ||
                  algo == BGSB_ALGO_STATIC_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN || algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING ||
-                 algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM,
-                 "unknown algorithm id (USTC_BGS ids: 0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL, 11 DPZivkovicAGMM)");
+                 algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM || algo == BGSB_ALGO_DP_ADAPTIVE_MEDIAN || algo == BGSB_ALGO_DP_MEAN ||
+                 algo == BGSB_ALGO_DP_WREN_GA,
+                 "unknown algorithm id (USTC_BGS ids: 0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL, 9 DPAdaptiveMedian, "
+                 "11 DPZivkovicAGMM, 12 DPMean, 13 DPWrenGA)");
     BGSB_REQUIRE(nstreams >= 1 && nstreams <= 65535, "nstreams out of range");
     BGSB_CUDA(cudaSetDevice(device));
     bgsb_ctx *c = new bgsb_ctx();
     c->algo = algo; c->device = device; c->nstreams = nstreams;
     if (algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) c->thr = 25;        // loadConfig default (.cpp:124)
     if (algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM) c->alpha = 0.001;                        // DPZivkovicAGMMBGS.cpp:98
+    // loadConfig defaults of the DP wrappers (DPAdaptiveMedianBGS.cpp:101-103, DPMeanBGS.cpp:103-105, DPWrenGABGS.cpp:103-105);
+    // the real-valued ones are float literals read into doubles
+    if (algo == BGSB_ALGO_DP_ADAPTIVE_MEDIAN) { c->dpz_threshold = 40; c->thr = 40; c->sampling_rate = 7; c->learning_frames = 30; }
+    if (algo == BGSB_ALGO_DP_MEAN) { c->dpz_threshold = 2700; c->thr = 2700; c->alpha = (double)1e-6f; c->learning_frames = 30; }
+    if (algo == BGSB_ALGO_DP_WREN_GA) { c->dpz_threshold = (double)12.25f; c->thr = 12; c->alpha = (double)0.005f; c->learning_frames = 30; }
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         set_error("cudaStreamCreate -> %s", cudaGetErrorString(e));
@@ -573,6 +620,7 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     if (k == "alpha") c->alpha = v;
     else if (k == "limit") c->limit = (int)v;
     else if (k == "learningFrames") c->learning_frames = (int)v;
+    else if (k == "samplingRate") { BGSB_REQUIRE(v >= 1 && v <= (double)(1 << 30), "samplingRate must be positive"); c->sampling_rate = (int)v; }
     else if (k == "alphaLearn") c->alpha_learn = v;
     else if (k == "alphaDetection") c->alpha_detection = v;
     else if (k == "enableThreshold") c->enable_thr = (v != 0);
@@ -626,7 +674,8 @@ int bgsb_get_param(bgsb_ctx *c, const char *key, double *v)
     else if (k == "alphaLearn") *v = c->alpha_learn;
     else if (k == "alphaDetection") *v = c->alpha_detection;
     else if (k == "enableThreshold") *v = c->enable_thr;
-    else if (k == "threshold") *v = c->algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM ? c->dpz_threshold : c->thr;
+    else if (k == "threshold") *v = (c->algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM || c->algo == BGSB_ALGO_DP_WREN_GA) ? c->dpz_threshold : c->thr;
+    else if (k == "samplingRate") *v = c->sampling_rate;
     else if (k == "gaussians") *v = c->gaussians;
     else if (k == "enableWeight") *v = c->enable_weight;
     else if (k == "grayVariant") *v = c->gray_variant;
@@ -674,6 +723,7 @@ int bgsb_state_bytes(bgsb_ctx *c, size_t *bytes)
     if (c->algo == BGSB_ALGO_MOG2) *bytes = (size_t)c->npx * (MOG2_PLANES * 4 + 1);
     else if (c->algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM) *bytes = (size_t)c->npx * ((c->nframes ? c->dpz_K_l : c->gaussians) * 20 + 1);
     else if (c->algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) *bytes = (size_t)c->npx;
+    else if (dp_float_planes(c->algo)) *bytes = (size_t)c->npx * dp_float_planes(c->algo) * 4;
     else if (history_images(c->algo) == 2) *bytes = (size_t)c->npx * 6;
     else *bytes = (size_t)c->npx * 3;
     return BGSB_OK;

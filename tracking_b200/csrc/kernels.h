@@ -122,6 +122,24 @@ struct DpzLaunch {
 };
 int launch_dpz(const DpzLaunch &L, int nstreams, cudaStream_t stream);
 
+// ---- DPAdaptiveMedianBGS / DPMeanBGS / DPWrenGABGS (the DP package's simple per-pixel models, dp_simple.cu) ----
+enum { DPS_MEDIAN = 0, DPS_MEAN = 1, DPS_WREN = 2 };
+struct DpsLaunch {
+    int kind;
+    const uint8_t *frame;    // [S] BGR frames, frame_stride bytes apart
+    uint8_t *fg;             // [S] high-threshold masks, fg_stride bytes apart
+    float *state;            // Mean: [S][3][pstride] (mean B, G, R); WrenGA: [S][4][pstride] (mu B, G, R, var[0])
+    uint8_t *median;         // AdaptiveMedian: [S][npx_frame * 3] 8-bit BGR model, median_stride bytes apart
+    size_t pstride, frame_stride, fg_stride, median_stride;
+    int npx;
+    int fresh;               // InitModel: the model starts from this frame
+    int update;              // AdaptiveMedian: this frame's Update() moves the model (frame_num % samplingRate == 1)
+    unsigned high_u;         // AdaptiveMedian: (unsigned char)(2 * (unsigned char)threshold)
+    float high_f;            // Mean: (float)(2u * threshold); WrenGA: 2 * (float)threshold
+    float alpha, one_minus_alpha;
+};
+int launch_dp_simple(const DpsLaunch &L, int nstreams, cudaStream_t stream);
+
 // ---- morphology -------------------------------------------------------------------------------
 int launch_morph_chain(const uint8_t *d_in, uint8_t *d_out, int w, int h, int nimages, const int *ops, int nops,
                        cudaStream_t stream);
