@@ -5,6 +5,7 @@ against libbgsb200.so.  What it writes is compared with the cv2-generated golden
 arithmetic the goldens were produced with) and with the oracle's OpenCV 2.4 variants (stand-in claiming 2.4, like the
 reference's real build)."""
 import hashlib
+import json
 import os
 import subprocess
 
@@ -83,6 +84,15 @@ def test_cpp_dropin_opencv4_arithmetic_matches_golden_hashes(tmp_path, clips, go
             assert sha_file(os.path.join(out, name + ".bg")) == exp["bg_sha256"], name
         else:
             assert not os.path.exists(os.path.join(out, name + ".bg")), name      # FD / WMV never write img_bgmodel
+    # the DP package's plugins (USTC_BGS types 9 / 12 / 13) against the masks a build of the reference's own sources produced
+    gdp = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_dp.json")))["plugins"]
+    for name in ("DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS"):
+        assert name + "()" in stdout and "~" + name + "()" in stdout
+        assert sha_file(os.path.join(out, name + ".fg")) == gdp[name]["video_clip"]["params"]["{}"]["masks_sha256"], name
+        assert not os.path.exists(os.path.join(out, name + ".bg")), name
+        xml = open(os.path.join(out, "config", name + ".xml")).read()
+        for key in ("threshold", "learningFrames", "showOutput", "samplingRate" if name == "DPAdaptiveMedianBGS" else "alpha"):
+            assert "<%s>" % key in xml, (name, key)
     # fan-out: the same masks with one upload per frame
     for name in ("FrameDifferenceBGS", "WeightedMovingVarianceBGS", "MixtureOfGaussianV2BGS", "AdaptiveBackgroundLearning"):
         assert sha_file(os.path.join(out, "fan_" + name + ".fg")) == algos[name]["fg_sha256"], name

@@ -594,6 +594,103 @@ private:
 };
 
 // ---------------------------------------------------------------------------------------------------------------
+// Sibling plugins of the DP package, USTC_BGS types 9 / 12 / 13 (ustc_src/ustc_bgs.cpp:19,22,23):
+// package_bgs/dp/{DPAdaptiveMedianBGS,DPMeanBGS,DPWrenGABGS}.{h,cpp}.  The three wrappers have one shape -- threshold, a
+// second parameter, learningFrames, showOutput; handed to the model once, on the first frame; the high-threshold mask
+// is the output, img_bgmodel is never written -- so they share one base; what differs is the XML file, the window title
+// and which of the two parameters are integers.
+namespace bgsb_adapter {
+class DPSimplePlugin : public PluginBase
+{
+protected:
+  const char *xml, *title, *key2;
+  bool thr_int, p2_int;
+  double threshold, p2, d_threshold, d_p2;
+  int learningFrames;
+  bool showOutput;
+
+  DPSimplePlugin(int algo, const char *xml_, const char *title_, const char *key2_, bool thr_int_, bool p2_int_, double thr, double second)
+    : PluginBase(algo), xml(xml_), title(title_), key2(key2_), thr_int(thr_int_), p2_int(p2_int_), threshold(thr), p2(second),
+      d_threshold(thr), d_p2(second), learningFrames(30), showOutput(true) {}
+
+public:
+  void configure()
+  {
+    loadConfig();
+    if (firstTime) {                         // e.g. DPMeanBGS.cpp:34-35, :56-61
+      saveConfig();
+      set("threshold", threshold);
+      set(key2, p2);
+      set("learningFrames", learningFrames);
+    }
+  }
+
+  void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
+  {
+    (void)img_bgmodel;                       // never written (e.g. DPMeanBGS.cpp:28-84)
+    if (img_input.empty()) return;
+    configure();
+    bool fg, bg;
+    run(img_input, fg, bg, false);
+    if (showOutput) cv::imshow(title, img_foreground);
+    img_foreground.copyTo(img_output);
+    firstTime = false;
+  }
+
+private:
+  void saveConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage(xml, 0, CV_STORAGE_WRITE);
+    if (thr_int) cvWriteInt(fs, "threshold", (int)threshold); else cvWriteReal(fs, "threshold", threshold);
+    if (p2_int) cvWriteInt(fs, key2, (int)p2); else cvWriteReal(fs, key2, p2);
+    cvWriteInt(fs, "learningFrames", learningFrames);
+    cvWriteInt(fs, "showOutput", showOutput);
+    cvReleaseFileStorage(&fs);
+  }
+  void loadConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage(xml, 0, CV_STORAGE_READ);
+    threshold = thr_int ? (double)cvReadIntByName(fs, 0, "threshold", (int)d_threshold) : cvReadRealByName(fs, 0, "threshold", d_threshold);
+    p2 = p2_int ? (double)cvReadIntByName(fs, 0, key2, (int)d_p2) : cvReadRealByName(fs, 0, key2, d_p2);
+    learningFrames = cvReadIntByName(fs, 0, "learningFrames", 30);
+    showOutput = cvReadIntByName(fs, 0, "showOutput", true);
+    cvReleaseFileStorage(&fs);
+  }
+};
+}  // namespace bgsb_adapter
+
+class DPAdaptiveMedianBGS : public bgsb_adapter::DPSimplePlugin
+{
+public:
+  DPAdaptiveMedianBGS() : DPSimplePlugin(BGSB_ALGO_DP_ADAPTIVE_MEDIAN, "./config/DPAdaptiveMedianBGS.xml", "Adaptive Median (McFarlane&Schofield)",
+                                         "samplingRate", true, true, 40, 7)
+  {
+    std::cout << "DPAdaptiveMedianBGS()" << std::endl;
+  }
+  ~DPAdaptiveMedianBGS() { std::cout << "~DPAdaptiveMedianBGS()" << std::endl; }
+};
+
+class DPMeanBGS : public bgsb_adapter::DPSimplePlugin
+{
+public:
+  DPMeanBGS() : DPSimplePlugin(BGSB_ALGO_DP_MEAN, "./config/DPMeanBGS.xml", "Temporal Mean (Donovan Parks)", "alpha", true, false, 2700, 1e-6f)
+  {
+    std::cout << "DPMeanBGS()" << std::endl;
+  }
+  ~DPMeanBGS() { std::cout << "~DPMeanBGS()" << std::endl; }
+};
+
+class DPWrenGABGS : public bgsb_adapter::DPSimplePlugin
+{
+public:
+  DPWrenGABGS() : DPSimplePlugin(BGSB_ALGO_DP_WREN_GA, "./config/DPWrenGABGS.xml", "Gaussian Average (Wren)", "alpha", false, false, 12.25f, 0.005f)
+  {
+    std::cout << "DPWrenGABGS()" << std::endl;
+  }
+  ~DPWrenGABGS() { std::cout << "~DPWrenGABGS()" << std::endl; }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 class MixtureOfGaussianV2BGS : public bgsb_adapter::PluginBase
 {
 private:

@@ -73,6 +73,9 @@ int main(int argc, char **argv)
         run_plugin<AdaptiveBackgroundLearning>("AdaptiveBackgroundLearning", frames, out);
         run_plugin<StaticFrameDifferenceBGS>("StaticFrameDifferenceBGS", frames, out);
         run_plugin<WeightedMovingMeanBGS>("WeightedMovingMeanBGS", frames, out);
+        run_plugin<DPAdaptiveMedianBGS>("DPAdaptiveMedianBGS", frames, out);      // DP package, USTC_BGS types 9 / 12 / 13
+        run_plugin<DPMeanBGS>("DPMeanBGS", frames, out);
+        run_plugin<DPWrenGABGS>("DPWrenGABGS", frames, out);
 
         // FrameProcessor::process with the one added line: a single upload feeds every enabled plugin
         {

@@ -37,7 +37,10 @@ public:
         case 5: bgs = new MixtureOfGaussianV2BGS; break;    // :13
         case 6: bgs = new AdaptiveBackgroundLearning; break;// :14
         case 7: bgs = new AdaptiveSelectiveBackgroundLearning; break;   // :15
+        case 9: bgs = new DPAdaptiveMedianBGS; break;       // :19
         case 11: bgs = new DPZivkovicAGMMBGS; break;        // :21
+        case 12: bgs = new DPMeanBGS; break;                // :22
+        case 13: bgs = new DPWrenGABGS; break;              // :23
         default: CV_Assert(!"this plugin id is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL, 11 DPZivkovicAGMM)");
         }
     }
