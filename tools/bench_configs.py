@@ -214,6 +214,11 @@ def main():
     if "--wmm" in sys.argv:                                   # just the WMM line
         simple_streams(tb.WeightedMovingMeanBGS, "WMM", 10 + 6 + 3)
         return
+    if "--dp" in sys.argv:                                    # just the DP package's simple models
+        simple_streams(tb.DPAdaptiveMedianBGS, "DPAdaptiveMedian (3 in + 3 model + 1 mask + 3/7 model write)", 7 + 3 / 7)
+        simple_streams(tb.DPMeanBGS, "DPMean (3 in + 12 + 12 mean + 1 mask)", 28)
+        simple_streams(tb.DPWrenGABGS, "DPWrenGA (3 in + 16 + 16 model + 1 mask)", 36)
+        return
     if "--asbl" in sys.argv:                                  # just the ASBL line
         simple_streams(tb.AdaptiveSelectiveBackgroundLearning, "ASBL", 3 + 2 + 1 + 1)
         return
@@ -228,6 +233,11 @@ def main():
     simple_streams(tb.WeightedMovingVarianceBGS, "WMV", 10 + 6)  # device path writes both history images
     simple_streams(tb.AdaptiveSelectiveBackgroundLearning, "ASBL", 3 + 2 + 1 + 1)   # in, gray model r/w, mask, gray bg image
     simple_streams(tb.DPZivkovicAGMMBGS, "DPZivkovicAGMM (3 modes; bytes = 3 in + 1 mask + 2 counts + 40 per live mode, 1.4 live modes assumed)", 62)
+    # the DP package's simple models: bytes = 3 in + model read + model written + 1 mask (AdaptiveMedian writes its model on
+    # one frame in samplingRate = 7)
+    simple_streams(tb.DPAdaptiveMedianBGS, "DPAdaptiveMedian (3 in + 3 model + 1 mask + 3/7 model write)", 7 + 3 / 7)
+    simple_streams(tb.DPMeanBGS, "DPMean (3 in + 12 + 12 mean + 1 mask)", 28)
+    simple_streams(tb.DPWrenGABGS, "DPWrenGA (3 in + 16 + 16 model + 1 mask)", 36)
     ccl_kernel_probe()
     import fanout_probe                                   # tools/fanout_probe.py: FrameProcessor fan-out vs four uploads
     fanout_probe.main()

@@ -12,8 +12,8 @@
 //   Mean            3 in + 12 mean read + 12 written + 1 mask                                                = 28 B/px
 //   WrenGA          3 in + 16 (mu, var) read + 16 written + 1 mask                                           = 36 B/px
 // fp32 arithmetic in the reference's order, unfused (the library is compiled with -fmad=false; the operations are
-// written with the _rn intrinsics anyway).  Parity: bit-exact against the C restatement, which is pinned to a build of
-// the reference's own sources (oracle/_ref/libdp_ref.so, tests/golden/golden_dp.json).
+// written with the _rn intrinsics anyway).  Parity: bit-exact against the CPU restatement, which is pinned to a build of
+// the reference's own sources (tests/golden/golden_dp.json, tests/test_oracle_pin.py).
 #include "common.cuh"
 #include "kernels.h"
 
