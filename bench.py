@@ -429,7 +429,7 @@ def run_e2e(ctx, args, frames):
             "mask_only": {"value": world * Ke * F * NPX / dt_mask / 1e6, "unit": UNIT, "d2h_bytes_per_step": F * NPX,
                           "note": "bgsb_process with bg = NULL: what a tracker-only caller (USTC_BGS -> CvBlobTracker) needs back"},
             "note": "bgsb_process (IBGS::process boundary): pinned host BGR frame in, mask + background image out, "
-                    "synchronous per frame; upload/kernel/download of 2 row bands overlap inside the call"}
+                    "synchronous per frame; upload/kernel/download of 3 row bands (2 without the background image) overlap inside the call"}
 
 
 def copy_ceiling(ctx):

@@ -122,7 +122,8 @@ BGSB_API int bgsb_reset(bgsb_ctx *ctx);
  * "ablBlend" (AdaptiveBackgroundLearning): 0 = cv::addWeighted as OpenCV 4.x computes it (double precision; pinned
  * against cv2 4.13, default), 1 = as OpenCV 2.4 does (fp32 arithmetic, scalars cast to float; SURVEY Appendix B --
  * "parity unpinned": no OpenCV 2.4 in the build image), table kernels only;
- * "hostBands" (default 2, 1..8): row bands of the upload / kernel / download pipeline inside bgsb_process;
+ * "hostBands" (1..8; default: 3 when the background image is returned too, else 2): row bands of the upload / kernel /
+ * download pipeline inside bgsb_process;
  * "trace" (default 0): per-stage timing of bgsb_process, see bgsb_trace_last;
  * "quietGroups" (WeightedMovingVariance, default 1): with the threshold on, a 16-pixel group whose bytes moved by at most
  * R over the three frames gets its all-zero mask without the arithmetic; R is derived from the threshold by running all

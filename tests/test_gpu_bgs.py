@@ -977,10 +977,18 @@ def test_trace_stage_times_and_toc_line(tmp_path):
     for x in f:
         p.process(x)
     t = p.trace_last()
-    assert t["frame"] == 2 and t["bands"] == 2
+    assert t["frame"] == 2 and t["bands"] == 3           # mask + background image go back: 3 row bands by default
     assert t["upload_ms"] > 0.02 and t["download_ms"] > 0.02 and t["kernel_ms"] > 0.005
     assert t["wall_ms"] >= max(t["upload_ms"], t["download_ms"]) * 0.9
     p.close()
+    big_fd = tb.FrameDifferenceBGS(trace=1)              # no background image: 2 bands; an explicit "hostBands" wins
+    for x in f:
+        big_fd.process(x)
+    assert big_fd.trace_last()["bands"] == 2
+    big_fd.set("hostBands", 4)
+    big_fd.process(f[0])
+    assert big_fd.trace_last()["bands"] == 4
+    big_fd.close()
     small = tb.FrameDifferenceBGS(trace=1)
     small.process(np.zeros((40, 50, 3), np.uint8))       # warm-up frame: uploaded, no kernel output
     small.process(np.zeros((40, 50, 3), np.uint8))
