@@ -351,6 +351,83 @@ ORC_API void orc_dp_wren(const uint8_t *in, int npx, int first, double threshold
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* DPPratiMediodBGS (USTC_BGS type 14): package_bgs/dp/PratiMediodBGS.cpp:52-275, wrapper DPPratiMediodBGS.cpp:28-88.  */
+/* Pure integer.  Per pixel a circular buffer of up to H sampled pixels with, for every sample, the sum of its L-inf   */
+/* distances to the other samples; the medoid (smallest sum, first wins) is the background.  Because the wrapper       */
+/* clears the update mask, every pixel is updated on every sampled frame, so the buffer length n and the write         */
+/* position pos are the same for all pixels: samples[s] (s < n) are whole frames, dist[s] whole int planes.            */
+/* Per frame (wrapper :66-68): Subtract with the medoid as it stands, then Update.                                     */
+/* The quirks are the reference's: when the buffer is full the sample being replaced still takes part in the medoid    */
+/* search with its old sum (:99-117 subtracts its distances from the OTHERS, UpdateMediod :128-165 then walks over     */
+/* all H samples), and the new sample's sum includes its distance to the one it replaces.  `weight` is never used.     */
+/* ------------------------------------------------------------------------------------ */
+static int orc_linf(const uint8_t *a, const uint8_t *b)
+{
+    int m = 0;
+    for (int ch = 0; ch < 3; ch++) { int d = abs(a[ch] - b[ch]); if (d > m) m = d; }
+    return m;
+}
+
+/* Subtract :236-262 + CalculateMasks :204-234 + Combine :167-202; fg = the combined mask (both outputs are the same) */
+ORC_API void orc_dp_prati_subtract(const uint8_t *in, int w, int h, int frame_num, int threshold, int history_size,
+                                   const uint8_t *median, uint8_t *fg, uint8_t *scratch /* 2 * w * h */)
+{
+    const unsigned int low = (unsigned int)threshold, high = 2 * low;        /* DPPratiMediodBGS.cpp:57-58, unsigned int members */
+    const int npx = w * h;
+    memset(fg, 0, (size_t)npx);
+    if (frame_num < history_size) return;                                    /* :239-244 */
+    uint8_t *lo = scratch, *hi = scratch + npx;
+    for (int i = 0; i < npx; i++) {
+        unsigned char dist = (unsigned char)orc_linf(in + 3 * i, median + 3 * i);
+        lo[i] = dist > low ? 255 : 0;
+        hi[i] = dist > high ? 255 : 0;
+    }
+    for (int r = 1; r < h - 1; r++)                                          /* the image border stays BACKGROUND :175-176 */
+        for (int c = 1; c < w - 1; c++) {
+            const int i = r * w + c;
+            if (hi[i]) fg[i] = 255;
+            else if (lo[i]) {
+                int any = 0;
+                for (int dr = -1; dr <= 1; dr++) for (int dc = -1; dc <= 1; dc++) if (dr || dc) any |= hi[i + dr * w + dc];
+                if (any) fg[i] = 255;
+            }
+        }
+}
+
+/* Update :70-126 + UpdateMediod :128-165 for a sampled frame (the caller checks frame_num % samplingRate == 0).       */
+/* samples: [H][npx * 3], dist: [H][npx], n = samples held so far (all pixels alike), pos = the slot to replace once   */
+/* n == H; median: [npx * 3].  The caller advances n / pos afterwards.                                                 */
+ORC_API void orc_dp_prati_update(const uint8_t *in, int npx, int n, int pos, int history_size, uint8_t *samples, int32_t *dist,
+                                 uint8_t *median)
+{
+    const size_t fb = (size_t)npx * 3;
+    const int full = n == history_size;
+    for (int i = 0; i < npx; i++) {
+        const uint8_t *px = in + 3 * (size_t)i;
+        if (full) {                                                          /* :84-95 */
+            const uint8_t *old = samples + pos * fb + 3 * (size_t)i;
+            for (int s = 0; s < n; s++) dist[(size_t)s * npx + i] -= orc_linf(old, samples + s * fb + 3 * (size_t)i);
+        }
+        int median_dist = 2147483647, L = 0;                                 /* UpdateMediod */
+        uint8_t med[3] = {median[3 * i], median[3 * i + 1], median[3 * i + 2]};
+        for (int s = 0; s < n; s++) {
+            const uint8_t *sp = samples + s * fb + 3 * (size_t)i;
+            const int d = orc_linf(sp, px);
+            int32_t *ds = dist + (size_t)s * npx + i;
+            *ds += d;
+            if (*ds < median_dist) { median_dist = *ds; med[0] = sp[0]; med[1] = sp[1]; med[2] = sp[2]; }
+            L += d;
+        }
+        if (L < median_dist) { med[0] = px[0]; med[1] = px[1]; med[2] = px[2]; }
+        median[3 * i] = med[0]; median[3 * i + 1] = med[1]; median[3 * i + 2] = med[2];
+        const int slot = full ? pos : n;                                     /* :97-100 / :119-121 */
+        dist[(size_t)slot * npx + i] = L;
+        uint8_t *dst = samples + slot * fb + 3 * (size_t)i;
+        dst[0] = px[0]; dst[1] = px[1]; dst[2] = px[2];
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* WeightedMovingVariance (package_bgs/WeightedMovingVarianceBGS.cpp:53-106,126-138)       */
 /* ------------------------------------------------------------------------------------ */
 ORC_API void orc_wmv(const uint8_t *cur, const uint8_t *p1, const uint8_t *p2, int npx,

@@ -8,6 +8,7 @@
 #include "AdaptiveMedianBGS.h"
 #include "MeanBGS.h"
 #include "WrenGA.h"
+#include "PratiMediodBGS.h"
 
 using namespace Algorithms::BackgroundSubtraction;
 
@@ -98,6 +99,7 @@ static void simple_process(R *r, const unsigned char *bgr, unsigned char *fg)
 typedef dp_simple_ref<AdaptiveMedianBGS, AdaptiveMedianParams> dpmed_ref;
 typedef dp_simple_ref<MeanBGS, MeanParams> dpmean_ref;
 typedef dp_simple_ref<WrenGA, WrenParams> dpwren_ref;
+typedef dp_simple_ref<PratiMediodBGS, PratiParams> dpprati_ref;
 #define DP_EXPORT __attribute__((visibility("default")))
 
 extern "C" {
@@ -137,5 +139,19 @@ DP_EXPORT dpwren_ref *dpwren_ref_create(int w, int h, double threshold, double a
 }
 DP_EXPORT void dpwren_ref_process(dpwren_ref *r, const unsigned char *bgr, unsigned char *fg) { simple_process(r, bgr, fg); }
 DP_EXPORT void dpwren_ref_destroy(dpwren_ref *r) { delete r; }
+
+
+DP_EXPORT dpprati_ref *dpprati_ref_create(int w, int h, int threshold, int samplingRate, int historySize, int weight)
+{
+    dpprati_ref *r = simple_create<dpprati_ref>(w, h);
+    r->params.LowThreshold() = threshold;                             // DPPratiMediodBGS.cpp:57-62
+    r->params.HighThreshold() = 2 * r->params.LowThreshold();
+    r->params.SamplingRate() = samplingRate;
+    r->params.HistorySize() = historySize;
+    r->params.Weight() = weight;
+    return r;
+}
+DP_EXPORT void dpprati_ref_process(dpprati_ref *r, const unsigned char *bgr, unsigned char *fg) { simple_process(r, bgr, fg); }
+DP_EXPORT void dpprati_ref_destroy(dpprati_ref *r) { delete r; }
 
 }

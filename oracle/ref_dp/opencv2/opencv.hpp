@@ -4,7 +4,8 @@
 // (IplImage, cvCreateImage, cvReleaseImage, cvZero, cvSet, cvSize) -- every arithmetic operation of the algorithm is
 // the reference's own C++.  Nothing here computes anything.
 #pragma once
-#include <cassert>      // the real header pulls these in; Image.h relies on it
+#include <cassert>      // the real header pulls these in; Image.h / PratiMediodBGS.cpp (INT_MAX) rely on it
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>

@@ -59,6 +59,8 @@ def lib():
         L.orc_dp_median.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, u8p]
         L.orc_dp_mean.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_double, f32p, u8p]
         L.orc_dp_wren.argtypes = [u8p, C.c_int, C.c_int, C.c_double, C.c_double, f32p, u8p]
+        L.orc_dp_prati_subtract.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, u8p, u8p]
+        L.orc_dp_prati_update.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, i32p, u8p]
         L.orc_wmv.argtypes = [u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
         L.orc_mog2_default_params.argtypes = [C.POINTER(Mog2Params)]
         L.orc_mog2_learning_rate.argtypes = [C.c_double, C.c_int, C.c_int]
@@ -338,8 +340,42 @@ class DPWrenGABGS:
         return fg, None
 
 
+class DPPratiMediodBGS:
+    """USTC_BGS type 14 (package_bgs/dp/DPPratiMediodBGS.cpp); defaults of its loadConfig (:104-108)."""
+
+    def __init__(self, threshold=30, samplingRate=5, historySize=16, weight=5):
+        self.threshold, self.samplingRate, self.historySize, self.weight = threshold, samplingRate, historySize, weight
+        self.samples = None
+        self.frame = 0
+
+    def process(self, img):
+        if img is None or img.size == 0:
+            return None, None
+        img = _dense(img)
+        h, w = img.shape[:2]
+        if self.samples is None:                             # parameters are handed over once (:57-62)
+            self._thr, self._rate, self._H = int(self.threshold), int(self.samplingRate), int(self.historySize)
+            self.samples = np.zeros((self._H, h, w, 3), np.uint8)
+            self.dist = np.zeros((self._H, h, w), np.int32)
+            self.median = np.zeros((h, w, 3), np.uint8)
+            self.n, self.pos = 0, 0
+        fg = np.empty((h, w), np.uint8)
+        scratch = np.empty(2 * h * w, np.uint8)
+        lib().orc_dp_prati_subtract(_u8(img), w, h, self.frame, self._thr, self._H, _u8(self.median), _u8(fg), _u8(scratch))
+        if self.frame % self._rate == 0:
+            lib().orc_dp_prati_update(_u8(img), h * w, self.n, self.pos, self._H, _u8(self.samples),
+                                      self.dist.ctypes.data_as(C.POINTER(C.c_int32)), _u8(self.median))
+            if self.n == self._H:
+                self.pos = (self.pos + 1) % self._H
+            else:
+                self.n += 1
+                self.pos = 0
+        self.frame += 1
+        return fg, None
+
+
 class ReferenceDPSimple:
-    """The reference's own AdaptiveMedianBGS / MeanBGS / WrenGA classes ("median" / "mean" / "wren"), compiled from
+    """The reference's own AdaptiveMedianBGS / MeanBGS / WrenGA / PratiMediodBGS classes ("median" / "mean" / "wren" / "prati"), compiled from
     /root/reference by `make -C oracle ref` (oracle/_ref/libdp_ref.so) and driven as their DP*BGS::process wrappers do.
     Raises FileNotFoundError when that build is absent."""
 
@@ -348,8 +384,9 @@ class ReferenceDPSimple:
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         self.L = C.CDLL(path)
-        pre = {"median": "dpmed", "mean": "dpmean", "wren": "dpwren"}[kind]
-        sig = {"median": [C.c_int, C.c_int, C.c_int], "mean": [C.c_int, C.c_double, C.c_int], "wren": [C.c_double, C.c_double, C.c_int]}[kind]
+        pre = {"median": "dpmed", "mean": "dpmean", "wren": "dpwren", "prati": "dpprati"}[kind]
+        sig = {"median": [C.c_int, C.c_int, C.c_int], "mean": [C.c_int, C.c_double, C.c_int], "wren": [C.c_double, C.c_double, C.c_int],
+               "prati": [C.c_int, C.c_int, C.c_int, C.c_int]}[kind]
         self._create, self._process, self._destroy = (getattr(self.L, pre + "_ref_" + n) for n in ("create", "process", "destroy"))
         self._create.restype = C.c_void_p
         self._create.argtypes = [C.c_int, C.c_int] + sig
@@ -441,7 +478,8 @@ class MixtureOfGaussianV2BGS:
 ALGOS = {0: FrameDifferenceBGS, 1: StaticFrameDifferenceBGS, 2: WeightedMovingMeanBGS,
          3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS,
          6: AdaptiveBackgroundLearning, 7: AdaptiveSelectiveBackgroundLearning,
-         9: DPAdaptiveMedianBGS, 11: DPZivkovicAGMMBGS, 12: DPMeanBGS, 13: DPWrenGABGS}   # ids of ustc_src/ustc_bgs.cpp:8-25
+         9: DPAdaptiveMedianBGS, 11: DPZivkovicAGMMBGS, 12: DPMeanBGS, 13: DPWrenGABGS,
+         14: DPPratiMediodBGS}   # ids of ustc_src/ustc_bgs.cpp:8-25
 
 
 def morph(mask, op, iterations=1):

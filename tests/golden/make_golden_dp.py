@@ -1,9 +1,9 @@
 #!/usr/bin/env python
-"""Golden vectors for DPAdaptiveMedianBGS / DPMeanBGS / DPWrenGABGS from a build of the REFERENCE's own sources.
+"""Golden vectors for DPAdaptiveMedianBGS / DPMeanBGS / DPWrenGABGS / DPPratiMediodBGS from a build of the REFERENCE's own sources.
 
 Run in the build container (needs /root/reference):  make -C oracle ref && python tests/golden/make_golden_dp.py
 Writes tests/golden/golden_dp.json: SHA-256 of the plugins' output masks (the high-threshold masks of
-package_bgs/dp/{AdaptiveMedianBGS,MeanBGS,WrenGA}.cpp, driven as the DP*BGS::process wrappers do) on the committed clips
+package_bgs/dp/{AdaptiveMedianBGS,MeanBGS,WrenGA,PratiMediodBGS}.cpp, driven as the DP*BGS::process wrappers do) on the committed clips
 and on the deterministic stress sequence of tests/conftest.py, for several parameter sets.
 """
 import hashlib
@@ -28,10 +28,14 @@ PLUGINS = {
                   [{}, {"threshold": 300, "alpha": 0.9}, {"threshold": 1200, "alpha": 0.5}, {"threshold": 50, "alpha": 0.999}]),
     "DPWrenGABGS": ("wren", ("threshold", "alpha", "learningFrames"),
                     [{}, {"threshold": 3.0, "alpha": 0.2}, {"threshold": 20.0, "alpha": 0.05}, {"threshold": 0.5, "alpha": 0.9}]),
+    "DPPratiMediodBGS": ("prati", ("threshold", "samplingRate", "historySize", "weight"),
+                         [{}, {"threshold": 10, "samplingRate": 1, "historySize": 4}, {"threshold": 20, "samplingRate": 3, "historySize": 7, "weight": 1},
+                          {"threshold": 5, "samplingRate": 20}]),
 }
 DEFAULTS = {"DPAdaptiveMedianBGS": {"threshold": 40, "samplingRate": 7, "learningFrames": 30},
             "DPMeanBGS": {"threshold": 2700, "alpha": F32(1e-6), "learningFrames": 30},
-            "DPWrenGABGS": {"threshold": 12.25, "alpha": F32(0.005), "learningFrames": 30}}
+            "DPWrenGABGS": {"threshold": 12.25, "alpha": F32(0.005), "learningFrames": 30},
+            "DPPratiMediodBGS": {"threshold": 30, "samplingRate": 5, "historySize": 16, "weight": 5}}
 
 
 def sequences():
@@ -44,7 +48,7 @@ def sequences():
 
 def main():
     out = {"generator": "tests/golden/make_golden_dp.py",
-           "source": "oracle/_ref/libdp_ref.so = /root/reference/package_bgs/dp/{AdaptiveMedianBGS,MeanBGS,WrenGA,Image}.cpp compiled by `make -C oracle ref`",
+           "source": "oracle/_ref/libdp_ref.so = /root/reference/package_bgs/dp/{AdaptiveMedianBGS,MeanBGS,WrenGA,PratiMediodBGS,Image}.cpp compiled by `make -C oracle ref`",
            "plugins": {}}
     seqs = sequences()
     for plugin, (kind, order, sets) in PLUGINS.items():
