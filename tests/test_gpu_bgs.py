@@ -496,7 +496,7 @@ def test_submit_wait_pipeline_matches_oracle(oracle, pinned):
     alloc = tb.pinned_empty if pinned else (lambda shape: np.empty(shape, np.uint8))
     names = ["FrameDifferenceBGS", "StaticFrameDifferenceBGS", "WeightedMovingMeanBGS", "WeightedMovingVarianceBGS",
              "MixtureOfGaussianV2BGS", "AdaptiveBackgroundLearning", "AdaptiveSelectiveBackgroundLearning",
-             "DPZivkovicAGMMBGS", "DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS"]
+             "DPZivkovicAGMMBGS", "DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS", "DPPratiMediodBGS"]
     for nm in names:
         p, o = getattr(tb, nm)(), getattr(oracle, nm)()
         bgshape = (h, w, 3) if p.BG_CHANNELS == 3 else (h, w)
@@ -540,7 +540,7 @@ def test_tiny_and_ragged_frames_all_plugins(oracle, shape):
     frames[3] = 255 - frames[3]
     for nm in ["FrameDifferenceBGS", "StaticFrameDifferenceBGS", "WeightedMovingMeanBGS", "WeightedMovingVarianceBGS",
                "MixtureOfGaussianV2BGS", "AdaptiveBackgroundLearning", "AdaptiveSelectiveBackgroundLearning",
-               "DPZivkovicAGMMBGS", "DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS"]:
+               "DPZivkovicAGMMBGS", "DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS", "DPPratiMediodBGS"]:
         p, q, o = getattr(tb, nm)(), getattr(tb, nm)(), getattr(oracle, nm)()
         bgshape = (h, w, 3) if q.BG_CHANNELS == 3 else (h, w)
         outs = []
@@ -733,15 +733,18 @@ def test_dpzivkovic_sibling_plugin(oracle, clips, kw):
 DP_SIMPLE_CASES = [("DPAdaptiveMedianBGS", {}), ("DPAdaptiveMedianBGS", {"threshold": 10, "samplingRate": 2}),
                    ("DPAdaptiveMedianBGS", {"threshold": 200, "samplingRate": 3}), ("DPAdaptiveMedianBGS", {"threshold": 25, "samplingRate": 1}),
                    ("DPMeanBGS", {}), ("DPMeanBGS", {"threshold": 300, "alpha": 0.9}), ("DPMeanBGS", {"threshold": 50, "alpha": 0.999}),
-                   ("DPWrenGABGS", {}), ("DPWrenGABGS", {"threshold": 3.0, "alpha": 0.2}), ("DPWrenGABGS", {"threshold": 0.5, "alpha": 0.9})]
+                   ("DPWrenGABGS", {}), ("DPWrenGABGS", {"threshold": 3.0, "alpha": 0.2}), ("DPWrenGABGS", {"threshold": 0.5, "alpha": 0.9}),
+                   ("DPPratiMediodBGS", {}), ("DPPratiMediodBGS", {"threshold": 10, "samplingRate": 1, "historySize": 4}),
+                   ("DPPratiMediodBGS", {"threshold": 20, "samplingRate": 3, "historySize": 7, "weight": 1}),
+                   ("DPPratiMediodBGS", {"threshold": 5, "samplingRate": 20})]
 
 
 @pytest.mark.parametrize("name,kw", DP_SIMPLE_CASES)
 def test_dp_simple_sibling_plugins(oracle, clips, name, kw):
-    """DPAdaptiveMedianBGS / DPMeanBGS / DPWrenGABGS (USTC_BGS types 9, 12, 13): bit-exact masks against the restatements
-    that are pinned to a build of the reference's own sources (tests/test_oracle_pin.py, golden_dp.json).  The reference
-    clip and the stress sequence through the host path (the clip is large enough... the stress frames are ragged: 40 x 52),
-    then the device path on the same model, a two-stream group, a temporal batch, parameters latched on the first frame,
+    """DPAdaptiveMedianBGS / DPMeanBGS / DPWrenGABGS / DPPratiMediodBGS (USTC_BGS types 9, 12, 13, 14): bit-exact masks
+    against the restatements that are pinned to a build of the reference's own sources (tests/test_oracle_pin.py,
+    golden_dp.json).  The reference clip and the stress sequence (ragged frames: 40 x 52) through the host path, then the
+    device path on the same model, a two-stream group, a temporal batch, parameters latched on the first frame,
     and reset."""
     import torch
     import tracking_b200 as tb
@@ -803,9 +806,9 @@ def test_dp_simple_plugins_at_1080p(oracle):
     synth.frames_dev(d.data_ptr(), 2, n, w, h)
     torch.cuda.synchronize()
     host = d.cpu().numpy()
-    for name in ("DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS"):
+    for name in ("DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS", "DPPratiMediodBGS"):
         kw = {"DPAdaptiveMedianBGS": {"threshold": 8, "samplingRate": 2}, "DPMeanBGS": {"threshold": 60, "alpha": 0.9},
-              "DPWrenGABGS": {"threshold": 2.0, "alpha": 0.05}}[name]
+              "DPWrenGABGS": {"threshold": 2.0, "alpha": 0.05}, "DPPratiMediodBGS": {"threshold": 4, "samplingRate": 2, "historySize": 3}}[name]
         p, g = getattr(tb, name)(**kw), getattr(tb, name)(nstreams=2, **kw)
         os_ = [getattr(oracle, name)(**kw) for _ in range(2)]
         d_in = torch.empty((2, h, w, 3), dtype=torch.uint8, device="cuda")
@@ -832,7 +835,7 @@ def test_second_device_in_one_process(oracle, clips):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     frames = _asbl_frames(600, 700, 4, 11)
-    for aid in (6, 5, 3, 0, 7, 11, 9, 12, 13):
+    for aid in (6, 5, 3, 0, 7, 11, 9, 12, 13, 14):
         p0, p1 = tb.ALGOS[aid](device=0), tb.ALGOS[aid](device=1)
         o = oracle.ALGOS[aid]()
         for f in frames:

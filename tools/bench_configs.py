@@ -45,7 +45,7 @@ def out(**kw):
     print(json.dumps(kw), flush=True)
 
 
-def simple_streams(algo_cls, name, bpp, S=16, w=1920, h=1080, NT=6, iters=40, retain=False):
+def simple_streams(algo_cls, name, bpp, S=16, w=1920, h=1080, NT=6, iters=40, retain=False, warm=4):
     st = torch.cuda.current_stream().cuda_stream
     frames = torch.empty((NT, S, h, w, 3), dtype=torch.uint8, device="cuda")
     for t in range(NT):        # layout per time step: [S][1][h][w][3]
@@ -58,7 +58,7 @@ def simple_streams(algo_cls, name, bpp, S=16, w=1920, h=1080, NT=6, iters=40, re
     def step():
         p.process_dev(frames[k[0] % NT].data_ptr(), w, h, fg.data_ptr(), bg.data_ptr(), stream=st)
         k[0] += 1
-    dt = timed(step, iters, warm=4)
+    dt = timed(step, iters, warm=warm)
     px = S * w * h
     out(config={"FD": "fd", "ABL": "3", "WMV": "3"}.get(name.split()[0], "sibling"), algo=name, streams=S, resolution=[w, h], ms_per_step=dt * 1e3,
         mpixel_s=px / dt / 1e6, algorithmic_bytes_per_px=bpp, achieved_gbs=px * bpp / dt / 1e9,
@@ -218,6 +218,8 @@ def main():
         simple_streams(tb.DPAdaptiveMedianBGS, "DPAdaptiveMedian (3 in + 3 model + 1 mask + 3/7 model write)", 7 + 3 / 7)
         simple_streams(tb.DPMeanBGS, "DPMean (3 in + 12 + 12 mean + 1 mask)", 28)
         simple_streams(tb.DPWrenGABGS, "DPWrenGA (3 in + 16 + 16 model + 1 mask)", 36)
+    # ring of 16 samples full after 76 frames; then one frame in 5 runs the update pass (16 x (3 sample + 2 + 2 sum) + 11 B/px)
+    simple_streams(tb.DPPratiMediodBGS, "DPPratiMediod (7 B/px every frame + 123 B/px on one frame in 5, ring full)", 7 + 123 / 5, S=8, warm=80)
         return
     if "--asbl" in sys.argv:                                  # just the ASBL line
         simple_streams(tb.AdaptiveSelectiveBackgroundLearning, "ASBL", 3 + 2 + 1 + 1)
@@ -238,6 +240,8 @@ def main():
     simple_streams(tb.DPAdaptiveMedianBGS, "DPAdaptiveMedian (3 in + 3 model + 1 mask + 3/7 model write)", 7 + 3 / 7)
     simple_streams(tb.DPMeanBGS, "DPMean (3 in + 12 + 12 mean + 1 mask)", 28)
     simple_streams(tb.DPWrenGABGS, "DPWrenGA (3 in + 16 + 16 model + 1 mask)", 36)
+    # ring of 16 samples full after 76 frames; then one frame in 5 runs the update pass (16 x (3 sample + 2 + 2 sum) + 11 B/px)
+    simple_streams(tb.DPPratiMediodBGS, "DPPratiMediod (7 B/px every frame + 123 B/px on one frame in 5, ring full)", 7 + 123 / 5, S=8, warm=80)
     ccl_kernel_probe()
     import fanout_probe                                   # tools/fanout_probe.py: FrameProcessor fan-out vs four uploads
     fanout_probe.main()

@@ -5,11 +5,11 @@ Everything that computes lives in CUDA kernels behind the C ABI of include/bgsb2
 Python host-side mirror of the reference's plugin interface; the C++ drop-in adapters are in
 tracking_b200/adapters/.  There is no CPU fallback.
 """
-from .bgs import (ALGOS, USTC_BGS, AdaptiveBackgroundLearning, AdaptiveSelectiveBackgroundLearning, DPAdaptiveMedianBGS, DPMeanBGS, DPWrenGABGS,  # noqa: F401
+from .bgs import (ALGOS, USTC_BGS, AdaptiveBackgroundLearning, AdaptiveSelectiveBackgroundLearning, DPAdaptiveMedianBGS, DPMeanBGS, DPPratiMediodBGS, DPWrenGABGS,  # noqa: F401
                   DPZivkovicAGMMBGS, FrameDifferenceBGS,
                   MixtureOfGaussianV2BGS, StaticFrameDifferenceBGS, WeightedMovingMeanBGS,
                   WeightedMovingVarianceBGS, pinned_empty, process_fanout)
 from .capi import BgsbError, kernel_launch_count  # noqa: F401
 
-__all__ = ["FrameDifferenceBGS", "StaticFrameDifferenceBGS", "WeightedMovingMeanBGS", "WeightedMovingVarianceBGS", "AdaptiveBackgroundLearning", "AdaptiveSelectiveBackgroundLearning", "DPZivkovicAGMMBGS", "DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS",
+__all__ = ["FrameDifferenceBGS", "StaticFrameDifferenceBGS", "WeightedMovingMeanBGS", "WeightedMovingVarianceBGS", "AdaptiveBackgroundLearning", "AdaptiveSelectiveBackgroundLearning", "DPZivkovicAGMMBGS", "DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS", "DPPratiMediodBGS",
            "MixtureOfGaussianV2BGS", "USTC_BGS", "ALGOS", "process_fanout", "pinned_empty", "BgsbError", "kernel_launch_count"]

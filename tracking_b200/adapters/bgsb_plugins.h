@@ -690,6 +690,70 @@ public:
   ~DPWrenGABGS() { std::cout << "~DPWrenGABGS()" << std::endl; }
 };
 
+// USTC_BGS type 14 (ustc_src/ustc_bgs.cpp:24): package_bgs/dp/DPPratiMediodBGS.{h,cpp}.
+class DPPratiMediodBGS : public bgsb_adapter::PluginBase
+{
+private:
+  int threshold;
+  int samplingRate;
+  int historySize;
+  int weight;
+  bool showOutput;
+
+public:
+  DPPratiMediodBGS() : PluginBase(BGSB_ALGO_DP_PRATI_MEDIOD), threshold(30), samplingRate(5), historySize(16), weight(5), showOutput(true)
+  {
+    std::cout << "DPPratiMediodBGS()" << std::endl;
+  }
+  ~DPPratiMediodBGS() { std::cout << "~DPPratiMediodBGS()" << std::endl; }
+
+  void configure()
+  {
+    loadConfig();
+    if (firstTime) {                         // handed to the model once, on the first frame (:57-62)
+      saveConfig();
+      set("threshold", threshold);
+      set("samplingRate", samplingRate);
+      set("historySize", historySize);
+      set("weight", weight);
+    }
+  }
+
+  void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
+  {
+    (void)img_bgmodel;                       // never written (DPPratiMediodBGS.cpp:28-88)
+    if (img_input.empty()) return;
+    configure();
+    bool fg, bg;
+    run(img_input, fg, bg, false);
+    if (showOutput) cv::imshow("Temporal Median (Cucchiara&Calderara)", img_foreground);
+    img_foreground.copyTo(img_output);       // :75
+    firstTime = false;
+  }
+
+private:
+  void saveConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/DPPratiMediodBGS.xml", 0, CV_STORAGE_WRITE);
+    cvWriteInt(fs, "threshold", threshold);
+    cvWriteInt(fs, "samplingRate", samplingRate);
+    cvWriteInt(fs, "historySize", historySize);
+    cvWriteInt(fs, "weight", weight);
+    cvWriteInt(fs, "showOutput", showOutput);
+    cvReleaseFileStorage(&fs);
+  }
+  void loadConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/DPPratiMediodBGS.xml", 0, CV_STORAGE_READ);
+    threshold = cvReadIntByName(fs, 0, "threshold", 30);
+    samplingRate = cvReadIntByName(fs, 0, "samplingRate", 5);
+    historySize = cvReadIntByName(fs, 0, "historySize", 16);
+    weight = cvReadIntByName(fs, 0, "weight", 5);
+    showOutput = cvReadIntByName(fs, 0, "showOutput", true);
+    cvReleaseFileStorage(&fs);
+  }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 class MixtureOfGaussianV2BGS : public bgsb_adapter::PluginBase
 {

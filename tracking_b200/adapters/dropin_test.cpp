@@ -76,6 +76,7 @@ int main(int argc, char **argv)
         run_plugin<DPAdaptiveMedianBGS>("DPAdaptiveMedianBGS", frames, out);      // DP package, USTC_BGS types 9 / 12 / 13
         run_plugin<DPMeanBGS>("DPMeanBGS", frames, out);
         run_plugin<DPWrenGABGS>("DPWrenGABGS", frames, out);
+        run_plugin<DPPratiMediodBGS>("DPPratiMediodBGS", frames, out);             // type 14
 
         // FrameProcessor::process with the one added line: a single upload feeds every enabled plugin
         {

@@ -205,6 +205,13 @@ class DPWrenGABGS(_Plugin):
     ALGO = capi.ALGO_DP_WREN_GA
 
 
+class DPPratiMediodBGS(_Plugin):
+    """package_bgs/dp/DPPratiMediodBGS.cpp (USTC_BGS type 14): temporal medoid over a ring of sampled frames (Cucchiara /
+    Calderara / Prati); keys threshold, samplingRate, historySize, weight (:90-110).  No mask before frame historySize;
+    never writes img_bgmodel."""
+    ALGO = capi.ALGO_DP_PRATI_MEDIOD
+
+
 class MixtureOfGaussianV2BGS(_Plugin):
     """package_bgs/MixtureOfGaussianV2BGS.cpp; keys alpha, enableThreshold, threshold (:92-95)."""
     ALGO = capi.ALGO_MOG2
@@ -276,7 +283,7 @@ def process_fanout(plugins, img_input, want_bg=True):
 ALGOS = {0: FrameDifferenceBGS, 1: StaticFrameDifferenceBGS, 2: WeightedMovingMeanBGS,
          3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS, 6: AdaptiveBackgroundLearning,
          7: AdaptiveSelectiveBackgroundLearning, 9: DPAdaptiveMedianBGS, 11: DPZivkovicAGMMBGS, 12: DPMeanBGS,
-         13: DPWrenGABGS}
+         13: DPWrenGABGS, 14: DPPratiMediodBGS}
 
 
 class USTC_BGS:
@@ -284,7 +291,7 @@ class USTC_BGS:
 
     def __init__(self, type, device=0):
         if type not in ALGOS:                   # CV_Assert(type>=0 && type<=37), .cpp:6
-            raise ValueError("USTC_BGS type %r is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL, 9 DPAdaptiveMedian, 11 DPZivkovicAGMM, 12 DPMean, 13 DPWrenGA)" % type)
+            raise ValueError("USTC_BGS type %r is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL, 9 DPAdaptiveMedian, 11 DPZivkovicAGMM, 12 DPMean, 13 DPWrenGA, 14 DPPratiMediod)" % type)
         self.bgs = ALGOS[type](device=device)
         self.frameNum = 0
         self.img_mask = None

@@ -58,6 +58,12 @@ struct bgsb_ctx {
     // DPAdaptiveMedianBGS / DPMeanBGS / DPWrenGABGS: "threshold" (kept in dpz_threshold), "alpha", "samplingRate",
     // "learningFrames"; handed to the model once, on the first frame, like DPZivkovic's (latched in dpz_thr_l / dpz_alpha_l)
     int sampling_rate = 7, sampling_rate_l = 7;
+    // DPPratiMediodBGS: "historySize", "weight" (never used by the reference); latched copy, ring counters (the same for
+    // every pixel because the wrapper clears the update mask), state block
+    int history_size = 16, history_size_l = 16, prati_weight = 5;
+    int prati_n = 0, prati_pos = 0;
+    uint8_t *d_prati = nullptr;
+    size_t prati_bytes = 0;
     int abl_table = 1;         // ABL: 1 = lookup-table kernel, 0 = arithmetic kernel (A/B, identical results)
     int abl_blend = 0, lut_blend = 0;   // ABL: 0 = OpenCV 4.x fp64 addWeighted, 1 = OpenCV 2.4 fp32 addWeighted (table kernels only)
     int mog2_variant = 0;      // see launch_mog2 (mog2.cu): 0 production, 1 straight restatement, 8/9 timing instruments
@@ -118,6 +124,7 @@ static const char *algo_name(int algo)
     case BGSB_ALGO_DP_ADAPTIVE_MEDIAN: return "DPAdaptiveMedianBGS";
     case BGSB_ALGO_DP_MEAN: return "DPMeanBGS";
     case BGSB_ALGO_DP_WREN_GA: return "DPWrenGABGS";
+    case BGSB_ALGO_DP_PRATI_MEDIOD: return "DPPratiMediodBGS";
     }
     return "?";
 }
@@ -141,6 +148,7 @@ static void free_buffers(bgsb_ctx *c)
     cudaFree(c->d_fg2); c->d_fg2 = nullptr;
     cudaFree(c->d_bg2); c->d_bg2 = nullptr;
     cudaFree(c->d_fan); c->d_fan = nullptr; c->d_fan_bytes = 0;
+    cudaFree(c->d_prati); c->d_prati = nullptr; c->prati_bytes = 0; c->prati_n = c->prati_pos = 0;
     c->w = c->h = c->npx = 0; c->pstride = 0;
     c->nframes = 0; c->have_hist = 0; c->ring_pos = 0;
 }
@@ -165,6 +173,8 @@ static int ensure_geometry(bgsb_ctx *c, int w, int h)
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_state, 0, fb, c->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(c->d_nmodes, 0, S * pstride, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    } else if (c->algo == BGSB_ALGO_DP_PRATI_MEDIOD) {
+        // the state is sized by "historySize", which is handed over with the first frame: allocated there (launch_range)
     } else if (dp_float_planes(c->algo)) {
         e = cudaMalloc(&c->d_state, S * dp_float_planes(c->algo) * pstride * sizeof(float));      // written in full by the first frame
     } else {
@@ -230,7 +240,7 @@ static int warmup_frames(int algo)
 static int history_images(int algo)
 {
     if (algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN) return 2;
-    return (gmm_state(algo) || dp_float_planes(algo)) ? 0 : 1;
+    return (gmm_state(algo) || dp_float_planes(algo) || algo == BGSB_ALGO_DP_PRATI_MEDIOD) ? 0 : 1;
 }
 // FD / WMV / WMM: the history is the previous input frame(s) -> on the host path it lives in the upload ring
 static bool ring_history(int algo)
@@ -245,7 +255,8 @@ static int dp_float_planes(int algo) { return algo == BGSB_ALGO_DP_MEAN ? 3 : (a
 // channels of img_bgmodel: ASBL's model is the gray image (AdaptiveSelectiveBackgroundLearning.cpp:103)
 static int bg_channels(int algo) { return algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING ? 1 : 3; }
 // the mask depends on neighbouring pixels (3x3 median): no row-band sub-launches
-static bool stencil_algo(int algo) { return algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING; }
+// (DPPratiMediod: its mask is the hysteresis of two thresholds over the 8 neighbours)
+static bool stencil_algo(int algo) { return algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING || algo == BGSB_ALGO_DP_PRATI_MEDIOD; }
 static bool writes_background(int algo)
 {
     return algo == BGSB_ALGO_MOG2 || algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING || algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING ||
@@ -344,6 +355,43 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
             L.alpha = (float)c->dpz_alpha_l; L.one_minus_alpha = 1.0f - L.alpha;
             int rc = launch_dp_simple(L, c->nstreams, stream);
             if (rc) return rc;
+        }
+    } else if (c->algo == BGSB_ALGO_DP_PRATI_MEDIOD) {
+        BGSB_REQUIRE(p0 == 0 && pcount == c->npx, "DPPratiMediod works on whole frames (8-neighbour hysteresis)");
+        for (int t = 0; t < T; t++) {
+            const int64_t frame_num = c->nframes + t;                      // the wrapper's frameNumber
+            if (frame_num == 0) {                                          // DPPratiMediodBGS.cpp:57-62, once
+                c->dpz_thr_l = c->dpz_threshold; c->sampling_rate_l = c->sampling_rate; c->history_size_l = c->history_size;
+                c->prati_n = 0; c->prati_pos = 0;
+            }
+            PratiLaunch L;
+            memset(&L, 0, sizeof(L));
+            prati_layout(c->npx, c->history_size_l, &L.plane3, &L.plane1, &L.stream_bytes);
+            const size_t need = L.stream_bytes * (size_t)c->nstreams;
+            if (!c->d_prati || c->prati_bytes < need) {
+                BGSB_REQUIRE(frame_num == 0, "DPPratiMediod: state missing");
+                cudaFree(c->d_prati); c->d_prati = nullptr; c->prati_bytes = 0;
+                BGSB_CUDA(cudaMalloc(&c->d_prati, need));
+                c->prati_bytes = need;
+            }
+            L.frame = d_frames + (size_t)t * c->npx * 3; L.frame_stride = (size_t)T * c->npx * 3;
+            L.fg = d_fg + (size_t)t * c->npx; L.fg_stride = (size_t)T * c->npx;
+            L.state = c->d_prati;
+            L.w = c->w; L.h = c->h; L.H = c->history_size_l; L.n = c->prati_n; L.pos = c->prati_pos;
+            L.low = (unsigned)(int)c->dpz_thr_l; L.high = 2u * L.low;      // unsigned int members (PratiMediodBGS.h:52-53)
+            if (frame_num < c->history_size_l) {                           // Subtract :239-244: both masks cleared
+                for (int s = 0; s < c->nstreams; s++)
+                    BGSB_CUDA(cudaMemsetAsync(L.fg + (size_t)s * L.fg_stride, 0, (size_t)c->npx, stream));
+            } else {
+                int rc = launch_prati_subtract(L, c->nstreams, stream);
+                if (rc) return rc;
+            }
+            if (frame_num % c->sampling_rate_l == 0) {                     // Update :73
+                int rc = launch_prati_update(L, c->nstreams, stream);
+                if (rc) return rc;
+                if (c->prati_n == c->history_size_l) c->prati_pos = (c->prati_pos + 1) % c->history_size_l;
+                else { c->prati_n++; c->prati_pos = 0; }
+            }
         }
     } else if (c->algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) {
         BGSB_REQUIRE(p0 == 0 && pcount == c->npx, "ASBL works on whole frames (3x3 median)");
@@ -561,9 +609,9 @@ int bgsb_create_group(bgsb_ctx **out, int algo, int device, int nstreams)
                  algo == BGSB_ALGO_MOG2 || algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING ||
                  algo == BGSB_ALGO_STATIC_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN || algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING ||
                  algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM || algo == BGSB_ALGO_DP_ADAPTIVE_MEDIAN || algo == BGSB_ALGO_DP_MEAN ||
-                 algo == BGSB_ALGO_DP_WREN_GA,
+                 algo == BGSB_ALGO_DP_WREN_GA || algo == BGSB_ALGO_DP_PRATI_MEDIOD,
                  "unknown algorithm id (USTC_BGS ids: 0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL, 9 DPAdaptiveMedian, "
-                 "11 DPZivkovicAGMM, 12 DPMean, 13 DPWrenGA)");
+                 "11 DPZivkovicAGMM, 12 DPMean, 13 DPWrenGA, 14 DPPratiMediod)");
     BGSB_REQUIRE(nstreams >= 1 && nstreams <= 65535, "nstreams out of range");
     BGSB_CUDA(cudaSetDevice(device));
     bgsb_ctx *c = new bgsb_ctx();
@@ -574,6 +622,7 @@ int bgsb_create_group(bgsb_ctx **out, int algo, int device, int nstreams)
     // the real-valued ones are float literals read into doubles
     if (algo == BGSB_ALGO_DP_ADAPTIVE_MEDIAN) { c->dpz_threshold = 40; c->thr = 40; c->sampling_rate = 7; c->learning_frames = 30; }
     if (algo == BGSB_ALGO_DP_MEAN) { c->dpz_threshold = 2700; c->thr = 2700; c->alpha = (double)1e-6f; c->learning_frames = 30; }
+    if (algo == BGSB_ALGO_DP_PRATI_MEDIOD) { c->dpz_threshold = 30; c->thr = 30; c->sampling_rate = 5; }   // DPPratiMediodBGS.cpp:104-107
     if (algo == BGSB_ALGO_DP_WREN_GA) { c->dpz_threshold = (double)12.25f; c->thr = 12; c->alpha = (double)0.005f; c->learning_frames = 30; }
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
@@ -622,6 +671,8 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     else if (k == "limit") c->limit = (int)v;
     else if (k == "learningFrames") c->learning_frames = (int)v;
     else if (k == "samplingRate") { BGSB_REQUIRE(v >= 1 && v <= (double)(1 << 30), "samplingRate must be positive"); c->sampling_rate = (int)v; }
+    else if (k == "historySize") { BGSB_REQUIRE(v >= 1 && v <= 64, "historySize in [1,64]"); c->history_size = (int)v; }
+    else if (k == "weight") c->prati_weight = (int)v;                        // stored for the XML round trip; the reference never reads it
     else if (k == "alphaLearn") c->alpha_learn = v;
     else if (k == "alphaDetection") c->alpha_detection = v;
     else if (k == "enableThreshold") c->enable_thr = (v != 0);
@@ -677,6 +728,8 @@ int bgsb_get_param(bgsb_ctx *c, const char *key, double *v)
     else if (k == "enableThreshold") *v = c->enable_thr;
     else if (k == "threshold") *v = (c->algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM || c->algo == BGSB_ALGO_DP_WREN_GA) ? c->dpz_threshold : c->thr;
     else if (k == "samplingRate") *v = c->sampling_rate;
+    else if (k == "historySize") *v = c->history_size;
+    else if (k == "weight") *v = c->prati_weight;
     else if (k == "gaussians") *v = c->gaussians;
     else if (k == "enableWeight") *v = c->enable_weight;
     else if (k == "grayVariant") *v = c->gray_variant;
@@ -725,6 +778,7 @@ int bgsb_state_bytes(bgsb_ctx *c, size_t *bytes)
     else if (c->algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM) *bytes = (size_t)c->npx * ((c->nframes ? c->dpz_K_l : c->gaussians) * 20 + 1);
     else if (c->algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) *bytes = (size_t)c->npx;
     else if (dp_float_planes(c->algo)) *bytes = (size_t)c->npx * dp_float_planes(c->algo) * 4;
+    else if (c->algo == BGSB_ALGO_DP_PRATI_MEDIOD) *bytes = (size_t)c->npx * ((c->nframes ? c->history_size_l : c->history_size) * 5 + 3);
     else if (history_images(c->algo) == 2) *bytes = (size_t)c->npx * 6;
     else *bytes = (size_t)c->npx * 3;
     return BGSB_OK;

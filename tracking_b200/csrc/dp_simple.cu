@@ -162,6 +162,158 @@ dps_float_kernel(DpsLaunch L)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K-PRATI: DPPratiMediodBGS, USTC_BGS type 14 (package_bgs/dp/PratiMediodBGS.cpp:52-275, wrapper DPPratiMediodBGS.cpp:28-88).
+// Pure integer.  The reference keeps, per pixel, std::vectors of up to H sampled pixels and of each sample's sum of L-inf
+// distances to the others; the medoid (smallest sum, first wins) is the background.  The wrapper clears the update mask,
+// so every pixel is sampled on the same frames: the per-pixel vectors are whole frames (samples[s]) and whole planes
+// (dist[s], 16 bit: a sum never exceeds (H + 1) * 255), buffer length n and write position pos are host counters.
+//   subtract (every frame >= H):  L-inf distance to the medoid against low / high threshold, then the hysteresis of
+//       Combine(): high -> foreground; low -> foreground iff one of the 8 neighbours is high; image border -> background.
+//       A thread owns 4 pixels; the neighbour test (rare: low-but-not-high pixels) recomputes the neighbours' distance.
+//   update (frames with frame_num % samplingRate == 0):  one pass over the n samples per pixel -- remove the replaced
+//       sample's distances (ring full), add the new pixel's, track the medoid -- then the new pixel takes the slot.
+//       The quirks are the reference's and are kept: the replaced sample still competes with its old sum, and the new
+//       sample's sum includes its distance to the sample it replaces.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned prati_linf3(unsigned px)           // max of the three low bytes
+{
+    const unsigned a = px & 0xffu, b = (px >> 8) & 0xffu, c = (px >> 16) & 0xffu;
+    return max(a, max(b, c));
+}
+// pixel j (0..3) of three words as B | G << 8 | R << 16 (+ garbage in the top byte)
+__device__ __forceinline__ unsigned prati_px(const unsigned (&w)[3], int j)
+{
+    return j == 0 ? w[0] : (j == 1 ? __byte_perm(w[0], w[1], 0x0543u) : (j == 2 ? __byte_perm(w[1], w[2], 0x0432u) : (w[2] >> 8)));
+}
+
+__global__ void __launch_bounds__(256)
+prati_subtract_kernel(PratiLaunch L)
+{
+    pdl_entry();
+    const int npx = L.w * L.h;
+    const long long px0 = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (px0 >= npx) return;
+    const int n = (int)min(4LL, (long long)npx - px0);
+    const size_t s = blockIdx.y;
+    const uint8_t *frame = L.frame + s * L.frame_stride;
+    const uint8_t *median = L.state + s * L.stream_bytes + (size_t)L.H * L.plane3;
+    uint8_t *gp = L.fg + s * L.fg_stride + px0;
+    const uint8_t *fp = frame + px0 * 3, *mp = median + px0 * 3;
+    const bool v12 = n == 4 && ((reinterpret_cast<uintptr_t>(fp) | reinterpret_cast<uintptr_t>(mp)) & 3) == 0;
+    const bool v4 = n == 4 && (reinterpret_cast<uintptr_t>(gp) & 3) == 0;
+    unsigned in[3], med[3], d[3];
+    dps_load12(fp, v12, n, in);
+    dps_load12(mp, v12, n, med);
+#pragma unroll
+    for (int k = 0; k < 3; k++) d[k] = __vabsdiffu4(in[k], med[k]);
+    unsigned m = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (j >= n) break;
+        const unsigned dist = prati_linf3(prati_px(d, j));                  // CalculateMasks :204-234
+        unsigned out = 0;
+        const int p = (int)px0 + j, r = p / L.w, c = p - r * L.w;
+        if (r > 0 && c > 0 && r < L.h - 1 && c < L.w - 1) {                 // Combine :167-202
+            if (dist > L.high) out = 255u;
+            else if (dist > L.low) {
+                for (int dr = -1; dr <= 1 && !out; dr++)
+                    for (int dc = -1; dc <= 1; dc++) {
+                        if (!dr && !dc) continue;
+                        const size_t q = (size_t)(p + dr * L.w + dc) * 3;
+                        const unsigned nd = max(max(__sad((int)frame[q], (int)median[q], 0u), __sad((int)frame[q + 1], (int)median[q + 1], 0u)),
+                                                __sad((int)frame[q + 2], (int)median[q + 2], 0u));
+                        if (nd > L.high) { out = 255u; break; }
+                    }
+            }
+        }
+        m |= out << (8 * j);
+    }
+    dps_store_mask(gp, v4, n, m);
+}
+
+__global__ void __launch_bounds__(256)
+prati_update_kernel(PratiLaunch L)
+{
+    pdl_entry();
+    const int npx = L.w * L.h;
+    const long long px0 = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (px0 >= npx) return;
+    const int n = (int)min(4LL, (long long)npx - px0);
+    const size_t s = blockIdx.y;
+    uint8_t *st = L.state + s * L.stream_bytes;
+    uint8_t *samples = st, *median = st + (size_t)L.H * L.plane3;
+    unsigned short *dist = reinterpret_cast<unsigned short *>(st + (size_t)(L.H + 1) * L.plane3);
+    const uint8_t *fp = L.frame + s * L.frame_stride + px0 * 3;
+    const bool vin = n == 4 && (reinterpret_cast<uintptr_t>(fp) & 3) == 0;
+    const bool vec = n == 4;                                                // the state planes are padded and 16-byte aligned
+    const bool full = L.n == L.H;
+    unsigned in[3], old[3] = {0u, 0u, 0u}, med[3];
+    dps_load12(fp, vin, n, in);
+    if (full) dps_load12(samples + (size_t)L.pos * L.plane3 + px0 * 3, vec, n, old);
+    dps_load12(median + px0 * 3, vec, n, med);                              // kept where no sample wins (cannot happen: n >= 0 -> the new pixel does)
+    unsigned best[4], Lsum[4] = {0u, 0u, 0u, 0u}, mpx[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { best[j] = 0x7fffffffu; mpx[j] = prati_px(med, j) & 0x00ffffffu; }
+    for (int k = 0; k < L.n; k++) {
+        unsigned sp[3], dn[3], dol[3];
+        dps_load12(samples + (size_t)k * L.plane3 + px0 * 3, vec, n, sp);
+        unsigned short *dp = dist + (size_t)k * L.plane1 + px0;
+        unsigned ds[4];
+        if (vec) { const uint2 v = *reinterpret_cast<const uint2 *>(dp); ds[0] = v.x & 0xffffu; ds[1] = v.x >> 16; ds[2] = v.y & 0xffffu; ds[3] = v.y >> 16; }
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) ds[j] = j < n ? dp[j] : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 3; q++) { dn[q] = __vabsdiffu4(sp[q], in[q]); dol[q] = __vabsdiffu4(sp[q], old[q]); }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned dnew = prati_linf3(prati_px(dn, j));
+            if (full) ds[j] -= prati_linf3(prati_px(dol, j));               // Update :84-95
+            ds[j] += dnew;                                                  // UpdateMediod :143-155
+            if (ds[j] < best[j]) { best[j] = ds[j]; mpx[j] = prati_px(sp, j) & 0x00ffffffu; }
+            Lsum[j] += dnew;
+        }
+        if (vec) *reinterpret_cast<uint2 *>(dp) = make_uint2(ds[0] | (ds[1] << 16), ds[2] | (ds[3] << 16));
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (j < n) dp[j] = (unsigned short)ds[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (Lsum[j] < best[j]) mpx[j] = prati_px(in, j) & 0x00ffffffu;      // the new point is the medoid :160-164
+    // medoid image, the new sample and its sum into the slot (:97-100 / :119-121)
+    unsigned mo[3];
+    mo[0] = mpx[0] | (mpx[1] << 24); mo[1] = (mpx[1] >> 8) | (mpx[2] << 16); mo[2] = (mpx[2] >> 16) | (mpx[3] << 8);
+    dps_store12(median + px0 * 3, vec, n, mo);
+    const int slot = full ? L.pos : L.n;
+    dps_store12(samples + (size_t)slot * L.plane3 + px0 * 3, vec, n, in);
+    unsigned short *dq = dist + (size_t)slot * L.plane1 + px0;
+    if (vec) *reinterpret_cast<uint2 *>(dq) = make_uint2(Lsum[0] | (Lsum[1] << 16), Lsum[2] | (Lsum[3] << 16));
+    else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (j < n) dq[j] = (unsigned short)Lsum[j];
+    }
+}
+
+int launch_prati_subtract(const PratiLaunch &L, int nstreams, cudaStream_t stream)
+{
+    const long long groups = ((long long)L.w * L.h + 3) / 4;
+    launch_pdl(prati_subtract_kernel, dim3((unsigned)((groups + 255) / 256), (unsigned)nstreams), dim3(256), 0, stream, L);
+    BGSB_LAUNCH_CHECK();
+    return BGSB_OK;
+}
+
+int launch_prati_update(const PratiLaunch &L, int nstreams, cudaStream_t stream)
+{
+    const long long groups = ((long long)L.w * L.h + 3) / 4;
+    launch_pdl(prati_update_kernel, dim3((unsigned)((groups + 255) / 256), (unsigned)nstreams), dim3(256), 0, stream, L);
+    BGSB_LAUNCH_CHECK();
+    return BGSB_OK;
+}
+
 int launch_dp_simple(const DpsLaunch &L, int nstreams, cudaStream_t stream)
 {
     const long long groups = ((long long)L.npx + 3) / 4;

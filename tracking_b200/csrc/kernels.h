@@ -140,6 +140,27 @@ struct DpsLaunch {
 };
 int launch_dp_simple(const DpsLaunch &L, int nstreams, cudaStream_t stream);
 
+// ---- DPPratiMediodBGS (temporal medoid over a ring of sampled frames, dp_simple.cu) ----
+// Per stream one block of `stream_bytes`: samples [H][plane3] u8 (whole BGR frames), medoid image [plane3] u8, distance
+// sums [H][plane1] u16 (plane3 = padded bytes of a frame, plane1 = padded pixels: prati_layout).
+struct PratiLaunch {
+    const uint8_t *frame;    // [S] BGR frames, frame_stride bytes apart
+    uint8_t *fg;             // [S] masks, fg_stride bytes apart
+    uint8_t *state;          // [S] state blocks, stream_bytes apart
+    size_t frame_stride, fg_stride, stream_bytes, plane3, plane1;
+    int w, h, H;
+    int n, pos;              // samples held so far / slot replaced once the ring is full (the same for every pixel)
+    unsigned low, high;      // unsigned int members of PratiParams
+};
+inline void prati_layout(int npx, int H, size_t *plane3, size_t *plane1, size_t *stream_bytes)
+{
+    *plane1 = ((size_t)npx + 15) / 16 * 16;
+    *plane3 = *plane1 * 3;
+    *stream_bytes = (size_t)(H + 1) * *plane3 + (size_t)H * *plane1 * 2;
+}
+int launch_prati_subtract(const PratiLaunch &L, int nstreams, cudaStream_t stream);
+int launch_prati_update(const PratiLaunch &L, int nstreams, cudaStream_t stream);
+
 // ---- morphology -------------------------------------------------------------------------------
 int launch_morph_chain(const uint8_t *d_in, uint8_t *d_out, int w, int h, int nimages, const int *ops, int nops,
                        cudaStream_t stream);
