@@ -171,21 +171,35 @@ dps_float_kernel(DpsLaunch L)
 //   subtract (every frame >= H):  L-inf distance to the medoid against low / high threshold, then the hysteresis of
 //       Combine(): high -> foreground; low -> foreground iff one of the 8 neighbours is high; image border -> background.
 //       A thread owns 4 pixels; the neighbour test (rare: low-but-not-high pixels) recomputes the neighbours' distance.
-//   update (frames with frame_num % samplingRate == 0):  one pass over the n samples per pixel -- remove the replaced
+//   update (frames with frame_num % samplingRate == 0):  one pass over the n samples per 4 pixels -- remove the replaced
 //       sample's distances (ring full), add the new pixel's, track the medoid -- then the new pixel takes the slot.
 //       The quirks are the reference's and are kept: the replaced sample still competes with its old sum, and the new
 //       sample's sum includes its distance to the sample it replaces.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned prati_linf3(unsigned px)           // max of the three low bytes
+// Internal layout (ours, not the reference's): everything the model keeps is PLANAR in groups of 4 pixels -- a sample is
+// three planes (B, G, R) of plane1 bytes, the medoid image likewise -- so that 4 pixels' channel values are one word per
+// channel and the L-inf distance of 4 pixels is 3 byte-SIMD differences and two 3-way 16-bit SIMD maxima (VIMNMX3 on the
+// even and on the odd bytes).  The distance sums are stored the way those maxima come out: per 4 pixels a uint2 whose
+// .x holds pixels 0 and 2, .y pixels 1 and 3 (16 bits each), so sums, minima and comparisons stay packed too.
+struct Planar4 { unsigned b, g, r; };
+// 4 interleaved pixels (B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3) -> one word per channel
+__device__ __forceinline__ Planar4 prati_planar(const unsigned (&w)[3])
 {
-    const unsigned a = px & 0xffu, b = (px >> 8) & 0xffu, c = (px >> 16) & 0xffu;
-    return max(a, max(b, c));
+    Planar4 p;
+    p.b = __byte_perm(__byte_perm(w[0], w[1], 0x0630u), w[2], 0x5210u);
+    p.g = __byte_perm(__byte_perm(w[0], w[1], 0x0741u), w[2], 0x6210u);
+    p.r = __byte_perm(__byte_perm(w[0], w[1], 0x0052u), w[2], 0x7410u);
+    return p;
 }
-// pixel j (0..3) of three words as B | G << 8 | R << 16 (+ garbage in the top byte)
-__device__ __forceinline__ unsigned prati_px(const unsigned (&w)[3], int j)
+// L-inf distances of 4 pixels: e = pixels 0 and 2, o = pixels 1 and 3 (16-bit lanes)
+__device__ __forceinline__ void prati_linf4(const Planar4 &x, const Planar4 &y, unsigned &e, unsigned &o)
 {
-    return j == 0 ? w[0] : (j == 1 ? __byte_perm(w[0], w[1], 0x0543u) : (j == 2 ? __byte_perm(w[1], w[2], 0x0432u) : (w[2] >> 8)));
+    const unsigned db = __vabsdiffu4(x.b, y.b), dg = __vabsdiffu4(x.g, y.g), dr = __vabsdiffu4(x.r, y.r);
+    e = __vimax3_u16x2(db & 0x00ff00ffu, dg & 0x00ff00ffu, dr & 0x00ff00ffu);
+    o = __vimax3_u16x2((db >> 8) & 0x00ff00ffu, (dg >> 8) & 0x00ff00ffu, (dr >> 8) & 0x00ff00ffu);
 }
+// byte mask (0xff per pixel) from the two lane masks (0xffff per 16-bit lane) of the even and the odd pixels
+__device__ __forceinline__ unsigned prati_bytemask(unsigned me, unsigned mo) { return (me & 0x00ff00ffu) | (mo & 0xff00ff00u); }
 
 __global__ void __launch_bounds__(256)
 prati_subtract_kernel(PratiLaunch L)
@@ -197,32 +211,40 @@ prati_subtract_kernel(PratiLaunch L)
     const int n = (int)min(4LL, (long long)npx - px0);
     const size_t s = blockIdx.y;
     const uint8_t *frame = L.frame + s * L.frame_stride;
-    const uint8_t *median = L.state + s * L.stream_bytes + (size_t)L.H * L.plane3;
+    const uint8_t *median = L.state + s * L.stream_bytes + (size_t)L.H * L.plane3;      // planar: B, G, R planes of plane1 bytes
     uint8_t *gp = L.fg + s * L.fg_stride + px0;
-    const uint8_t *fp = frame + px0 * 3, *mp = median + px0 * 3;
-    const bool v12 = n == 4 && ((reinterpret_cast<uintptr_t>(fp) | reinterpret_cast<uintptr_t>(mp)) & 3) == 0;
+    const uint8_t *fp = frame + px0 * 3;
+    const bool v12 = n == 4 && (reinterpret_cast<uintptr_t>(fp) & 3) == 0;
     const bool v4 = n == 4 && (reinterpret_cast<uintptr_t>(gp) & 3) == 0;
-    unsigned in[3], med[3], d[3];
+    unsigned in[3];
     dps_load12(fp, v12, n, in);
-    dps_load12(mp, v12, n, med);
-#pragma unroll
-    for (int k = 0; k < 3; k++) d[k] = __vabsdiffu4(in[k], med[k]);
+    Planar4 med;
+    med.b = *reinterpret_cast<const unsigned *>(median + px0);
+    med.g = *reinterpret_cast<const unsigned *>(median + L.plane1 + px0);
+    med.r = *reinterpret_cast<const unsigned *>(median + 2 * L.plane1 + px0);
+    unsigned de, dodd;
+    prati_linf4(prati_planar(in), med, de, dodd);                            // CalculateMasks :204-234
+    const unsigned dist4[4] = {de & 0xffffu, dodd & 0xffffu, de >> 16, dodd >> 16};
     unsigned m = 0;
+    const int r0 = (int)(px0 / L.w), c0 = (int)(px0 - (long long)r0 * L.w);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         if (j >= n) break;
-        const unsigned dist = prati_linf3(prati_px(d, j));                  // CalculateMasks :204-234
+        const unsigned dist = dist4[j];
         unsigned out = 0;
-        const int p = (int)px0 + j, r = p / L.w, c = p - r * L.w;
+        int r = r0, c = c0 + j;
+        if (c >= L.w) { c -= L.w; r++; if (c >= L.w) { r += c / L.w; c %= L.w; } }
+        const int p = (int)px0 + j;
         if (r > 0 && c > 0 && r < L.h - 1 && c < L.w - 1) {                 // Combine :167-202
             if (dist > L.high) out = 255u;
             else if (dist > L.low) {
                 for (int dr = -1; dr <= 1 && !out; dr++)
                     for (int dc = -1; dc <= 1; dc++) {
                         if (!dr && !dc) continue;
-                        const size_t q = (size_t)(p + dr * L.w + dc) * 3;
-                        const unsigned nd = max(max(__sad((int)frame[q], (int)median[q], 0u), __sad((int)frame[q + 1], (int)median[q + 1], 0u)),
-                                                __sad((int)frame[q + 2], (int)median[q + 2], 0u));
+                        const size_t qi = (size_t)(p + dr * L.w + dc), q = qi * 3;
+                        const unsigned nd = max(max(__sad((int)frame[q], (int)median[qi], 0u),
+                                                    __sad((int)frame[q + 1], (int)median[L.plane1 + qi], 0u)),
+                                                __sad((int)frame[q + 2], (int)median[2 * L.plane1 + qi], 0u));
                         if (nd > L.high) { out = 255u; break; }
                     }
             }
@@ -242,60 +264,63 @@ prati_update_kernel(PratiLaunch L)
     const int n = (int)min(4LL, (long long)npx - px0);
     const size_t s = blockIdx.y;
     uint8_t *st = L.state + s * L.stream_bytes;
-    uint8_t *samples = st, *median = st + (size_t)L.H * L.plane3;
-    unsigned short *dist = reinterpret_cast<unsigned short *>(st + (size_t)(L.H + 1) * L.plane3);
+    uint8_t *samples = st + px0, *median = st + (size_t)L.H * L.plane3 + px0;
+    uint2 *dist = reinterpret_cast<uint2 *>(st + (size_t)(L.H + 1) * L.plane3) + px0 / 4;      // plane k: + k * plane1 / 4
+    const size_t dstride = L.plane1 / 4;
     const uint8_t *fp = L.frame + s * L.frame_stride + px0 * 3;
     const bool vin = n == 4 && (reinterpret_cast<uintptr_t>(fp) & 3) == 0;
-    const bool vec = n == 4;                                                // the state planes are padded and 16-byte aligned
     const bool full = L.n == L.H;
-    unsigned in[3], old[3] = {0u, 0u, 0u}, med[3];
-    dps_load12(fp, vin, n, in);
-    if (full) dps_load12(samples + (size_t)L.pos * L.plane3 + px0 * 3, vec, n, old);
-    dps_load12(median + px0 * 3, vec, n, med);                              // kept where no sample wins (cannot happen: n >= 0 -> the new pixel does)
-    unsigned best[4], Lsum[4] = {0u, 0u, 0u, 0u}, mpx[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) { best[j] = 0x7fffffffu; mpx[j] = prati_px(med, j) & 0x00ffffffu; }
+    unsigned in[3];
+    dps_load12(fp, vin, n, in);                                             // ragged tail: zero fill; the planes are padded
+    const Planar4 x = prati_planar(in);
+    auto load_sample = [&](int k) {
+        const uint8_t *p = samples + (size_t)k * L.plane3;
+        Planar4 v;
+        v.b = *reinterpret_cast<const unsigned *>(p);
+        v.g = *reinterpret_cast<const unsigned *>(p + L.plane1);
+        v.r = *reinterpret_cast<const unsigned *>(p + 2 * L.plane1);
+        return v;
+    };
+    Planar4 old = {0u, 0u, 0u};
+    if (full) old = load_sample(L.pos);
+    unsigned best_e = 0xffffffffu, best_o = 0xffffffffu, sum_e = 0u, sum_o = 0u;       // best: INT_MAX stand-in per 16-bit lane
+    Planar4 med = {0u, 0u, 0u};
+    // sample k + 1 and its sums are requested before sample k is worked on
+    Planar4 spn = {0u, 0u, 0u};
+    uint2 dvn = make_uint2(0u, 0u);
+    if (L.n > 0) { spn = load_sample(0); dvn = dist[0]; }
     for (int k = 0; k < L.n; k++) {
-        unsigned sp[3], dn[3], dol[3];
-        dps_load12(samples + (size_t)k * L.plane3 + px0 * 3, vec, n, sp);
-        unsigned short *dp = dist + (size_t)k * L.plane1 + px0;
-        unsigned ds[4];
-        if (vec) { const uint2 v = *reinterpret_cast<const uint2 *>(dp); ds[0] = v.x & 0xffffu; ds[1] = v.x >> 16; ds[2] = v.y & 0xffffu; ds[3] = v.y >> 16; }
-        else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) ds[j] = j < n ? dp[j] : 0u;
+        const Planar4 sp = spn;
+        uint2 ds = dvn;
+        if (k + 1 < L.n) { spn = load_sample(k + 1); dvn = dist[(size_t)(k + 1) * dstride]; }
+        unsigned ne, no;
+        prati_linf4(sp, x, ne, no);
+        if (full) {                                                         // Update :84-95
+            unsigned oe, oo;
+            prati_linf4(sp, old, oe, oo);
+            ds.x -= oe; ds.y -= oo;                                         // per 16-bit lane: a sum holds every distance it loses
         }
-#pragma unroll
-        for (int q = 0; q < 3; q++) { dn[q] = __vabsdiffu4(sp[q], in[q]); dol[q] = __vabsdiffu4(sp[q], old[q]); }
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const unsigned dnew = prati_linf3(prati_px(dn, j));
-            if (full) ds[j] -= prati_linf3(prati_px(dol, j));               // Update :84-95
-            ds[j] += dnew;                                                  // UpdateMediod :143-155
-            if (ds[j] < best[j]) { best[j] = ds[j]; mpx[j] = prati_px(sp, j) & 0x00ffffffu; }
-            Lsum[j] += dnew;
-        }
-        if (vec) *reinterpret_cast<uint2 *>(dp) = make_uint2(ds[0] | (ds[1] << 16), ds[2] | (ds[3] << 16));
-        else {
-#pragma unroll
-            for (int j = 0; j < 4; j++) if (j < n) dp[j] = (unsigned short)ds[j];
-        }
+        ds.x += ne; ds.y += no;                                             // UpdateMediod :143-155
+        const unsigned bm = prati_bytemask(__vcmpltu2(ds.x, best_e), __vcmpltu2(ds.y, best_o));
+        best_e = __vimin3_u16x2(best_e, ds.x, ds.x); best_o = __vimin3_u16x2(best_o, ds.y, ds.y);
+        med.b = (sp.b & bm) | (med.b & ~bm); med.g = (sp.g & bm) | (med.g & ~bm); med.r = (sp.r & bm) | (med.r & ~bm);
+        sum_e += ne; sum_o += no;
+        dist[(size_t)k * dstride] = ds;
     }
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-        if (Lsum[j] < best[j]) mpx[j] = prati_px(in, j) & 0x00ffffffu;      // the new point is the medoid :160-164
-    // medoid image, the new sample and its sum into the slot (:97-100 / :119-121)
-    unsigned mo[3];
-    mo[0] = mpx[0] | (mpx[1] << 24); mo[1] = (mpx[1] >> 8) | (mpx[2] << 16); mo[2] = (mpx[2] >> 16) | (mpx[3] << 8);
-    dps_store12(median + px0 * 3, vec, n, mo);
+    {   // the new point is the medoid :160-164
+        const unsigned bm = prati_bytemask(__vcmpltu2(sum_e, best_e), __vcmpltu2(sum_o, best_o));
+        med.b = (x.b & bm) | (med.b & ~bm); med.g = (x.g & bm) | (med.g & ~bm); med.r = (x.r & bm) | (med.r & ~bm);
+    }
+    *reinterpret_cast<unsigned *>(median) = med.b;
+    *reinterpret_cast<unsigned *>(median + L.plane1) = med.g;
+    *reinterpret_cast<unsigned *>(median + 2 * L.plane1) = med.r;
+    // the new sample and its sum into the slot (:97-100 / :119-121)
     const int slot = full ? L.pos : L.n;
-    dps_store12(samples + (size_t)slot * L.plane3 + px0 * 3, vec, n, in);
-    unsigned short *dq = dist + (size_t)slot * L.plane1 + px0;
-    if (vec) *reinterpret_cast<uint2 *>(dq) = make_uint2(Lsum[0] | (Lsum[1] << 16), Lsum[2] | (Lsum[3] << 16));
-    else {
-#pragma unroll
-        for (int j = 0; j < 4; j++) if (j < n) dq[j] = (unsigned short)Lsum[j];
-    }
+    uint8_t *sl = samples + (size_t)slot * L.plane3;
+    *reinterpret_cast<unsigned *>(sl) = x.b;
+    *reinterpret_cast<unsigned *>(sl + L.plane1) = x.g;
+    *reinterpret_cast<unsigned *>(sl + 2 * L.plane1) = x.r;
+    dist[(size_t)slot * dstride] = make_uint2(sum_e, sum_o);
 }
 
 int launch_prati_subtract(const PratiLaunch &L, int nstreams, cudaStream_t stream)

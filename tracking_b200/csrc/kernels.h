@@ -141,8 +141,9 @@ struct DpsLaunch {
 int launch_dp_simple(const DpsLaunch &L, int nstreams, cudaStream_t stream);
 
 // ---- DPPratiMediodBGS (temporal medoid over a ring of sampled frames, dp_simple.cu) ----
-// Per stream one block of `stream_bytes`: samples [H][plane3] u8 (whole BGR frames), medoid image [plane3] u8, distance
-// sums [H][plane1] u16 (plane3 = padded bytes of a frame, plane1 = padded pixels: prati_layout).
+// Per stream one block of `stream_bytes`: samples [H][3][plane1] u8 (planar B, G, R), medoid image [3][plane1] u8 (planar),
+// distance sums [H][plane1] u16 stored per 4 pixels as (px0, px2 | px1, px3) (plane1 = padded pixels, plane3 = 3 * plane1:
+// prati_layout); see dp_simple.cu.
 struct PratiLaunch {
     const uint8_t *frame;    // [S] BGR frames, frame_stride bytes apart
     uint8_t *fg;             // [S] masks, fg_stride bytes apart
