@@ -226,14 +226,14 @@ prati_subtract_kernel(PratiLaunch L)
     prati_linf4(prati_planar(in), med, de, dodd);                            // CalculateMasks :204-234
     const unsigned dist4[4] = {de & 0xffffu, dodd & 0xffffu, de >> 16, dodd >> 16};
     unsigned m = 0;
-    const int r0 = (int)(px0 / L.w), c0 = (int)(px0 - (long long)r0 * L.w);
+    const int r0 = (int)((unsigned)px0 / (unsigned)L.w), c0 = (int)((unsigned)px0 - (unsigned)r0 * (unsigned)L.w);      // 32-bit: frames hold < 2^30 pixels
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         if (j >= n) break;
         const unsigned dist = dist4[j];
         unsigned out = 0;
         int r = r0, c = c0 + j;
-        if (c >= L.w) { c -= L.w; r++; if (c >= L.w) { r += c / L.w; c %= L.w; } }
+        while (c >= L.w) { c -= L.w; r++; }                                  // (widths below 4: a group spans several rows)
         const int p = (int)px0 + j;
         if (r > 0 && c > 0 && r < L.h - 1 && c < L.w - 1) {                 // Combine :167-202
             if (dist > L.high) out = 255u;
