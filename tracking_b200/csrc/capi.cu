@@ -874,7 +874,9 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
     // kernel on band i and the download of band i-1 overlap on three streams (pixels are independent),
     // so a synchronous IBGS::process costs ~max(H2D, D2H) instead of H2D + kernel + D2H.
     int nchunks = 1, band = h;
-    const int host_bands = c->host_bands_auto ? (want_bg ? 3 : 2) : c->host_bands;
+    // BGSB_HOST_BANDS=n: the default band count of contexts that did not set "hostBands" (A/B across processes, e.g. under torchrun)
+    static const int env_bands = [] { const char *e = getenv("BGSB_HOST_BANDS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 8) ? v : 0; }();
+    const int host_bands = c->host_bands_auto ? (env_bands ? env_bands : (want_bg ? 3 : 2)) : c->host_bands;
     if (c->nstreams == 1 && host_bands > 1 && (size_t)w * h * 3 >= (1u << 20) && out_fg && !stencil_algo(c->algo)) {
         band = ((h + host_bands - 1) / host_bands + 31) / 32 * 32;
         if (((size_t)band * w) % MOG2_TILE) band += 32;          // bands start on a state tile
