@@ -428,6 +428,47 @@ ORC_API void orc_dp_prati_update(const uint8_t *in, int npx, int n, int pos, int
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* SigmaDeltaBGS (USTC_BGS type 35): package_bgs/bl/sdLaMa091.cpp:117-232 (init), :470-636 (update), wrapper          */
+/* package_bgs/bl/SigmaDeltaBGS.cpp:21-50.  Pure integer, per byte of the interleaved BGR row:                        */
+/*   Mt moves one step towards the pixel; Ot = absVal((int8_t)(Mt - I)) -- the difference passes through a signed     */
+/*   char, so |d| > 128 wraps (:74-76, :559); Vt moves one step towards N * Ot in uint8_t arithmetic (it wraps) and   */
+/*   is clamped by the uint8_t min / max helpers to the parameters truncated to a byte (:62-63, :574-584); a pixel    */
+/*   is foreground when Ot >= Vt in any channel (:604-624).  The first frame only initialises: Mt = frame, Vt = Vmin  */
+/*   for the first `width` BYTES of every row and -- the C3R initialiser delegates to the C1R one -- nothing for the  */
+/*   rest, taken as zero here (oracle/ref_dp/sd_ref.cpp says why).  Parameters are applied before every frame.        */
+/* ------------------------------------------------------------------------------------ */
+ORC_API void orc_sigma_delta(const uint8_t *in, int w, int h, int first, int amp, int min_var, int max_var,
+                             uint8_t *Mt, uint8_t *Vt, uint8_t *fg)
+{
+    const size_t nb = (size_t)w * h * 3;
+    const uint32_t N = (uint32_t)amp, Vmin = (uint32_t)min_var, Vmax = (uint32_t)max_var;
+    if (first) {
+        memcpy(Mt, in, nb);                                                   /* :155 */
+        for (int r = 0; r < h; r++)                                           /* :204-216 with width, not rgbWidth */
+            for (int j = 0; j < 3 * w; j++) Vt[(size_t)r * 3 * w + j] = j < w ? (uint8_t)Vmin : 0;
+        return;
+    }
+    for (size_t i = 0; i < nb; i += 3) {
+        int fgpx = 0;
+        for (int ch = 0; ch < 3; ch++) {
+            uint8_t m = Mt[i + ch], v = Vt[i + ch];
+            const uint8_t x = in[i + ch];
+            if (m < x) ++m; else if (m > x) --m;                             /* :536-539 */
+            Mt[i + ch] = m;
+            const int8_t d8 = (int8_t)(m - x);                                /* absVal's parameter type */
+            const uint8_t o = d8 < 0 ? (uint8_t)-d8 : (uint8_t)d8;            /* :74-76 */
+            const uint32_t amp_o = N * o;                                     /* :574 */
+            if (v < amp_o) ++v; else if (v > amp_o) --v;                      /* :576-579, uint8_t */
+            const uint8_t lo = v < (uint8_t)Vmax ? v : (uint8_t)Vmax;         /* min(uint8_t, uint8_t) :581 */
+            v = lo > (uint8_t)Vmin ? lo : (uint8_t)Vmin;
+            Vt[i + ch] = v;
+            if (o >= v) fgpx = 1;                                             /* :604-605 */
+        }
+        fg[i / 3] = fgpx ? 255 : 0;
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* WeightedMovingVariance (package_bgs/WeightedMovingVarianceBGS.cpp:53-106,126-138)       */
 /* ------------------------------------------------------------------------------------ */
 ORC_API void orc_wmv(const uint8_t *cur, const uint8_t *p1, const uint8_t *p2, int npx,

@@ -59,6 +59,7 @@ def lib():
         L.orc_dp_median.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, u8p]
         L.orc_dp_mean.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_double, f32p, u8p]
         L.orc_dp_wren.argtypes = [u8p, C.c_int, C.c_int, C.c_double, C.c_double, f32p, u8p]
+        L.orc_sigma_delta.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, u8p, u8p]
         L.orc_dp_prati_subtract.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, u8p, u8p]
         L.orc_dp_prati_update.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, i32p, u8p]
         L.orc_wmv.argtypes = [u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p]
@@ -374,6 +375,58 @@ class DPPratiMediodBGS:
         return fg, None
 
 
+class SigmaDeltaBGS:
+    """USTC_BGS type 35 (package_bgs/bl/SigmaDeltaBGS.cpp); defaults of its loadConfig (:68-70).  The first frame only
+    initialises the model (no outputs); parameters are applied before every frame; never writes img_bgmodel."""
+
+    def __init__(self, ampFactor=1, minVar=15, maxVar=255):
+        self.ampFactor, self.minVar, self.maxVar = ampFactor, minVar, maxVar
+        self.Mt = None
+
+    def process(self, img):
+        if img is None or img.size == 0:
+            return None, None
+        img = _dense(img)
+        h, w = img.shape[:2]
+        first = self.Mt is None
+        if first:
+            self.Mt = np.zeros((h, w, 3), np.uint8)
+            self.Vt = np.zeros((h, w, 3), np.uint8)
+        fg = np.empty((h, w), np.uint8)
+        lib().orc_sigma_delta(_u8(img), w, h, int(first), int(self.ampFactor), int(self.minVar), int(self.maxVar),
+                              _u8(self.Mt), _u8(self.Vt), _u8(fg))
+        return (None, None) if first else (fg, None)
+
+
+class ReferenceSigmaDelta:
+    """The reference's own sdLaMa091 implementation (oracle/_ref/libdp_ref.so, oracle/ref_dp/sd_ref.cpp), driven as
+    SigmaDeltaBGS::process does.  Raises FileNotFoundError / AttributeError when that build is absent or older."""
+
+    def __init__(self, w, h, ampFactor=1, minVar=15, maxVar=255):
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libdp_ref.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.L = C.CDLL(path)
+        self.L.sd_ref_create.restype = C.c_void_p
+        self.L.sd_ref_create.argtypes = [C.c_int, C.c_int]
+        self.L.sd_ref_process.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int]
+        self.L.sd_ref_destroy.argtypes = [C.c_void_p]
+        self.w, self.h = w, h
+        self.ampFactor, self.minVar, self.maxVar = ampFactor, minVar, maxVar
+        self.p = self.L.sd_ref_create(w, h)
+
+    def process(self, img):
+        img = _dense(img)
+        fg = np.empty((self.h, self.w), np.uint8)
+        ok = self.L.sd_ref_process(self.p, _u8(img), _u8(fg), int(self.ampFactor), int(self.minVar), int(self.maxVar))
+        return (fg, None) if ok else (None, None)
+
+    def close(self):
+        if self.p:
+            self.L.sd_ref_destroy(self.p)
+            self.p = None
+
+
 class ReferenceDPSimple:
     """The reference's own AdaptiveMedianBGS / MeanBGS / WrenGA / PratiMediodBGS classes ("median" / "mean" / "wren" / "prati"), compiled from
     /root/reference by `make -C oracle ref` (oracle/_ref/libdp_ref.so) and driven as their DP*BGS::process wrappers do.
@@ -479,7 +532,7 @@ ALGOS = {0: FrameDifferenceBGS, 1: StaticFrameDifferenceBGS, 2: WeightedMovingMe
          3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS,
          6: AdaptiveBackgroundLearning, 7: AdaptiveSelectiveBackgroundLearning,
          9: DPAdaptiveMedianBGS, 11: DPZivkovicAGMMBGS, 12: DPMeanBGS, 13: DPWrenGABGS,
-         14: DPPratiMediodBGS}   # ids of ustc_src/ustc_bgs.cpp:8-25
+         14: DPPratiMediodBGS, 35: SigmaDeltaBGS}   # ids of ustc_src/ustc_bgs.cpp:8-25
 
 
 def morph(mask, op, iterations=1):

@@ -1,9 +1,9 @@
 #!/usr/bin/env python
-"""Golden vectors for DPAdaptiveMedianBGS / DPMeanBGS / DPWrenGABGS / DPPratiMediodBGS from a build of the REFERENCE's own sources.
+"""Golden vectors for DPAdaptiveMedianBGS / DPMeanBGS / DPWrenGABGS / DPPratiMediodBGS / SigmaDeltaBGS from a build of the REFERENCE's own sources.
 
 Run in the build container (needs /root/reference):  make -C oracle ref && python tests/golden/make_golden_dp.py
 Writes tests/golden/golden_dp.json: SHA-256 of the plugins' output masks (the high-threshold masks of
-package_bgs/dp/{AdaptiveMedianBGS,MeanBGS,WrenGA,PratiMediodBGS}.cpp, driven as the DP*BGS::process wrappers do) on the committed clips
+package_bgs/dp/{AdaptiveMedianBGS,MeanBGS,WrenGA,PratiMediodBGS}.cpp and package_bgs/bl/sdLaMa091.cpp, driven as the DP*BGS::process wrappers do) on the committed clips
 and on the deterministic stress sequence of tests/conftest.py, for several parameter sets.
 """
 import hashlib
@@ -31,11 +31,21 @@ PLUGINS = {
     "DPPratiMediodBGS": ("prati", ("threshold", "samplingRate", "historySize", "weight"),
                          [{}, {"threshold": 10, "samplingRate": 1, "historySize": 4}, {"threshold": 20, "samplingRate": 3, "historySize": 7, "weight": 1},
                           {"threshold": 5, "samplingRate": 20}]),
+    "SigmaDeltaBGS": ("sigmadelta", ("ampFactor", "minVar", "maxVar"),
+                      [{}, {"ampFactor": 3, "minVar": 2, "maxVar": 40}, {"ampFactor": 2, "minVar": 300, "maxVar": 700}, {"ampFactor": 5, "minVar": 1}]),
 }
 DEFAULTS = {"DPAdaptiveMedianBGS": {"threshold": 40, "samplingRate": 7, "learningFrames": 30},
             "DPMeanBGS": {"threshold": 2700, "alpha": F32(1e-6), "learningFrames": 30},
             "DPWrenGABGS": {"threshold": 12.25, "alpha": F32(0.005), "learningFrames": 30},
-            "DPPratiMediodBGS": {"threshold": 30, "samplingRate": 5, "historySize": 16, "weight": 5}}
+            "DPPratiMediodBGS": {"threshold": 30, "samplingRate": 5, "historySize": 16, "weight": 5},
+            "SigmaDeltaBGS": {"ampFactor": 1, "minVar": 15, "maxVar": 255}}
+
+
+def make_ref(kind, w, h, params):
+    """The compiled reference class for a plugin (package_bgs/dp/*, or package_bgs/bl/sdLaMa091.cpp for "sigmadelta")."""
+    if kind == "sigmadelta":
+        return restate.ReferenceSigmaDelta(w, h, *params)
+    return restate.ReferenceDPSimple(kind, w, h, *params)
 
 
 def sequences():
@@ -58,11 +68,13 @@ def main():
             entry = {}
             for kw in sets:
                 full = dict(DEFAULTS[plugin], **kw)
-                ref = restate.ReferenceDPSimple(kind, w, h, *[full[k] for k in order])
+                ref = make_ref(kind, w, h, [full[k] for k in order])
                 hs = hashlib.sha256()
                 fgsum = 0
                 for f in frames:
                     fg, _ = ref.process(f)
+                    if fg is None:                       # SigmaDeltaBGS: the first frame only initialises
+                        continue
                     hs.update(fg.tobytes())
                     fgsum += int((fg != 0).sum())
                 ref.close()
