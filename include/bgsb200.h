@@ -61,7 +61,8 @@ enum {
     BGSB_ALGO_DP_ZIVKOVIC_AGMM = 11,              /* ustc_bgs.cpp:21  sibling plugin; never writes img_bgmodel */
     BGSB_ALGO_DP_MEAN = 12,                       /* ustc_bgs.cpp:22  sibling plugin (DP package); never writes img_bgmodel */
     BGSB_ALGO_DP_WREN_GA = 13,                    /* ustc_bgs.cpp:23  sibling plugin (DP package); never writes img_bgmodel */
-    BGSB_ALGO_DP_PRATI_MEDIOD = 14                /* ustc_bgs.cpp:24  sibling plugin (DP package); never writes img_bgmodel */
+    BGSB_ALGO_DP_PRATI_MEDIOD = 14,               /* ustc_bgs.cpp:24  sibling plugin (DP package); never writes img_bgmodel */
+    BGSB_ALGO_SIGMA_DELTA = 35                    /* ustc_bgs.cpp:62  sibling plugin (BL package); first frame: no outputs */
 };
 
 typedef struct bgsb_ctx bgsb_ctx;

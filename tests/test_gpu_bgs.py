@@ -496,7 +496,7 @@ def test_submit_wait_pipeline_matches_oracle(oracle, pinned):
     alloc = tb.pinned_empty if pinned else (lambda shape: np.empty(shape, np.uint8))
     names = ["FrameDifferenceBGS", "StaticFrameDifferenceBGS", "WeightedMovingMeanBGS", "WeightedMovingVarianceBGS",
              "MixtureOfGaussianV2BGS", "AdaptiveBackgroundLearning", "AdaptiveSelectiveBackgroundLearning",
-             "DPZivkovicAGMMBGS", "DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS", "DPPratiMediodBGS"]
+             "DPZivkovicAGMMBGS", "DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS", "DPPratiMediodBGS", "SigmaDeltaBGS"]
     for nm in names:
         p, o = getattr(tb, nm)(), getattr(oracle, nm)()
         bgshape = (h, w, 3) if p.BG_CHANNELS == 3 else (h, w)
@@ -540,7 +540,7 @@ def test_tiny_and_ragged_frames_all_plugins(oracle, shape):
     frames[3] = 255 - frames[3]
     for nm in ["FrameDifferenceBGS", "StaticFrameDifferenceBGS", "WeightedMovingMeanBGS", "WeightedMovingVarianceBGS",
                "MixtureOfGaussianV2BGS", "AdaptiveBackgroundLearning", "AdaptiveSelectiveBackgroundLearning",
-               "DPZivkovicAGMMBGS", "DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS", "DPPratiMediodBGS"]:
+               "DPZivkovicAGMMBGS", "DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS", "DPPratiMediodBGS", "SigmaDeltaBGS"]:
         p, q, o = getattr(tb, nm)(), getattr(tb, nm)(), getattr(oracle, nm)()
         bgshape = (h, w, 3) if q.BG_CHANNELS == 3 else (h, w)
         outs = []
@@ -795,6 +795,68 @@ def test_dp_simple_sibling_plugins(oracle, clips, name, kw):
     g.close()
 
 
+@pytest.mark.parametrize("kw", [{}, {"ampFactor": 3, "minVar": 2, "maxVar": 40}, {"ampFactor": 2, "minVar": 300, "maxVar": 700},
+                                {"ampFactor": 5, "minVar": 1}])
+def test_sigma_delta_sibling_plugin(oracle, clips, kw):
+    """SigmaDeltaBGS (USTC_BGS type 35): bit-exact against the restatement pinned to a build of the reference's
+    sdLaMa091.cpp -- including the signed-char wrap of large differences (an inverted frame mid-sequence), the uint8_t wrap
+    of the variance with N > 1, parameters truncated to a byte, and the initialiser's first-third-of-every-row rule.  First
+    frame: no outputs.  Host path, device path, live parameter change, a two-stream group, a temporal batch that starts on
+    the warm-up frame, a 1080p frame through the row-banded host path."""
+    import torch
+    import tracking_b200 as tb
+    from conftest import stress_sequence
+    for frames in (list(clips["video_clip"][:24]), stress_sequence(40, 40, 52)):
+        frames = [f.copy() for f in frames]
+        frames[7] = 255 - frames[7]
+        h, w = frames[0].shape[:2]
+        p, o = tb.SigmaDeltaBGS(**kw), oracle.SigmaDeltaBGS(**kw)
+        d_fg = torch.full((h, w), 9, dtype=torch.uint8, device="cuda")
+        for i, f in enumerate(frames):
+            if i == 12:
+                p.set("minVar", 7); o.minVar = 7                  # parameters are applied before every frame
+            fb, bb = o.process(f)
+            if i % 2 == 0:
+                fa, ba = p.process(f)
+                assert ba is None and (fa is None) == (fb is None), i
+                if fb is not None:
+                    assert np.array_equal(fa, fb), (kw, i)
+            else:
+                d_in = torch.from_numpy(np.ascontiguousarray(f)).cuda()
+                fv, bv = p.process_dev(d_in.data_ptr(), w, h, d_fg.data_ptr(), None)
+                assert fv == (fb is not None) and not bv
+                if fb is not None:
+                    assert np.array_equal(d_fg.cpu().numpy(), fb), (kw, i)
+        p.close()
+    fa_, fb_ = list(clips["video_clip"][:8]), list(clips["video_clip"][16:24])
+    h, w = fa_[0].shape[:2]
+    g = tb.SigmaDeltaBGS(nstreams=2, **kw)
+    oa, ob = oracle.SigmaDeltaBGS(**kw), oracle.SigmaDeltaBGS(**kw)
+    batch = np.stack([np.stack(fa_[:4]), np.stack(fb_[:4])])                     # [S][T][h][w][3], frame 0 = warm-up
+    d_b = torch.from_numpy(batch).cuda()
+    d_fg = torch.full((2, 4, h, w), 9, dtype=torch.uint8, device="cuda")
+    first, _ = g.process_batch_dev(d_b.data_ptr(), 4, w, h, d_fg.data_ptr(), None)
+    assert first == 1
+    out = d_fg.cpu().numpy()
+    for t in range(4):
+        ra, rb = oa.process(fa_[t])[0], ob.process(fb_[t])[0]
+        if t == 0:
+            assert ra is None and (out[:, 0] == 9).all()                         # untouched
+        else:
+            assert np.array_equal(out[0, t], ra) and np.array_equal(out[1, t], rb), (kw, t)
+    for i in range(4, 8):
+        fg, _ = g.process(np.stack([fa_[i], fb_[i]]))
+        assert np.array_equal(fg[0], oa.process(fa_[i])[0]) and np.array_equal(fg[1], ob.process(fb_[i])[0]), (kw, i)
+    g.close()
+    from tracking_b200 import synth
+    big = [synth.frame(1920, 1080, t) for t in range(4)]
+    p, o = tb.SigmaDeltaBGS(**kw), oracle.SigmaDeltaBGS(**kw)
+    for i, f in enumerate(big):
+        fa, fb = p.process(f)[0], o.process(f)[0]
+        assert (fa is None) == (fb is None) and (fb is None or np.array_equal(fa, fb)), (kw, "1080p", i)
+    p.close()
+
+
 def test_dp_simple_plugins_at_1080p(oracle):
     """The three DP models on a 1080p K-GEN stream through the banded host path (row-band sub-launches) and on a
     two-stream device group: 12 frames against the restatements."""
@@ -835,7 +897,7 @@ def test_second_device_in_one_process(oracle, clips):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     frames = _asbl_frames(600, 700, 4, 11)
-    for aid in (6, 5, 3, 0, 7, 11, 9, 12, 13, 14):
+    for aid in (6, 5, 3, 0, 7, 11, 9, 12, 13, 14, 35):
         p0, p1 = tb.ALGOS[aid](device=0), tb.ALGOS[aid](device=1)
         o = oracle.ALGOS[aid]()
         for f in frames:

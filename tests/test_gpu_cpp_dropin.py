@@ -86,13 +86,14 @@ def test_cpp_dropin_opencv4_arithmetic_matches_golden_hashes(tmp_path, clips, go
             assert not os.path.exists(os.path.join(out, name + ".bg")), name      # FD / WMV never write img_bgmodel
     # the DP package's plugins (USTC_BGS types 9 / 12 / 13) against the masks a build of the reference's own sources produced
     gdp = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_dp.json")))["plugins"]
-    for name in ("DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS", "DPPratiMediodBGS"):
+    for name in ("DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS", "DPPratiMediodBGS", "SigmaDeltaBGS"):
         assert name + "()" in stdout and "~" + name + "()" in stdout
         assert sha_file(os.path.join(out, name + ".fg")) == gdp[name]["video_clip"]["params"]["{}"]["masks_sha256"], name
         assert not os.path.exists(os.path.join(out, name + ".bg")), name
         xml = open(os.path.join(out, "config", name + ".xml")).read()
-        keys = {"DPAdaptiveMedianBGS": ("samplingRate", "learningFrames"), "DPPratiMediodBGS": ("samplingRate", "historySize", "weight")}
-        for key in ("threshold", "showOutput") + keys.get(name, ("alpha", "learningFrames")):
+        keys = {"DPAdaptiveMedianBGS": ("threshold", "samplingRate", "learningFrames"), "DPPratiMediodBGS": ("threshold", "samplingRate", "historySize", "weight"),
+                "SigmaDeltaBGS": ("ampFactor", "minVar", "maxVar")}
+        for key in ("showOutput",) + keys.get(name, ("threshold", "alpha", "learningFrames")):
             assert "<%s>" % key in xml, (name, key)
     # fan-out: the same masks with one upload per frame
     for name in ("FrameDifferenceBGS", "WeightedMovingVarianceBGS", "MixtureOfGaussianV2BGS", "AdaptiveBackgroundLearning"):

@@ -220,6 +220,7 @@ def main():
         simple_streams(tb.DPWrenGABGS, "DPWrenGA (3 in + 16 + 16 model + 1 mask)", 36)
         # ring of 16 samples full after 76 frames; then one frame in 5 runs the update pass (16 x (3 sample + 2 + 2 sum) + 11 B/px)
         simple_streams(tb.DPPratiMediodBGS, "DPPratiMediod (7 B/px every frame + 123 B/px on one frame in 5, ring full)", 7 + 123 / 5, S=8, warm=80)
+        simple_streams(tb.SigmaDeltaBGS, "SigmaDelta (3 in + 3 + 3 Mt + 3 + 3 Vt + 1 mask)", 16)
         return
     if "--asbl" in sys.argv:                                  # just the ASBL line
         simple_streams(tb.AdaptiveSelectiveBackgroundLearning, "ASBL", 3 + 2 + 1 + 1)
@@ -242,6 +243,7 @@ def main():
     simple_streams(tb.DPWrenGABGS, "DPWrenGA (3 in + 16 + 16 model + 1 mask)", 36)
     # ring of 16 samples full after 76 frames; then one frame in 5 runs the update pass (16 x (3 sample + 2 + 2 sum) + 11 B/px)
     simple_streams(tb.DPPratiMediodBGS, "DPPratiMediod (7 B/px every frame + 123 B/px on one frame in 5, ring full)", 7 + 123 / 5, S=8, warm=80)
+    simple_streams(tb.SigmaDeltaBGS, "SigmaDelta (3 in + 3 + 3 Mt + 3 + 3 Vt + 1 mask)", 16)
     ccl_kernel_probe()
     import fanout_probe                                   # tools/fanout_probe.py: FrameProcessor fan-out vs four uploads
     fanout_probe.main()

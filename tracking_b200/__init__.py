@@ -6,10 +6,10 @@ Python host-side mirror of the reference's plugin interface; the C++ drop-in ada
 tracking_b200/adapters/.  There is no CPU fallback.
 """
 from .bgs import (ALGOS, USTC_BGS, AdaptiveBackgroundLearning, AdaptiveSelectiveBackgroundLearning, DPAdaptiveMedianBGS, DPMeanBGS, DPPratiMediodBGS, DPWrenGABGS,  # noqa: F401
-                  DPZivkovicAGMMBGS, FrameDifferenceBGS,
+                  DPZivkovicAGMMBGS, FrameDifferenceBGS, SigmaDeltaBGS,
                   MixtureOfGaussianV2BGS, StaticFrameDifferenceBGS, WeightedMovingMeanBGS,
                   WeightedMovingVarianceBGS, pinned_empty, process_fanout)
 from .capi import BgsbError, kernel_launch_count  # noqa: F401
 
-__all__ = ["FrameDifferenceBGS", "StaticFrameDifferenceBGS", "WeightedMovingMeanBGS", "WeightedMovingVarianceBGS", "AdaptiveBackgroundLearning", "AdaptiveSelectiveBackgroundLearning", "DPZivkovicAGMMBGS", "DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS", "DPPratiMediodBGS",
+__all__ = ["FrameDifferenceBGS", "StaticFrameDifferenceBGS", "WeightedMovingMeanBGS", "WeightedMovingVarianceBGS", "AdaptiveBackgroundLearning", "AdaptiveSelectiveBackgroundLearning", "DPZivkovicAGMMBGS", "DPAdaptiveMedianBGS", "DPMeanBGS", "DPWrenGABGS", "DPPratiMediodBGS", "SigmaDeltaBGS",
            "MixtureOfGaussianV2BGS", "USTC_BGS", "ALGOS", "process_fanout", "pinned_empty", "BgsbError", "kernel_launch_count"]

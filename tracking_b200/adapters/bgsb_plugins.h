@@ -754,6 +754,65 @@ private:
   }
 };
 
+// USTC_BGS type 35 (ustc_src/ustc_bgs.cpp:62): package_bgs/bl/SigmaDeltaBGS.{h,cpp} (+ sdLaMa091.{h,cpp}).
+class SigmaDeltaBGS : public bgsb_adapter::PluginBase
+{
+private:
+  int ampFactor;
+  int minVar;
+  int maxVar;
+  bool showOutput;
+
+public:
+  SigmaDeltaBGS() : PluginBase(BGSB_ALGO_SIGMA_DELTA), ampFactor(1), minVar(15), maxVar(255), showOutput(true)
+  {
+    std::cout << "SigmaDeltaBGS()" << std::endl;
+  }
+  ~SigmaDeltaBGS() { std::cout << "~SigmaDeltaBGS()" << std::endl; }
+
+  void configure()
+  {
+    loadConfig();                            // applies the parameters, every frame (:26, :74)
+    if (firstTime) saveConfig();
+  }
+
+  void process(const cv::Mat &img_input, cv::Mat &img_output, cv::Mat &img_bgmodel)
+  {
+    (void)img_bgmodel;                       // never written (SigmaDeltaBGS.cpp:16-50)
+    if (img_input.empty()) return;
+    configure();
+    bool fg, bg;
+    run(img_input, fg, bg, false);
+    firstTime = false;
+    if (!fg) return;                         // first frame: the model is initialised, img_output stays untouched (:28-33)
+    if (showOutput) cv::imshow("Sigma-Delta", img_foreground);
+    img_foreground.copyTo(img_output);
+  }
+
+private:
+  void saveConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/SigmaDeltaBGS.xml", 0, CV_STORAGE_WRITE);
+    cvWriteInt(fs, "ampFactor", ampFactor);
+    cvWriteInt(fs, "minVar", minVar);
+    cvWriteInt(fs, "maxVar", maxVar);
+    cvWriteInt(fs, "showOutput", showOutput);
+    cvReleaseFileStorage(&fs);
+  }
+  void loadConfig()
+  {
+    CvFileStorage *fs = cvOpenFileStorage("./config/SigmaDeltaBGS.xml", 0, CV_STORAGE_READ);
+    ampFactor = cvReadIntByName(fs, 0, "ampFactor", 1);
+    minVar = cvReadIntByName(fs, 0, "minVar", 15);
+    maxVar = cvReadIntByName(fs, 0, "maxVar", 255);
+    showOutput = cvReadIntByName(fs, 0, "showOutput", true);
+    set("ampFactor", ampFactor);
+    set("minVar", minVar);
+    set("maxVar", maxVar);
+    cvReleaseFileStorage(&fs);
+  }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 class MixtureOfGaussianV2BGS : public bgsb_adapter::PluginBase
 {

@@ -4,16 +4,16 @@
 int compile_check_calls()
 {
     // FrameProcessor.cpp:40-59,157-167 pattern
-    IBGS *plugins[12] = {new FrameDifferenceBGS, new WeightedMovingVarianceBGS, new MixtureOfGaussianV2BGS,
+    IBGS *plugins[13] = {new FrameDifferenceBGS, new WeightedMovingVarianceBGS, new MixtureOfGaussianV2BGS,
                          new AdaptiveBackgroundLearning, new StaticFrameDifferenceBGS, new WeightedMovingMeanBGS,
                          new AdaptiveSelectiveBackgroundLearning, new DPZivkovicAGMMBGS, new DPAdaptiveMedianBGS,
-                         new DPMeanBGS, new DPWrenGABGS, new DPPratiMediodBGS};
+                         new DPMeanBGS, new DPWrenGABGS, new DPPratiMediodBGS, new SigmaDeltaBGS};
     cv::Mat img_input, img_bgs, img_bkgmodel;
     // FrameProcessor.cpp:169-215 with the one added line: a single upload feeds all enabled plugins
     bgsb_adapter::FanOut fanout;
-    for (int i = 0; i < 12; i++) fanout.add(plugins[i]);
+    for (int i = 0; i < 13; i++) fanout.add(plugins[i]);
     fanout.process(img_input);
-    for (int i = 0; i < 12; i++) {
+    for (int i = 0; i < 13; i++) {
         plugins[i]->process(img_input, img_bgs, img_bkgmodel);
         // capture-loop form (VideoCapture.cpp:151-239): queue the frame, collect later
         bgsb_adapter::PluginBase *q = dynamic_cast<bgsb_adapter::PluginBase *>(plugins[i]);

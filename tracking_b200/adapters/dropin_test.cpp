@@ -77,6 +77,7 @@ int main(int argc, char **argv)
         run_plugin<DPMeanBGS>("DPMeanBGS", frames, out);
         run_plugin<DPWrenGABGS>("DPWrenGABGS", frames, out);
         run_plugin<DPPratiMediodBGS>("DPPratiMediodBGS", frames, out);             // type 14
+        run_plugin<SigmaDeltaBGS>("SigmaDeltaBGS", frames, out);                   // BL package, type 35
 
         // FrameProcessor::process with the one added line: a single upload feeds every enabled plugin
         {

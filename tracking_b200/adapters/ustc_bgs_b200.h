@@ -42,6 +42,7 @@ public:
         case 12: bgs = new DPMeanBGS; break;                // :22
         case 13: bgs = new DPWrenGABGS; break;              // :23
         case 14: bgs = new DPPratiMediodBGS; break;         // :24
+        case 35: bgs = new SigmaDeltaBGS; break;            // :62
         default: CV_Assert(!"this plugin id is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL, 11 DPZivkovicAGMM)");
         }
     }

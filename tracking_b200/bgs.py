@@ -212,6 +212,13 @@ class DPPratiMediodBGS(_Plugin):
     ALGO = capi.ALGO_DP_PRATI_MEDIOD
 
 
+class SigmaDeltaBGS(_Plugin):
+    """package_bgs/bl/SigmaDeltaBGS.cpp (USTC_BGS type 35): the Sigma-Delta estimator of Lacassagne / Manzanera
+    (package_bgs/bl/sdLaMa091.cpp); keys ampFactor, minVar, maxVar (:56-70), applied before every frame.  The first frame
+    only initialises the model (no outputs); never writes img_bgmodel."""
+    ALGO = capi.ALGO_SIGMA_DELTA
+
+
 class MixtureOfGaussianV2BGS(_Plugin):
     """package_bgs/MixtureOfGaussianV2BGS.cpp; keys alpha, enableThreshold, threshold (:92-95)."""
     ALGO = capi.ALGO_MOG2
@@ -283,7 +290,7 @@ def process_fanout(plugins, img_input, want_bg=True):
 ALGOS = {0: FrameDifferenceBGS, 1: StaticFrameDifferenceBGS, 2: WeightedMovingMeanBGS,
          3: WeightedMovingVarianceBGS, 5: MixtureOfGaussianV2BGS, 6: AdaptiveBackgroundLearning,
          7: AdaptiveSelectiveBackgroundLearning, 9: DPAdaptiveMedianBGS, 11: DPZivkovicAGMMBGS, 12: DPMeanBGS,
-         13: DPWrenGABGS, 14: DPPratiMediodBGS}
+         13: DPWrenGABGS, 14: DPPratiMediodBGS, 35: SigmaDeltaBGS}
 
 
 class USTC_BGS:
@@ -291,7 +298,7 @@ class USTC_BGS:
 
     def __init__(self, type, device=0):
         if type not in ALGOS:                   # CV_Assert(type>=0 && type<=37), .cpp:6
-            raise ValueError("USTC_BGS type %r is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL, 9 DPAdaptiveMedian, 11 DPZivkovicAGMM, 12 DPMean, 13 DPWrenGA, 14 DPPratiMediod)" % type)
+            raise ValueError("USTC_BGS type %r is not on the B200 hot path (0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL, 9 DPAdaptiveMedian, 11 DPZivkovicAGMM, 12 DPMean, 13 DPWrenGA, 14 DPPratiMediod, 35 SigmaDelta)" % type)
         self.bgs = ALGOS[type](device=device)
         self.frameNum = 0
         self.img_mask = None

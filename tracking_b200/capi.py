@@ -17,6 +17,7 @@ ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING = 7
 ALGO_DP_ZIVKOVIC_AGMM = 11
 ALGO_DP_ADAPTIVE_MEDIAN, ALGO_DP_MEAN, ALGO_DP_WREN_GA = 9, 12, 13     # the DP package's simple per-pixel models
 ALGO_DP_PRATI_MEDIOD = 14
+ALGO_SIGMA_DELTA = 35
 MORPH_ERODE, MORPH_DILATE = 0, 1
 
 

@@ -61,6 +61,8 @@ struct bgsb_ctx {
     // DPPratiMediodBGS: "historySize", "weight" (never used by the reference); latched copy, ring counters (the same for
     // every pixel because the wrapper clears the update mask), state block
     int history_size = 16, history_size_l = 16, prati_weight = 5;
+    // SigmaDeltaBGS: "ampFactor", "minVar", "maxVar" (defaults of its loadConfig, SigmaDeltaBGS.cpp:68-70); applied before every frame
+    int sd_amp = 1, sd_min_var = 15, sd_max_var = 255;
     int prati_n = 0, prati_pos = 0;
     uint8_t *d_prati = nullptr;
     size_t prati_bytes = 0;
@@ -125,6 +127,7 @@ static const char *algo_name(int algo)
     case BGSB_ALGO_DP_MEAN: return "DPMeanBGS";
     case BGSB_ALGO_DP_WREN_GA: return "DPWrenGABGS";
     case BGSB_ALGO_DP_PRATI_MEDIOD: return "DPPratiMediodBGS";
+    case BGSB_ALGO_SIGMA_DELTA: return "SigmaDeltaBGS";
     }
     return "?";
 }
@@ -179,8 +182,9 @@ static int ensure_geometry(bgsb_ctx *c, int w, int h)
         e = cudaMalloc(&c->d_state, S * dp_float_planes(c->algo) * pstride * sizeof(float));      // written in full by the first frame
     } else {
         // ASBL: d_hist[0] = gray model, d_hist[1] = scratch (gray input + pre-median mask)
+        // SigmaDelta: d_hist[0] = Mt, d_hist[1] = Vt
         int nh = (c->algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE || c->algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN ||
-                  c->algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) ? 2 : 1;
+                  c->algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING || c->algo == BGSB_ALGO_SIGMA_DELTA) ? 2 : 1;
         for (int i = 0; i < nh && e == cudaSuccess; i++) e = cudaMalloc(&c->d_hist[i], S * npx * 3);
     }
     if (e != cudaSuccess) {                       // e.g. out of memory on a 2160p group: leave a context without geometry
@@ -232,10 +236,12 @@ static cudaError_t copy_rows(void *dst, size_t dpitch, const void *src, size_t s
 
 static int warmup_frames(int algo)
 {
-    if (algo == BGSB_ALGO_FRAME_DIFFERENCE) return 1;
+    if (algo == BGSB_ALGO_FRAME_DIFFERENCE || algo == BGSB_ALGO_SIGMA_DELTA) return 1;
     if (algo == BGSB_ALGO_WEIGHTED_MOVING_VARIANCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN) return 2;
     return 0;
 }
+// a warm-up frame still needs a kernel: the model is initialised from it (FD / WMV / WMM just keep the uploaded frame)
+static bool init_launch_on_warmup(int algo) { return algo == BGSB_ALGO_SIGMA_DELTA; }
 // history images a plugin keeps: FD 1 (previous frame), WMV/WMM 2, ABL/StaticFD 1 (8-bit background)
 static int history_images(int algo)
 {
@@ -354,6 +360,21 @@ static int launch_range(bgsb_ctx *c, const uint8_t *d_frames, int T, uint8_t *d_
             }
             L.alpha = (float)c->dpz_alpha_l; L.one_minus_alpha = 1.0f - L.alpha;
             int rc = launch_dp_simple(L, c->nstreams, stream);
+            if (rc) return rc;
+        }
+    } else if (c->algo == BGSB_ALGO_SIGMA_DELTA) {
+        for (int t = 0; t < T; t++) {
+            SdLaunch L;
+            memset(&L, 0, sizeof(L));
+            const int64_t frame_num = c->nframes + t;
+            L.frame = d_frames + ((size_t)t * c->npx + p0) * 3; L.frame_stride = (size_t)T * c->npx * 3;
+            L.first = frame_num == 0;                                      // SigmaDeltaBGS.cpp:28-33: initialise, no output
+            L.fg = (d_fg && !L.first) ? d_fg + (size_t)t * c->npx + p0 : nullptr; L.fg_stride = (size_t)T * c->npx;
+            L.Mt = c->d_hist[0] + p0 * 3; L.Vt = c->d_hist[1] + p0 * 3; L.model_stride = (size_t)c->npx * 3;
+            L.npx = pcount; L.w = c->w; L.p0 = (long long)p0;
+            // uint32_t parameters; the clamp goes through uint8_t helpers (sdLaMa091.cpp:62-63, :581)
+            L.N = (unsigned)c->sd_amp; L.vmin8 = (unsigned)c->sd_min_var & 0xffu; L.vmax8 = (unsigned)c->sd_max_var & 0xffu;
+            int rc = launch_sigma_delta(L, c->nstreams, stream);
             if (rc) return rc;
         }
     } else if (c->algo == BGSB_ALGO_DP_PRATI_MEDIOD) {
@@ -609,9 +630,9 @@ int bgsb_create_group(bgsb_ctx **out, int algo, int device, int nstreams)
                  algo == BGSB_ALGO_MOG2 || algo == BGSB_ALGO_ADAPTIVE_BG_LEARNING ||
                  algo == BGSB_ALGO_STATIC_FRAME_DIFFERENCE || algo == BGSB_ALGO_WEIGHTED_MOVING_MEAN || algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING ||
                  algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM || algo == BGSB_ALGO_DP_ADAPTIVE_MEDIAN || algo == BGSB_ALGO_DP_MEAN ||
-                 algo == BGSB_ALGO_DP_WREN_GA || algo == BGSB_ALGO_DP_PRATI_MEDIOD,
+                 algo == BGSB_ALGO_DP_WREN_GA || algo == BGSB_ALGO_DP_PRATI_MEDIOD || algo == BGSB_ALGO_SIGMA_DELTA,
                  "unknown algorithm id (USTC_BGS ids: 0 FD, 1 StaticFD, 2 WMM, 3 WMV, 5 MOG2, 6 ABL, 7 ASBL, 9 DPAdaptiveMedian, "
-                 "11 DPZivkovicAGMM, 12 DPMean, 13 DPWrenGA, 14 DPPratiMediod)");
+                 "11 DPZivkovicAGMM, 12 DPMean, 13 DPWrenGA, 14 DPPratiMediod, 35 SigmaDelta)");
     BGSB_REQUIRE(nstreams >= 1 && nstreams <= 65535, "nstreams out of range");
     BGSB_CUDA(cudaSetDevice(device));
     bgsb_ctx *c = new bgsb_ctx();
@@ -672,6 +693,9 @@ int bgsb_set_param(bgsb_ctx *c, const char *key, double v)
     else if (k == "learningFrames") c->learning_frames = (int)v;
     else if (k == "samplingRate") { BGSB_REQUIRE(v >= 1 && v <= (double)(1 << 30), "samplingRate must be positive"); c->sampling_rate = (int)v; }
     else if (k == "historySize") { BGSB_REQUIRE(v >= 1 && v <= 64, "historySize in [1,64]"); c->history_size = (int)v; }
+    else if (k == "ampFactor") { BGSB_REQUIRE(v >= 0 && v <= 16777216., "ampFactor out of range"); c->sd_amp = (int)v; }
+    else if (k == "minVar") { BGSB_REQUIRE(v >= 0 && v <= 2147483647., "minVar out of range"); c->sd_min_var = (int)v; }
+    else if (k == "maxVar") { BGSB_REQUIRE(v >= 0 && v <= 2147483647., "maxVar out of range"); c->sd_max_var = (int)v; }
     else if (k == "weight") c->prati_weight = (int)v;                        // stored for the XML round trip; the reference never reads it
     else if (k == "alphaLearn") c->alpha_learn = v;
     else if (k == "alphaDetection") c->alpha_detection = v;
@@ -729,6 +753,9 @@ int bgsb_get_param(bgsb_ctx *c, const char *key, double *v)
     else if (k == "threshold") *v = (c->algo == BGSB_ALGO_DP_ZIVKOVIC_AGMM || c->algo == BGSB_ALGO_DP_WREN_GA) ? c->dpz_threshold : c->thr;
     else if (k == "samplingRate") *v = c->sampling_rate;
     else if (k == "historySize") *v = c->history_size;
+    else if (k == "ampFactor") *v = c->sd_amp;
+    else if (k == "minVar") *v = c->sd_min_var;
+    else if (k == "maxVar") *v = c->sd_max_var;
     else if (k == "weight") *v = c->prati_weight;
     else if (k == "gaussians") *v = c->gaussians;
     else if (k == "enableWeight") *v = c->enable_weight;
@@ -779,7 +806,7 @@ int bgsb_state_bytes(bgsb_ctx *c, size_t *bytes)
     else if (c->algo == BGSB_ALGO_ADAPTIVE_SELECTIVE_BG_LEARNING) *bytes = (size_t)c->npx;
     else if (dp_float_planes(c->algo)) *bytes = (size_t)c->npx * dp_float_planes(c->algo) * 4;
     else if (c->algo == BGSB_ALGO_DP_PRATI_MEDIOD) *bytes = (size_t)c->npx * ((c->nframes ? c->history_size_l : c->history_size) * 5 + 3);
-    else if (history_images(c->algo) == 2) *bytes = (size_t)c->npx * 6;
+    else if (history_images(c->algo) == 2 || c->algo == BGSB_ALGO_SIGMA_DELTA) *bytes = (size_t)c->npx * 6;
     else *bytes = (size_t)c->npx * 3;
     return BGSB_OK;
 }
@@ -898,6 +925,10 @@ int bgsb_process(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, u
         mark(0, c->stream);
         BGSB_CUDA(copy_rows(d_in, (size_t)w * 3, bgr, stride, (size_t)w * 3, rows, cudaMemcpyHostToDevice, c->stream));
         mark(1, c->stream); mark(2, c->stream);
+        if (!out_fg && init_launch_on_warmup(c->algo)) {
+            rc = launch_range(c, d_in, 1, c->d_fg, nullptr, 0, own_hist, c->stream, 0, c->npx);
+            if (rc) return rc;
+        }
         if (out_fg) {
             rc = launch_range(c, d_in, 1, c->d_fg, want_bg ? c->d_bg : nullptr, 0, own_hist, c->stream, 0, c->npx);
             if (rc) return rc;
@@ -1012,9 +1043,9 @@ int bgsb_submit(bgsb_ctx *c, const uint8_t *bgr, int w, int h, size_t stride, ui
     BGSB_CUDA(copy_rows(d_in, (size_t)w * 3, bgr, stride, (size_t)w * 3, rows, cudaMemcpyHostToDevice, c->s_h2d));
     BGSB_CUDA(cudaEventRecord(c->ev_up[slot], c->s_h2d));
     BGSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_up[slot], 0));
-    if (out_fg) {
+    if (out_fg || init_launch_on_warmup(c->algo)) {
         BGSB_CUDA(cudaStreamWaitEvent(c->stream, c->ev_dn[slot], 0));       // output slot free (no-op until recorded)
-        rc = launch_range(c, d_in, 1, o_fg, want_bg ? o_bg : nullptr, 0, own_hist, c->stream, 0, c->npx);
+        rc = launch_range(c, d_in, 1, o_fg, (want_bg && out_fg) ? o_bg : nullptr, 0, own_hist, c->stream, 0, c->npx);
         if (rc) return rc;
     }
     BGSB_CUDA(cudaEventRecord(c->ev_k[slot], c->stream));

@@ -339,6 +339,80 @@ int launch_prati_update(const PratiLaunch &L, int nstreams, cudaStream_t stream)
     return BGSB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// K-SD: SigmaDeltaBGS, USTC_BGS type 35 (package_bgs/bl/sdLaMa091.cpp:117-232, :470-636; wrapper SigmaDeltaBGS.cpp:21-50).
+// Pure integer and byte-wise, so 4 pixels = three words of byte-SIMD: the reference makes four passes over three images;
+// here frame, Mt and Vt are read once and Mt, Vt and the mask written once (13 B/px).  Its byte-arithmetic quirks are kept:
+// the difference passes through a signed char before the absolute value (|d| > 128 wraps), Vt steps in uint8_t (wraps when
+// N > 1 pushes it past 255) and is clamped to the parameters truncated to a byte; the initialiser fills only the first
+// `width` bytes of every row of Vt with Vmin (the rest is zero, see the oracle's notes).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+sigma_delta_kernel(SdLaunch L)
+{
+    pdl_entry();
+    const long long px0 = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (px0 >= L.npx) return;
+    const int n = (int)min(4LL, (long long)L.npx - px0);
+    const size_t s = blockIdx.y;
+    const uint8_t *fp = L.frame + s * L.frame_stride + px0 * 3;
+    uint8_t *mp = L.Mt + s * L.model_stride + px0 * 3, *vp = L.Vt + s * L.model_stride + px0 * 3;
+    uint8_t *gp = L.fg ? L.fg + s * L.fg_stride + px0 : nullptr;
+    const bool v12 = n == 4 && ((reinterpret_cast<uintptr_t>(fp) | reinterpret_cast<uintptr_t>(mp) | reinterpret_cast<uintptr_t>(vp)) & 3) == 0;
+    unsigned in[3], m[3], v[3];
+    dps_load12(fp, v12, n, in);
+    if (L.first) {                                                          // sdLaMa091AllocInit_8u_C3R -> _C1R (:155, :204-216)
+        unsigned long long cb = (unsigned long long)((L.p0 + px0) * 3) % (unsigned long long)(3 * L.w);      // byte position inside the row
+        v[0] = v[1] = v[2] = 0u;
+        for (int i = 0; i < 12; i++) {
+            if (cb < (unsigned long long)L.w) v[i >> 2] |= L.vmin8 << (8 * (i & 3));
+            if (++cb == (unsigned long long)(3 * L.w)) cb = 0;
+        }
+        dps_store12(mp, v12, n, in);
+        dps_store12(vp, v12, n, v);
+        return;
+    }
+    dps_load12(mp, v12, n, m);
+    dps_load12(vp, v12, n, v);
+    const unsigned vmax4 = L.vmax8 * 0x01010101u, vmin4 = L.vmin8 * 0x01010101u;
+    unsigned ge[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        m[k] = m[k] + (__vcmpltu4(m[k], in[k]) & 0x01010101u) - (__vcmpgtu4(m[k], in[k]) & 0x01010101u);      // :536-539 (no byte carries)
+        const unsigned o = __vabs4(__vsub4(m[k], in[k]));                   // absVal((int8_t)(Mt - I)) :74-76, :559
+        unsigned nv;
+        if (L.N == 1u) nv = v[k] + (__vcmpltu4(v[k], o) & 0x01010101u) - (__vcmpgtu4(v[k], o) & 0x01010101u);  // :574-579
+        else {
+            nv = 0u;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                unsigned vb = (v[k] >> (8 * b)) & 0xffu;
+                const unsigned amp = L.N * ((o >> (8 * b)) & 0xffu);
+                if (vb < amp) vb = (vb + 1u) & 0xffu; else if (vb > amp) vb = vb - 1u;      // uint8_t ++ wraps
+                nv |= vb << (8 * b);
+            }
+        }
+        v[k] = __vmaxu4(__vminu4(nv, vmax4), vmin4);                        // max(min(Vt, Vmax), Vmin) on bytes :581
+        ge[k] = __vcmpgeu4(o, v[k]) & 0x01010101u;                          // :604-605
+    }
+    dps_store12(mp, v12, n, m);
+    dps_store12(vp, v12, n, v);
+    if (gp) {
+        const unsigned p0 = ge[0] & 0x00ffffffu, p1 = __byte_perm(ge[0], ge[1], 0x0543u) & 0x00ffffffu;
+        const unsigned p2 = __byte_perm(ge[1], ge[2], 0x0432u) & 0x00ffffffu, p3 = ge[2] >> 8;
+        const unsigned mask = (p0 ? 0xffu : 0u) | (p1 ? 0xff00u : 0u) | (p2 ? 0xff0000u : 0u) | (p3 ? 0xff000000u : 0u);
+        dps_store_mask(gp, n == 4 && (reinterpret_cast<uintptr_t>(gp) & 3) == 0, n, mask);
+    }
+}
+
+int launch_sigma_delta(const SdLaunch &L, int nstreams, cudaStream_t stream)
+{
+    const long long groups = ((long long)L.npx + 3) / 4;
+    launch_pdl(sigma_delta_kernel, dim3((unsigned)((groups + 255) / 256), (unsigned)nstreams), dim3(256), 0, stream, L);
+    BGSB_LAUNCH_CHECK();
+    return BGSB_OK;
+}
+
 int launch_dp_simple(const DpsLaunch &L, int nstreams, cudaStream_t stream)
 {
     const long long groups = ((long long)L.npx + 3) / 4;

@@ -162,6 +162,20 @@ inline void prati_layout(int npx, int H, size_t *plane3, size_t *plane1, size_t 
 int launch_prati_subtract(const PratiLaunch &L, int nstreams, cudaStream_t stream);
 int launch_prati_update(const PratiLaunch &L, int nstreams, cudaStream_t stream);
 
+// ---- SigmaDeltaBGS (Lacassagne / Manzanera, the reference's sdLaMa091.cpp; dp_simple.cu) ----
+struct SdLaunch {
+    const uint8_t *frame;    // [S] BGR frames, frame_stride bytes apart
+    uint8_t *fg;             // [S] masks, fg_stride bytes apart
+    uint8_t *Mt, *Vt;        // [S] running median / variance images (interleaved like the frame), model_stride bytes apart
+    size_t frame_stride, fg_stride, model_stride;
+    int npx;                 // pixels of this launch
+    int w;                   // frame width and ...
+    long long p0;            // ... first pixel of this launch inside the frame (the initialiser's row rule needs positions)
+    int first;               // no model yet: initialise from this frame, no mask
+    unsigned N, vmin8, vmax8;    // amplification factor; minimal / maximal variance as the uint8_t helpers see them
+};
+int launch_sigma_delta(const SdLaunch &L, int nstreams, cudaStream_t stream);
+
 // ---- morphology -------------------------------------------------------------------------------
 int launch_morph_chain(const uint8_t *d_in, uint8_t *d_out, int w, int h, int nimages, const int *ops, int nops,
                        cudaStream_t stream);
