@@ -35,7 +35,7 @@ class Mog2Params(C.Structure):
 
 
 def build_ref(reference="/root/reference"):
-    """Compile the reference's own DP Zivkovic sources into oracle/_ref/libdp_ref.so (`make ref`) when the
+    """Compile the reference's own DP-package models and Sigma-Delta library into oracle/_ref/libdp_ref.so (`make ref`) when the
     reference tree is there; returns True if the library exists afterwards."""
     here = os.path.dirname(os.path.abspath(__file__))
     if os.path.exists(os.path.join(reference, "package_bgs", "dp", "ZivkovicAGMM.cpp")):
