@@ -14,6 +14,8 @@
 // fp32 arithmetic in the reference's order, unfused (the library is compiled with -fmad=false; the operations are
 // written with the _rn intrinsics anyway).  Parity: bit-exact against the CPU restatement, which is pinned to a build of
 // the reference's own sources (tests/golden/golden_dp.json, tests/test_oracle_pin.py).
+#include <stdlib.h>
+#include <initializer_list>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -405,8 +407,143 @@ sigma_delta_kernel(SdLaunch L)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-coalesced forms of the two byte-wise models (AdaptiveMedian, SigmaDelta) for launches of whole 512-pixel chunks
+// with 16-byte aligned images.  In the 4-pixel kernels above every access is a 32-bit word at a 12-byte stride: three
+// instructions walk over the same twelve sectors, and with L1::no_allocate each of them goes to the L2 again -- the kernels
+// move three times their bytes between L2 and SM (SigmaDelta: 0.50 of the HBM roofline).  The model arithmetic is
+// byte-wise, so it does not care which pixel a byte belongs to: a warp takes 512 pixels = 1536 bytes per image and lane i
+// moves bytes [512 k + 16 i, + 16), k = 0..2, with 128-bit accesses (fd_coalesced_kernel's scheme).  Only the mask needs
+// whole pixels: the per-byte flags pass through a 1536-byte per-warp shared-memory buffer, from which every lane takes the
+// 48 flag bytes of the 16 pixels whose mask bytes it writes.
+constexpr int BW_CHUNK_PX = 512, BW_CHUNK_BYTES = BW_CHUNK_PX * 3;
+
+// the 16 mask bytes of a lane from the 1536 flag bytes of its warp (0x01 where a channel says foreground)
+__device__ __forceinline__ uint4 bw_mask_from_flags(unsigned char *tbuf, const uint4 (&flags)[3], unsigned lane)
+{
+    uint4 *tb = reinterpret_cast<uint4 *>(tbuf);
+#pragma unroll
+    for (int k = 0; k < 3; k++) tb[k * 32 + lane] = flags[k];
+    __syncwarp();
+    const uint4 *mine = reinterpret_cast<const uint4 *>(tbuf + lane * 48);
+    const uint4 a = mine[0], b = mine[1], c = mine[2];
+    __syncwarp();
+    const unsigned w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    unsigned m[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const unsigned w0 = w[3 * g], w1 = w[3 * g + 1], w2 = w[3 * g + 2];
+        const unsigned p0 = w0 & 0x00ffffffu, p1 = __byte_perm(w0, w1, 0x0543u) & 0x00ffffffu;
+        const unsigned p2 = __byte_perm(w1, w2, 0x0432u) & 0x00ffffffu, p3 = w2 >> 8;
+        m[g] = (p0 ? 0xffu : 0u) | (p1 ? 0xff00u : 0u) | (p2 ? 0xff0000u : 0u) | (p3 ? 0xff000000u : 0u);
+    }
+    return make_uint4(m[0], m[1], m[2], m[3]);
+}
+
+__device__ __forceinline__ void bw_ld3(const uint8_t *img, unsigned lane, uint4 (&v)[3])
+{
+    const uint4 *p = reinterpret_cast<const uint4 *>(img) + lane;
+    v[0] = ld_stream_u4(p); v[1] = ld_stream_u4(p + 32); v[2] = ld_stream_u4(p + 64);
+}
+__device__ __forceinline__ void bw_st3(uint8_t *img, unsigned lane, const uint4 (&v)[3])
+{
+    uint4 *p = reinterpret_cast<uint4 *>(img) + lane;
+    st_stream_u4(p, v[0]); st_stream_u4(p + 32, v[1]); st_stream_u4(p + 64, v[2]);
+}
+
+__global__ void __launch_bounds__(256)
+sigma_delta_coalesced_kernel(SdLaunch L)
+{
+    pdl_entry();
+    __shared__ __align__(16) unsigned char s_t[8][BW_CHUNK_BYTES];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const long long chunk = (long long)blockIdx.x * 8 + warp;
+    if (chunk >= L.npx / BW_CHUNK_PX) return;                                // whole warps leave
+    const size_t s = blockIdx.y, off = (size_t)chunk * BW_CHUNK_BYTES;
+    uint8_t *mp = L.Mt + s * L.model_stride + off, *vp = L.Vt + s * L.model_stride + off;
+    uint4 in[3], m[3], v[3], ge[3];
+    bw_ld3(L.frame + s * L.frame_stride + off, lane, in);
+    bw_ld3(mp, lane, m);
+    bw_ld3(vp, lane, v);
+    const unsigned vmax4 = L.vmax8 * 0x01010101u, vmin4 = L.vmin8 * 0x01010101u;
+    auto word = [&](unsigned x, unsigned &mw, unsigned &vw) -> unsigned {     // one word of sigma_delta_kernel's update
+        mw = mw + (__vcmpltu4(mw, x) & 0x01010101u) - (__vcmpgtu4(mw, x) & 0x01010101u);
+        const unsigned o = __vabs4(__vsub4(mw, x));
+        unsigned nv;
+        if (L.N == 1u) nv = vw + (__vcmpltu4(vw, o) & 0x01010101u) - (__vcmpgtu4(vw, o) & 0x01010101u);
+        else {
+            nv = 0u;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                unsigned vb = (vw >> (8 * b)) & 0xffu;
+                const unsigned amp = L.N * ((o >> (8 * b)) & 0xffu);
+                if (vb < amp) vb = (vb + 1u) & 0xffu; else if (vb > amp) vb = vb - 1u;
+                nv |= vb << (8 * b);
+            }
+        }
+        vw = __vmaxu4(__vminu4(nv, vmax4), vmin4);
+        return __vcmpgeu4(o, vw) & 0x01010101u;
+    };
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        ge[k].x = word(in[k].x, m[k].x, v[k].x); ge[k].y = word(in[k].y, m[k].y, v[k].y);
+        ge[k].z = word(in[k].z, m[k].z, v[k].z); ge[k].w = word(in[k].w, m[k].w, v[k].w);
+    }
+    bw_st3(mp, lane, m);
+    bw_st3(vp, lane, v);
+    const uint4 mask = bw_mask_from_flags(s_t[warp], ge, lane);
+    if (L.fg) st_stream_u4(L.fg + s * L.fg_stride + (size_t)chunk * BW_CHUNK_PX + lane * 16u, mask);
+}
+
+__global__ void __launch_bounds__(256)
+dps_median_coalesced_kernel(DpsLaunch L)
+{
+    pdl_entry();
+    __shared__ __align__(16) unsigned char s_t[8][BW_CHUNK_BYTES];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const long long chunk = (long long)blockIdx.x * 8 + warp;
+    if (chunk >= L.npx / BW_CHUNK_PX) return;
+    const size_t s = blockIdx.y, off = (size_t)chunk * BW_CHUNK_BYTES;
+    uint8_t *mp = L.median + s * L.median_stride + off;
+    uint4 in[3], med[3], gt[3];
+    bw_ld3(L.frame + s * L.frame_stride + off, lane, in);
+    bw_ld3(mp, lane, med);
+    const unsigned hi = L.high_u * 0x01010101u;
+    auto flag = [&](unsigned x, unsigned m) { return __vcmpgtu4(__vabsdiffu4(x, m), hi) & 0x01010101u; };
+    auto step = [&](unsigned x, unsigned m) { return m + (__vcmpgtu4(x, m) & 0x01010101u) - (__vcmpltu4(x, m) & 0x01010101u); };
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        gt[k].x = flag(in[k].x, med[k].x); gt[k].y = flag(in[k].y, med[k].y); gt[k].z = flag(in[k].z, med[k].z); gt[k].w = flag(in[k].w, med[k].w);
+    }
+    if (L.update) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            med[k].x = step(in[k].x, med[k].x); med[k].y = step(in[k].y, med[k].y); med[k].z = step(in[k].z, med[k].z); med[k].w = step(in[k].w, med[k].w);
+        }
+        bw_st3(mp, lane, med);
+    }
+    const uint4 mask = bw_mask_from_flags(s_t[warp], gt, lane);
+    st_stream_u4(L.fg + s * L.fg_stride + (size_t)chunk * BW_CHUNK_PX + lane * 16u, mask);
+}
+
+// whole chunks, 16-byte aligned images and strides; BGSB_BYTEWISE_COALESCED=0 keeps the 4-pixel kernels (A/B)
+static bool bw_coalesced_ok(int npx, int nstreams, std::initializer_list<const void *> ptrs, std::initializer_list<size_t> strides)
+{
+    static const bool off = [] { const char *e = getenv("BGSB_BYTEWISE_COALESCED"); return e && e[0] == '0'; }();
+    if (off || npx < BW_CHUNK_PX || npx % BW_CHUNK_PX) return false;
+    for (const void *p : ptrs) if (reinterpret_cast<uintptr_t>(p) & 15) return false;
+    if (nstreams > 1) for (size_t st : strides) if (st & 15) return false;
+    return true;
+}
+
 int launch_sigma_delta(const SdLaunch &L, int nstreams, cudaStream_t stream)
 {
+    if (!L.first && bw_coalesced_ok(L.npx, nstreams, {L.frame, L.fg, L.Mt, L.Vt}, {L.frame_stride, L.fg_stride, L.model_stride})) {
+        const long long chunks = L.npx / BW_CHUNK_PX;
+        launch_pdl(sigma_delta_coalesced_kernel, dim3((unsigned)((chunks + 7) / 8), (unsigned)nstreams), dim3(256), 0, stream, L);
+        BGSB_LAUNCH_CHECK();
+        return BGSB_OK;
+    }
     const long long groups = ((long long)L.npx + 3) / 4;
     launch_pdl(sigma_delta_kernel, dim3((unsigned)((groups + 255) / 256), (unsigned)nstreams), dim3(256), 0, stream, L);
     BGSB_LAUNCH_CHECK();
@@ -417,7 +554,10 @@ int launch_dp_simple(const DpsLaunch &L, int nstreams, cudaStream_t stream)
 {
     const long long groups = ((long long)L.npx + 3) / 4;
     const dim3 grid((unsigned)((groups + 255) / 256), (unsigned)nstreams);
-    if (L.kind == DPS_MEDIAN) launch_pdl(dps_median_kernel, grid, dim3(256), 0, stream, L);
+    if (L.kind == DPS_MEDIAN && !L.fresh && bw_coalesced_ok(L.npx, nstreams, {L.frame, L.fg, L.median}, {L.frame_stride, L.fg_stride, L.median_stride})) {
+        const long long chunks = L.npx / BW_CHUNK_PX;
+        launch_pdl(dps_median_coalesced_kernel, dim3((unsigned)((chunks + 7) / 8), (unsigned)nstreams), dim3(256), 0, stream, L);
+    } else if (L.kind == DPS_MEDIAN) launch_pdl(dps_median_kernel, grid, dim3(256), 0, stream, L);
     else if (L.kind == DPS_MEAN) launch_pdl(dps_float_kernel<DPS_MEAN>, grid, dim3(256), 0, stream, L);
     else if (L.kind == DPS_WREN) launch_pdl(dps_float_kernel<DPS_WREN>, grid, dim3(256), 0, stream, L);
     else { set_error("launch_dp_simple: bad kind %d", L.kind); return BGSB_ERR_ARG; }
